@@ -1,0 +1,199 @@
+/*
+ * pfx_b200.h — C-ABI of libpfx_b200.so, the B200-native staggered phase-field fracture
+ * load-step engine behind the PhaseFieldX driver API.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers/sizes, returns an int status
+ * (0 = PFX_OK, >0 = PFX_ERR_*), never throws and never calls exit().  The caller owns all
+ * host arrays passed in (the library copies them during the call and retains no host
+ * pointer); the library owns the device memory behind the opaque `pfx_ctx*`.
+ * One host thread drives a context; distinct contexts are independent.
+ *
+ * Each function cites the reference interface it replaces (paths relative to the
+ * reference repository root, `src/phasefieldx/` abbreviated as `pfx/`).
+ *
+ * Layouts: coordinates [N_n,3] f64 (dolfinx pads to 3), cells [N_e,n_v] i32,
+ * u interleaved [N_n*d] f64, scalar nodal fields [N_n] f64, all in the CALLER's node order.
+ */
+#ifndef PFX_B200_H
+#define PFX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ---------------------------------------------------------------- */
+enum {
+    PFX_OK = 0,
+    PFX_ERR_BAD_ARG = 1,
+    PFX_ERR_CUDA = 2,
+    PFX_ERR_NOT_CONVERGED_U = 3,     /* SNES-like reason <= 0 on the displacement solve   */
+    PFX_ERR_NOT_CONVERGED_PHI = 4,   /* ... on the phase-field solve                      */
+    PFX_ERR_NOT_CONVERGED_PROJ = 5,  /* mass-matrix PCG of the L2 projection              */
+    PFX_ERR_NAN = 6,
+    PFX_ERR_UNSUPPORTED = 7,
+    PFX_ERR_COMM = 8,
+    PFX_ERR_NO_DEVICE = 9
+};
+
+/* ---- enumerations ---------------------------------------------------------------- */
+enum { PFX_CELL_TRIANGLE = 0, PFX_CELL_QUADRILATERAL = 1, PFX_CELL_TETRAHEDRON = 2 };
+/* pfx/Element/Phase_Field_Fracture/split_energy_stress_tangent_functions.py:234-354 */
+enum { PFX_MODEL_ISOTROPIC = 0, PFX_MODEL_SPECTRAL = 1, PFX_MODEL_DEVIATORIC = 2,
+       PFX_MODEL_HYBRID_SPECTRAL = 3, PFX_MODEL_HYBRID_DEVIATORIC = 4 };
+enum { PFX_FIELD_U = 0, PFX_FIELD_PHI = 1, PFX_FIELD_H = 2, PFX_FIELD_VC = 3, PFX_FIELD_VN = 4,
+       PFX_FIELD_FATIGUE = 5, PFX_FIELD_ALPHA_BAR = 6, PFX_FIELD_ALPHA_C = 7, PFX_FIELD_U_OLD = 8,
+       PFX_FIELD_PHI_OLD = 9, PFX_FIELD_ALPHA_N = 10, PFX_FIELD_ALPHA_BAR_N = 11 };
+
+/* ---- plain-data structs ---------------------------------------------------------- */
+typedef struct pfx_ctx pfx_ctx;
+
+typedef struct {
+    int32_t cell_type;        /* PFX_CELL_*                                                */
+    int64_t n_nodes;          /* nodes held by this context (owned first, then ghosts)     */
+    int64_t n_cells;
+    const double* coords;     /* [n_nodes,3]  (msh.geometry.x)                             */
+    const int32_t* cells;     /* [n_cells,n_v] (V.dofmap.list; quads in tensor order)      */
+    /* distributed runs only (NULL / 0 for one GPU): see pfx_partition()                   */
+    int64_t n_owned;          /* 0 => all nodes owned                                      */
+    const uint8_t* cell_primary; /* [n_cells] 1 if this rank integrates the cell in scalar
+                                    reductions (energies, norms); NULL => all              */
+} pfx_mesh;
+
+/* pfx/Element/Phase_Field_Fracture/Input.py:66-102 */
+typedef struct {
+    double lambda_, mu, Gc, l, k;
+    int32_t model;            /* PFX_MODEL_*                                               */
+    int32_t irreversibility;  /* 1 = "miehe": H = max(V_c, V_n); 0: H = V_c (solver.py:357) */
+    int32_t fatigue;          /* 0/1 (solver.py:362-375)                                   */
+    double fatigue_val;       /* alpha_T of the asymptotic f (fatigue_degradation_functions.py:19-38) */
+    /* solver controls (PETSc option dicts are hard-coded in solver.py:188-196, 227-235)   */
+    double snes_rtol, snes_atol, snes_stol;  /* 1e-8, 1e-9, 1e-8                            */
+    int32_t snes_max_it;                     /* 50                                         */
+    double cg_rtol;           /* PCG ||r|| <= cg_rtol*||b|| standing in for MUMPS (default 1e-11) */
+    int32_t cg_max_it;        /* default 200000                                            */
+    double proj_rtol;         /* mass-PCG tolerance of project() (default 1e-13) */
+    int32_t quad_points_1d;   /* Gauss points per direction for Q1 cells (default 3)       */
+    int32_t block_nodes;      /* owned nodes per CTA tile, 0 = auto                         */
+    int32_t cg_chunk;         /* CG iterations per CUDA-graph launch, 0 = auto             */
+} pfx_params;
+
+typedef struct {
+    double dt;                /* solver.py:55, used by the fatigue heaviside argument      */
+    int32_t min_stagger_iter, max_stagger_iter;
+    double stagger_tol;       /* solver.py:58-60                                            */
+    int32_t history_capacity; /* length of the per-stagger-iteration arrays below (may be 0) */
+} pfx_step_opts;
+
+/* per-stagger-iteration log lines of solver.py:326-350, 378-396 */
+typedef struct {
+    int32_t stagger_iters;
+    int32_t u_newton_its, phi_newton_its;        /* of the LAST stagger iteration (phasefieldx.conv) */
+    int32_t u_reason, phi_reason;                /* SNES-like converged reason (2,3,4 / <=0)  */
+    double err_u, err_phi;                       /* eval_error_L2_normalized, errors_functions.py:190-228 */
+    double fnorm_u, fnorm_phi;
+    int64_t cg_its_u, cg_its_phi, cg_its_proj;   /* totals over the load step                */
+    int32_t history_len;
+    int32_t* hist_u_its;      /* caller-allocated [history_capacity] or NULL                */
+    int32_t* hist_phi_its;
+    double* hist_err_u;
+    double* hist_err_phi;
+    double* hist_fnorm_u;
+    double* hist_fnorm_phi;
+} pfx_step_report;
+
+/* ---- library-level ---------------------------------------------------------------- */
+const char* pfx_version(void);
+int pfx_device_count(int* n);
+const char* pfx_status_string(int status);
+
+/* ---- context ---------------------------------------------------------------------- */
+/* Replaces the form/solver construction of solver.py:148-245 (Functions, F_u/J_u, F_phi/J_phi,
+ * NonlinearProblem objects).  `device` = CUDA ordinal. */
+int pfx_create(const pfx_mesh* mesh, const pfx_params* params, int device, pfx_ctx** out);
+int pfx_destroy(pfx_ctx* ctx);
+const char* pfx_last_error(const pfx_ctx* ctx);
+void pfx_default_params(pfx_params* p);
+
+/* ---- Dirichlet data: dolfinx.fem.dirichletbc objects built by pfx/Boundary/boundary_conditions.py:23-234.
+ * `dofs` are unrolled (bc.dof_indices()[0]); BCs are applied in id order, later ids win on
+ * shared dofs (dolfinx set_bc order).  Values are re-sent every step after the user callback
+ * (solver.py:306-309): one value per dof. */
+int pfx_set_bc_u(pfx_ctx* ctx, int bc_id, const int32_t* dofs, int64_t n);
+int pfx_set_bc_values_u(pfx_ctx* ctx, int bc_id, const double* values, int64_t n);
+int pfx_set_bc_phi(pfx_ctx* ctx, int bc_id, const int32_t* dofs, int64_t n);
+int pfx_set_bc_values_phi(pfx_ctx* ctx, int bc_id, const double* values, int64_t n);
+/* Neumann data of solver.py:179-184 (T_list_u): pre-integrated nodal weights w_i = ∫ N_i ds of
+ * the tagged boundary (host side computes them once); load vector = w_i * T_c, T re-sent per step. */
+int pfx_set_traction(pfx_ctx* ctx, int t_id, const int32_t* nodes, const double* weights, int64_t n);
+int pfx_set_traction_value(pfx_ctx* ctx, int t_id, const double* T /* [d] */);
+
+/* ---- the hot path: one load step = the whole stagger loop of solver.py:319-411 on device */
+int pfx_load_step(pfx_ctx* ctx, const pfx_step_opts* opts, pfx_step_report* out);
+
+/* ---- per-step outputs --------------------------------------------------------------- */
+/* pfx/Reactions/reactions_forces.py:12-65, called per BC at solver.py:428-431 */
+int pfx_reaction(pfx_ctx* ctx, int bc_id, double R[3]);
+/* total.energy columns of solver.py:455: EplusW,E,W,W_phi,W_gradphi,gamma,gamma_phi,gamma_gradphi,PSI_a,PSI_b,alpha_acum */
+int pfx_energies(pfx_ctx* ctx, double out[11]);
+/* fields in caller node order; `host` has n_nodes*(d or 1) doubles */
+int pfx_get_field(pfx_ctx* ctx, int field, double* host, int64_t n);
+int pfx_set_field(pfx_ctx* ctx, int field, const double* host, int64_t n);
+
+/* ---- operator-level hooks (bench + kernel parity tests) ----------------------------- */
+/* y = J_u(u,phi)·v (solver.py:186-187), J_phi(H,Fatigue)·v (:223), mass·v (Math/projection.py:35-40),
+ * with Dirichlet rows/cols = identity when use_bc != 0 (dolfinx assemble_matrix(bcs)). */
+int pfx_apply_u(pfx_ctx* ctx, const double* v, double* y, int use_bc);
+int pfx_apply_phi(pfx_ctx* ctx, const double* v, double* y, int use_bc);
+int pfx_apply_mass(pfx_ctx* ctx, const double* v, double* y);
+int pfx_residual_u(pfx_ctx* ctx, double* f);                 /* F_u_form, solver.py:176-177   */
+int pfx_diag_u(pfx_ctx* ctx, double* diag);                  /* Jacobi preconditioner data    */
+int pfx_rhs_psi(pfx_ctx* ctx, double* b);                    /* ∫ psi_a(u) N_i, projection RHS */
+int pfx_l2_error(pfx_ctx* ctx, int field_a, int field_b, double* err); /* errors_functions.py:190-228 */
+/* Device-resident timing of `reps` back-to-back launches of one operator (kind: 0 apply_u,
+ * 1 apply_phi, 2 apply_mass, 3 residual_u, 4 one full u-PCG iteration); CUDA events on the
+ * context stream, L2 flushed between launches when flush_l2 != 0.  ms_out[reps]. */
+int pfx_time_operator(pfx_ctx* ctx, int kind, int reps, int flush_l2, float* ms_out);
+/* algorithmic bytes of one launch of `kind` for this mesh (SURVEY §8d formulas) */
+int pfx_algorithmic_bytes(pfx_ctx* ctx, int kind, double* bytes);
+/* kernels launched by this context since creation (bench `gpu_launches`) */
+int pfx_launch_count(pfx_ctx* ctx, int64_t* n);
+int pfx_block_stats(pfx_ctx* ctx, int64_t out[8]);
+
+/* ---- multi-GPU: partition + ghost maps (dolfinx IndexMap/Scatterer + graph partitioner) ---
+ * Host-only, deterministic.  cell_rank_in may supply an external partition (replay of a
+ * dolfinx partition) or be NULL (recursive coordinate bisection of cell centroids).
+ * Two-call protocol: pfx_partition_create builds everything, the getters copy out. */
+typedef struct pfx_partition pfx_partition;
+int pfx_partition_create(int32_t cell_type, int64_t n_nodes, int64_t n_cells, const double* coords,
+                         const int32_t* cells, int n_ranks, const int32_t* cell_rank_in,
+                         pfx_partition** out);
+int pfx_partition_destroy(pfx_partition* p);
+int pfx_partition_cell_rank(const pfx_partition* p, int32_t* cell_rank /* [n_cells] */);
+int pfx_partition_node_owner(const pfx_partition* p, int32_t* node_owner /* [n_nodes] */);
+/* sizes for rank r: out = {n_local_nodes, n_owned, n_local_cells, n_send_total, n_neighbors} */
+int pfx_partition_rank_sizes(const pfx_partition* p, int rank, int64_t out[5]);
+/* local->global node map (owned first, ghosts grouped by owner rank ascending, each group by
+ * global id), local cells as global cell ids, ghost owners, primary flags */
+int pfx_partition_rank_maps(const pfx_partition* p, int rank, int64_t* local_to_global_node,
+                            int64_t* local_cell_global, int32_t* ghost_owner, uint8_t* cell_primary);
+/* exchange plan of rank r: neighbors[n_neighbors], send_offsets[n_neighbors+1] into
+ * send_local_idx[n_send_total] (local owned indices to pack), recv_offsets[n_neighbors+1]
+ * (ghost ranges, relative to n_owned) */
+int pfx_partition_rank_plan(const pfx_partition* p, int rank, int32_t* neighbors, int64_t* send_offsets,
+                            int32_t* send_local_idx, int64_t* recv_offsets);
+
+/* Attach the exchange plan + NCCL communicator to a context (one process per GPU).
+ * nccl_unique_id: 128 bytes from pfx_comm_unique_id() on rank 0, broadcast by the host
+ * (torch.distributed).  After this call halo exchange and scalar all-reduces run inside
+ * pfx_load_step / pfx_apply_* on the context stream. */
+int pfx_comm_unique_id(uint8_t id[128]);
+int pfx_comm_attach(pfx_ctx* ctx, int rank, int n_ranks, const uint8_t id[128], int n_neighbors,
+                    const int32_t* neighbors, const int64_t* send_offsets, const int32_t* send_local_idx,
+                    const int64_t* recv_offsets);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFX_B200_H */

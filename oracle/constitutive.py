@@ -118,7 +118,7 @@ def split_numpy(A, lam, mu, degradation, split_energy, want_tangent=True):
             psi_a, psi_b, sig_a, C_a = _spectral2_np(A, lam, mu)
         else:
             r = split_torch(A, lam, mu, "anisotropic", "spectral", want_tangent)
-            psi_a, psi_b, sig_a, C_a = r["psi_a"], r["psi_b"], r["sig_a"], r["C_a"]
+            psi_a, psi_b, sig_a, C_a = r["psi_a"], r["psi_b"], r["sig_a"], r.get("C_a", np.zeros_like(C))
     else:
         raise ValueError("Invalid")
     if degradation == "hybrid":
