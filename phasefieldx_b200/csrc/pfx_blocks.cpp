@@ -1,0 +1,268 @@
+// pfx_blocks.cpp — see pfx_blocks.h.  Pure host C++ (also compiled into the CPU test helper).
+#include "pfx_blocks.h"
+
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+
+namespace pfx {
+
+namespace {
+
+// Recursive coordinate bisection into `nparts` parts of (almost) equal size.  Deterministic:
+// ties on the coordinate are broken by the item index.
+struct Rcb {
+    const double* xyz;   // [n,3]
+    int dim;
+    std::vector<int32_t>& ids;
+    std::vector<int32_t>& part;
+    void run(int64_t lo, int64_t hi, int nparts, int base) {
+        if (nparts <= 1) {
+            for (int64_t i = lo; i < hi; ++i) part[ids[i]] = base;
+            return;
+        }
+        int pl = nparts / 2;
+        int64_t n = hi - lo;
+        int64_t nl = (n * pl + nparts / 2) / nparts;
+        double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+        for (int64_t i = lo; i < hi; ++i)
+            for (int a = 0; a < dim; ++a) {
+                double v = xyz[3 * (int64_t)ids[i] + a];
+                mn[a] = std::min(mn[a], v);
+                mx[a] = std::max(mx[a], v);
+            }
+        int ax = 0;
+        for (int a = 1; a < dim; ++a)
+            if (mx[a] - mn[a] > mx[ax] - mn[ax]) ax = a;
+        const double* c = xyz;
+        auto cmp = [c, ax](int32_t p, int32_t q) {
+            double vp = c[3 * (int64_t)p + ax], vq = c[3 * (int64_t)q + ax];
+            return vp < vq || (vp == vq && p < q);
+        };
+        std::nth_element(ids.begin() + lo, ids.begin() + lo + nl, ids.begin() + hi, cmp);
+        run(lo, lo + nl, pl, base);
+        run(lo + nl, hi, nparts - pl, base + pl);
+    }
+};
+
+}  // namespace
+
+std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int64_t n_cells, const double* coords,
+                         const int32_t* cells, const uint8_t* cell_primary, int max_own, BlockMesh& bm) {
+    if (n_owned <= 0 || n_owned > n_nodes) return "bad n_owned";
+    if (max_own < 8) return "block size too small";
+    bm = BlockMesh();
+    bm.nv = nv; bm.dim = dim; bm.n_nodes = n_nodes; bm.n_owned = n_owned; bm.n_cells = n_cells;
+
+    // ---- 1. blocks of owned nodes (retry with more blocks until every block fits) ---------
+    std::vector<int32_t> part(n_owned), ids(n_owned);
+    int nb = (int)((n_owned + max_own - 1) / max_own);
+    for (;;) {
+        std::iota(ids.begin(), ids.end(), 0);
+        Rcb r{coords, dim, ids, part};
+        r.run(0, n_owned, nb, 0);
+        std::vector<int32_t> cnt(nb, 0);
+        for (int64_t i = 0; i < n_owned; ++i) cnt[part[i]]++;
+        int mx = *std::max_element(cnt.begin(), cnt.end());
+        if (mx <= max_own) break;
+        nb += std::max(1, nb / 64);
+    }
+    bm.nb = nb;
+
+    // ---- 2. renumber: block-contiguous owned nodes (ascending old id inside a block) ------
+    bm.node0.assign(nb + 1, 0);
+    for (int64_t i = 0; i < n_owned; ++i) bm.node0[part[i] + 1]++;
+    for (int b = 0; b < nb; ++b) bm.node0[b + 1] += bm.node0[b];
+    bm.perm.resize(n_nodes); bm.iperm.resize(n_nodes);
+    {
+        std::vector<int32_t> cur(bm.node0.begin(), bm.node0.end() - 1);
+        for (int64_t i = 0; i < n_owned; ++i) {
+            int32_t nw = cur[part[i]]++;
+            bm.perm[nw] = (int32_t)i; bm.iperm[i] = nw;
+        }
+        for (int64_t i = n_owned; i < n_nodes; ++i) { bm.perm[i] = (int32_t)i; bm.iperm[i] = (int32_t)i; }
+    }
+    auto block_of_new = [&](int32_t nw) -> int { return nw < n_owned ? part[bm.perm[nw]] : -1; };
+
+    // ---- 3. element lists per block (primary first) --------------------------------------
+    std::vector<int32_t> cnt_p(nb, 0), cnt_s(nb, 0);
+    auto visit = [&](auto&& fn) {
+        for (int64_t c = 0; c < n_cells; ++c) {
+            int blk[4]; int nblk = 0; int32_t low = INT32_MAX; int lowb = -1;
+            for (int a = 0; a < nv; ++a) {
+                int32_t nw = bm.iperm[cells[c * nv + a]];
+                int b = block_of_new(nw);
+                if (b < 0) continue;
+                if (nw < low) { low = nw; lowb = b; }
+                bool seen = false;
+                for (int k = 0; k < nblk; ++k) seen |= (blk[k] == b);
+                if (!seen) blk[nblk++] = b;
+            }
+            bool prim = cell_primary ? cell_primary[c] != 0 : true;
+            for (int k = 0; k < nblk; ++k) fn(c, blk[k], prim && blk[k] == lowb);
+        }
+    };
+    visit([&](int64_t, int b, bool p) { (p ? cnt_p : cnt_s)[b]++; });
+    bm.elem_off.assign(nb + 1, 0);
+    bm.nprim.assign(nb, 0);
+    for (int b = 0; b < nb; ++b) { bm.elem_off[b + 1] = bm.elem_off[b] + cnt_p[b] + cnt_s[b]; bm.nprim[b] = cnt_p[b]; }
+    bm.total_elems = bm.elem_off[nb];
+    bm.elem_gid.resize(bm.total_elems);
+    {
+        std::vector<int32_t> cp(nb), cs(nb);
+        for (int b = 0; b < nb; ++b) { cp[b] = bm.elem_off[b]; cs[b] = bm.elem_off[b] + cnt_p[b]; }
+        visit([&](int64_t c, int b, bool p) { bm.elem_gid[(p ? cp : cs)[b]++] = (int32_t)c; });
+    }
+
+    // ---- 4. halo lists + local connectivity ------------------------------------------------
+    bm.lconn.assign(4 * bm.total_elems, 0);
+    bm.halo_off.assign(nb + 1, 0);
+    std::vector<int32_t> stamp(n_nodes, -1), loc(n_nodes, 0), tmp;
+    for (int b = 0; b < nb; ++b) {
+        int32_t n0 = bm.node0[b], n1 = bm.node0[b + 1];
+        tmp.clear();
+        for (int32_t e = bm.elem_off[b]; e < bm.elem_off[b + 1]; ++e)
+            for (int a = 0; a < nv; ++a) {
+                int32_t nw = bm.iperm[cells[(int64_t)bm.elem_gid[e] * nv + a]];
+                if (nw >= n0 && nw < n1) continue;
+                if (stamp[nw] != b) { stamp[nw] = b; tmp.push_back(nw); }
+            }
+        std::sort(tmp.begin(), tmp.end());
+        int n_own = n1 - n0;
+        for (size_t k = 0; k < tmp.size(); ++k) loc[tmp[k]] = n_own + (int32_t)k;
+        bm.halo.insert(bm.halo.end(), tmp.begin(), tmp.end());
+        bm.halo_off[b + 1] = (int32_t)bm.halo.size();
+        int n_loc = n_own + (int)tmp.size();
+        if (n_loc > 65535) return "block has more than 65535 local nodes";
+        int ne = bm.elem_off[b + 1] - bm.elem_off[b];
+        if (ne > 16383) return "block has more than 16383 elements; lower block_nodes";
+        bm.max_own = std::max(bm.max_own, n_own);
+        bm.max_loc = std::max(bm.max_loc, n_loc);
+        bm.max_elems = std::max(bm.max_elems, ne);
+        for (int32_t e = bm.elem_off[b]; e < bm.elem_off[b + 1]; ++e)
+            for (int a = 0; a < nv; ++a) {
+                int32_t nw = bm.iperm[cells[(int64_t)bm.elem_gid[e] * nv + a]];
+                bm.lconn[4 * (int64_t)e + a] = (uint16_t)((nw >= n0 && nw < n1) ? nw - n0 : loc[nw]);
+            }
+    }
+
+    // ---- 5. node -> (element, vertex) incidence of owned nodes ------------------------------
+    bm.inc_ptr.assign(n_owned + 1, 0);
+    for (int b = 0; b < nb; ++b) {
+        int n_own = bm.node0[b + 1] - bm.node0[b];
+        for (int32_t e = bm.elem_off[b]; e < bm.elem_off[b + 1]; ++e)
+            for (int a = 0; a < nv; ++a) {
+                int l = bm.lconn[4 * (int64_t)e + a];
+                if (l < n_own) bm.inc_ptr[bm.node0[b] + l + 1]++;
+            }
+    }
+    for (int64_t i = 0; i < n_owned; ++i) bm.inc_ptr[i + 1] += bm.inc_ptr[i];
+    bm.inc.resize(bm.inc_ptr[n_owned]);
+    {
+        std::vector<int32_t> cur(bm.inc_ptr.begin(), bm.inc_ptr.end() - 1);
+        for (int b = 0; b < nb; ++b) {
+            int n_own = bm.node0[b + 1] - bm.node0[b];
+            for (int32_t e = bm.elem_off[b]; e < bm.elem_off[b + 1]; ++e)
+                for (int a = 0; a < nv; ++a) {
+                    int l = bm.lconn[4 * (int64_t)e + a];
+                    if (l < n_own) bm.inc[cur[bm.node0[b] + l]++] = (uint16_t)(((e - bm.elem_off[b]) << 2) | a);
+                }
+        }
+    }
+    return "";
+}
+
+// =============================================================================== partition
+std::string build_partition(int nv, int64_t n_nodes, int64_t n_cells, const double* coords, const int32_t* cells,
+                            int n_ranks, const int32_t* cell_rank_in, Partition& P) {
+    if (n_ranks < 1) return "n_ranks < 1";
+    P = Partition();
+    P.n_ranks = n_ranks; P.n_nodes = n_nodes; P.n_cells = n_cells;
+    P.cell_rank.assign(n_cells, 0);
+    if (cell_rank_in) {
+        for (int64_t c = 0; c < n_cells; ++c) {
+            if (cell_rank_in[c] < 0 || cell_rank_in[c] >= n_ranks) return "cell_rank out of range";
+            P.cell_rank[c] = cell_rank_in[c];
+        }
+    } else if (n_ranks > 1) {
+        std::vector<double> cen(3 * n_cells, 0.0);
+        for (int64_t c = 0; c < n_cells; ++c)
+            for (int a = 0; a < nv; ++a)
+                for (int i = 0; i < 3; ++i) cen[3 * c + i] += coords[3 * (int64_t)cells[c * nv + a] + i] / nv;
+        std::vector<int32_t> ids(n_cells);
+        std::iota(ids.begin(), ids.end(), 0);
+        Rcb r{cen.data(), 3, ids, P.cell_rank};
+        r.run(0, n_cells, n_ranks, 0);
+    }
+    // node owner = lowest adjacent cell rank
+    P.node_owner.assign(n_nodes, INT32_MAX);
+    for (int64_t c = 0; c < n_cells; ++c)
+        for (int a = 0; a < nv; ++a) {
+            int32_t& o = P.node_owner[cells[c * nv + a]];
+            o = std::min(o, P.cell_rank[c]);
+        }
+    for (int64_t i = 0; i < n_nodes; ++i)
+        if (P.node_owner[i] == INT32_MAX) return "mesh has a node without cells";
+
+    P.ranks.assign(n_ranks, RankPart());
+    std::vector<int64_t> g2l(n_nodes);
+    for (int r = 0; r < n_ranks; ++r) {
+        RankPart& R = P.ranks[r];
+        // local cells = every cell touching a node owned by r (ascending global id)
+        std::vector<uint8_t> need(n_nodes, 0);
+        for (int64_t c = 0; c < n_cells; ++c) {
+            bool touch = false;
+            for (int a = 0; a < nv; ++a) touch |= (P.node_owner[cells[c * nv + a]] == r);
+            if (!touch) continue;
+            R.cell_gid.push_back(c);
+            for (int a = 0; a < nv; ++a) need[cells[c * nv + a]] = 1;
+            // primary: the rank owning the cell's lowest-numbered node integrates it
+            int32_t low = cells[c * nv];
+            for (int a = 1; a < nv; ++a) low = std::min(low, cells[c * nv + a]);
+            R.cell_primary.push_back(P.node_owner[low] == r ? 1 : 0);
+        }
+        for (int64_t i = 0; i < n_nodes; ++i)
+            if (P.node_owner[i] == r) R.l2g.push_back(i);
+        R.n_owned = (int64_t)R.l2g.size();
+        std::vector<std::pair<int32_t, int64_t>> gh;
+        for (int64_t i = 0; i < n_nodes; ++i)
+            if (need[i] && P.node_owner[i] != r) gh.push_back({P.node_owner[i], i});
+        std::sort(gh.begin(), gh.end());
+        for (auto& g : gh) { R.l2g.push_back(g.second); R.ghost_owner.push_back(g.first); }
+        // receive plan: ghost ranges per owner
+        R.recv_off.push_back(0);
+        for (size_t k = 0; k < gh.size(); ++k) {
+            if (R.neighbors.empty() || R.neighbors.back() != gh[k].first) {
+                if (!R.neighbors.empty()) R.recv_off.push_back((int64_t)k);
+                R.neighbors.push_back(gh[k].first);
+            }
+        }
+        if (!R.neighbors.empty()) R.recv_off.push_back((int64_t)gh.size());
+    }
+    // send plan: what neighbour q receives from r, in q's ghost order.  Neighbour sets are made
+    // symmetric (a rank may send to a rank it receives nothing from).
+    std::vector<std::vector<std::vector<int64_t>>> want(n_ranks, std::vector<std::vector<int64_t>>(n_ranks));
+    for (int q = 0; q < n_ranks; ++q) {
+        RankPart& Q = P.ranks[q];
+        for (size_t k = 0; k < Q.ghost_owner.size(); ++k) want[Q.ghost_owner[k]][q].push_back(Q.l2g[Q.n_owned + k]);
+    }
+    for (int r = 0; r < n_ranks; ++r) {
+        RankPart& R = P.ranks[r];
+        std::vector<int32_t> nb;
+        for (int q = 0; q < n_ranks; ++q)
+            if (q != r && (!want[r][q].empty() || !want[q][r].empty())) nb.push_back(q);
+        // rebuild recv offsets on the symmetric neighbour list
+        std::vector<int64_t> roff(1, 0);
+        for (int q : nb) roff.push_back(roff.back() + (int64_t)want[q][r].size());
+        R.neighbors = nb; R.recv_off = roff;
+        for (int64_t l = 0; l < R.n_owned; ++l) g2l[R.l2g[l]] = l;
+        R.send_off.assign(1, 0);
+        for (int q : nb) {
+            for (int64_t g : want[r][q]) R.send_idx.push_back((int32_t)g2l[g]);
+            R.send_off.push_back((int64_t)R.send_idx.size());
+        }
+    }
+    return "";
+}
+
+}  // namespace pfx

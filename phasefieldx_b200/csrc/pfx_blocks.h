@@ -1,0 +1,68 @@
+// pfx_blocks.h — host-side mesh preprocessing: CTA tiles ("blocks") and rank partitions.
+//
+// Replaces what dolfinx does at mesh/function-space creation for the reference (graph
+// partitioner, IndexMap, Scatterer, dofmap reordering; third-party, not in the reference
+// tree).  Two levels share one idea — owner computes, with one overlap layer of cells:
+//   * ranks  (GPUs): owned nodes first, ghosts after; every cell touching an owned node is
+//     kept locally, so an operator apply needs only a FORWARD halo of its input vector;
+//   * blocks (CTAs): each block owns a contiguous range of (renumbered) nodes and lists every
+//     cell touching one of them, so a CTA accumulates its own rows in shared memory and
+//     writes them coalesced — no atomics, deterministic summation order.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace pfx {
+
+struct BlockMesh {
+    int nv = 0, dim = 0;
+    int64_t n_nodes = 0;      // local nodes (owned + ghosts)
+    int64_t n_owned = 0;
+    int64_t n_cells = 0;
+    int nb = 0;               // number of blocks
+    std::vector<int32_t> perm;       // new -> old (caller) node id, size n_nodes
+    std::vector<int32_t> iperm;      // old -> new
+    std::vector<int32_t> node0;      // [nb+1] owned range of each block (new ids)
+    std::vector<int32_t> halo_off;   // [nb+1]
+    std::vector<int32_t> halo;       // new ids of non-owned nodes referenced by the block, sorted
+    std::vector<int32_t> elem_off;   // [nb+1]
+    std::vector<int32_t> nprim;      // [nb] leading elements of the block integrated in scalar reductions
+    std::vector<uint16_t> lconn;     // [4*sum elems] block-local vertex ids (triangles: 4th = 0)
+    std::vector<int32_t> elem_gid;   // [sum elems] caller cell id (diagnostics/tests)
+    std::vector<int32_t> inc_ptr;    // [n_owned+1] into inc
+    std::vector<uint16_t> inc;       // per owned node: (local elem << 2 | vertex), ascending
+    int max_own = 0, max_loc = 0, max_elems = 0;
+    int64_t total_elems = 0;         // with overlap duplicates
+};
+
+// Build blocks of at most `max_own` owned nodes by recursive coordinate bisection of the owned
+// nodes.  coords [n_nodes,3]; cells [n_cells,nv] (caller ids; every cell must touch >=1 owned
+// node or it is ignored); cell_primary may be null (= all 1).  Returns "" or an error text.
+std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int64_t n_cells, const double* coords,
+                         const int32_t* cells, const uint8_t* cell_primary, int max_own, BlockMesh& out);
+
+struct RankPart {
+    std::vector<int64_t> l2g;            // local -> global node (owned first, then ghosts by owner, by gid)
+    int64_t n_owned = 0;
+    std::vector<int64_t> cell_gid;       // local cells (global ids, ascending)
+    std::vector<int32_t> ghost_owner;    // [n_ghost]
+    std::vector<uint8_t> cell_primary;   // [n_local_cells]
+    std::vector<int32_t> neighbors;      // ranks exchanged with (ascending)
+    std::vector<int64_t> send_off, recv_off;   // [n_neighbors+1]
+    std::vector<int32_t> send_idx;       // local owned indices to pack, grouped by neighbor
+};
+
+struct Partition {
+    int n_ranks = 0;
+    int64_t n_nodes = 0, n_cells = 0;
+    std::vector<int32_t> cell_rank, node_owner;
+    std::vector<RankPart> ranks;
+};
+
+// cell_rank_in may be null -> recursive coordinate bisection of the cell centroids.
+// node owner = lowest rank among the adjacent cells' ranks (deterministic rule).
+std::string build_partition(int nv, int64_t n_nodes, int64_t n_cells, const double* coords, const int32_t* cells,
+                            int n_ranks, const int32_t* cell_rank_in, Partition& out);
+
+}  // namespace pfx

@@ -45,7 +45,7 @@ template <> struct Geo<Tri> {
         G[1][0] = by * inv;  G[1][1] = -bx * inv;
         G[2][0] = -ay * inv; G[2][1] = ax * inv;
         G[0][0] = -(G[1][0] + G[2][0]); G[0][1] = -(G[1][1] + G[2][1]);
-        vol = 0.5 * fabs(det);
+        vol = 0.5 * ::fabs(det);
         nq = 9;
     }
     PFX_HD double eval(int q, double* N, double (*Gq)[2]) const {
@@ -80,7 +80,7 @@ template <> struct Geo<Tet> {
             G[1][i] = Ji[0][i]; G[2][i] = Ji[1][i]; G[3][i] = Ji[2][i];
             G[0][i] = -(Ji[0][i] + Ji[1][i] + Ji[2][i]);
         }
-        vol = fabs(det) / 6.0;
+        vol = ::fabs(det) / 6.0;
         nq = 27;
     }
     PFX_HD double eval(int q, double* N, double (*Gq)[3]) const {
@@ -114,7 +114,7 @@ template <> struct Geo<Quad> {
             Gq[a][0] = (dr[a][0] * J11 - dr[a][1] * J10) * inv;
             Gq[a][1] = (-dr[a][0] * J01 + dr[a][1] * J00) * inv;
         }
-        return fabs(det) * w;
+        return ::fabs(det) * w;
     }
 };
 

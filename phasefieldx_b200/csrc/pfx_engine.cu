@@ -1,0 +1,1135 @@
+// pfx_engine.cu — context, device-resident staggered load step, and the C-ABI of include/pfx_b200.h.
+//
+// Host control flow restates pfx/Element/Phase_Field_Fracture/solver/solver.py:319-411 (stagger
+// loop) with dolfinx NonlinearProblem/PETSc SNES semantics and a Jacobi-PCG in
+// place of the MUMPS factorisation.  All arithmetic on fields runs in the kernels of
+// pfx_kernels.cuh; there is no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pfx_b200.h"
+#include "pfx_blocks.h"
+#include "pfx_comm.h"
+#include "pfx_kernels.cuh"
+
+using namespace pfx;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            c->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return PFX_ERR_CUDA;                                                                   \
+        }                                                                                          \
+    } while (0)
+
+namespace {
+
+enum LinKind { LIN_U = 0, LIN_PHI = 1, LIN_MASS = 2 };
+
+struct BCSet {
+    std::vector<int32_t> dofs;    // internal (block-order) dof ids
+    int32_t* d_dofs = nullptr;
+    int32_t* d_owned = nullptr;   // subset on owned nodes (reactions)
+    int64_t n_owned = 0;
+    double* d_vals = nullptr;
+    int64_t n = 0;
+};
+
+struct Traction {
+    int32_t* d_nodes = nullptr;
+    double* d_w = nullptr;
+    int64_t n = 0;
+    double T[3] = {0, 0, 0};
+};
+
+struct DevBuf {
+    void* p = nullptr;
+};
+
+}  // namespace
+
+struct pfx_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int cell_type = 0, nv = 0, dim = 0;
+    pfx_params prm;
+    Material mat;
+    BlockMesh bm;
+    BlockView bv;
+    int64_t n_nodes = 0, n_owned = 0;
+    // fields (block order, length n_nodes or n_nodes*dim)
+    double *X = nullptr, *u = nullptr, *u_old = nullptr, *phi = nullptr, *phi_old = nullptr, *H = nullptr,
+           *Vc = nullptr, *Vn = nullptr, *Fat = nullptr, *alpha_c = nullptr, *alpha_n = nullptr, *abar_c = nullptr,
+           *abar_n = nullptr, *dinv_mass = nullptr;
+    // work vectors (u-space sized)
+    double *w_r = nullptr, *w_p = nullptr, *w_Ap = nullptr, *w_x = nullptr, *w_F = nullptr, *w_dinv = nullptr,
+           *w_t0 = nullptr, *w_t1 = nullptr, *g_u = nullptr, *g_phi = nullptr, *fext = nullptr;
+    uint8_t *mask_u = nullptr, *mask_phi = nullptr;
+    bool has_fext = false;
+    std::vector<BCSet> bcs_u, bcs_phi;
+    std::vector<Traction> tractions;
+    bool bc_dirty_u = true, bc_dirty_phi = true;
+    // reductions
+    double* partial = nullptr;
+    double* S = nullptr;          // PCG scalars
+    double* red = nullptr;        // generic result buffer [kMaxRed]
+    unsigned int* counter = nullptr;
+    double* h_pinned = nullptr;   // [64]
+    int vec_grid = 0;
+    // graphs
+    cudaGraphExec_t graph[3] = {nullptr, nullptr, nullptr};
+    int graph_iters = 0;
+    bool use_graph = true;
+    // comm
+    nccl_comm_t comm = nullptr;
+    int rank = 0, n_ranks = 1;
+    std::vector<int32_t> nbrs;
+    std::vector<int64_t> send_off, recv_off;
+    int32_t* d_send_idx = nullptr;
+    double* d_send_buf = nullptr;
+    int64_t n_send = 0;
+    // misc
+    std::vector<void*> allocs;
+    std::string err;
+    int64_t launches = 0;
+    double* flush_buf = nullptr;
+    int64_t flush_n = 0;
+    std::vector<std::vector<int32_t>> tmp_idx;
+    bool configuring = false;
+};
+
+namespace {
+
+template <class T>
+int dev_alloc(pfx_ctx* c, T** p, size_t n) {
+    CK(cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T)));
+    CK(cudaMemsetAsync(*p, 0, std::max<size_t>(n, 1) * sizeof(T), c->stream));
+    c->allocs.push_back((void*)*p);
+    return PFX_OK;
+}
+
+template <class T>
+int dev_upload(pfx_ctx* c, T** p, const std::vector<T>& h) {
+    int st = dev_alloc(c, p, h.size());
+    if (st) return st;
+    if (!h.empty()) CK(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PFX_OK;
+}
+
+inline int vgrid(const pfx_ctx* c, int64_t n) {
+    int64_t g = (n + kThreads - 1) / kThreads;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(g, c->vec_grid));
+}
+
+// --------------------------------------------------------------------------- kernel dispatch
+template <class Op>
+int launch_scatter_op(pfx_ctx* c, const KArgs& a) {
+    BlockView bv = c->bv;
+    int per_elem = Op::NV * Op::NOUT;
+    int cap = std::max(32, (24 * 1024 / (per_elem * 8)) / 32 * 32);
+    bv.chunk = std::min((c->bm.max_elems + 31) / 32 * 32, cap);
+    size_t smem = ((size_t)c->bm.max_loc * Op::NF + (size_t)per_elem * bv.chunk) * sizeof(double);
+    if (c->configuring) {           // pfx_create: opt in to > 48 KB dynamic shared memory, no launch
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(scatter_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return PFX_OK;
+    }
+    scatter_kernel<Op><<<c->bm.nb, kThreads, smem, c->stream>>>(bv, a);
+    c->launches++;
+    CK(cudaGetLastError());
+    return PFX_OK;
+}
+
+template <class Cell>
+int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
+    switch (op) {
+        case OP_APPLY_U:
+            return (a.m.smodel == M_ISO) ? launch_scatter_op<OpApplyU<Cell, false>>(c, a)
+                                         : launch_scatter_op<OpApplyU<Cell, true>>(c, a);
+        case OP_RESIDUAL_U: return launch_scatter_op<OpResidualU<Cell>>(c, a);
+        case OP_DIAG_U: return launch_scatter_op<OpDiagU<Cell>>(c, a);
+        case OP_APPLY_PHI: return launch_scatter_op<OpApplyPhi<Cell>>(c, a);
+        case OP_RESIDUAL_PHI: return launch_scatter_op<OpResidualPhi<Cell>>(c, a);
+        case OP_DIAG_PHI: return launch_scatter_op<OpDiagPhi<Cell>>(c, a);
+        case OP_APPLY_MASS: return launch_scatter_op<OpApplyMass<Cell>>(c, a);
+        case OP_DIAG_MASS: return launch_scatter_op<OpDiagMass<Cell>>(c, a);
+        case OP_RHS_PSI: return launch_scatter_op<OpRhsPsi<Cell>>(c, a);
+        case OP_RHS_FATIGUE: return launch_scatter_op<OpRhsFatigue<Cell>>(c, a);
+    }
+    c->err = "unknown op";
+    return PFX_ERR_BAD_ARG;
+}
+
+int launch_scatter(pfx_ctx* c, int op, const KArgs& a) {
+    if (c->cell_type == PFX_CELL_TRIANGLE) return launch_scatter_cell<Tri>(c, op, a);
+    if (c->cell_type == PFX_CELL_QUADRILATERAL) return launch_scatter_cell<Quad>(c, op, a);
+    return launch_scatter_cell<Tet>(c, op, a);
+}
+
+template <class Cell, int KIND>
+int launch_reduce_k(pfx_ctx* c, const KArgs& a) {
+    constexpr int D = Cell::D;
+    constexpr int NC = (KIND == RED_L2_U) ? D : 1;
+    constexpr int NF = odd<(KIND == RED_ENERGY) ? (2 * D + 3) : (D + 2 * NC)>::value;
+    size_t smem = (size_t)c->bm.max_loc * NF * sizeof(double);
+    if (c->configuring) {
+        if (smem > 48 * 1024)
+            CK(cudaFuncSetAttribute(reduce_kernel<Cell, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return PFX_OK;
+    }
+    reduce_kernel<Cell, KIND><<<c->bm.nb, kThreads, smem, c->stream>>>(c->bv, a);
+    c->launches++;
+    CK(cudaGetLastError());
+    return PFX_OK;
+}
+
+template <int KIND>
+int launch_reduce(pfx_ctx* c, const KArgs& a) {
+    if (c->cell_type == PFX_CELL_TRIANGLE) return launch_reduce_k<Tri, KIND>(c, a);
+    if (c->cell_type == PFX_CELL_QUADRILATERAL) return launch_reduce_k<Quad, KIND>(c, a);
+    return launch_reduce_k<Tet, KIND>(c, a);
+}
+
+KArgs base_args(pfx_ctx* c) {
+    KArgs a;
+    memset(&a, 0, sizeof(a));
+    a.m = c->mat;
+    a.n1d = c->prm.quad_points_1d;
+    a.X = c->X; a.u = c->u; a.phi = c->phi; a.H = c->H; a.Fat = c->Fat;
+    a.partial = c->partial; a.result = c->red; a.counter = c->counter;
+    return a;
+}
+
+// --------------------------------------------------------------------------- communication
+int allreduce(pfx_ctx* c, double* buf, int n) {
+    if (c->n_ranks <= 1) return PFX_OK;
+    int r = nccl().AllReduce(buf, buf, (size_t)n, kNcclFloat64, kNcclSum, c->comm, c->stream);
+    if (r != 0) { c->err = std::string("ncclAllReduce: ") + nccl().GetErrorString(r); return PFX_ERR_COMM; }
+    return PFX_OK;
+}
+
+// forward halo: owners send the values of their boundary nodes, ghosts receive in place
+int exchange(pfx_ctx* c, double* v, int nc) {
+    if (c->n_ranks <= 1 || c->nbrs.empty()) return PFX_OK;
+    if (c->n_send > 0) {
+        pack_kernel<<<vgrid(c, c->n_send * nc), kThreads, 0, c->stream>>>(c->n_send, c->d_send_idx, nc, v, c->d_send_buf);
+        c->launches++;
+    }
+    int r = nccl().GroupStart();
+    for (size_t k = 0; k < c->nbrs.size() && r == 0; ++k) {
+        int64_t ns = c->send_off[k + 1] - c->send_off[k], nr = c->recv_off[k + 1] - c->recv_off[k];
+        if (ns > 0) r = nccl().Send(c->d_send_buf + c->send_off[k] * nc, (size_t)(ns * nc), kNcclFloat64, c->nbrs[k], c->comm, c->stream);
+        if (nr > 0 && r == 0)
+            r = nccl().Recv(v + (c->n_owned + c->recv_off[k]) * nc, (size_t)(nr * nc), kNcclFloat64, c->nbrs[k], c->comm, c->stream);
+    }
+    int r2 = nccl().GroupEnd();
+    if (r != 0 || r2 != 0) { c->err = std::string("halo exchange: ") + nccl().GetErrorString(r ? r : r2); return PFX_ERR_COMM; }
+    return PFX_OK;
+}
+
+// device result buffer -> host (after optional all-reduce); synchronises the stream
+int fetch(pfx_ctx* c, double* dev, int n, double* out) {
+    int st = allreduce(c, dev, n);
+    if (st) return st;
+    CK(cudaMemcpyAsync(c->h_pinned, dev, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i) out[i] = c->h_pinned[i];
+    return PFX_OK;
+}
+
+// --------------------------------------------------------------------------- Dirichlet data
+int rebuild_bc(pfx_ctx* c, bool is_u) {
+    int64_t n = c->n_nodes * (is_u ? c->dim : 1);
+    uint8_t* mask = is_u ? c->mask_u : c->mask_phi;
+    double* g = is_u ? c->g_u : c->g_phi;
+    std::vector<BCSet>& sets = is_u ? c->bcs_u : c->bcs_phi;
+    std::vector<uint8_t> hm(n, 0);
+    for (auto& s : sets)
+        for (int32_t d : s.dofs) hm[d] = 1;
+    CK(cudaMemcpyAsync(mask, hm.data(), n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    (void)g;
+    return PFX_OK;
+}
+
+// values of all BC sets -> g (later ids win: launched in id order on one stream)
+int push_bc_values(pfx_ctx* c, bool is_u) {
+    double* g = is_u ? c->g_u : c->g_phi;
+    std::vector<BCSet>& sets = is_u ? c->bcs_u : c->bcs_phi;
+    for (auto& s : sets)
+        if (s.n > 0) {
+            scatter_set_kernel<<<vgrid(c, s.n), kThreads, 0, c->stream>>>(s.n, s.d_dofs, s.d_vals, g);
+            c->launches++;
+        }
+    CK(cudaGetLastError());
+    return PFX_OK;
+}
+
+__global__ void traction_add_kernel(int64_t n, const int32_t* nodes, const double* w, double t0, double t1, double t2,
+                                    int d, double* fext) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        double* f = fext + (int64_t)nodes[k] * d;
+        f[0] += w[k] * t0;
+        f[1] += w[k] * t1;
+        if (d == 3) f[2] += w[k] * t2;
+    }
+}
+
+int rebuild_fext(pfx_ctx* c) {
+    if (!c->has_fext) return PFX_OK;
+    int64_t n = c->n_nodes * c->dim;
+    CK(cudaMemsetAsync(c->fext, 0, n * sizeof(double), c->stream));
+    for (auto& t : c->tractions)
+        if (t.n > 0) {
+            traction_add_kernel<<<vgrid(c, t.n), kThreads, 0, c->stream>>>(t.n, t.d_nodes, t.d_w, t.T[0], t.T[1], t.T[2], c->dim, c->fext);
+            c->launches++;
+        }
+    CK(cudaGetLastError());
+    return PFX_OK;
+}
+
+// --------------------------------------------------------------------------- PCG
+__global__ void pcg_setup_kernel(double* S, double rtol2) {
+    double rz = S[S_STAGE], rr = S[S_STAGE + 1];
+    S[S_RZ0] = rz; S[S_RZ1] = 0.0; S[S_RR] = rr; S[S_PAP] = 1.0;
+    S[S_THRESH] = rtol2 * rr;
+    S[S_ITERS] = 0.0;
+    S[S_DONE] = (rr > 0.0 && rr > S[S_THRESH]) ? 0.0 : 1.0;
+}
+
+int apply_lin(pfx_ctx* c, int kind, const double* v, double* y, const uint8_t* mask, double* result, const double* stop) {
+    KArgs a = base_args(c);
+    a.v = v; a.y = y; a.mask = mask; a.result = result; a.stop = stop;
+    int op = kind == LIN_U ? OP_APPLY_U : (kind == LIN_PHI ? OP_APPLY_PHI : OP_APPLY_MASS);
+    return launch_scatter(c, op, a);
+}
+
+// one PCG iteration (parity par) enqueued on the stream
+int pcg_iteration(pfx_ctx* c, int kind, int par, int64_t n, const uint8_t* mask, const double* dinv) {
+    int nc = (kind == LIN_U) ? c->dim : 1;
+    int st = exchange(c, c->w_p, nc);
+    if (st) return st;
+    bool multi = c->n_ranks > 1;
+    st = apply_lin(c, kind, c->w_p, c->w_Ap, mask, multi ? c->S + S_STAGE : c->S + S_PAP, c->S + S_DONE);
+    if (st) return st;
+    if (multi) {
+        // skipped launches leave the stage untouched; the guarded copy below keeps S_PAP sane
+        st = allreduce(c, c->S + S_STAGE, 1);
+        if (st) return st;
+        axpby_kernel<<<1, 1, 0, c->stream>>>(1, c->S + S_PAP, c->S + S_STAGE, 1.0, nullptr, 0.0);
+        c->launches++;
+    }
+    int g = vgrid(c, n);
+    pcg_update_kernel<<<g, kThreads, 0, c->stream>>>(n, c->w_x, c->w_r, c->w_p, c->w_Ap, dinv, c->S, par, multi ? 0 : 1,
+                                                    c->partial, c->counter);
+    c->launches++;
+    if (multi) {
+        st = allreduce(c, c->S + S_STAGE, 2);
+        if (st) return st;
+        pcg_publish_kernel<<<1, 1, 0, c->stream>>>(c->S, par);
+        c->launches++;
+    }
+    pcg_direction_kernel<<<g, kThreads, 0, c->stream>>>(n, c->w_p, c->w_r, dinv, c->S, par);
+    c->launches++;
+    CK(cudaGetLastError());
+    return PFX_OK;
+}
+
+int build_graph(pfx_ctx* c, int kind, int64_t n, const uint8_t* mask, const double* dinv) {
+    int iters = c->graph_iters;
+    cudaGraph_t g;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int st = PFX_OK;
+    for (int k = 0; k < iters && st == PFX_OK; ++k) st = pcg_iteration(c, kind, k & 1, n, mask, dinv);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    if (st) return st;
+    CK(e);
+    CK(cudaGraphInstantiate(&c->graph[kind], g, 0));
+    CK(cudaGraphDestroy(g));
+    return PFX_OK;
+}
+
+// Solve A x = b (A = J_u | J_phi | M with Dirichlet rows/cols = identity), Jacobi preconditioned.
+// b in w_F (Dirichlet entries ignored), solution in w_x.  Returns iterations through `iters`.
+int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged) {
+    int nc = (kind == LIN_U) ? c->dim : 1;
+    int64_t n = c->n_owned * nc;
+    const uint8_t* mask = kind == LIN_U ? c->mask_u : (kind == LIN_PHI ? c->mask_phi : nullptr);
+    const double* dinv = kind == LIN_MASS ? c->dinv_mass : c->w_dinv;
+    int g = vgrid(c, n);
+    pcg_init_kernel<<<g, kThreads, 0, c->stream>>>(n, c->w_F, mask, dinv, nullptr, nullptr, c->w_x, c->w_r, c->w_p,
+                                                  c->partial, c->S + S_STAGE, c->counter);
+    c->launches++;
+    int st = allreduce(c, c->S + S_STAGE, 2);
+    if (st) return st;
+    pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, rtol * rtol);
+    c->launches++;
+    CK(cudaGetLastError());
+    int64_t max_it = c->prm.cg_max_it;
+    *converged = false;
+    *iters = 0;
+    for (;;) {
+        if (c->use_graph) {
+            if (!c->graph[kind]) {
+                st = build_graph(c, kind, n, mask, dinv);
+                if (st) return st;
+            }
+            CK(cudaGraphLaunch(c->graph[kind], c->stream));
+            c->launches += (int64_t)c->graph_iters * 3;
+        } else {
+            for (int k = 0; k < c->graph_iters; ++k) {
+                st = pcg_iteration(c, kind, k & 1, n, mask, dinv);
+                if (st) return st;
+            }
+        }
+        CK(cudaMemcpyAsync(c->h_pinned, c->S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        *iters = (int64_t)c->h_pinned[S_ITERS];
+        double rr = c->h_pinned[S_RR];
+        if (!(rr == rr)) { c->err = "NaN in PCG"; return PFX_ERR_NAN; }
+        if (c->h_pinned[S_DONE] != 0.0) { *converged = true; break; }
+        if (*iters >= max_it) break;
+    }
+    return PFX_OK;
+}
+
+// --------------------------------------------------------------------------- SNES-like Newton
+struct NewtonOut {
+    int its = 0, reason = 0;
+    double fnorm = 0;
+    int64_t cg_its = 0;
+};
+
+// is_u: displacement problem (solver.py:198-205) else phase-field problem (:237-244)
+int newton(pfx_ctx* c, bool is_u, NewtonOut* out) {
+    const int nc = is_u ? c->dim : 1;
+    const int64_t n = c->n_owned * nc;
+    double* x = is_u ? c->u : c->phi;
+    const double* g = is_u ? c->g_u : c->g_phi;
+    const uint8_t* mask = is_u ? c->mask_u : c->mask_phi;
+    const int kind = is_u ? LIN_U : LIN_PHI;
+    const int gr = vgrid(c, n);
+    double ttol = 0, snorm = 0, xnorm = 0, vals[4];
+    int st;
+    for (int it = 0;; ++it) {
+        // residual with lifting (dolfinx assemble_residual idiom)
+        KArgs a = base_args(c);
+        a.y = c->w_t0;
+        st = launch_scatter(c, is_u ? OP_RESIDUAL_U : OP_RESIDUAL_PHI, a);
+        if (st) return st;
+        const double* lift = nullptr;
+        if (it == 0) {
+            // gap on every local dof (ghost entries feed the halo elements of the apply)
+            int64_t nall = c->n_nodes * nc;
+            bc_gap_kernel<<<vgrid(c, nall), kThreads, 0, c->stream>>>(nall, x, g, mask, c->w_p, c->partial, c->red, c->counter);
+            c->launches++;
+            st = apply_lin(c, kind, c->w_p, c->w_t1, nullptr, c->red, nullptr);
+            if (st) return st;
+            lift = c->w_t1;
+        }
+        snes_residual_kernel<<<gr, kThreads, 0, c->stream>>>(n, c->w_t0, lift, (is_u && c->has_fext) ? c->fext : nullptr, x, g,
+                                                            mask, c->w_F, c->partial, c->red, c->counter);
+        c->launches++;
+        CK(cudaGetLastError());
+        st = fetch(c, c->red, 2, vals);
+        if (st) return st;
+        double fnorm = std::sqrt(vals[0]);
+        xnorm = std::sqrt(vals[1]);
+        out->fnorm = fnorm;
+        out->its = it;
+        if (!(fnorm == fnorm) || std::isinf(fnorm)) { out->reason = -4; return PFX_OK; }
+        if (it == 0) ttol = fnorm * c->prm.snes_rtol;
+        if (fnorm < c->prm.snes_atol) { out->reason = 2; return PFX_OK; }
+        if (it > 0) {
+            if (fnorm <= ttol) { out->reason = 3; return PFX_OK; }
+            if (snorm < c->prm.snes_stol * xnorm) { out->reason = 4; return PFX_OK; }
+        }
+        if (it >= c->prm.snes_max_it) { out->reason = -5; return PFX_OK; }
+        // Jacobi data of the current tangent
+        KArgs d = base_args(c);
+        d.y = c->w_dinv; d.mask = mask;
+        st = launch_scatter(c, is_u ? OP_DIAG_U : OP_DIAG_PHI, d);
+        if (st) return st;
+        int64_t cg = 0; bool conv = false;
+        st = pcg_solve(c, kind, c->prm.cg_rtol, &cg, &conv);
+        if (st) return st;
+        out->cg_its += cg;
+        if (!conv) { out->reason = -3; return PFX_OK; }      // linear solve failed (KSP analogue)
+        newton_update_kernel<<<gr, kThreads, 0, c->stream>>>(n, x, c->w_x, c->w_F, mask, c->partial, c->red, c->counter);
+        c->launches++;
+        CK(cudaGetLastError());
+        st = fetch(c, c->red, 1, vals);
+        if (st) return st;
+        snorm = std::sqrt(vals[0]);
+        st = exchange(c, x, nc);
+        if (st) return st;
+    }
+}
+
+// L2 projection: solve M h = b (b already in w_F), result copied to `dst` (Math/projection.py:19-59)
+int project_solve(pfx_ctx* c, double* dst, int64_t* cg_its) {
+    bool conv = false; int64_t it = 0;
+    int st = pcg_solve(c, LIN_MASS, c->prm.proj_rtol, &it, &conv);
+    if (st) return st;
+    *cg_its += it;
+    if (!conv) { c->err = "projection PCG did not converge"; return PFX_ERR_NOT_CONVERGED_PROJ; }
+    CK(cudaMemcpyAsync(dst, c->w_x, c->n_owned * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return exchange(c, dst, 1);
+}
+
+int l2_error(pfx_ctx* c, bool is_u, const double* a_, const double* b_, double* err) {
+    KArgs a = base_args(c);
+    a.f1 = a_; a.f2 = b_;
+    int st = is_u ? launch_reduce<RED_L2_U>(c, a) : launch_reduce<RED_L2_PHI>(c, a);
+    if (st) return st;
+    double v[2];
+    st = fetch(c, c->red, 2, v);
+    if (st) return st;
+    double num = std::sqrt(v[0]), den = std::sqrt(v[1]);
+    *err = (den == 0.0) ? 0.0 : num / den;
+    return PFX_OK;
+}
+
+const double* field_ptr(pfx_ctx* c, int f, int* nc) {
+    *nc = 1;
+    switch (f) {
+        case PFX_FIELD_U: *nc = c->dim; return c->u;
+        case PFX_FIELD_U_OLD: *nc = c->dim; return c->u_old;
+        case PFX_FIELD_PHI: return c->phi;
+        case PFX_FIELD_PHI_OLD: return c->phi_old;
+        case PFX_FIELD_H: return c->H;
+        case PFX_FIELD_VC: return c->Vc;
+        case PFX_FIELD_VN: return c->Vn;
+        case PFX_FIELD_FATIGUE: return c->Fat;
+        case PFX_FIELD_ALPHA_BAR: return c->abar_c;
+        case PFX_FIELD_ALPHA_BAR_N: return c->abar_n;
+        case PFX_FIELD_ALPHA_C: return c->alpha_c;
+        case PFX_FIELD_ALPHA_N: return c->alpha_n;
+    }
+    return nullptr;
+}
+
+int set_bc_common(pfx_ctx* c, bool is_u, int bc_id, const int32_t* dofs, int64_t n) {
+    if (!c || bc_id < 0 || n < 0 || (n > 0 && !dofs)) return PFX_ERR_BAD_ARG;
+    std::vector<BCSet>& sets = is_u ? c->bcs_u : c->bcs_phi;
+    if ((size_t)bc_id >= sets.size()) sets.resize(bc_id + 1);
+    BCSet& s = sets[bc_id];
+    int nc = is_u ? c->dim : 1;
+    int64_t ndof = c->n_nodes * nc;
+    s.dofs.resize(n);
+    std::vector<int32_t> owned;
+    for (int64_t k = 0; k < n; ++k) {
+        if (dofs[k] < 0 || dofs[k] >= ndof) { c->err = "bc dof out of range"; return PFX_ERR_BAD_ARG; }
+        int32_t node = dofs[k] / nc, comp = dofs[k] % nc;
+        s.dofs[k] = c->bm.iperm[node] * nc + comp;
+        if (c->bm.iperm[node] < c->n_owned) owned.push_back(s.dofs[k]);
+    }
+    s.n = n; s.n_owned = (int64_t)owned.size();
+    int st = dev_upload(c, &s.d_dofs, s.dofs);
+    if (st) return st;
+    st = dev_upload(c, &s.d_owned, owned);
+    if (st) return st;
+    st = dev_alloc(c, &s.d_vals, (size_t)n);
+    if (st) return st;
+    return rebuild_bc(c, is_u);
+}
+
+int set_bc_values_common(pfx_ctx* c, bool is_u, int bc_id, const double* values, int64_t n) {
+    if (!c) return PFX_ERR_BAD_ARG;
+    std::vector<BCSet>& sets = is_u ? c->bcs_u : c->bcs_phi;
+    if (bc_id < 0 || (size_t)bc_id >= sets.size() || sets[bc_id].n != n || (n > 0 && !values)) {
+        c->err = "bc values: unknown id or length mismatch";
+        return PFX_ERR_BAD_ARG;
+    }
+    if (n > 0) CK(cudaMemcpyAsync(sets[bc_id].d_vals, values, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return push_bc_values(c, is_u);
+}
+
+}  // namespace
+
+// ================================================================================= C-ABI
+extern "C" {
+
+const char* pfx_version(void) { return "pfx-b200 0.1.0 (sm_100a)"; }
+
+const char* pfx_status_string(int s) {
+    switch (s) {
+        case PFX_OK: return "ok";
+        case PFX_ERR_BAD_ARG: return "bad argument";
+        case PFX_ERR_CUDA: return "CUDA error";
+        case PFX_ERR_NOT_CONVERGED_U: return "displacement solve did not converge";
+        case PFX_ERR_NOT_CONVERGED_PHI: return "phase-field solve did not converge";
+        case PFX_ERR_NOT_CONVERGED_PROJ: return "projection solve did not converge";
+        case PFX_ERR_NAN: return "NaN encountered";
+        case PFX_ERR_UNSUPPORTED: return "unsupported configuration";
+        case PFX_ERR_COMM: return "communication error";
+        case PFX_ERR_NO_DEVICE: return "no CUDA device";
+    }
+    return "unknown";
+}
+
+int pfx_device_count(int* n) {
+    if (!n) return PFX_ERR_BAD_ARG;
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) { *n = 0; cudaGetLastError(); return PFX_ERR_NO_DEVICE; }
+    return PFX_OK;
+}
+
+void pfx_default_params(pfx_params* p) {
+    if (!p) return;
+    memset(p, 0, sizeof(*p));
+    p->lambda_ = 121.15384615384615; p->mu = 80.76923076923077; p->Gc = 0.0027; p->l = 0.015; p->k = 0.0;
+    p->model = PFX_MODEL_ISOTROPIC; p->irreversibility = 0; p->fatigue = 0; p->fatigue_val = 0.05625;
+    p->snes_rtol = 1e-8; p->snes_atol = 1e-9; p->snes_stol = 1e-8; p->snes_max_it = 50;
+    p->cg_rtol = 1e-11; p->cg_max_it = 200000; p->proj_rtol = 1e-13;
+    p->quad_points_1d = 3; p->block_nodes = 0; p->cg_chunk = 0;
+}
+
+const char* pfx_last_error(const pfx_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx** out) {
+    if (!mesh || !prm || !out || !mesh->coords || !mesh->cells || mesh->n_nodes <= 0 || mesh->n_cells <= 0) return PFX_ERR_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return PFX_ERR_NO_DEVICE; }
+    if (device < 0 || device >= ndev) return PFX_ERR_BAD_ARG;
+    pfx_ctx* c = new pfx_ctx();
+    *out = c;                       // returned even on failure so pfx_last_error() can be read
+    c->device = device;
+    c->prm = *prm;
+    c->cell_type = mesh->cell_type;
+    switch (mesh->cell_type) {
+        case PFX_CELL_TRIANGLE: c->nv = 3; c->dim = 2; break;
+        case PFX_CELL_QUADRILATERAL: c->nv = 4; c->dim = 2; break;
+        case PFX_CELL_TETRAHEDRON: c->nv = 4; c->dim = 3; break;
+        default: c->err = "unknown cell type"; return PFX_ERR_BAD_ARG;
+    }
+    if (prm->quad_points_1d < 1 || prm->quad_points_1d > 4) { c->err = "quad_points_1d must be 1..4"; return PFX_ERR_BAD_ARG; }
+    Material& m = c->mat;
+    m.lam = prm->lambda_; m.mu = prm->mu; m.Gc = prm->Gc; m.l = prm->l; m.k = prm->k;
+    m.fatigue = prm->fatigue; m.alpha_T = prm->fatigue_val;
+    switch (prm->model) {
+        case PFX_MODEL_ISOTROPIC: m.smodel = M_ISO; m.emodel = M_ISO; break;
+        case PFX_MODEL_SPECTRAL: m.smodel = M_SPECTRAL; m.emodel = M_SPECTRAL; break;
+        case PFX_MODEL_DEVIATORIC: m.smodel = M_VOLDEV; m.emodel = M_VOLDEV; break;
+        case PFX_MODEL_HYBRID_SPECTRAL: m.smodel = M_ISO; m.emodel = M_SPECTRAL; break;
+        case PFX_MODEL_HYBRID_DEVIATORIC: m.smodel = M_ISO; m.emodel = M_VOLDEV; break;
+        default: c->err = "unknown model"; return PFX_ERR_BAD_ARG;
+    }
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->n_nodes = mesh->n_nodes;
+    c->n_owned = mesh->n_owned > 0 ? mesh->n_owned : mesh->n_nodes;
+    const char* ng = getenv("PFX_NO_GRAPH");
+    c->use_graph = !(ng && ng[0] == '1');
+
+    // ---- blocks
+    int target = prm->block_nodes;
+    if (target <= 0) {
+        // fill the machine (>= 2 CTAs per SM when the mesh allows), cap by the CTA width
+        int64_t want = c->n_owned / (148 * 2);
+        target = (int)std::min<int64_t>(kThreads - 16, std::max<int64_t>(64, want));
+    }
+    target = std::min(target, kThreads);
+    for (int64_t e = 0; e < mesh->n_cells * c->nv; ++e)
+        if (mesh->cells[e] < 0 || mesh->cells[e] >= mesh->n_nodes) { c->err = "cell vertex out of range"; return PFX_ERR_BAD_ARG; }
+    std::string er = build_blocks(c->nv, c->dim, c->n_nodes, c->n_owned, mesh->n_cells, mesh->coords, mesh->cells,
+                                  mesh->cell_primary, target, c->bm);
+    if (!er.empty()) { c->err = er; return PFX_ERR_BAD_ARG; }
+    BlockMesh& bm = c->bm;
+    int32_t *d_node0, *d_hoff, *d_halo, *d_eoff, *d_nprim, *d_incp;
+    uint16_t *d_lconn, *d_inc;
+    int st;
+    if ((st = dev_upload(c, &d_node0, bm.node0))) return st;
+    if ((st = dev_upload(c, &d_hoff, bm.halo_off))) return st;
+    if ((st = dev_upload(c, &d_halo, bm.halo))) return st;
+    if ((st = dev_upload(c, &d_eoff, bm.elem_off))) return st;
+    if ((st = dev_upload(c, &d_nprim, bm.nprim))) return st;
+    if ((st = dev_upload(c, &d_incp, bm.inc_ptr))) return st;
+    if ((st = dev_upload(c, &d_lconn, bm.lconn))) return st;
+    if ((st = dev_upload(c, &d_inc, bm.inc))) return st;
+    c->bv.nb = bm.nb; c->bv.node0 = d_node0; c->bv.halo_off = d_hoff; c->bv.halo = d_halo; c->bv.elem_off = d_eoff;
+    c->bv.nprim = d_nprim; c->bv.lconn = (const ushort4*)d_lconn; c->bv.inc_ptr = d_incp; c->bv.inc = d_inc;
+    c->bv.max_loc = bm.max_loc; c->bv.chunk = 256;
+
+    // ---- fields
+    int64_t N = c->n_nodes, D = c->dim;
+    std::vector<double> hx(N * D);
+    for (int64_t i = 0; i < N; ++i)
+        for (int k = 0; k < D; ++k) hx[i * D + k] = mesh->coords[3 * (int64_t)bm.perm[i] + k];
+    if ((st = dev_upload(c, &c->X, hx))) return st;
+    double** vecs[] = {&c->u, &c->u_old, &c->w_r, &c->w_p, &c->w_Ap, &c->w_x, &c->w_F, &c->w_dinv, &c->w_t0, &c->w_t1, &c->g_u};
+    for (auto v : vecs)
+        if ((st = dev_alloc(c, v, (size_t)(N * D)))) return st;
+    double** scal[] = {&c->phi, &c->phi_old, &c->H, &c->Vc, &c->Vn, &c->Fat, &c->alpha_c, &c->alpha_n, &c->abar_c, &c->abar_n, &c->dinv_mass, &c->g_phi};
+    for (auto v : scal)
+        if ((st = dev_alloc(c, v, (size_t)N))) return st;
+    if ((st = dev_alloc(c, &c->mask_u, (size_t)(N * D)))) return st;
+    if ((st = dev_alloc(c, &c->mask_phi, (size_t)N))) return st;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->vec_grid = prop.multiProcessorCount * 8;
+    if ((st = dev_alloc(c, &c->partial, (size_t)std::max(bm.nb, c->vec_grid) * kMaxRed))) return st;
+    if ((st = dev_alloc(c, &c->S, (size_t)S_COUNT))) return st;
+    if ((st = dev_alloc(c, &c->red, (size_t)kMaxRed))) return st;
+    if ((st = dev_alloc(c, &c->counter, (size_t)4))) return st;
+    CK(cudaMallocHost((void**)&c->h_pinned, 64 * sizeof(double)));
+    c->graph_iters = prm->cg_chunk > 0 ? (prm->cg_chunk + 1) / 2 * 2 : 32;
+
+    // ---- opt every kernel instantiation of this mesh/model in to its shared-memory size
+    {
+        c->configuring = true;
+        KArgs z = base_args(c);
+        for (int op = OP_APPLY_U; op <= OP_RHS_FATIGUE; ++op)
+            if ((st = launch_scatter(c, op, z))) return st;
+        if ((st = launch_reduce<RED_L2_U>(c, z))) return st;
+        if ((st = launch_reduce<RED_L2_PHI>(c, z))) return st;
+        if ((st = launch_reduce<RED_ENERGY>(c, z))) return st;
+        c->configuring = false;
+    }
+    // ---- constant data: 1/diag(M)
+    KArgs a = base_args(c);
+    a.y = c->dinv_mass;
+    if ((st = launch_scatter(c, OP_DIAG_MASS, a))) return st;
+    CK(cudaStreamSynchronize(c->stream));
+    return PFX_OK;
+}
+
+int pfx_destroy(pfx_ctx* c) {
+    if (!c) return PFX_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < 3; ++k)
+        if (c->graph[k]) cudaGraphExecDestroy(c->graph[k]);
+    if (c->comm) nccl().CommDestroy(c->comm);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return PFX_OK;
+}
+
+int pfx_set_bc_u(pfx_ctx* c, int id, const int32_t* dofs, int64_t n) { return set_bc_common(c, true, id, dofs, n); }
+int pfx_set_bc_phi(pfx_ctx* c, int id, const int32_t* dofs, int64_t n) { return set_bc_common(c, false, id, dofs, n); }
+int pfx_set_bc_values_u(pfx_ctx* c, int id, const double* v, int64_t n) { return set_bc_values_common(c, true, id, v, n); }
+int pfx_set_bc_values_phi(pfx_ctx* c, int id, const double* v, int64_t n) { return set_bc_values_common(c, false, id, v, n); }
+
+int pfx_set_traction(pfx_ctx* c, int t_id, const int32_t* nodes, const double* w, int64_t n) {
+    if (!c || t_id < 0 || n < 0 || (n > 0 && (!nodes || !w))) return PFX_ERR_BAD_ARG;
+    if ((size_t)t_id >= c->tractions.size()) c->tractions.resize(t_id + 1);
+    Traction& t = c->tractions[t_id];
+    std::vector<int32_t> nn(n);
+    std::vector<double> ww(w, w + n);
+    for (int64_t k = 0; k < n; ++k) {
+        if (nodes[k] < 0 || nodes[k] >= c->n_nodes) { c->err = "traction node out of range"; return PFX_ERR_BAD_ARG; }
+        nn[k] = c->bm.iperm[nodes[k]];
+    }
+    int st;
+    if ((st = dev_upload(c, &t.d_nodes, nn))) return st;
+    if ((st = dev_upload(c, &t.d_w, ww))) return st;
+    t.n = n;
+    if (!c->fext && (st = dev_alloc(c, &c->fext, (size_t)(c->n_nodes * c->dim)))) return st;
+    c->has_fext = true;
+    return rebuild_fext(c);
+}
+
+int pfx_set_traction_value(pfx_ctx* c, int t_id, const double* T) {
+    if (!c || !T || t_id < 0 || (size_t)t_id >= c->tractions.size()) return PFX_ERR_BAD_ARG;
+    for (int k = 0; k < c->dim; ++k) c->tractions[t_id].T[k] = T[k];
+    return rebuild_fext(c);
+}
+
+int pfx_get_field(pfx_ctx* c, int field, double* host, int64_t n) {
+    if (!c || !host) return PFX_ERR_BAD_ARG;
+    int nc;
+    const double* d = field_ptr(c, field, &nc);
+    if (!d || n != c->n_nodes * nc) { c->err = "get_field: unknown field or wrong length"; return PFX_ERR_BAD_ARG; }
+    std::vector<double> tmp(n);
+    CK(cudaMemcpyAsync(tmp.data(), d, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < c->n_nodes; ++i)
+        for (int k = 0; k < nc; ++k) host[(int64_t)c->bm.perm[i] * nc + k] = tmp[i * nc + k];
+    return PFX_OK;
+}
+
+int pfx_set_field(pfx_ctx* c, int field, const double* host, int64_t n) {
+    if (!c || !host) return PFX_ERR_BAD_ARG;
+    int nc;
+    double* d = const_cast<double*>(field_ptr(c, field, &nc));
+    if (!d || n != c->n_nodes * nc) { c->err = "set_field: unknown field or wrong length"; return PFX_ERR_BAD_ARG; }
+    std::vector<double> tmp(n);
+    for (int64_t i = 0; i < c->n_nodes; ++i)
+        for (int k = 0; k < nc; ++k) tmp[i * nc + k] = host[(int64_t)c->bm.perm[i] * nc + k];
+    CK(cudaMemcpyAsync(d, tmp.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PFX_OK;
+}
+
+// ------------------------------------------------------------------------------- load step
+int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
+    if (!c || !o || !rep) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    const int64_t N = c->n_nodes, D = c->dim;
+    int cap = o->history_capacity;
+    int32_t *hu = rep->hist_u_its, *hp = rep->hist_phi_its;
+    double *heu = rep->hist_err_u, *hep = rep->hist_err_phi, *hfu = rep->hist_fnorm_u, *hfp = rep->hist_fnorm_phi;
+    memset(rep, 0, sizeof(*rep));
+    rep->hist_u_its = hu; rep->hist_phi_its = hp; rep->hist_err_u = heu; rep->hist_err_phi = hep;
+    rep->hist_fnorm_u = hfu; rep->hist_fnorm_phi = hfp;
+    double err_phi = 1.0, err_u = 1.0;
+    int it = 0, st;
+    const int gN = vgrid(c, N);
+    while ((err_phi > o->stagger_tol || err_u > o->stagger_tol || it < o->min_stagger_iter) && it < o->max_stagger_iter) {
+        ++it;
+        // ---- displacement (solver.py:333-352)
+        NewtonOut nu;
+        if ((st = newton(c, true, &nu))) return st;
+        rep->u_newton_its = nu.its; rep->u_reason = nu.reason; rep->fnorm_u = nu.fnorm; rep->cg_its_u += nu.cg_its;
+        if ((st = l2_error(c, true, c->u, c->u_old, &err_u))) return st;
+        if (nu.reason <= 0) {
+            rep->stagger_iters = it;
+            c->err = "Solver did not converge, got " + std::to_string(nu.reason) + ".";
+            return PFX_ERR_NOT_CONVERGED_U;
+        }
+        CK(cudaMemcpyAsync(c->u_old, c->u, N * D * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        // ---- history (solver.py:355-360)
+        KArgs a = base_args(c);
+        a.y = c->w_F;
+        if ((st = launch_scatter(c, OP_RHS_PSI, a))) return st;
+        if ((st = project_solve(c, c->Vc, &rep->cg_its_proj))) return st;
+        if (c->prm.irreversibility) {
+            nodal_max_kernel<<<gN, kThreads, 0, c->stream>>>(N, c->H, c->Vc, c->Vn);
+            c->launches++;
+        } else {
+            CK(cudaMemcpyAsync(c->H, c->Vc, N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        }
+        // ---- fatigue (solver.py:362-375)
+        if (c->prm.fatigue) {
+            KArgs f = base_args(c);
+            f.f1 = c->phi_old; f.f2 = c->Vc; f.y = c->w_F;
+            if ((st = launch_scatter(c, OP_RHS_FATIGUE, f))) return st;
+            if ((st = project_solve(c, c->alpha_c, &rep->cg_its_proj))) return st;
+            fatigue_update_kernel<<<gN, kThreads, 0, c->stream>>>(N, c->alpha_c, c->alpha_n, c->abar_n, c->abar_c, c->Fat,
+                                                                 o->dt, c->prm.fatigue_val);
+            c->launches++;
+        }
+        // ---- phase field (solver.py:380-398)
+        NewtonOut np;
+        if ((st = newton(c, false, &np))) return st;
+        rep->phi_newton_its = np.its; rep->phi_reason = np.reason; rep->fnorm_phi = np.fnorm; rep->cg_its_phi += np.cg_its;
+        if ((st = l2_error(c, false, c->phi, c->phi_old, &err_phi))) return st;
+        if (np.reason <= 0) {
+            rep->stagger_iters = it;
+            c->err = "Solver did not converge, got " + std::to_string(np.reason) + ".";
+            return PFX_ERR_NOT_CONVERGED_PHI;
+        }
+        CK(cudaMemcpyAsync(c->phi_old, c->phi, N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        if (it <= cap) {
+            int k = it - 1;
+            if (hu) hu[k] = nu.its;
+            if (hp) hp[k] = np.its;
+            if (heu) heu[k] = err_u;
+            if (hep) hep[k] = err_phi;
+            if (hfu) hfu[k] = nu.fnorm;
+            if (hfp) hfp[k] = np.fnorm;
+            rep->history_len = it;
+        }
+    }
+    // ---- end of step (solver.py:401-411)
+    if (c->prm.irreversibility) {
+        nodal_max_kernel<<<gN, kThreads, 0, c->stream>>>(N, c->Vn, c->Vc, c->Vn);
+        c->launches++;
+    }
+    if (c->prm.fatigue) {
+        CK(cudaMemcpyAsync(c->abar_n, c->abar_c, N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->alpha_n, c->alpha_c, N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    rep->stagger_iters = it;
+    rep->err_u = err_u; rep->err_phi = err_phi;
+    return PFX_OK;
+}
+
+// ------------------------------------------------------------------------------- outputs
+int pfx_reaction(pfx_ctx* c, int bc_id, double R[3]) {
+    if (!c || !R || bc_id < 0 || (size_t)bc_id >= c->bcs_u.size()) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    KArgs a = base_args(c);
+    a.y = c->w_t0;
+    int st = launch_scatter(c, OP_RESIDUAL_U, a);
+    if (st) return st;
+    BCSet& s = c->bcs_u[bc_id];
+    gather_sum_kernel<<<vgrid(c, std::max<int64_t>(s.n_owned, 1)), kThreads, 0, c->stream>>>(s.n_owned, s.d_owned, c->w_t0, c->dim,
+                                                                                              c->partial, c->red, c->counter);
+    c->launches++;
+    CK(cudaGetLastError());
+    double v[3];
+    if ((st = fetch(c, c->red, 3, v))) return st;
+    R[0] = v[0]; R[1] = v[1]; R[2] = (c->dim == 3) ? v[2] : 0.0;
+    return PFX_OK;
+}
+
+int pfx_energies(pfx_ctx* c, double out[11]) {
+    if (!c || !out) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    KArgs a = base_args(c);
+    a.f1 = c->abar_c;
+    int st = launch_reduce<RED_ENERGY>(c, a);
+    if (st) return st;
+    double s[8];
+    if ((st = fetch(c, c->red, 8, s))) return st;
+    const Material& m = c->mat;
+    double E = s[0] + s[2], PSI_a = s[1], PSI_b = s[2];
+    double gamma_phi = s[3] / (2.0 * m.l), gamma_grad = s[4] * m.l / 2.0, gamma = gamma_phi + gamma_grad;
+    double W_phi, W_grad, alpha_acum;
+    if (m.fatigue) { W_phi = s[5] * m.Gc / (2.0 * m.l); W_grad = s[6] * m.Gc * m.l / 2.0; alpha_acum = s[7]; }
+    else { W_phi = m.Gc * gamma_phi; W_grad = m.Gc * gamma_grad; alpha_acum = 0.0; }
+    double W = W_phi + W_grad;
+    double vals[11] = {E + W, E, W, W_phi, W_grad, gamma, gamma_phi, gamma_grad, PSI_a, PSI_b, alpha_acum};
+    for (int k = 0; k < 11; ++k) out[k] = vals[k];
+    return PFX_OK;
+}
+
+// ------------------------------------------------------------------------------- operator hooks
+static int host_apply(pfx_ctx* c, int op, int nc, const double* v, double* y, const uint8_t* mask) {
+    int64_t n = c->n_nodes * nc;
+    std::vector<double> tmp(n);
+    if (v) {
+        for (int64_t i = 0; i < c->n_nodes; ++i)
+            for (int k = 0; k < nc; ++k) tmp[i * nc + k] = v[(int64_t)c->bm.perm[i] * nc + k];
+        CK(cudaMemcpyAsync(c->w_p, tmp.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    KArgs a = base_args(c);
+    a.v = c->w_p; a.y = c->w_Ap; a.mask = mask;
+    int st = launch_scatter(c, op, a);
+    if (st) return st;
+    CK(cudaMemcpyAsync(tmp.data(), c->w_Ap, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < c->n_owned; ++i)
+        for (int k = 0; k < nc; ++k) y[(int64_t)c->bm.perm[i] * nc + k] = tmp[i * nc + k];
+    return PFX_OK;
+}
+
+int pfx_apply_u(pfx_ctx* c, const double* v, double* y, int use_bc) {
+    if (!c || !v || !y) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    return host_apply(c, OP_APPLY_U, c->dim, v, y, use_bc ? c->mask_u : nullptr);
+}
+int pfx_apply_phi(pfx_ctx* c, const double* v, double* y, int use_bc) {
+    if (!c || !v || !y) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    return host_apply(c, OP_APPLY_PHI, 1, v, y, use_bc ? c->mask_phi : nullptr);
+}
+int pfx_apply_mass(pfx_ctx* c, const double* v, double* y) {
+    if (!c || !v || !y) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    return host_apply(c, OP_APPLY_MASS, 1, v, y, nullptr);
+}
+int pfx_residual_u(pfx_ctx* c, double* f) {
+    if (!c || !f) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    return host_apply(c, OP_RESIDUAL_U, c->dim, nullptr, f, nullptr);
+}
+int pfx_diag_u(pfx_ctx* c, double* d) {
+    if (!c || !d) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    int st = host_apply(c, OP_DIAG_U, c->dim, nullptr, d, c->mask_u);
+    if (st) return st;
+    for (int64_t i = 0; i < c->n_owned; ++i)                                 // kernel stores 1/diag
+        for (int k = 0; k < c->dim; ++k) { double& v = d[(int64_t)c->bm.perm[i] * c->dim + k]; v = 1.0 / v; }
+    return PFX_OK;
+}
+int pfx_rhs_psi(pfx_ctx* c, double* b) {
+    if (!c || !b) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    return host_apply(c, OP_RHS_PSI, 1, nullptr, b, nullptr);
+}
+
+int pfx_l2_error(pfx_ctx* c, int fa, int fb, double* err) {
+    if (!c || !err) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    int na, nb;
+    const double *a = field_ptr(c, fa, &na), *b = field_ptr(c, fb, &nb);
+    if (!a || !b || na != nb) return PFX_ERR_BAD_ARG;
+    return l2_error(c, na > 1, a, b, err);
+}
+
+int pfx_algorithmic_bytes(pfx_ctx* c, int kind, double* bytes) {
+    if (!c || !bytes) return PFX_ERR_BAD_ARG;
+    double Ne = (double)c->bm.n_cells, Nn = (double)c->n_owned, d = c->dim, nv = c->nv;
+    double conn = 4.0 * nv * Ne;
+    bool nl = c->mat.smodel != M_ISO;
+    switch (kind) {
+        case 0: *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d + (nl ? 8 * d : 0)); break;       // u-apply
+        case 1: *bytes = conn + Nn * (8 * d + 24 + (c->mat.fatigue ? 8 : 0)); break;             // phi-apply
+        case 2: *bytes = conn + Nn * (8 * d + 16); break;                                        // mass-apply
+        case 3: *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d); break;                         // residual_u
+        case 4: *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d + (nl ? 8 * d : 0)) + 11.0 * 8.0 * d * Nn; break;  // u-PCG iteration
+        default: return PFX_ERR_BAD_ARG;
+    }
+    return PFX_OK;
+}
+
+int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_out) {
+    if (!c || !ms_out || reps <= 0) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    if (flush_l2 && !c->flush_buf) {
+        c->flush_n = (int64_t)256 * 1024 * 1024 / 8;
+        int st = dev_alloc(c, &c->flush_buf, (size_t)c->flush_n);
+        if (st) return st;
+    }
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    // kind 4: a genuine PCG on J_u with right-hand side = current contents of w_p and a
+    // tolerance of zero, so every timed iteration does full work
+    if (kind == 4) {
+        KArgs d = base_args(c);
+        d.y = c->w_dinv; d.mask = c->mask_u;
+        int st = launch_scatter(c, OP_DIAG_U, d);
+        if (st) return st;
+        int64_t n = c->n_owned * c->dim;
+        CK(cudaMemcpyAsync(c->w_F, c->w_p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        pcg_init_kernel<<<vgrid(c, n), kThreads, 0, c->stream>>>(n, c->w_F, c->mask_u, c->w_dinv, nullptr, nullptr, c->w_x, c->w_r,
+                                                               c->w_p, c->partial, c->S + S_STAGE, c->counter);
+        if ((st = allreduce(c, c->S + S_STAGE, 2))) return st;
+        pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, 0.0);
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    for (int r = 0; r < reps; ++r) {
+        if (flush_l2) {
+            flush_kernel<<<c->vec_grid, kThreads, 0, c->stream>>>(c->flush_n, c->flush_buf);
+        }
+        CK(cudaEventRecord(e0, c->stream));
+        int st = PFX_OK;
+        if (kind == 0) st = apply_lin(c, LIN_U, c->w_p, c->w_Ap, c->mask_u, c->red, nullptr);
+        else if (kind == 1) st = apply_lin(c, LIN_PHI, c->w_p, c->w_Ap, c->mask_phi, c->red, nullptr);
+        else if (kind == 2) st = apply_lin(c, LIN_MASS, c->w_p, c->w_Ap, nullptr, c->red, nullptr);
+        else if (kind == 3) { KArgs a = base_args(c); a.y = c->w_t0; st = launch_scatter(c, OP_RESIDUAL_U, a); }
+        else if (kind == 4) {
+            st = pcg_iteration(c, LIN_U, r & 1, c->n_owned * c->dim, c->mask_u, c->w_dinv);
+        } else st = PFX_ERR_BAD_ARG;
+        if (st) return st;
+        CK(cudaEventRecord(e1, c->stream));
+        CK(cudaEventSynchronize(e1));
+        CK(cudaEventElapsedTime(&ms_out[r], e0, e1));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return PFX_OK;
+}
+
+int pfx_launch_count(pfx_ctx* c, int64_t* n) {
+    if (!c || !n) return PFX_ERR_BAD_ARG;
+    *n = c->launches;
+    return PFX_OK;
+}
+
+int pfx_block_stats(pfx_ctx* c, int64_t out[8]) {
+    if (!c || !out) return PFX_ERR_BAD_ARG;
+    out[0] = c->bm.nb; out[1] = c->bm.max_own; out[2] = c->bm.max_loc; out[3] = c->bm.max_elems;
+    out[4] = c->bm.total_elems; out[5] = c->bm.n_cells; out[6] = (int64_t)c->bm.halo.size(); out[7] = c->n_owned;
+    return PFX_OK;
+}
+
+// ------------------------------------------------------------------------------- partition API
+struct pfx_partition {
+    Partition P;
+};
+
+int pfx_partition_create(int32_t cell_type, int64_t n_nodes, int64_t n_cells, const double* coords, const int32_t* cells,
+                         int n_ranks, const int32_t* cell_rank_in, pfx_partition** out) {
+    if (!coords || !cells || !out || n_nodes <= 0 || n_cells <= 0) return PFX_ERR_BAD_ARG;
+    int nv = (cell_type == PFX_CELL_TRIANGLE) ? 3 : 4;
+    pfx_partition* p = new pfx_partition();
+    std::string er = build_partition(nv, n_nodes, n_cells, coords, cells, n_ranks, cell_rank_in, p->P);
+    if (!er.empty()) { delete p; return PFX_ERR_BAD_ARG; }
+    *out = p;
+    return PFX_OK;
+}
+int pfx_partition_destroy(pfx_partition* p) { delete p; return PFX_OK; }
+int pfx_partition_cell_rank(const pfx_partition* p, int32_t* cr) {
+    if (!p || !cr) return PFX_ERR_BAD_ARG;
+    std::copy(p->P.cell_rank.begin(), p->P.cell_rank.end(), cr);
+    return PFX_OK;
+}
+int pfx_partition_node_owner(const pfx_partition* p, int32_t* no) {
+    if (!p || !no) return PFX_ERR_BAD_ARG;
+    std::copy(p->P.node_owner.begin(), p->P.node_owner.end(), no);
+    return PFX_OK;
+}
+int pfx_partition_rank_sizes(const pfx_partition* p, int rank, int64_t out[5]) {
+    if (!p || !out || rank < 0 || rank >= p->P.n_ranks) return PFX_ERR_BAD_ARG;
+    const RankPart& R = p->P.ranks[rank];
+    out[0] = (int64_t)R.l2g.size(); out[1] = R.n_owned; out[2] = (int64_t)R.cell_gid.size();
+    out[3] = (int64_t)R.send_idx.size(); out[4] = (int64_t)R.neighbors.size();
+    return PFX_OK;
+}
+int pfx_partition_rank_maps(const pfx_partition* p, int rank, int64_t* l2g, int64_t* cell_gid, int32_t* ghost_owner,
+                            uint8_t* cell_primary) {
+    if (!p || rank < 0 || rank >= p->P.n_ranks) return PFX_ERR_BAD_ARG;
+    const RankPart& R = p->P.ranks[rank];
+    if (l2g) std::copy(R.l2g.begin(), R.l2g.end(), l2g);
+    if (cell_gid) std::copy(R.cell_gid.begin(), R.cell_gid.end(), cell_gid);
+    if (ghost_owner) std::copy(R.ghost_owner.begin(), R.ghost_owner.end(), ghost_owner);
+    if (cell_primary) std::copy(R.cell_primary.begin(), R.cell_primary.end(), cell_primary);
+    return PFX_OK;
+}
+int pfx_partition_rank_plan(const pfx_partition* p, int rank, int32_t* nbrs, int64_t* send_off, int32_t* send_idx,
+                            int64_t* recv_off) {
+    if (!p || rank < 0 || rank >= p->P.n_ranks) return PFX_ERR_BAD_ARG;
+    const RankPart& R = p->P.ranks[rank];
+    if (nbrs) std::copy(R.neighbors.begin(), R.neighbors.end(), nbrs);
+    if (send_off) std::copy(R.send_off.begin(), R.send_off.end(), send_off);
+    if (send_idx) std::copy(R.send_idx.begin(), R.send_idx.end(), send_idx);
+    if (recv_off) std::copy(R.recv_off.begin(), R.recv_off.end(), recv_off);
+    return PFX_OK;
+}
+
+int pfx_comm_unique_id(uint8_t id[128]) {
+    if (!id) return PFX_ERR_BAD_ARG;
+    std::string er = nccl().load();
+    if (!er.empty()) return PFX_ERR_COMM;
+    nccl_uid u;
+    if (nccl().GetUniqueId(&u) != 0) return PFX_ERR_COMM;
+    memcpy(id, u.internal, 128);
+    return PFX_OK;
+}
+
+int pfx_comm_attach(pfx_ctx* c, int rank, int n_ranks, const uint8_t id[128], int n_nbrs, const int32_t* nbrs,
+                    const int64_t* send_off, const int32_t* send_idx, const int64_t* recv_off) {
+    if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    std::string er = nccl().load();
+    if (!er.empty()) { c->err = er; return PFX_ERR_COMM; }
+    nccl_uid u;
+    memcpy(u.internal, id, 128);
+    int r = nccl().CommInitRank(&c->comm, n_ranks, u, rank);
+    if (r != 0) { c->err = std::string("ncclCommInitRank: ") + nccl().GetErrorString(r); return PFX_ERR_COMM; }
+    c->rank = rank; c->n_ranks = n_ranks;
+    c->nbrs.assign(nbrs, nbrs + n_nbrs);
+    c->send_off.assign(send_off, send_off + n_nbrs + 1);
+    c->recv_off.assign(recv_off, recv_off + n_nbrs + 1);
+    c->n_send = n_nbrs > 0 ? c->send_off[n_nbrs] : 0;
+    std::vector<int32_t> idx(c->n_send);
+    for (int64_t k = 0; k < c->n_send; ++k) idx[k] = c->bm.iperm[send_idx[k]];
+    int st;
+    if ((st = dev_upload(c, &c->d_send_idx, idx))) return st;
+    if ((st = dev_alloc(c, &c->d_send_buf, (size_t)(c->n_send * c->dim)))) return st;
+    // graphs captured before the attach (none normally) would miss the collectives
+    for (int k = 0; k < 3; ++k)
+        if (c->graph[k]) { cudaGraphExecDestroy(c->graph[k]); c->graph[k] = nullptr; }
+    return PFX_OK;
+}
+
+}  // extern "C"

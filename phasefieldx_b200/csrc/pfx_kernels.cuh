@@ -1,0 +1,662 @@
+// pfx_kernels.cuh — sm_100a kernels of the staggered load step (fp64, HBM-bound, no tensor cores).
+//
+// Block-scatter kernels: one CTA per mesh block (pfx_blocks.h).  Phase A stages the nodal
+// fields of the block's owned + halo nodes in shared memory (owned range: coalesced; halo:
+// gathered, normally L2 hits because neighbouring blocks are scheduled together).  Phase B
+// (one thread per element, chunked) evaluates the element vector in registers and parks it in
+// a shared element buffer.  Phase C (one thread per owned node) sums the node's incident
+// entries in a fixed order — atomic-free, bit-reproducible — and writes its rows coalesced.
+// Optional epilogue: per-block partial sums (dot products, norms) + last-block final reduce.
+//
+// Replaces (reference call sites): dolfinx assemble_vector/assemble_matrix on F_u/J_u/F_phi/
+// J_phi (solver.py:173-245), the mass assembly of Math/projection.py:35-44, assemble_scalar of
+// energy.py / errors_functions.py, and PETSc Vec/KSP kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pfx_elements.cuh"
+
+namespace pfx {
+
+constexpr int kThreads = 256;
+constexpr int kMaxRed = 8;
+
+struct BlockView {
+    int nb;
+    const int32_t* node0;
+    const int32_t* halo_off;
+    const int32_t* halo;
+    const int32_t* elem_off;
+    const int32_t* nprim;
+    const ushort4* lconn;
+    const int32_t* inc_ptr;
+    const uint16_t* inc;
+    int max_loc;      // smem sizing
+    int chunk;        // elements per phase-B pass
+};
+
+struct KArgs {
+    Material m;
+    int n1d;
+    const double* X;        // [N][D] compact coordinates, block order
+    const double* u;        // [N*D]
+    const double* phi;      // [N]
+    const double* v;        // input vector (u- or phi-space)
+    const double* H;
+    const double* Fat;
+    const double* f1;       // op-specific extra nodal fields
+    const double* f2;
+    const uint8_t* mask;    // Dirichlet flags per dof (may be null)
+    double* y;              // output vector
+    double* partial;        // [nb][kMaxRed]
+    double* result;         // [kMaxRed] final sums (written by the last block)
+    unsigned int* counter;
+    const double* stop;     // optional sticky DONE flag of the running PCG: skip the launch when set
+    int nred;
+};
+
+// ----------------------------------------------------------------------------- reductions
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block sum of up to NR values per thread; result valid in thread 0.
+template <int NR>
+__device__ __forceinline__ void block_sum(double* vals, double* s_red /*[NR*32]*/) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        double v = warp_sum(vals[k]);
+        if (lane == 0) s_red[k * 32 + w] = v;
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            double v = (lane < nw) ? s_red[k * 32 + lane] : 0.0;
+            vals[k] = warp_sum(v);
+        }
+    }
+    __syncthreads();
+}
+
+// Per-block partials -> global result by the last block to finish (fixed summation order).
+template <int NR>
+__device__ __forceinline__ void grid_reduce(double* vals, double* partial, double* result, unsigned int* counter,
+                                            double* s_red) {
+    __shared__ bool is_last;
+    block_sum<NR>(vals, s_red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k) partial[(size_t)blockIdx.x * kMaxRed + k] = vals[k];
+        __threadfence();
+        unsigned int t = atomicInc(counter, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double acc[NR];
+#pragma unroll
+        for (int k = 0; k < NR; ++k) acc[k] = 0.0;
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+#pragma unroll
+            for (int k = 0; k < NR; ++k) acc[k] += __ldcg(&partial[(size_t)b * kMaxRed + k]);
+        block_sum<NR>(acc, s_red);
+        if (threadIdx.x == 0)
+#pragma unroll
+            for (int k = 0; k < NR; ++k) result[k] = acc[k];
+    }
+}
+
+// ============================================================================= scatter ops
+// Each Op: NF staged doubles per local node (odd => conflict-free AoS), NOUT rows per node,
+// NRED partial sums; load(), elem(), store().
+enum { OP_APPLY_U, OP_RESIDUAL_U, OP_DIAG_U, OP_APPLY_PHI, OP_RESIDUAL_PHI, OP_DIAG_PHI, OP_APPLY_MASS,
+       OP_DIAG_MASS, OP_RHS_PSI, OP_RHS_FATIGUE };
+
+template <int V> struct odd { static constexpr int value = (V & 1) ? V : V + 1; };
+
+template <class Cell, bool NL>
+struct OpApplyU {          // staged: X[D] phi v[D] (u[D])
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = D, NRED = 1;
+    static constexpr int NF = odd<D + 1 + D + (NL ? D : 0)>::value;
+    __device__ static void load(const KArgs& a, int g, double* s) {
+        for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i];
+        s[D] = a.phi[g];
+        for (int i = 0; i < D; ++i) {
+            double vv = a.v[(size_t)g * D + i];
+            if (a.mask && a.mask[(size_t)g * D + i]) vv = 0.0;
+            s[D + 1 + i] = vv;
+        }
+        if (NL) for (int i = 0; i < D; ++i) s[2 * D + 1 + i] = a.u[(size_t)g * D + i];
+    }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+        double X[NV * D], ph[NV], V[NV * D], U[NV * D];
+        for (int k = 0; k < NV; ++k) {
+            for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; V[k * D + i] = nd[k][D + 1 + i]; U[k * D + i] = NL ? nd[k][2 * D + 1 + i] : 0.0; }
+            ph[k] = nd[k][D];
+        }
+        elem_apply_u<Cell>(a.m, a.n1d, X, ph, U, V, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double* red) {
+        for (int i = 0; i < D; ++i) {
+            double vin = a.v[(size_t)g * D + i];
+            double yv = (a.mask && a.mask[(size_t)g * D + i]) ? vin : acc[i];
+            a.y[(size_t)g * D + i] = yv;
+            red[0] += vin * yv;
+        }
+    }
+};
+
+template <class Cell>
+struct OpResidualU {       // staged: X phi u
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = D, NRED = 0;
+    static constexpr int NF = odd<D + 1 + D>::value;
+    __device__ static void load(const KArgs& a, int g, double* s) {
+        for (int i = 0; i < D; ++i) { s[i] = a.X[(size_t)g * D + i]; s[D + 1 + i] = a.u[(size_t)g * D + i]; }
+        s[D] = a.phi[g];
+    }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+        double X[NV * D], ph[NV], U[NV * D];
+        for (int k = 0; k < NV; ++k) {
+            for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; U[k * D + i] = nd[k][D + 1 + i]; }
+            ph[k] = nd[k][D];
+        }
+        elem_residual_u<Cell>(a.m, a.n1d, X, ph, U, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double*) {
+        for (int i = 0; i < D; ++i) a.y[(size_t)g * D + i] = acc[i];
+    }
+};
+
+template <class Cell>
+struct OpDiagU {           // writes 1/diag (1 at Dirichlet dofs)
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = D, NRED = 0;
+    static constexpr int NF = odd<D + 1 + D>::value;
+    __device__ static void load(const KArgs& a, int g, double* s) { OpResidualU<Cell>::load(a, g, s); }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+        double X[NV * D], ph[NV], U[NV * D];
+        for (int k = 0; k < NV; ++k) {
+            for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; U[k * D + i] = nd[k][D + 1 + i]; }
+            ph[k] = nd[k][D];
+        }
+        elem_diag_u<Cell>(a.m, a.n1d, X, ph, U, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double*) {
+        for (int i = 0; i < D; ++i) {
+            bool bc = a.mask && a.mask[(size_t)g * D + i];
+            a.y[(size_t)g * D + i] = bc ? 1.0 : 1.0 / acc[i];
+        }
+    }
+};
+
+// φ-space coefficient fields: cm = 2H + F·Gc/l, cg = F·Gc·l (F ≡ 1 without fatigue)
+__device__ __forceinline__ void phi_coeffs(const KArgs& a, int g, double& cm, double& cg) {
+    double F = a.m.fatigue ? a.Fat[g] : 1.0;
+    cm = 2.0 * a.H[g] + F * a.m.Gc / a.m.l;
+    cg = F * a.m.Gc * a.m.l;
+}
+
+template <class Cell>
+struct OpApplyPhi {        // staged: X cm cg p
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = 1, NRED = 1;
+    static constexpr int NF = odd<D + 3>::value;
+    __device__ static void load(const KArgs& a, int g, double* s) {
+        for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i];
+        phi_coeffs(a, g, s[D], s[D + 1]);
+        double vv = a.v[g];
+        if (a.mask && a.mask[g]) vv = 0.0;
+        s[D + 2] = vv;
+    }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+        double X[NV * D], cm[NV], cg[NV], p[NV];
+        for (int k = 0; k < NV; ++k) {
+            for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i];
+            cm[k] = nd[k][D]; cg[k] = nd[k][D + 1]; p[k] = nd[k][D + 2];
+        }
+        elem_apply_phi<Cell>(a.n1d, X, cm, cg, p, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double* red) {
+        double vin = a.v[g];
+        double yv = (a.mask && a.mask[g]) ? vin : acc[0];
+        a.y[g] = yv;
+        red[0] += vin * yv;
+    }
+};
+
+template <class Cell>
+struct OpResidualPhi {     // staged: X cm cg H phi
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = 1, NRED = 0;
+    static constexpr int NF = odd<D + 4>::value;
+    __device__ static void load(const KArgs& a, int g, double* s) {
+        for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i];
+        phi_coeffs(a, g, s[D], s[D + 1]);
+        s[D + 2] = a.H[g];
+        s[D + 3] = a.phi[g];
+    }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+        double X[NV * D], cm[NV], cg[NV], H[NV], p[NV];
+        for (int k = 0; k < NV; ++k) {
+            for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i];
+            cm[k] = nd[k][D]; cg[k] = nd[k][D + 1]; H[k] = nd[k][D + 2]; p[k] = nd[k][D + 3];
+        }
+        elem_residual_phi<Cell>(a.n1d, X, cm, cg, H, p, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double*) { a.y[g] = acc[0]; }
+};
+
+template <class Cell>
+struct OpDiagPhi {
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = 1, NRED = 0;
+    static constexpr int NF = odd<D + 2>::value;
+    __device__ static void load(const KArgs& a, int g, double* s) {
+        for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i];
+        phi_coeffs(a, g, s[D], s[D + 1]);
+    }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+        double X[NV * D], cm[NV], cg[NV];
+        for (int k = 0; k < NV; ++k) {
+            for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i];
+            cm[k] = nd[k][D]; cg[k] = nd[k][D + 1];
+        }
+        elem_diag_phi<Cell>(a.n1d, X, cm, cg, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double*) {
+        a.y[g] = (a.mask && a.mask[g]) ? 1.0 : 1.0 / acc[0];
+    }
+};
+
+template <class Cell>
+struct OpApplyMass {       // staged: X p
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = 1, NRED = 1;
+    static constexpr int NF = odd<D + 1>::value;
+    __device__ static void load(const KArgs& a, int g, double* s) {
+        for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i];
+        s[D] = a.v[g];
+    }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+        double X[NV * D], p[NV];
+        for (int k = 0; k < NV; ++k) { for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i]; p[k] = nd[k][D]; }
+        elem_apply_mass<Cell>(a.n1d, X, p, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double* red) {
+        a.y[g] = acc[0];
+        red[0] += a.v[g] * acc[0];
+    }
+};
+
+template <class Cell>
+struct OpDiagMass {
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = 1, NRED = 0;
+    static constexpr int NF = odd<D>::value;
+    __device__ static void load(const KArgs& a, int g, double* s) { for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i]; }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+        double X[NV * D];
+        for (int k = 0; k < NV; ++k) for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i];
+        elem_diag_mass<Cell>(a.n1d, X, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double*) { a.y[g] = 1.0 / acc[0]; }
+};
+
+template <class Cell>
+struct OpRhsPsi {          // staged: X u ; y = ∫ψ_a(u) N
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = 1, NRED = 0;
+    static constexpr int NF = odd<2 * D>::value;
+    __device__ static void load(const KArgs& a, int g, double* s) {
+        for (int i = 0; i < D; ++i) { s[i] = a.X[(size_t)g * D + i]; s[D + i] = a.u[(size_t)g * D + i]; }
+    }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+        double X[NV * D], U[NV * D];
+        for (int k = 0; k < NV; ++k) for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; U[k * D + i] = nd[k][D + i]; }
+        elem_rhs_psi<Cell>(a.m, a.n1d, X, U, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double*) { a.y[g] = acc[0]; }
+};
+
+template <class Cell>
+struct OpRhsFatigue {      // staged: X f1(=phi_old) f2(=V_c)
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = 1, NRED = 0;
+    static constexpr int NF = odd<D + 2>::value;
+    __device__ static void load(const KArgs& a, int g, double* s) {
+        for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i];
+        s[D] = a.f1[g]; s[D + 1] = a.f2[g];
+    }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+        double X[NV * D], p[NV], v[NV];
+        for (int k = 0; k < NV; ++k) { for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i]; p[k] = nd[k][D]; v[k] = nd[k][D + 1]; }
+        elem_rhs_fatigue<Cell>(a.n1d, X, p, v, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double*) { a.y[g] = acc[0]; }
+};
+
+template <class Op>
+__global__ void __launch_bounds__(kThreads) scatter_kernel(BlockView bv, KArgs a) {
+    constexpr int NV = Op::NV, NF = Op::NF, NOUT = Op::NOUT;
+    extern __shared__ double smem[];
+    __shared__ double s_red[kMaxRed * 32];
+    if (a.stop && a.stop[0] != 0.0) return;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n0 = bv.node0[b], n_own = bv.node0[b + 1] - n0;
+    const int h0 = bv.halo_off[b], n_loc = n_own + bv.halo_off[b + 1] - h0;
+    double* s_nodes = smem;
+    double* s_ebuf = smem + (size_t)bv.max_loc * NF;
+    const int chunk = bv.chunk;
+    // ---- phase A: stage nodal fields
+    for (int i = tid; i < n_loc; i += kThreads) {
+        int g = (i < n_own) ? n0 + i : bv.halo[h0 + i - n_own];
+        Op::load(a, g, s_nodes + (size_t)i * NF);
+    }
+    __syncthreads();
+    const int e0 = bv.elem_off[b], ne = bv.elem_off[b + 1] - e0;
+    double acc[NOUT];
+#pragma unroll
+    for (int c = 0; c < NOUT; ++c) acc[c] = 0.0;
+    int cur = 0, end = 0;
+    if (tid < n_own) { cur = bv.inc_ptr[n0 + tid]; end = bv.inc_ptr[n0 + tid + 1]; }
+    for (int c0 = 0; c0 < ne; c0 += chunk) {
+        const int nc = min(chunk, ne - c0);
+        // ---- phase B: element vectors
+        for (int j = tid; j < nc; j += kThreads) {
+            ushort4 lc = bv.lconn[e0 + c0 + j];
+            const double* nd[4] = {s_nodes + (size_t)lc.x * NF, s_nodes + (size_t)lc.y * NF,
+                                   s_nodes + (size_t)lc.z * NF, s_nodes + (size_t)lc.w * NF};
+            double out[NV * NOUT];
+            Op::elem(a, nd, out);
+#pragma unroll
+            for (int k = 0; k < NV * NOUT; ++k) s_ebuf[k * chunk + j] = out[k];
+        }
+        __syncthreads();
+        // ---- phase C: node-wise gather of incident element rows (fixed order)
+        if (tid < n_own) {
+            while (cur < end) {
+                int code = bv.inc[cur];
+                int j = (code >> 2) - c0;
+                if (j >= nc) break;
+                int v = code & 3;
+#pragma unroll
+                for (int c = 0; c < NOUT; ++c) acc[c] += s_ebuf[(v * NOUT + c) * chunk + j];
+                ++cur;
+            }
+        }
+        __syncthreads();
+    }
+    double red[Op::NRED > 0 ? Op::NRED : 1];
+#pragma unroll
+    for (int k = 0; k < (Op::NRED > 0 ? Op::NRED : 1); ++k) red[k] = 0.0;
+    if (tid < n_own) Op::store(a, n0 + tid, acc, red);
+    if (Op::NRED > 0) grid_reduce<(Op::NRED > 0 ? Op::NRED : 1)>(red, a.partial, a.result, a.counter, s_red);
+}
+
+// ============================================================================= element reductions
+// One thread per PRIMARY element of the block; sums NR scalars over the whole mesh.
+enum { RED_L2_U, RED_L2_PHI, RED_ENERGY };
+
+template <class Cell, int KIND>
+__global__ void __launch_bounds__(kThreads) reduce_kernel(BlockView bv, KArgs a) {
+    constexpr int NV = Cell::NV, D = Cell::D;
+    constexpr int NR = (KIND == RED_ENERGY) ? 8 : 2;
+    constexpr int NC = (KIND == RED_L2_U) ? D : 1;
+    constexpr int NF = odd<(KIND == RED_ENERGY) ? (2 * D + 3) : (D + 2 * NC)>::value;
+    extern __shared__ double smem[];
+    __shared__ double s_red[kMaxRed * 32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n0 = bv.node0[b], n_own = bv.node0[b + 1] - n0;
+    const int h0 = bv.halo_off[b], n_loc = n_own + bv.halo_off[b + 1] - h0;
+    double* s_nodes = smem;
+    for (int i = tid; i < n_loc; i += kThreads) {
+        int g = (i < n_own) ? n0 + i : bv.halo[h0 + i - n_own];
+        double* s = s_nodes + (size_t)i * NF;
+        for (int k = 0; k < D; ++k) s[k] = a.X[(size_t)g * D + k];
+        if (KIND == RED_ENERGY) {
+            for (int k = 0; k < D; ++k) s[D + k] = a.u[(size_t)g * D + k];
+            s[2 * D] = a.phi[g];
+            s[2 * D + 1] = a.m.fatigue ? a.Fat[g] : 1.0;
+            s[2 * D + 2] = a.m.fatigue ? a.f1[g] : 0.0;
+        } else {
+            for (int k = 0; k < NC; ++k) { s[D + k] = a.f1[(size_t)g * NC + k]; s[D + NC + k] = a.f2[(size_t)g * NC + k]; }
+        }
+    }
+    __syncthreads();
+    double vals[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) vals[k] = 0.0;
+    const int e0 = bv.elem_off[b], ne = bv.nprim[b];
+    for (int j = tid; j < ne; j += kThreads) {
+        ushort4 lc = bv.lconn[e0 + j];
+        const double* nd[4] = {s_nodes + (size_t)lc.x * NF, s_nodes + (size_t)lc.y * NF,
+                               s_nodes + (size_t)lc.z * NF, s_nodes + (size_t)lc.w * NF};
+        double X[NV * D];
+        for (int k = 0; k < NV; ++k) for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i];
+        if (KIND == RED_ENERGY) {
+            double U[NV * D], ph[NV], F[NV], ab[NV];
+            for (int k = 0; k < NV; ++k) {
+                for (int i = 0; i < D; ++i) U[k * D + i] = nd[k][D + i];
+                ph[k] = nd[k][2 * D]; F[k] = nd[k][2 * D + 1]; ab[k] = nd[k][2 * D + 2];
+            }
+            elem_energies<Cell>(a.m, a.n1d, X, U, ph, F, ab, vals);
+        } else {
+            double A[NV * NC], B[NV * NC];
+            for (int k = 0; k < NV; ++k) for (int i = 0; i < NC; ++i) { A[k * NC + i] = nd[k][D + i]; B[k * NC + i] = nd[k][D + NC + i]; }
+            elem_l2<Cell, NC>(a.n1d, X, A, B, vals);
+        }
+    }
+    grid_reduce<NR>(vals, a.partial, a.result, a.counter, s_red);
+}
+
+// ============================================================================= vector kernels
+// PCG state scalars (device resident).  Indices into the scalar array S.
+enum { S_PAP = 0, S_RZ0 = 1, S_RZ1 = 2, S_RR = 3, S_THRESH = 4, S_ITERS = 5, S_DONE = 6, S_STAGE = 8, S_COUNT = 16 };
+
+// Publishes the two sums of an update step: rz_next, rr; bumps the iteration count and sets
+// the sticky DONE flag (all later launches of the captured graph then return immediately).
+__device__ __forceinline__ void pcg_finalize(double* S, int par, double rz_new, double rr_new) {
+    S[S_RZ0 + (par ^ 1)] = rz_new;
+    S[S_RR] = rr_new;
+    S[S_ITERS] += 1.0;
+    if (!(rr_new > S[S_THRESH])) S[S_DONE] = 1.0;     // also stops on NaN
+}
+
+// x += α p ; r −= α Ap ; sums Σ r·Dinv·r, Σ r·r     (α = rz[par]/pAp)
+// finalize != 0 (one GPU): the last block publishes directly; else the sums go to S[S_STAGE..]
+// for the all-reduce + pcg_publish_kernel.
+__global__ void __launch_bounds__(kThreads) pcg_update_kernel(int64_t n, double* __restrict__ x, double* __restrict__ r,
+                                                              const double* __restrict__ p, const double* __restrict__ Ap,
+                                                              const double* __restrict__ dinv, double* S, int par,
+                                                              int finalize, double* partial, unsigned int* counter) {
+    __shared__ double s_red[kMaxRed * 32];
+    __shared__ bool is_last;
+    if (S[S_DONE] != 0.0) return;
+    const double alpha = S[S_RZ0 + par] / S[S_PAP];
+    double vals[2] = {0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double pi = p[i], ri = r[i] - alpha * Ap[i];
+        x[i] += alpha * pi;
+        r[i] = ri;
+        vals[0] += ri * dinv[i] * ri;
+        vals[1] += ri * ri;
+    }
+    block_sum<2>(vals, s_red);
+    if (threadIdx.x == 0) {
+        partial[(size_t)blockIdx.x * kMaxRed + 0] = vals[0];
+        partial[(size_t)blockIdx.x * kMaxRed + 1] = vals[1];
+        __threadfence();
+        unsigned int t = atomicInc(counter, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double acc[2] = {0.0, 0.0};
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            acc[0] += __ldcg(&partial[(size_t)b * kMaxRed + 0]);
+            acc[1] += __ldcg(&partial[(size_t)b * kMaxRed + 1]);
+        }
+        block_sum<2>(acc, s_red);
+        if (threadIdx.x == 0) {
+            if (finalize) pcg_finalize(S, par, acc[0], acc[1]);
+            else { S[S_STAGE] = acc[0]; S[S_STAGE + 1] = acc[1]; }
+        }
+    }
+}
+
+// multi-GPU: after the all-reduce of S[S_STAGE..S_STAGE+1]
+__global__ void pcg_publish_kernel(double* S, int par) {
+    if (S[S_DONE] != 0.0) return;
+    pcg_finalize(S, par, S[S_STAGE], S[S_STAGE + 1]);
+}
+
+// p = Dinv r + β p   (β = rz[par^1]/rz[par])
+__global__ void __launch_bounds__(kThreads) pcg_direction_kernel(int64_t n, double* __restrict__ p, const double* __restrict__ r,
+                                                                 const double* __restrict__ dinv, const double* S, int par) {
+    if (S[S_DONE] != 0.0) return;
+    const double beta = S[S_RZ0 + (par ^ 1)] / S[S_RZ0 + par];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = dinv[i] * r[i] + beta * p[i];
+}
+
+// generic fused vector helpers -------------------------------------------------------------
+// out = a + s*b  (b may be null => copy/scale)
+__global__ void axpby_kernel(int64_t n, double* out, const double* a, double sa, const double* b, double sb) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = (a ? sa * a[i] : 0.0) + (b ? sb * b[i] : 0.0);
+}
+
+__global__ void fill_kernel(int64_t n, double* out, double v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
+}
+
+// dots: res[0] = Σ a·b, res[1] = Σ a·a·w (optional w), deterministic two-stage
+__global__ void __launch_bounds__(kThreads) dot2_kernel(int64_t n, const double* a, const double* b, const double* c,
+                                                        const double* d, double* partial, double* result,
+                                                        unsigned int* counter) {
+    __shared__ double s_red[kMaxRed * 32];
+    double vals[2] = {0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        vals[0] += a[i] * b[i];
+        if (c) vals[1] += c[i] * d[i];
+    }
+    grid_reduce<2>(vals, partial, result, counter, s_red);
+}
+
+// SNES residual assembly (dolfinx NonlinearProblem idiom):
+//   F_free = f_int + lift (− f_ext),  F_bc = x − g ;  rhs b = F on free dofs, 0 on Dirichlet dofs;
+//   also delta_bc = F_bc.  Partial sums: ||F||², ||x||².
+__global__ void __launch_bounds__(kThreads) snes_residual_kernel(int64_t n, const double* fint, const double* lift,
+                                                                 const double* fext, const double* x, const double* g,
+                                                                 const uint8_t* mask, double* F, double* partial,
+                                                                 double* result, unsigned int* counter) {
+    __shared__ double s_red[kMaxRed * 32];
+    double vals[2] = {0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double f;
+        if (mask[i]) f = x[i] - g[i];
+        else f = fint[i] + (lift ? lift[i] : 0.0) - (fext ? fext[i] : 0.0);
+        F[i] = f;
+        vals[0] += f * f;
+        vals[1] += x[i] * x[i];
+    }
+    grid_reduce<2>(vals, partial, result, counter, s_red);
+}
+
+// dbc = mask ? g − x : 0 ; result[0] = Σ dbc²
+__global__ void __launch_bounds__(kThreads) bc_gap_kernel(int64_t n, const double* x, const double* g, const uint8_t* mask,
+                                                          double* dbc, double* partial, double* result,
+                                                          unsigned int* counter) {
+    __shared__ double s_red[kMaxRed * 32];
+    double vals[1] = {0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double d = mask[i] ? g[i] - x[i] : 0.0;
+        dbc[i] = d;
+        vals[0] += d * d;
+    }
+    grid_reduce<1>(vals, partial, result, counter, s_red);
+}
+
+// PCG start: r = mask ? 0 : F ; x(=δ) = 0 ; p = Dinv r ; sums rz, rr
+__global__ void __launch_bounds__(kThreads) pcg_init_kernel(int64_t n, const double* F, const uint8_t* mask, const double* dinv,
+                                                            const double* x0, const double* Ax0, double* x, double* r,
+                                                            double* p, double* partial, double* result,
+                                                            unsigned int* counter) {
+    __shared__ double s_red[kMaxRed * 32];
+    double vals[2] = {0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double ri = (mask && mask[i]) ? 0.0 : F[i];
+        if (x0) { ri -= Ax0[i]; x[i] = x0[i]; } else x[i] = 0.0;
+        if (mask && mask[i]) ri = 0.0;
+        r[i] = ri;
+        double zi = dinv[i] * ri;
+        p[i] = zi;
+        vals[0] += ri * zi;
+        vals[1] += ri * ri;
+    }
+    grid_reduce<2>(vals, partial, result, counter, s_red);
+}
+
+// Newton update x −= δ on free dofs, x = g on Dirichlet dofs; sums ||δ_total||² for the stol test
+__global__ void __launch_bounds__(kThreads) newton_update_kernel(int64_t n, double* x, const double* delta, const double* F,
+                                                                 const uint8_t* mask, double* partial, double* result,
+                                                                 unsigned int* counter) {
+    __shared__ double s_red[kMaxRed * 32];
+    double vals[1] = {0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double d = mask[i] ? F[i] : delta[i];
+        x[i] -= d;
+        vals[0] += d * d;
+    }
+    grid_reduce<1>(vals, partial, result, counter, s_red);
+}
+
+// nodal history / fatigue updates (solver.py:357-375, 401-411)
+__global__ void nodal_max_kernel(int64_t n, double* out, const double* a, const double* b) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = fmax(a[i], b[i]);
+}
+
+__global__ void fatigue_update_kernel(int64_t n, const double* alpha_c, const double* alpha_n, const double* abar_n,
+                                      double* abar_c, double* Fat, double dt, double alpha_T) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double da = alpha_c[i] - alpha_n[i];
+        double hv = (da / dt < 0.0) ? 0.0 : 1.0;            // np.heaviside(x, 1)
+        double ab = abar_n[i] + fabs(da) * hv;
+        abar_c[i] = ab;
+        double t = 2.0 * alpha_T / (ab + alpha_T);
+        Fat[i] = (ab >= alpha_T) ? t * t : 1.0;
+    }
+}
+
+// gather-sum of a vector over an index list (reactions): result[c] = Σ_{k, comp(idx)=c} f[idx[k]]
+__global__ void __launch_bounds__(kThreads) gather_sum_kernel(int64_t n, const int32_t* idx, const double* f, int d,
+                                                              double* partial, double* result, unsigned int* counter) {
+    __shared__ double s_red[kMaxRed * 32];
+    double vals[3] = {0.0, 0.0, 0.0};
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        int i = idx[k];
+        int c = i % d;
+        double v = f[i];
+        vals[0] += (c == 0) ? v : 0.0; vals[1] += (c == 1) ? v : 0.0; vals[2] += (c == 2) ? v : 0.0;
+    }
+    grid_reduce<3>(vals, partial, result, counter, s_red);
+}
+
+// scatter values into a vector at an index list (Dirichlet values, tractions)
+__global__ void scatter_set_kernel(int64_t n, const int32_t* idx, const double* vals, double* out) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x)
+        out[idx[k]] = vals[k];
+}
+
+// halo exchange pack: buf[k] = v[idx[k]*nc + c]
+__global__ void pack_kernel(int64_t n, const int32_t* idx, int nc, const double* v, double* buf) {
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n * nc; k += (int64_t)gridDim.x * blockDim.x) {
+        int64_t j = k / nc; int c = (int)(k - j * nc);
+        buf[k] = v[(int64_t)idx[j] * nc + c];
+    }
+}
+
+// L2 flush helper for timing
+__global__ void flush_kernel(int64_t n, double* buf) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) buf[i] += 1.0;
+}
+
+}  // namespace pfx

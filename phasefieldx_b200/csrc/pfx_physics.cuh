@@ -54,26 +54,26 @@ PFX_HD Dual operator*(Dual a, double b) { return Dual(a.v * b, a.d * b); }
 PFX_HD Dual operator*(double a, Dual b) { return Dual(a * b.v, a * b.d); }
 PFX_HD Dual operator/(Dual a, double b) { return Dual(a.v / b, a.d / b); }
 PFX_HD Dual operator/(double a, Dual b) { double q = a / b.v; return Dual(q, -q * b.d / b.v); }
-PFX_HD Dual sqrt(Dual a) { double s = ::sqrt(a.v); return Dual(s, 0.5 * a.d / s); }
-PFX_HD Dual cos(Dual a) { return Dual(::cos(a.v), -::sin(a.v) * a.d); }
-PFX_HD Dual sin(Dual a) { return Dual(::sin(a.v), ::cos(a.v) * a.d); }
-PFX_HD Dual atan2(Dual y, Dual x) {
+PFX_HD Dual m_sqrt(Dual a) { double s = ::sqrt(a.v); return Dual(s, 0.5 * a.d / s); }
+PFX_HD Dual m_cos(Dual a) { return Dual(::cos(a.v), -::sin(a.v) * a.d); }
+PFX_HD Dual m_sin(Dual a) { return Dual(::sin(a.v), ::cos(a.v) * a.d); }
+PFX_HD Dual m_atan2(Dual y, Dual x) {
     double r2 = x.v * x.v + y.v * y.v;
     return Dual(::atan2(y.v, x.v), (x.v * y.d - y.v * x.d) / r2);
 }
 PFX_HD double sgn(double x) { return (x > 0.0) - (x < 0.0); }
-// double overloads so unqualified calls inside this namespace never promote to Dual
-PFX_HD double sqrt(double a) { return ::sqrt(a); }
-PFX_HD double cos(double a) { return ::cos(a); }
-PFX_HD double sin(double a) { return ::sin(a); }
-PFX_HD double atan2(double y, double x) { return ::atan2(y, x); }
-PFX_HD double fabs(double a) { return ::fabs(a); }
-PFX_HD Dual fabs(Dual a) { return Dual(::fabs(a.v), sgn(a.v) * a.d); }
+// double overloads of the m_* math wrappers used by the templated formulas
+PFX_HD double m_sqrt(double a) { return ::sqrt(a); }
+PFX_HD double m_cos(double a) { return ::cos(a); }
+PFX_HD double m_sin(double a) { return ::sin(a); }
+PFX_HD double m_atan2(double y, double x) { return ::atan2(y, x); }
+PFX_HD double m_abs(double a) { return ::fabs(a); }
+PFX_HD Dual m_abs(Dual a) { return Dual(::fabs(a.v), sgn(a.v) * a.d); }
 PFX_HD double val(double a) { return a; }
 PFX_HD double val(Dual a) { return a.v; }
 
-template <class T> PFX_HD T mac_p(T x) { return 0.5 * (x + fabs(x)); }
-template <class T> PFX_HD T mac_n(T x) { return 0.5 * (x - fabs(x)); }
+template <class T> PFX_HD T mac_p(T x) { return 0.5 * (x + m_abs(x)); }
+template <class T> PFX_HD T mac_n(T x) { return 0.5 * (x - m_abs(x)); }
 template <class T> PFX_HD T sq(T x) { return x * x; }
 
 // ----------------------------------------------------------------------------- 2×2 spectral
@@ -84,7 +84,7 @@ PFX_HD void spectral_parts2(const T e[3], T eP[3], T eN[3]) {
     T a = e[0], c = e[1], b = e[2];
     T tr = a + c;
     T amc = a - c;
-    T s = sqrt(amc * amc + 4.0 * (b * b) + kEps * kEps);
+    T s = m_sqrt(amc * amc + 4.0 * (b * b) + kEps * kEps);
     T l0 = 0.5 * (tr - s), l1 = 0.5 * (tr + s);
     T m00 = amc / s, m01 = (2.0 * b) / s;            // M/s (m11 = -m00)
     T E0[3] = {0.5 * (1.0 - m00), 0.5 * (1.0 + m00), -0.5 * m01};
@@ -120,10 +120,10 @@ PFX_HD void spectral_parts3(const T e[6], T eP[6], T eN[6]) {
     dp = dp + kEps * kEps;
     Dl = Dl + kEps * kEps;
     const double s27 = 5.196152422706632;   // sqrt(27)
-    T sD = sqrt(Dl);
+    T sD = m_sqrt(Dl);
     T y = s27 * sD;
-    T phi3 = atan2(y, dq);
-    T sdp = sqrt(dp);
+    T phi3 = m_atan2(y, dq);
+    T sdp = m_sqrt(dp);
     // gradients wrt A_kl (row-major kl)
     T gI2[9], gdq[9], gdp[9], gph[9];
     T r2 = dq * dq + y * y;
@@ -145,7 +145,7 @@ PFX_HD void spectral_parts3(const T e[6], T eP[6], T eN[6]) {
     const int sym_tr[6] = {0, 4, 8, 3, 6, 7};       // transposed partner (E = grad^T)
     for (int k = 1; k <= 3; ++k) {
         T th = (phi3 + (2.0 * 3.14159265358979323846 * k)) / 3.0;
-        T ck = cos(th), sk = sin(th);
+        T ck = m_cos(th), sk = m_sin(th);
         T lk = (I1 + 2.0 * (sdp * ck)) / 3.0;
         T c1 = ck / sdp;
         T c2 = (2.0 / 3.0) * (sdp * sk);

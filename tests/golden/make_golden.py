@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Generates the committed fixtures under tests/golden/ from /root/reference (run in the build
+container only; the GPU box has no /root/reference).
+
+  c1_mesh.npz        config-1 mesh parsed from reference examples/PhaseFieldFracture/mesh/mesh.msh
+  ref_1711.npz       first rows of the stored outputs of example 1711 (bottom.reaction,
+                     total.energy, phasefieldx.conv, top.dof)
+  ref_1713.npz       same for example 1713 (structured 200x100 Q1 mesh, no mesh file needed)
+  ref_1712.npz       same for example 1712 (shear, spectral)
+  ref_constitutive.npz  outputs of the reference's own constitutive layer
+                     (Math/invariants.py, Math/tensor_decomposition.py, Materials/elastic_isotropic.py,
+                     split_energy_stress_tangent_functions.py) executed UNMODIFIED under the torch-fp64
+                     `ufl` stand-in of tests/golden/ufl_shim.py, at seeded random strains.
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+EX = os.path.join(REF, "examples", "PhaseFieldFracture")
+
+
+def table(path, nrows):
+    a = np.loadtxt(path, skiprows=1)
+    return a[:nrows]
+
+
+def main():
+    from phasefieldx_b200 import mesh as M
+    md = M.read_from_msh(os.path.join(EX, "mesh", "mesh.msh"), None, 0, 2)
+    msh = md.mesh
+    np.savez_compressed(os.path.join(HERE, "c1_mesh.npz"), points=msh.geometry.x[:, :2], cells=msh.cells,
+                        bottom_nodes=M.facet_nodes(msh, md.facet_tags.find(9)),
+                        top_nodes=M.facet_nodes(msh, md.facet_tags.find(10)))
+    for tag, folder, n in (("1711", "1711_Single_Edge_Notched_Tension_Test", 150),
+                           ("1713", "1713_Symmetry_Single_Edge_Notched_Tension_Test", 60),
+                           ("1712", "1712_Single_Edge_Notched_Shear_Test", 104)):
+        d = os.path.join(EX, folder)
+        np.savez_compressed(os.path.join(HERE, f"ref_{tag}.npz"),
+                            bottom_reaction=table(os.path.join(d, "bottom.reaction"), n),
+                            energy=table(os.path.join(d, "total.energy"), n),
+                            conv=table(os.path.join(d, "phasefieldx.conv"), n),
+                            dof=table(os.path.join(d, "top.dof"), n))
+    from ufl_shim import reference_constitutive
+    np.savez_compressed(os.path.join(HERE, "ref_constitutive.npz"), **reference_constitutive())
+    print("fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, HERE)
+    main()

@@ -66,3 +66,78 @@ void hc_assemble(int op, int cell_type, const double* mat, int smodel, int emode
     else assemble<Tet>(op, m, n1d, ne, coords, cells, f0, f1, f2, f3, out);
 }
 }
+
+// ---------------------------------------------------------------------------------------------
+// CPU mirror of scatter_kernel's index logic (phase A/B/C over the BlockMesh arrays) for the
+// u-apply, used to validate pfx_blocks.cpp before any GPU run.  Same chunking, same cursors.
+#include "../../phasefieldx_b200/csrc/pfx_blocks.h"
+
+template <class Cell>
+static void emulate_apply_u(const BlockMesh& bm, const Material& m, int n1d, const double* coords, const double* phi,
+                            const double* u, const double* v, int chunk, double* y, double* dot) {
+    constexpr int NV = Cell::NV, D = Cell::D, NF = 3 * D + 1;
+    std::vector<double> s_nodes, s_ebuf((size_t)NV * D * chunk);
+    *dot = 0.0;
+    for (int b = 0; b < bm.nb; ++b) {
+        int n0 = bm.node0[b], n_own = bm.node0[b + 1] - n0, h0 = bm.halo_off[b], n_loc = n_own + bm.halo_off[b + 1] - h0;
+        s_nodes.assign((size_t)n_loc * NF, 0.0);
+        for (int i = 0; i < n_loc; ++i) {
+            int g = i < n_own ? n0 + i : bm.halo[h0 + i - n_own];
+            int old = bm.perm[g];
+            double* s = &s_nodes[(size_t)i * NF];
+            for (int k = 0; k < D; ++k) { s[k] = coords[3 * (size_t)old + k]; s[D + 1 + k] = v[(size_t)old * D + k]; s[2 * D + 1 + k] = u[(size_t)old * D + k]; }
+            s[D] = phi[old];
+        }
+        int e0 = bm.elem_off[b], ne = bm.elem_off[b + 1] - e0;
+        std::vector<double> acc((size_t)n_own * D, 0.0);
+        std::vector<int> cur(n_own), end(n_own);
+        for (int t = 0; t < n_own; ++t) { cur[t] = bm.inc_ptr[n0 + t]; end[t] = bm.inc_ptr[n0 + t + 1]; }
+        for (int c0 = 0; c0 < ne; c0 += chunk) {
+            int nc = std::min(chunk, ne - c0);
+            for (int j = 0; j < nc; ++j) {
+                const uint16_t* lc = &bm.lconn[4 * (size_t)(e0 + c0 + j)];
+                double X[NV * D], ph[NV], V[NV * D], U[NV * D], out[NV * D];
+                for (int k = 0; k < NV; ++k) {
+                    const double* nd = &s_nodes[(size_t)lc[k] * NF];
+                    for (int i = 0; i < D; ++i) { X[k * D + i] = nd[i]; V[k * D + i] = nd[D + 1 + i]; U[k * D + i] = nd[2 * D + 1 + i]; }
+                    ph[k] = nd[D];
+                }
+                elem_apply_u<Cell>(m, n1d, X, ph, U, V, out);
+                for (int k = 0; k < NV * D; ++k) s_ebuf[(size_t)k * chunk + j] = out[k];
+            }
+            for (int t = 0; t < n_own; ++t)
+                while (cur[t] < end[t]) {
+                    int code = bm.inc[cur[t]], j = (code >> 2) - c0;
+                    if (j >= nc) break;
+                    int vtx = code & 3;
+                    for (int c = 0; c < D; ++c) acc[(size_t)t * D + c] += s_ebuf[(size_t)(vtx * D + c) * chunk + j];
+                    ++cur[t];
+                }
+        }
+        for (int t = 0; t < n_own; ++t) {
+            int old = bm.perm[n0 + t];
+            for (int c = 0; c < D; ++c) { y[(size_t)old * D + c] = acc[(size_t)t * D + c]; *dot += v[(size_t)old * D + c] * acc[(size_t)t * D + c]; }
+        }
+    }
+}
+
+extern "C" {
+// returns 0 on success; stats = {nb, max_own, max_loc, max_elems, total_elems, sum_nprim}
+int hc_blocks_apply_u(int cell_type, const double* mat, int smodel, int n1d, int64_t n_nodes, int64_t n_owned,
+                      int64_t n_cells, const double* coords, const int32_t* cells, const uint8_t* cell_primary,
+                      int max_own, int chunk, const double* phi, const double* u, const double* v, double* y,
+                      double* dot, int64_t* stats) {
+    Material m{mat[0], mat[1], mat[2], mat[3], mat[4], smodel, smodel, 0, 0.0};
+    int nv = cell_type == 0 ? 3 : 4, dim = cell_type == 2 ? 3 : 2;
+    BlockMesh bm;
+    std::string er = build_blocks(nv, dim, n_nodes, n_owned, n_cells, coords, cells, cell_primary, max_own, bm);
+    if (!er.empty()) return 1;
+    int64_t np = 0;
+    for (int b = 0; b < bm.nb; ++b) np += bm.nprim[b];
+    stats[0] = bm.nb; stats[1] = bm.max_own; stats[2] = bm.max_loc; stats[3] = bm.max_elems; stats[4] = bm.total_elems; stats[5] = np;
+    if (cell_type == 0) emulate_apply_u<Tri>(bm, m, n1d, coords, phi, u, v, chunk, y, dot);
+    else if (cell_type == 1) emulate_apply_u<Quad>(bm, m, n1d, coords, phi, u, v, chunk, y, dot);
+    else emulate_apply_u<Tet>(bm, m, n1d, coords, phi, u, v, chunk, y, dot);
+    return 0;
+}
+}

@@ -1,0 +1,218 @@
+"""GPU parity of the whole staggered load step (pfx_load_step through the C-ABI) against the
+CPU oracle on the same mesh and loading: u, phi, H within 1e-8 relative L2 per step, reactions
+within 1e-6 relative (BASELINE.json north_star), plus the reference's own analytic tests."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_FIELD = 1e-8
+TOL_REACTION = 1e-6
+
+
+def _pair(msh, ctype, deg, sp, irr="miehe", fatigue=False, Gc=0.0027, l=0.015, E=210.0, nu=0.3, fatigue_val=0.05625,
+          **opts):
+    from oracle.solver import Oracle, Params
+    from phasefieldx_b200 import _lib
+    P = Params(E=E, nu=nu, Gc=Gc, l=l, degradation=deg, split_energy=sp, irreversibility=irr, fatigue=fatigue,
+               fatigue_val=fatigue_val)
+    o = Oracle(msh.geometry.x, msh.cells, msh.cell_type, P)
+    e = _lib.Engine(msh.geometry.x, msh.cells, ctype, P.lambda_, P.mu, P.Gc, P.l, k=P.k,
+                    model=_lib.model_code(deg, None if sp == "no" else sp), irreversibility=(irr == "miehe"),
+                    fatigue=fatigue, fatigue_val=fatigue_val, **opts)
+    return o, e, P
+
+
+def _compare_step(o, e, bcs, step, names=("u", "phi", "H")):
+    from conftest import rel_l2
+    fields = {"u": o.u, "phi": o.phi, "H": o.H, "V_c": o.V_c, "fatigue": o.Fatigue, "alpha_cum_bar_c": o.abar_c}
+    for nm in names:
+        err = rel_l2(e.get_field(nm), fields[nm])
+        assert err < TOL_FIELD, (step, nm, err)
+    for i, bc in enumerate(bcs):
+        Rg, Ro = e.reaction(i), o.reaction(bc)
+        assert np.all(np.abs(Rg - Ro) <= TOL_REACTION * np.abs(Ro).max() + 1e-12), (step, i, Rg, Ro)
+
+
+def test_one_element_isotropic_reference_test():
+    """reference test/Element/Phase_Field_Fracture/test_phase_field_fracture_element.py:16-136"""
+    from phasefieldx_b200 import mesh as M, _lib
+    from oracle.solver import Params
+    msh = M.create_rectangle(None, [np.array([0, 0]), np.array([1, 1])], [1, 1], M.CellType.quadrilateral)
+    P = Params(E=210.0, nu=0.3, Gc=0.005, l=0.1)
+    e = _lib.Engine(msh.geometry.x, msh.cells, "quadrilateral", P.lambda_, P.mu, P.Gc, P.l)
+    x = msh.geometry.x
+    top = np.nonzero(np.isclose(x[:, 1], 1))[0]
+    bot = np.nonzero(np.isclose(x[:, 1], 0))[0]
+    e.set_bc_u(0, (top[:, None] * 2 + np.arange(2)).ravel())
+    e.set_bc_u(1, (bot[:, None] * 2 + np.arange(2)).ravel())
+    e.set_bc_values_u(1, np.zeros(2 * len(bot)))
+    for step in range(200):
+        t = float(step)
+        val = 0.0003 * t if t <= 50 else (-0.0003 * (t - 50) + 0.015 if t <= 100 else 0.0003 * (t - 100))
+        e.set_bc_values_u(0, np.tile([0.0, val], len(top)))
+        e.load_step(max_stagger_iter=500)
+        psi_t = 0.5 * val**2 * (P.lambda_ + 2 * P.mu)
+        phi_t = 2 * psi_t / (P.Gc / P.l + 2 * psi_t)
+        sigma_t = val * (P.lambda_ + 2 * P.mu) * (1 - phi_t) ** 2
+        np.testing.assert_allclose(e.reaction(0)[1], sigma_t, rtol=1e-3, atol=1e-8)
+    e.close()
+
+
+def test_one_element_spectral_reference_test():
+    """reference test_phase_field_fracture_element_anisotropic.py:17-157 (tension -> compression)"""
+    from phasefieldx_b200 import mesh as M, _lib
+    from oracle.solver import Params
+    msh = M.create_rectangle(None, [np.array([0, 0]), np.array([1, 1])], [1, 1], M.CellType.quadrilateral)
+    P = Params(E=210.0, nu=0.3, Gc=0.005, l=0.1, degradation="anisotropic", split_energy="spectral")
+    e = _lib.Engine(msh.geometry.x, msh.cells, "quadrilateral", P.lambda_, P.mu, P.Gc, P.l, model=1)
+    x = msh.geometry.x
+    top = np.nonzero(np.isclose(x[:, 1], 1))[0]
+    bot = np.nonzero(np.isclose(x[:, 1], 0))[0]
+    e.set_bc_u(0, (top[:, None] * 2 + np.arange(2)).ravel())
+    e.set_bc_u(1, (bot[:, None] * 2 + np.arange(2)).ravel())
+    e.set_bc_values_u(1, np.zeros(2 * len(bot)))
+    mp = lambda v: 0.5 * (v + abs(v))
+    mn = lambda v: 0.5 * (v - abs(v))
+    for step in range(200):
+        t = float(step)
+        val = 0.0003 * t if t <= 50 else (-0.0003 * (t - 50) + 0.015 if t <= 150 else 0.0003 * (t - 150) - 0.015)
+        e.set_bc_values_u(0, np.tile([0.0, val], len(top)))
+        e.load_step(max_stagger_iter=500)
+        psi_t = 0.5 * mp(val) ** 2 * (P.lambda_ + 2 * P.mu)
+        phi_t = 2 * psi_t / (P.Gc / P.l + 2 * psi_t)
+        sigma_t = mp(val) * (P.lambda_ + 2 * P.mu) * (1 - phi_t) ** 2 + mn(val) * (P.lambda_ + 2 * P.mu)
+        np.testing.assert_allclose(e.reaction(0)[1], sigma_t, rtol=1e-3, atol=1e-8)
+    e.close()
+
+
+def test_config1_sent_isotropic_vs_oracle_and_stored_reference(c1_mesh):
+    """Config 1 (reference examples/PhaseFieldFracture/plot_1711.py): first load steps against the
+    oracle (1e-8 fields, 1e-6 reactions) and against the reference's stored bottom.reaction."""
+    import os
+    from conftest import GOLDEN
+    from oracle.solver import BC
+    msh, bot, top = c1_mesh
+    o, e, P = _pair(msh, "triangle", "isotropic", "no")
+    dofs_b = (bot[:, None] * 2 + np.arange(2)).ravel()
+    dofs_t = top * 2 + 1
+    bt, bb = BC(dofs_t), BC(dofs_b)
+    e.set_bc_u(0, dofs_t)
+    e.set_bc_u(1, dofs_b)
+    e.set_bc_values_u(1, np.zeros(len(dofs_b)))
+    ref = np.load(os.path.join(GOLDEN, "ref_1711.npz"))
+    for step in range(5):
+        bt.values[:] = 1e-4 * step
+        e.set_bc_values_u(0, bt.values)
+        ro = o.load_step([bt, bb], [], max_stagger_iter=500)
+        rg = e.load_step(max_stagger_iter=500)
+        assert rg["stagger"] == ro["stagger"], (step, rg["stagger"], ro["stagger"])
+        assert rg["u_its"] == ro["u_its"] and rg["phi_its"] == ro["phi_its"]
+        _compare_step(o, e, [bt, bb], step)
+        Ry = e.reaction(1)[1]
+        stored = ref["bottom_reaction"][step, 2]
+        assert abs(Ry - stored) <= 1e-7 * abs(stored) + 1e-14, (step, Ry, stored)
+        eg, eo = e.energies(), o.energies()
+        for key in eo:
+            assert abs(eg[key] - eo[key]) <= 1e-7 * abs(eo[key]) + 1e-20, (step, key)
+    e.close()
+
+
+@pytest.mark.parametrize("deg,sp", [("anisotropic", "spectral"), ("anisotropic", "deviatoric"), ("hybrid", "spectral")])
+def test_notched_shear_triangles_vs_oracle(deg, sp):
+    """Config-2-like (reference plot_1712.py) at oracle size: slit square, shear loading."""
+    from phasefieldx_b200 import mesh as M
+    from oracle.solver import BC
+    n = 24
+    msh = M.create_rectangle(None, [[-0.5, -0.5], [0.5, 0.5]], [n, n])
+    msh = M.cut_slit(msh, lambda x: np.isclose(x[1], 0.0) & (x[0] < -1e-9), lambda c: c[1] > 0)
+    o, e, P = _pair(msh, "triangle", deg, sp, l=0.06)
+    x = msh.geometry.x
+    top = np.nonzero(np.isclose(x[:, 1], 0.5))[0]
+    bot = np.nonzero(np.isclose(x[:, 1], -0.5))[0]
+    side = np.nonzero((np.isclose(x[:, 0], -0.5) | np.isclose(x[:, 0], 0.5)) & (np.abs(x[:, 1]) < 0.5 - 1e-9))[0]
+    d_top = (top[:, None] * 2 + np.arange(2)).ravel()
+    d_bot = (bot[:, None] * 2 + np.arange(2)).ravel()
+    d_side = side * 2 + 1
+    bcs = [BC(d_top), BC(d_bot), BC(d_side)]
+    for i, bc in enumerate(bcs):
+        e.set_bc_u(i, bc.dofs)
+        e.set_bc_values_u(i, bc.values)
+    for step in range(1, 5):
+        bcs[0].values = np.tile([2e-3 * step, 0.0], len(top))
+        e.set_bc_values_u(0, bcs[0].values)
+        ro = o.load_step(bcs, [], max_stagger_iter=60)
+        rg = e.load_step(max_stagger_iter=60)
+        assert rg["stagger"] == ro["stagger"], (step, rg["stagger"], ro["stagger"])
+        _compare_step(o, e, bcs, step)
+    e.close()
+
+
+def test_tet_spectral_vs_oracle():
+    """Config-5-like at oracle size: notched beam of P1 tets, spectral split."""
+    from phasefieldx_b200 import mesh as M
+    from oracle.solver import BC
+    msh = M.create_box(None, [[0, 0, 0], [3.0, 1.0, 0.5]], [9, 4, 2])
+    o, e, P = _pair(msh, "tetrahedron", "anisotropic", "spectral", E=0.6, nu=0.2, Gc=0.00013, l=0.4)
+    x = msh.geometry.x
+    left = np.nonzero(np.isclose(x[:, 0], 0.0))[0]
+    right = np.nonzero(np.isclose(x[:, 0], 3.0))[0]
+    bcs = [BC((left[:, None] * 3 + np.arange(3)).ravel()), BC(right * 3 + 0)]
+    for i, bc in enumerate(bcs):
+        e.set_bc_u(i, bc.dofs)
+        e.set_bc_values_u(i, bc.values)
+    for step in range(1, 4):
+        bcs[1].values[:] = 4e-2 * step
+        e.set_bc_values_u(1, bcs[1].values)
+        ro = o.load_step(bcs, [], max_stagger_iter=40)
+        rg = e.load_step(max_stagger_iter=40)
+        assert rg["stagger"] == ro["stagger"], (step, rg["stagger"], ro["stagger"])
+        _compare_step(o, e, bcs, step)
+    e.close()
+
+
+def test_fatigue_vs_oracle(c1_mesh):
+    """Config-3-like (reference examples/Fatigue/plot_1800.py) on a coarse mesh: cyclic loading,
+    fatigue degradation; checks alpha_bar and the fatigue field too."""
+    from phasefieldx_b200 import mesh as M
+    from oracle.solver import BC
+    n = 20
+    msh = M.create_rectangle(None, [[-0.5, -0.5], [0.5, 0.5]], [n, n])
+    msh = M.cut_slit(msh, lambda x: np.isclose(x[1], 0.0) & (x[0] < -1e-9), lambda c: c[1] > 0)
+    o, e, P = _pair(msh, "triangle", "isotropic", "no", fatigue=True, l=0.05, fatigue_val=0.002)
+    x = msh.geometry.x
+    top = np.nonzero(np.isclose(x[:, 1], 0.5))[0]
+    bot = np.nonzero(np.isclose(x[:, 1], -0.5))[0]
+    bcs = [BC(top * 2 + 1), BC((bot[:, None] * 2 + np.arange(2)).ravel())]
+    for i, bc in enumerate(bcs):
+        e.set_bc_u(i, bc.dofs)
+        e.set_bc_values_u(i, bc.values)
+    for step in range(0, 12):
+        val = (2 / np.pi) * 0.004 * np.arcsin(np.sin(2 * np.pi * step / 8))
+        bcs[0].values[:] = val
+        e.set_bc_values_u(0, bcs[0].values)
+        ro = o.load_step(bcs, [], max_stagger_iter=60)
+        rg = e.load_step(max_stagger_iter=60)
+        assert rg["stagger"] == ro["stagger"], (step, rg["stagger"], ro["stagger"])
+        _compare_step(o, e, bcs, step, names=("u", "phi", "H", "alpha_cum_bar_c", "fatigue"))
+    eg, eo = e.energies(), o.energies()
+    assert abs(eg["alpha_acum"] - eo["alpha_acum"]) <= 1e-7 * abs(eo["alpha_acum"])
+    e.close()
+
+
+def test_non_convergence_raises_reference_error():
+    """reference solver.py:341-344: RuntimeError('Solver did not converge, got <reason>.')"""
+    from phasefieldx_b200 import mesh as M, _lib
+    msh = M.create_rectangle(None, [[0, 0], [1, 1]], [8, 8])
+    e = _lib.Engine(msh.geometry.x, msh.cells, "triangle", 121.15, 80.77, 0.0027, 0.015, cg_max_it=2, cg_chunk=2)
+    x = msh.geometry.x
+    top = np.nonzero(np.isclose(x[:, 1], 1))[0]
+    bot = np.nonzero(np.isclose(x[:, 1], 0))[0]
+    e.set_bc_u(0, top * 2 + 1)
+    e.set_bc_u(1, (bot[:, None] * 2 + np.arange(2)).ravel())
+    e.set_bc_values_u(0, np.full(len(top), 1e-3))
+    with pytest.raises(RuntimeError, match="Solver did not converge, got -3."):
+        e.load_step()
+    e.close()
