@@ -55,7 +55,7 @@ typedef struct {
     int64_t n_cells;
     const double* coords;     /* [n_nodes,3]  (msh.geometry.x)                             */
     const int32_t* cells;     /* [n_cells,n_v] (V.dofmap.list; quads in tensor order)      */
-    /* distributed runs only (NULL / 0 for one GPU): see pfx_partition()                   */
+    /* distributed runs only (NULL / 0 for one GPU): see pfx_partition_create                   */
     int64_t n_owned;          /* 0 => all nodes owned                                      */
     const uint8_t* cell_primary; /* [n_cells] 1 if this rank integrates the cell in scalar
                                     reductions (energies, norms); NULL => all              */
@@ -94,6 +94,7 @@ typedef struct {
     double err_u, err_phi;                       /* eval_error_L2_normalized, errors_functions.py:190-228 */
     double fnorm_u, fnorm_phi;
     int64_t cg_its_u, cg_its_phi, cg_its_proj;   /* totals over the load step                */
+    double gpu_ms;            /* CUDA-event time of the whole step on the context stream   */
     int32_t history_len;
     int32_t* hist_u_its;      /* caller-allocated [history_capacity] or NULL                */
     int32_t* hist_phi_its;

@@ -45,7 +45,7 @@ class PfxStepReport(C.Structure):
     _fields_ = [("stagger_iters", C.c_int32), ("u_newton_its", C.c_int32), ("phi_newton_its", C.c_int32),
                 ("u_reason", C.c_int32), ("phi_reason", C.c_int32), ("err_u", C.c_double), ("err_phi", C.c_double),
                 ("fnorm_u", C.c_double), ("fnorm_phi", C.c_double), ("cg_its_u", C.c_int64), ("cg_its_phi", C.c_int64),
-                ("cg_its_proj", C.c_int64), ("history_len", C.c_int32), ("hist_u_its", C.POINTER(C.c_int32)),
+                ("cg_its_proj", C.c_int64), ("gpu_ms", C.c_double), ("history_len", C.c_int32), ("hist_u_its", C.POINTER(C.c_int32)),
                 ("hist_phi_its", C.POINTER(C.c_int32)), ("hist_err_u", C.POINTER(C.c_double)),
                 ("hist_err_phi", C.POINTER(C.c_double)), ("hist_fnorm_u", C.POINTER(C.c_double)),
                 ("hist_fnorm_phi", C.POINTER(C.c_double))]
@@ -305,7 +305,7 @@ class Engine:
         st = self.lib.pfx_load_step(self.h, C.byref(o), C.byref(r))
         rep = dict(stagger=r.stagger_iters, u_its=r.u_newton_its, phi_its=r.phi_newton_its, u_reason=r.u_reason,
                    phi_reason=r.phi_reason, err_u=r.err_u, err_phi=r.err_phi, fnorm_u=r.fnorm_u, fnorm_phi=r.fnorm_phi,
-                   cg_its_u=r.cg_its_u, cg_its_phi=r.cg_its_phi, cg_its_proj=r.cg_its_proj,
+                   cg_its_u=r.cg_its_u, cg_its_phi=r.cg_its_phi, cg_its_proj=r.cg_its_proj, gpu_ms=r.gpu_ms,
                    history={k: v[: r.history_len].copy() for k, v in hist.items()}, status=st)
         if st in (PFX_ERR_NOT_CONVERGED_U, PFX_ERR_NOT_CONVERGED_PHI):
             # reference solver.py:343-344 / :389-390

@@ -156,8 +156,19 @@ std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int6
                 if (l < n_own) bm.inc_ptr[bm.node0[b] + l + 1]++;
             }
     }
+    // pad every block's list to a multiple of 8 entries (16-byte vector staging in the kernels);
+    // the padding (sentinel 0xFFFF = element 16383, never valid) hangs off the block's last node
+    {
+        int64_t run = 0;
+        for (int b = 0; b < nb; ++b) {
+            for (int32_t i = bm.node0[b]; i < bm.node0[b + 1]; ++i) run += bm.inc_ptr[i + 1];
+            int pad = (int)((8 - run % 8) % 8);
+            if (bm.node0[b + 1] > bm.node0[b]) bm.inc_ptr[bm.node0[b + 1]] += pad;
+            run += pad;
+        }
+    }
     for (int64_t i = 0; i < n_owned; ++i) bm.inc_ptr[i + 1] += bm.inc_ptr[i];
-    bm.inc.resize(bm.inc_ptr[n_owned]);
+    bm.inc.assign(bm.inc_ptr[n_owned], (uint16_t)0xFFFF);
     {
         std::vector<int32_t> cur(bm.inc_ptr.begin(), bm.inc_ptr.end() - 1);
         for (int b = 0; b < nb; ++b) {

@@ -178,18 +178,21 @@ template <class Cell> PFX_HD double gbar_simplex(const double* phi) {
 // ============================================================================= u-space
 // out[NV*D] = ∫ ((g(φ)+k) dσ_a + dσ_b) : ε(N_a e_i)   with dσ the tangent action on ε(v)
 // (J_u·v, solver.py:186); nl = stress law nonlinear in u (needs U)
-template <class Cell>
-PFX_HD void elem_apply_u(const Material& m, int n1d, const double* X, const double* phi,
+template <class Cell, int SM = -1>
+PFX_HD void elem_apply_u(const Material& m_, int n1d, const double* X, const double* phi,
                          const double* U, const double* V, double* out) {
     constexpr int NV = Cell::NV, D = Cell::D, NS = SymN<D>::N;
+    struct { double lam, mu, k; int smodel; } m = {m_.lam, m_.mu, m_.k, SM >= 0 ? SM : m_.smodel};
+    Material mm = m_;
+    mm.smodel = m.smodel;
     for (int i = 0; i < NV * D; ++i) out[i] = 0.0;
     Geo<Cell> geo; geo.init(X, n1d);
-    double e[NS], de[NS], dsa[NS], dsb[NS], S[NS];
+    double e[NS] = {}, de[NS], dsa[NS], dsb[NS], S[NS];
     if constexpr (Cell::simplex) {
         double gb = gbar_simplex<Cell>(phi) + m.k;
         if (m.smodel != M_ISO) sym_grad<Cell>(geo.G, U, e);
         sym_grad<Cell>(geo.G, V, de);
-        dstress_split<D>(m, m.smodel, e, de, dsa, dsb);
+        dstress_split<D>(mm, m.smodel, e, de, dsa, dsb);
         for (int i = 0; i < NS; ++i) S[i] = gb * dsa[i] + dsb[i];
         add_div<Cell>(geo.G, S, geo.vol, out);
     } else {
@@ -199,7 +202,7 @@ PFX_HD void elem_apply_u(const Material& m, int n1d, const double* X, const doub
             double ph = interp<NV>(N, phi), gq = (1.0 - ph) * (1.0 - ph) + m.k;
             if (m.smodel != M_ISO) sym_grad<Cell>(G, U, e);
             sym_grad<Cell>(G, V, de);
-            dstress_split<D>(m, m.smodel, e, de, dsa, dsb);
+            dstress_split<D>(mm, m.smodel, e, de, dsa, dsb);
             for (int i = 0; i < NS; ++i) S[i] = gq * dsa[i] + dsb[i];
             add_div<Cell>(G, S, w, out);
         }
@@ -280,23 +283,19 @@ PFX_HD void elem_apply_phi(int n1d, const double* X, const double* cm, const dou
     for (int a = 0; a < NV; ++a) out[a] = 0.0;
     Geo<Cell> geo; geo.init(X, n1d);
     if constexpr (Cell::simplex) {
-        double cgm = 0.0, gp[D];
+        // ∫N_aN_bN_c = vol·base·(1 + δab + δac + δbc + 2δabc), base = 1/60 (tri), 1/120 (tet)
+        double cgm = 0.0, gp[D], C = 0.0, P = 0.0, Q = 0.0;
         for (int i = 0; i < D; ++i) gp[i] = 0.0;
         for (int a = 0; a < NV; ++a) {
-            cgm += cg[a];
+            cgm += cg[a]; C += cm[a]; P += p[a]; Q += cm[a] * p[a];
             for (int i = 0; i < D; ++i) gp[i] += geo.G[a][i] * p[a];
         }
         cgm *= geo.vol / NV;
+        const double vb = geo.vol * ((D == 2) ? 1.0 / 60.0 : 1.0 / 120.0), cpq = C * P + Q;
         for (int a = 0; a < NV; ++a) {
-            double s = 0.0;
-            for (int b = 0; b < NV; ++b) {
-                double t = 0.0;
-                for (int c = 0; c < NV; ++c) t += cm[c] * m3<Cell>(a, b, c);
-                s += t * p[b];
-            }
             double gg = 0.0;
             for (int i = 0; i < D; ++i) gg += geo.G[a][i] * gp[i];
-            out[a] = geo.vol * s + cgm * gg;
+            out[a] = vb * (cpq + C * p[a] + cm[a] * P + 2.0 * cm[a] * p[a]) + cgm * gg;
         }
     } else {
         double N[NV], G[NV][D];

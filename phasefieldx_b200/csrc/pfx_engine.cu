@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/pfx_b200.h"
@@ -101,9 +102,11 @@ struct pfx_ctx {
     std::string err;
     int64_t launches = 0;
     double* flush_buf = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t flush_n = 0;
     std::vector<std::vector<int32_t>> tmp_idx;
     bool configuring = false;
+    bool generic_apply = false;   // PFX_GENERIC_APPLY=1: use the generic scatter kernel for J_u·v on triangles
 };
 
 namespace {
@@ -135,11 +138,12 @@ template <class Op>
 int launch_scatter_op(pfx_ctx* c, const KArgs& a) {
     BlockView bv = c->bv;
     int per_elem = Op::NV * Op::NOUT;
-    int cap = std::max(32, (24 * 1024 / (per_elem * 8)) / 32 * 32);
+    int cap = std::max(32, (32 * 1024 / (per_elem * 8)) / 32 * 32);
     bv.chunk = std::min((c->bm.max_elems + 31) / 32 * 32, cap);
-    size_t smem = ((size_t)c->bm.max_loc * Op::NF + (size_t)per_elem * bv.chunk) * sizeof(double);
+    size_t smem = ((((size_t)c->bm.max_loc * Op::NF + (size_t)per_elem * bv.chunk) + 1) & ~(size_t)1) * sizeof(double) +
+                  ((size_t)c->bv.max_inc * sizeof(uint16_t) + 15) / 16 * 16;
     if (c->configuring) {           // pfx_create: opt in to > 48 KB dynamic shared memory, no launch
-        if (smem > 48 * 1024)
+        if (smem + 4096 > 48 * 1024)      // static (reduction scratch) + dynamic must stay below 48 KB unless opted in
             CK(cudaFuncSetAttribute(scatter_kernel<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return PFX_OK;
     }
@@ -149,12 +153,35 @@ int launch_scatter_op(pfx_ctx* c, const KArgs& a) {
     return PFX_OK;
 }
 
+template <int SM>
+int launch_apply_u_tri(pfx_ctx* c, const KArgs& a) {
+    BlockView bv = c->bv;
+    bv.chunk = std::min((c->bm.max_elems + 31) / 32 * 32, 2 * kThreads + 64);
+    size_t ML = (size_t)c->bm.max_loc;
+    size_t smem = (ML * (SM != M_ISO ? 3 : 2)) * sizeof(double2) + ((ML + 1) & ~(size_t)1) * sizeof(double) +
+                  3 * (size_t)bv.chunk * sizeof(double2) + ((size_t)c->bv.max_inc * sizeof(uint16_t) + 15) / 16 * 16;
+    if (c->configuring) {
+        CK(cudaFuncSetAttribute(apply_u_tri_kernel<SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return PFX_OK;
+    }
+    apply_u_tri_kernel<SM><<<c->bm.nb, kThreads, smem, c->stream>>>(bv, a);
+    c->launches++;
+    CK(cudaGetLastError());
+    return PFX_OK;
+}
+
 template <class Cell>
 int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
     switch (op) {
         case OP_APPLY_U:
-            return (a.m.smodel == M_ISO) ? launch_scatter_op<OpApplyU<Cell, false>>(c, a)
-                                         : launch_scatter_op<OpApplyU<Cell, true>>(c, a);
+            if (std::is_same<Cell, Tri>::value && !c->generic_apply) {
+                if (a.m.smodel == M_ISO) return launch_apply_u_tri<M_ISO>(c, a);
+                if (a.m.smodel == M_SPECTRAL) return launch_apply_u_tri<M_SPECTRAL>(c, a);
+                return launch_apply_u_tri<M_VOLDEV>(c, a);
+            }
+            if (a.m.smodel == M_ISO) return launch_scatter_op<OpApplyU<Cell, M_ISO>>(c, a);
+            if (a.m.smodel == M_SPECTRAL) return launch_scatter_op<OpApplyU<Cell, M_SPECTRAL>>(c, a);
+            return launch_scatter_op<OpApplyU<Cell, M_VOLDEV>>(c, a);
         case OP_RESIDUAL_U: return launch_scatter_op<OpResidualU<Cell>>(c, a);
         case OP_DIAG_U: return launch_scatter_op<OpDiagU<Cell>>(c, a);
         case OP_APPLY_PHI: return launch_scatter_op<OpApplyPhi<Cell>>(c, a);
@@ -182,7 +209,7 @@ int launch_reduce_k(pfx_ctx* c, const KArgs& a) {
     constexpr int NF = odd<(KIND == RED_ENERGY) ? (2 * D + 3) : (D + 2 * NC)>::value;
     size_t smem = (size_t)c->bm.max_loc * NF * sizeof(double);
     if (c->configuring) {
-        if (smem > 48 * 1024)
+        if (smem + 4096 > 48 * 1024)
             CK(cudaFuncSetAttribute(reduce_kernel<Cell, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return PFX_OK;
     }
@@ -632,6 +659,8 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     c->n_owned = mesh->n_owned > 0 ? mesh->n_owned : mesh->n_nodes;
     const char* ng = getenv("PFX_NO_GRAPH");
     c->use_graph = !(ng && ng[0] == '1');
+    const char* ga = getenv("PFX_GENERIC_APPLY");
+    c->generic_apply = (ga && ga[0] == '1');
 
     // ---- blocks
     int target = prm->block_nodes;
@@ -643,9 +672,17 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     target = std::min(target, kThreads);
     for (int64_t e = 0; e < mesh->n_cells * c->nv; ++e)
         if (mesh->cells[e] < 0 || mesh->cells[e] >= mesh->n_nodes) { c->err = "cell vertex out of range"; return PFX_ERR_BAD_ARG; }
-    std::string er = build_blocks(c->nv, c->dim, c->n_nodes, c->n_owned, mesh->n_cells, mesh->coords, mesh->cells,
-                                  mesh->cell_primary, target, c->bm);
-    if (!er.empty()) { c->err = er; return PFX_ERR_BAD_ARG; }
+    std::string er;
+    for (int attempt = 0;; ++attempt) {
+        er = build_blocks(c->nv, c->dim, c->n_nodes, c->n_owned, mesh->n_cells, mesh->coords, mesh->cells,
+                          mesh->cell_primary, target, c->bm);
+        if (!er.empty()) { c->err = er; return PFX_ERR_BAD_ARG; }
+        // triangles: keep every block within two element passes of the CTA (2 x kThreads)
+        if (c->cell_type != PFX_CELL_TRIANGLE || prm->block_nodes > 0 || c->bm.max_elems <= 2 * kThreads ||
+            target <= 64 || attempt >= 8)
+            break;
+        target = std::max(64, target - std::max(4, (c->bm.max_elems - 2 * kThreads) / 4));
+    }
     BlockMesh& bm = c->bm;
     int32_t *d_node0, *d_hoff, *d_halo, *d_eoff, *d_nprim, *d_incp;
     uint16_t *d_lconn, *d_inc;
@@ -661,6 +698,11 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     c->bv.nb = bm.nb; c->bv.node0 = d_node0; c->bv.halo_off = d_hoff; c->bv.halo = d_halo; c->bv.elem_off = d_eoff;
     c->bv.nprim = d_nprim; c->bv.lconn = (const ushort4*)d_lconn; c->bv.inc_ptr = d_incp; c->bv.inc = d_inc;
     c->bv.max_loc = bm.max_loc; c->bv.chunk = 256;
+    {
+        int mi = 0;
+        for (int b = 0; b < bm.nb; ++b) mi = std::max(mi, bm.inc_ptr[bm.node0[b + 1]] - bm.inc_ptr[bm.node0[b]]);
+        c->bv.max_inc = mi;
+    }
 
     // ---- fields
     int64_t N = c->n_nodes, D = c->dim;
@@ -684,6 +726,8 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     if ((st = dev_alloc(c, &c->red, (size_t)kMaxRed))) return st;
     if ((st = dev_alloc(c, &c->counter, (size_t)4))) return st;
     CK(cudaMallocHost((void**)&c->h_pinned, 64 * sizeof(double)));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
     c->graph_iters = prm->cg_chunk > 0 ? (prm->cg_chunk + 1) / 2 * 2 : 32;
 
     // ---- opt every kernel instantiation of this mesh/model in to its shared-memory size
@@ -714,6 +758,8 @@ int pfx_destroy(pfx_ctx* c) {
     if (c->comm) nccl().CommDestroy(c->comm);
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return PFX_OK;
@@ -788,6 +834,7 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
     rep->hist_fnorm_u = hfu; rep->hist_fnorm_phi = hfp;
     double err_phi = 1.0, err_u = 1.0;
     int it = 0, st;
+    CK(cudaEventRecord(c->ev0, c->stream));
     const int gN = vgrid(c, N);
     while ((err_phi > o->stagger_tol || err_u > o->stagger_tol || it < o->min_stagger_iter) && it < o->max_stagger_iter) {
         ++it;
@@ -854,7 +901,11 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
         CK(cudaMemcpyAsync(c->abar_n, c->abar_c, N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         CK(cudaMemcpyAsync(c->alpha_n, c->alpha_c, N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     }
+    CK(cudaEventRecord(c->ev1, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    rep->gpu_ms = ms;
     rep->stagger_iters = it;
     rep->err_u = err_u; rep->err_phi = err_phi;
     return PFX_OK;

@@ -32,6 +32,7 @@ struct BlockView {
     const int32_t* inc_ptr;
     const uint16_t* inc;
     int max_loc;      // smem sizing
+    int max_inc;      // largest per-block incidence list
     int chunk;        // elements per phase-B pass
 };
 
@@ -82,32 +83,35 @@ __device__ __forceinline__ void block_sum(double* vals, double* s_red /*[NR*32]*
 }
 
 // Per-block partials -> global result by the last block to finish (fixed summation order).
+// After the block sum only warp 0 stays: lane 0 publishes the partial and takes a ticket; the
+// last block's warp 0 adds the partials in a fixed order (deterministic result).
 template <int NR>
 __device__ __forceinline__ void grid_reduce(double* vals, double* partial, double* result, unsigned int* counter,
                                             double* s_red) {
-    __shared__ bool is_last;
     block_sum<NR>(vals, s_red);
+    if (threadIdx.x >= 32) return;
+    unsigned int last = 0;
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < NR; ++k) partial[(size_t)blockIdx.x * kMaxRed + k] = vals[k];
         __threadfence();
         unsigned int t = atomicInc(counter, gridDim.x - 1);
-        is_last = (t == gridDim.x - 1);
+        last = (t == gridDim.x - 1);
     }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        double acc[NR];
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (!last) return;
+    __threadfence();
+    double acc[NR];
 #pragma unroll
-        for (int k = 0; k < NR; ++k) acc[k] = 0.0;
-        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x)
+    for (int k = 0; k < NR; ++k) acc[k] = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += 32)
 #pragma unroll
-            for (int k = 0; k < NR; ++k) acc[k] += __ldcg(&partial[(size_t)b * kMaxRed + k]);
-        block_sum<NR>(acc, s_red);
-        if (threadIdx.x == 0)
+        for (int k = 0; k < NR; ++k) acc[k] += __ldcg(&partial[(size_t)b * kMaxRed + k]);
 #pragma unroll
-            for (int k = 0; k < NR; ++k) result[k] = acc[k];
-    }
+    for (int k = 0; k < NR; ++k) acc[k] = warp_sum(acc[k]);
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int k = 0; k < NR; ++k) result[k] = acc[k];
 }
 
 // ============================================================================= scatter ops
@@ -117,10 +121,14 @@ enum { OP_APPLY_U, OP_RESIDUAL_U, OP_DIAG_U, OP_APPLY_PHI, OP_RESIDUAL_PHI, OP_D
        OP_DIAG_MASS, OP_RHS_PSI, OP_RHS_FATIGUE };
 
 template <int V> struct odd { static constexpr int value = (V & 1) ? V : V + 1; };
+template <class Op, class = void> struct min_blocks { static constexpr int value = (Op::NV == 3) ? 4 : (Op::D == 2 ? 3 : (Op::NOUT == 1 ? 2 : 1)); };
+template <class Op> struct min_blocks<Op, decltype((void)Op::MINB)> { static constexpr int value = Op::MINB; };
 
-template <class Cell, bool NL>
-struct OpApplyU {          // staged: X[D] phi v[D] (u[D])
+template <class Cell, int SM>
+struct OpApplyU {          // staged: X[D] phi v[D] (u[D]); SM = compile-time stress split
+    static constexpr bool NL = (SM != M_ISO);
     static constexpr int D = Cell::D, NV = Cell::NV, NOUT = D, NRED = 1;
+    static constexpr int MINB = (NV == 3) ? 4 : (D == 2 ? 2 : 1);
     static constexpr int NF = odd<D + 1 + D + (NL ? D : 0)>::value;
     __device__ static void load(const KArgs& a, int g, double* s) {
         for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i];
@@ -138,7 +146,7 @@ struct OpApplyU {          // staged: X[D] phi v[D] (u[D])
             for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; V[k * D + i] = nd[k][D + 1 + i]; U[k * D + i] = NL ? nd[k][2 * D + 1 + i] : 0.0; }
             ph[k] = nd[k][D];
         }
-        elem_apply_u<Cell>(a.m, a.n1d, X, ph, U, V, out);
+        elem_apply_u<Cell, SM>(a.m, a.n1d, X, ph, U, V, out);
     }
     __device__ static void store(const KArgs& a, int g, const double* acc, double* red) {
         for (int i = 0; i < D; ++i) {
@@ -332,7 +340,7 @@ struct OpRhsFatigue {      // staged: X f1(=phi_old) f2(=V_c)
 };
 
 template <class Op>
-__global__ void __launch_bounds__(kThreads) scatter_kernel(BlockView bv, KArgs a) {
+__global__ void __launch_bounds__(kThreads, min_blocks<Op>::value) scatter_kernel(BlockView bv, KArgs a) {
     constexpr int NV = Op::NV, NF = Op::NF, NOUT = Op::NOUT;
     extern __shared__ double smem[];
     __shared__ double s_red[kMaxRed * 32];
@@ -340,26 +348,34 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(BlockView bv, KArgs a
     const int b = blockIdx.x, tid = threadIdx.x;
     const int n0 = bv.node0[b], n_own = bv.node0[b + 1] - n0;
     const int h0 = bv.halo_off[b], n_loc = n_own + bv.halo_off[b + 1] - h0;
+    const int e0 = bv.elem_off[b], ne = bv.elem_off[b + 1] - e0;
+    const int chunk = bv.chunk;
     double* s_nodes = smem;
     double* s_ebuf = smem + (size_t)bv.max_loc * NF;
-    const int chunk = bv.chunk;
-    // ---- phase A: stage nodal fields
+    uint16_t* s_inc = reinterpret_cast<uint16_t*>(smem + ((((size_t)bv.max_loc * NF + (size_t)NV * NOUT * chunk) + 1) & ~(size_t)1));   // 16-byte aligned
+    // prefetch this thread's first two element connectivities (independent of phase A)
+    ushort4 lc0 = make_ushort4(0, 0, 0, 0), lc1 = lc0;
+    if (tid < ne) lc0 = bv.lconn[e0 + tid];
+    if (tid + kThreads < ne) lc1 = bv.lconn[e0 + tid + kThreads];
+    // ---- phase A: stage nodal fields and the block's incidence list
+    const int i0 = bv.inc_ptr[n0], ninc = bv.inc_ptr[n0 + n_own] - i0;
     for (int i = tid; i < n_loc; i += kThreads) {
         int g = (i < n_own) ? n0 + i : bv.halo[h0 + i - n_own];
         Op::load(a, g, s_nodes + (size_t)i * NF);
     }
+    for (int i = tid; i < (ninc >> 3); i += kThreads)        // lists are padded to 8 entries per block
+        reinterpret_cast<uint4*>(s_inc)[i] = reinterpret_cast<const uint4*>(bv.inc + i0)[i];
+    int cur = 0, end = 0;
+    if (tid < n_own) { cur = bv.inc_ptr[n0 + tid] - i0; end = bv.inc_ptr[n0 + tid + 1] - i0; }
     __syncthreads();
-    const int e0 = bv.elem_off[b], ne = bv.elem_off[b + 1] - e0;
     double acc[NOUT];
 #pragma unroll
     for (int c = 0; c < NOUT; ++c) acc[c] = 0.0;
-    int cur = 0, end = 0;
-    if (tid < n_own) { cur = bv.inc_ptr[n0 + tid]; end = bv.inc_ptr[n0 + tid + 1]; }
     for (int c0 = 0; c0 < ne; c0 += chunk) {
         const int nc = min(chunk, ne - c0);
         // ---- phase B: element vectors
         for (int j = tid; j < nc; j += kThreads) {
-            ushort4 lc = bv.lconn[e0 + c0 + j];
+            ushort4 lc = (c0 + j == tid) ? lc0 : ((c0 + j == tid + kThreads) ? lc1 : bv.lconn[e0 + c0 + j]);
             const double* nd[4] = {s_nodes + (size_t)lc.x * NF, s_nodes + (size_t)lc.y * NF,
                                    s_nodes + (size_t)lc.z * NF, s_nodes + (size_t)lc.w * NF};
             double out[NV * NOUT];
@@ -371,7 +387,7 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(BlockView bv, KArgs a
         // ---- phase C: node-wise gather of incident element rows (fixed order)
         if (tid < n_own) {
             while (cur < end) {
-                int code = bv.inc[cur];
+                int code = s_inc[cur];
                 int j = (code >> 2) - c0;
                 if (j >= nc) break;
                 int v = code & 3;
@@ -380,13 +396,146 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(BlockView bv, KArgs a
                 ++cur;
             }
         }
-        __syncthreads();
+        if (c0 + chunk < ne) __syncthreads();
     }
     double red[Op::NRED > 0 ? Op::NRED : 1];
 #pragma unroll
     for (int k = 0; k < (Op::NRED > 0 ? Op::NRED : 1); ++k) red[k] = 0.0;
     if (tid < n_own) Op::store(a, n0 + tid, acc, red);
     if (Op::NRED > 0) grid_reduce<(Op::NRED > 0 ? Op::NRED : 1)>(red, a.partial, a.result, a.counter, s_red);
+}
+
+// ============================================================================= hot kernel
+// J_u·v on P1 triangles (config 1-3 meshes): same three phases as scatter_kernel, specialised:
+// SoA double2 staging (128-bit shared loads/stores), element rows parked as double2 per vertex,
+// two register-prefetched elements per thread (blocks are sized to <= 2·kThreads elements),
+// reciprocal / rsqrt intrinsics, model fixed at compile time.
+template <int SM>
+__device__ __forceinline__ void tri_apply_elem(const Material& m, double2 x0, double2 x1, double2 x2, double p0, double p1,
+                                               double p2, double2 v0, double2 v1, double2 v2, double2 u0, double2 u1,
+                                               double2 u2, double2& f0, double2& f1, double2& f2) {
+    const double ax = x1.x - x0.x, ay = x1.y - x0.y, bx = x2.x - x0.x, by = x2.y - x0.y;
+    const double det = ax * by - ay * bx, inv = __drcp_rn(det);
+    // gradients G1 = (by, -bx)/det, G2 = (-ay, ax)/det, G0 = -(G1+G2)
+    const double g1x = by * inv, g1y = -bx * inv, g2x = -ay * inv, g2y = ax * inv;
+    const double g0x = -(g1x + g2x), g0y = -(g1y + g2y);
+    const double t0 = 1.0 - p0, t1 = 1.0 - p1, t2 = 1.0 - p2, ts = t0 + t1 + t2;
+    const double gb = (t0 * t0 + t1 * t1 + t2 * t2 + ts * ts) * (1.0 / 12.0) + m.k;
+    double de[3] = {g0x * v0.x + g1x * v1.x + g2x * v2.x, g0y * v0.y + g1y * v1.y + g2y * v2.y,
+                    0.5 * (g0y * v0.x + g1y * v1.x + g2y * v2.x + g0x * v0.y + g1x * v1.y + g2x * v2.y)};
+    double S[3];
+    if (SM == M_ISO) {
+        const double lt = m.lam * (de[0] + de[1]), mu2 = 2.0 * m.mu;
+        S[0] = gb * (lt + mu2 * de[0]); S[1] = gb * (lt + mu2 * de[1]); S[2] = gb * (mu2 * de[2]);
+    } else {
+        double e[3] = {g0x * u0.x + g1x * u1.x + g2x * u2.x, g0y * u0.y + g1y * u1.y + g2y * u2.y,
+                       0.5 * (g0y * u0.x + g1y * u1.x + g2y * u2.x + g0x * u0.y + g1x * u1.y + g2x * u2.y)};
+        double dsa[3], dsb[3];
+        if (SM == M_SPECTRAL) {
+            const double a = e[0], c = e[1], b = e[2], dd = de[0] - de[1], dtr = de[0] + de[1];
+            const double amc = a - c, tr = a + c;
+            const double Dl = amc * amc + 4.0 * b * b + kEps * kEps;
+            const double is = rsqrt(Dl), s = Dl * is;
+            const double l0 = 0.5 * (tr - s), l1 = 0.5 * (tr + s);
+            const double m0 = amc * is, m1 = 2.0 * b * is;
+            const double ds = m0 * dd + 2.0 * m1 * de[2];
+            const double w0 = (l0 > 0.0 ? 0.5 : (l0 < 0.0 ? 0.0 : 0.25)) * (dtr - ds);
+            const double w1 = (l1 > 0.0 ? 0.5 : (l1 < 0.0 ? 0.0 : 0.25)) * (dtr + ds);
+            const double pd = 0.5 * (fmax(l1, 0.0) - fmax(l0, 0.0)) * is;
+            const double dm0 = dd - m0 * ds, dm1 = 2.0 * de[2] - m1 * ds;
+            const double e1x = 0.5 * (1.0 + m0), e1y = 0.5 * (1.0 - m0), e1s = 0.5 * m1;
+            const double lt = m.lam * (tr > 0.0 ? 1.0 : (tr < 0.0 ? 0.0 : 0.5)) * dtr, mu2 = 2.0 * m.mu;
+            dsa[0] = lt + mu2 * (w0 * (1.0 - e1x) + w1 * e1x + pd * dm0);
+            dsa[1] = lt + mu2 * (w0 * (1.0 - e1y) + w1 * e1y - pd * dm0);
+            dsa[2] = mu2 * ((w1 - w0) * e1s + pd * dm1);
+            const double lf = m.lam * dtr;
+            dsb[0] = lf + mu2 * de[0] - dsa[0]; dsb[1] = lf + mu2 * de[1] - dsa[1]; dsb[2] = mu2 * de[2] - dsa[2];
+        } else {
+            dstress_split<2>(m, SM, e, de, dsa, dsb);
+        }
+        S[0] = gb * dsa[0] + dsb[0]; S[1] = gb * dsa[1] + dsb[1]; S[2] = gb * dsa[2] + dsb[2];
+    }
+    const double vol = 0.5 * fabs(det);
+    S[0] *= vol; S[1] *= vol; S[2] *= vol;
+    f1 = make_double2(S[0] * g1x + S[2] * g1y, S[2] * g1x + S[1] * g1y);
+    f2 = make_double2(S[0] * g2x + S[2] * g2y, S[2] * g2x + S[1] * g2y);
+    f0 = make_double2(-(f1.x + f2.x), -(f1.y + f2.y));
+}
+
+template <int SM>
+__global__ void __launch_bounds__(kThreads, 4) apply_u_tri_kernel(BlockView bv, KArgs a) {
+    constexpr bool NL = (SM != M_ISO);
+    extern __shared__ double smem[];
+    __shared__ double s_red[kMaxRed * 32];
+    if (a.stop && a.stop[0] != 0.0) return;
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int n0 = bv.node0[b], n_own = bv.node0[b + 1] - n0;
+    const int h0 = bv.halo_off[b], n_loc = n_own + bv.halo_off[b + 1] - h0;
+    const int e0 = bv.elem_off[b], ne = bv.elem_off[b + 1] - e0;
+    const int ML = bv.max_loc, chunk = bv.chunk;
+    double2* sX = reinterpret_cast<double2*>(smem);
+    double2* sV = sX + ML;
+    double2* sU = sV + ML;                          // only used when NL
+    double* sP = reinterpret_cast<double*>(sU + (NL ? ML : 0));
+    double2* sE = reinterpret_cast<double2*>(sP + ((ML + 1) & ~1));     // [3][chunk]
+    uint16_t* s_inc = reinterpret_cast<uint16_t*>(sE + 3 * (size_t)chunk);
+    ushort4 lc0 = make_ushort4(0, 0, 0, 0), lc1 = lc0;
+    if (tid < ne) lc0 = bv.lconn[e0 + tid];
+    if (tid + kThreads < ne) lc1 = bv.lconn[e0 + tid + kThreads];
+    const int i0 = bv.inc_ptr[n0], ninc = bv.inc_ptr[n0 + n_own] - i0;
+    int cur = 0, end = 0;
+    if (tid < n_own) { cur = bv.inc_ptr[n0 + tid] - i0; end = bv.inc_ptr[n0 + tid + 1] - i0; }
+    const double2* X2 = reinterpret_cast<const double2*>(a.X);
+    const double2* V2 = reinterpret_cast<const double2*>(a.v);
+    const double2* U2 = reinterpret_cast<const double2*>(a.u);
+    const uchar2* M2 = reinterpret_cast<const uchar2*>(a.mask);
+    // ---- phase A
+    for (int i = tid; i < n_loc; i += kThreads) {
+        int g = (i < n_own) ? n0 + i : bv.halo[h0 + i - n_own];
+        double2 vv = V2[g];
+        if (M2) { uchar2 mk = M2[g]; if (mk.x) vv.x = 0.0; if (mk.y) vv.y = 0.0; }
+        sX[i] = X2[g]; sV[i] = vv; sP[i] = a.phi[g];
+        if (NL) sU[i] = U2[g];
+    }
+    for (int i = tid; i < (ninc >> 3); i += kThreads)
+        reinterpret_cast<uint4*>(s_inc)[i] = reinterpret_cast<const uint4*>(bv.inc + i0)[i];
+    __syncthreads();
+    double2 acc = make_double2(0.0, 0.0);
+    for (int c0 = 0; c0 < ne; c0 += chunk) {
+        const int nc = min(chunk, ne - c0);
+        // ---- phase B
+        for (int j = tid; j < nc; j += kThreads) {
+            const int eid = c0 + j;
+            ushort4 lc = (eid == tid) ? lc0 : ((eid == tid + kThreads) ? lc1 : bv.lconn[e0 + eid]);
+            double2 f0, f1, f2;
+            const double2 z = make_double2(0.0, 0.0);
+            tri_apply_elem<SM>(a.m, sX[lc.x], sX[lc.y], sX[lc.z], sP[lc.x], sP[lc.y], sP[lc.z], sV[lc.x], sV[lc.y], sV[lc.z],
+                               NL ? sU[lc.x] : z, NL ? sU[lc.y] : z, NL ? sU[lc.z] : z, f0, f1, f2);
+            sE[j] = f0; sE[chunk + j] = f1; sE[2 * chunk + j] = f2;
+        }
+        __syncthreads();
+        // ---- phase C
+        if (tid < n_own) {
+            while (cur < end) {
+                int code = s_inc[cur];
+                int j = (code >> 2) - c0;
+                if (j >= nc) break;
+                double2 f = sE[(code & 3) * chunk + j];
+                acc.x += f.x; acc.y += f.y;
+                ++cur;
+            }
+        }
+        if (c0 + chunk < ne) __syncthreads();
+    }
+    double red[1] = {0.0};
+    if (tid < n_own) {
+        const int g = n0 + tid;
+        double2 vin = V2[g];
+        if (M2) { uchar2 mk = M2[g]; if (mk.x) acc.x = vin.x; if (mk.y) acc.y = vin.y; }
+        reinterpret_cast<double2*>(a.y)[g] = acc;
+        red[0] = vin.x * acc.x + vin.y * acc.y;
+    }
+    grid_reduce<1>(red, a.partial, a.result, a.counter, s_red);
 }
 
 // ============================================================================= element reductions

@@ -227,16 +227,62 @@ PFX_HD void energy_split(const Material& m, int model, const double* e, double& 
     pb = 0.5 * m.lam * sq(mac_n(tr)) + m.mu * ddot<D, double>(eN, eN);
 }
 
+// Closed-form tangent action of the 2×2 spectral split (hand-derived from eigenstate2; equals
+// the dual-number evaluation to round-off, tests/test_elements_host.py): one sqrt, one divide.
+PFX_HD void dstress_spectral2(const Material& m, const double* e, const double* de, double* dsa, double* dsb) {
+    const double a = e[0], c = e[1], b = e[2], da = de[0], dc = de[1], db = de[2];
+    const double amc = a - c, tr = a + c, dtr = da + dc, dd = da - dc;
+    const double s = ::sqrt(amc * amc + 4.0 * b * b + kEps * kEps), is = 1.0 / s;
+    const double l0 = 0.5 * (tr - s), l1 = 0.5 * (tr + s);
+    const double m0 = amc * is, m1 = 2.0 * b * is;
+    const double ds = m0 * dd + 2.0 * m1 * db;
+    const double h0 = 0.5 * (1.0 + sgn(l0)), h1 = 0.5 * (1.0 + sgn(l1));
+    const double w0 = h0 * 0.5 * (dtr - ds), w1 = h1 * 0.5 * (dtr + ds);       // H(λk) dλk
+    const double pd = 0.5 * (mac_p(l1) - mac_p(l0)) * is;                      // (p1-p0)/2s
+    const double dm0 = dd - m0 * ds, dm1 = 2.0 * db - m1 * ds;
+    // E1 = ½(I + M/s), E0 = I − E1
+    const double e1x = 0.5 * (1.0 + m0), e1y = 0.5 * (1.0 - m0), e1s = 0.5 * m1;
+    const double dPx = w0 * (1.0 - e1x) + w1 * e1x + pd * dm0;
+    const double dPy = w0 * (1.0 - e1y) + w1 * e1y - pd * dm0;
+    const double dPs = (w1 - w0) * e1s + pd * dm1;
+    const double lt = m.lam * 0.5 * (1.0 + sgn(tr)) * dtr, mu2 = 2.0 * m.mu;
+    dsa[0] = lt + mu2 * dPx; dsa[1] = lt + mu2 * dPy; dsa[2] = mu2 * dPs;
+    const double lf = m.lam * dtr;
+    dsb[0] = lf + mu2 * da - dsa[0]; dsb[1] = lf + mu2 * dc - dsa[1]; dsb[2] = mu2 * db - dsa[2];
+}
+
 // directional derivative of (σ_a, σ_b) at e along de
 template <int D>
 PFX_HD void dstress_split(const Material& m, int model, const double* e, const double* de, double* dsa, double* dsb) {
     constexpr int N = SymN<D>::N;
+    double tr = trace<D, double>(de);
     if (model == M_ISO) {
-        double tr = trace<D, double>(de);
         for (int i = 0; i < N; ++i) { dsa[i] = 2.0 * m.mu * de[i]; dsb[i] = 0.0; }
         for (int i = 0; i < D; ++i) dsa[i] += m.lam * tr;
         return;
     }
+    if (model == M_VOLDEV) {
+        // σ_a = k0<tr>+ I + 2μ dev ε  (split_energy_stress_tangent_functions.py:190-212)
+        double k0 = m.lam + 2.0 / D * m.mu;
+        double hp = 0.5 * (1.0 + sgn(trace<D, double>(e)));
+        for (int i = 0; i < N; ++i) { dsa[i] = 2.0 * m.mu * de[i]; dsb[i] = 0.0; }
+        for (int i = 0; i < D; ++i) {
+            dsa[i] += (k0 * hp - 2.0 * m.mu / D) * tr;
+            dsb[i] = (m.lam + 2.0 * m.mu / D - k0 * hp) * tr;
+        }
+        return;
+    }
+    if (D == 2) { dstress_spectral2(m, e, de, dsa, dsb); return; }
+    Dual ed[N], sa[N], sb[N];
+    for (int i = 0; i < N; ++i) ed[i] = Dual(e[i], de[i]);
+    stress_split<D, Dual>(m, model, ed, sa, sb);
+    for (int i = 0; i < N; ++i) { dsa[i] = sa[i].d; dsb[i] = sb[i].d; }
+}
+
+// reference-faithful dual-number evaluation (used by the tests to pin the closed forms)
+template <int D>
+PFX_HD void dstress_split_dual(const Material& m, int model, const double* e, const double* de, double* dsa, double* dsb) {
+    constexpr int N = SymN<D>::N;
     Dual ed[N], sa[N], sb[N];
     for (int i = 0; i < N; ++i) ed[i] = Dual(e[i], de[i]);
     stress_split<D, Dual>(m, model, ed, sa, sb);

@@ -10,12 +10,13 @@ using namespace pfx;
 
 template <int D>
 static void split_pts(const Material& m, int64_t n, const double* e, const double* de, double* sa, double* sb,
-                      double* pa, double* pb, double* dsa, double* dsb) {
+                      double* pa, double* pb, double* dsa, double* dsb, int dual = 0) {
     constexpr int NS = SymN<D>::N;
     for (int64_t i = 0; i < n; ++i) {
         stress_split<D, double>(m, m.smodel, e + i * NS, sa + i * NS, sb + i * NS);
         energy_split<D>(m, m.emodel, e + i * NS, pa[i], pb[i]);
-        dstress_split<D>(m, m.smodel, e + i * NS, de + i * NS, dsa + i * NS, dsb + i * NS);
+        if (dual) dstress_split_dual<D>(m, m.smodel, e + i * NS, de + i * NS, dsa + i * NS, dsb + i * NS);
+        else dstress_split<D>(m, m.smodel, e + i * NS, de + i * NS, dsa + i * NS, dsb + i * NS);
     }
 }
 
@@ -56,6 +57,13 @@ void hc_split(int d, const double* mat /*lam,mu,Gc,l,k*/, int smodel, int emodel
     Material m{mat[0], mat[1], mat[2], mat[3], mat[4], smodel, emodel, 0, 0.0};
     if (d == 2) split_pts<2>(m, n, e, de, sa, sb, pa, pb, dsa, dsb);
     else split_pts<3>(m, n, e, de, sa, sb, pa, pb, dsa, dsb);
+}
+// same, tangent action by the reference-faithful dual-number evaluation
+void hc_split_dual(int d, const double* mat, int smodel, int emodel, int64_t n, const double* e,
+                   const double* de, double* sa, double* sb, double* pa, double* pb, double* dsa, double* dsb) {
+    Material m{mat[0], mat[1], mat[2], mat[3], mat[4], smodel, emodel, 0, 0.0};
+    if (d == 2) split_pts<2>(m, n, e, de, sa, sb, pa, pb, dsa, dsb, 1);
+    else split_pts<3>(m, n, e, de, sa, sb, pa, pb, dsa, dsb, 1);
 }
 void hc_assemble(int op, int cell_type, const double* mat, int smodel, int emodel, int fatigue, int n1d, int64_t ne,
                  const double* coords, const int32_t* cells, const double* f0, const double* f1, const double* f2,

@@ -1,0 +1,69 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/pfx_b200.h
+declares; context creation fails loudly without a GPU (no CPU fallback); the host-only
+partition / ghost-map API is bit-exact against the Python restatement (oracle/partition.py)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from phasefieldx_b200 import _lib
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "pfx_b200.h")).read()
+    declared = set(re.findall(r"\b(pfx_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.pfx_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    from phasefieldx_b200 import _lib, mesh as M
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = M.create_rectangle(None, [[0, 0], [1, 1]], [4, 4])
+    with pytest.raises(_lib.PfxError, match="no CUDA device"):
+        _lib.Engine(m.geometry.x, m.cells, "triangle", 1.0, 1.0, 1.0, 1.0)
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirrors of pfx_params / pfx_step_report have the C field order of the header."""
+    from phasefieldx_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "pfx_b200.h")).read()
+    body = re.search(r"typedef struct \{([^}]*)\} pfx_params;", header).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        typ, rest = decl.split(None, 1)
+        names += [n.strip() for n in rest.split(",")]
+    assert names == [f[0] for f in _lib.PfxParams._fields_]
+
+
+@pytest.mark.parametrize("n_ranks", [2, 3, 8])
+def test_partition_and_ghost_maps_bit_exact(n_ranks):
+    from oracle.partition import partition
+    from phasefieldx_b200 import _lib, mesh as M
+    for m in (M.create_rectangle(None, [[0, 0], [1, 1]], [23, 17]), M.create_box(None, [[0, 0, 0], [2, 1, 1]], [7, 5, 4]),
+              M.create_rectangle(None, [[0, 0], [2, 1]], [16, 9], M.CellType.quadrilateral)):
+        P = _lib.Partition(m.cell_type, m.geometry.x, m.cells, n_ranks)
+        cr, ow, ranks = partition(m.geometry.x, m.cells, n_ranks)
+        assert np.array_equal(P.cell_rank(), cr) and np.array_equal(P.node_owner(), ow)
+        seen_primary = np.zeros(m.num_cells, dtype=int)
+        for r in range(n_ranks):
+            A, B = P.rank(r), ranks[r]
+            assert A["n_owned"] == B["n_owned"]
+            for k in ("l2g", "cell_gid", "ghost_owner", "cell_primary", "neighbors", "send_off", "send_idx", "recv_off"):
+                assert np.array_equal(A[k], B[k]), (r, k)
+            seen_primary[A["cell_gid"][A["cell_primary"] == 1]] += 1
+        assert np.all(seen_primary == 1)          # every cell integrated exactly once
+        # replay of an external partition
+        P2 = _lib.Partition(m.cell_type, m.geometry.x, m.cells, n_ranks, cell_rank=cr[::-1].copy())
+        assert np.array_equal(P2.cell_rank(), cr[::-1])

@@ -1,0 +1,146 @@
+"""The exact C++ formulas the CUDA kernels evaluate (pfx_physics.cuh / pfx_elements.cuh, compiled
+for the host by tests/native/hostcheck.cpp) against the oracle: pointwise splits + tangent
+action, every element integral, and the block (CTA tile) builder driving a CPU mirror of the
+scatter kernel's index logic."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import MODELS, perturbed_meshes, rel
+from oracle import constitutive as cons
+from oracle.solver import Oracle, Params
+
+PD = ctypes.POINTER(ctypes.c_double)
+PI = ctypes.POINTER(ctypes.c_int32)
+CODES = {("isotropic", "no"): (0, 0), ("anisotropic", "spectral"): (1, 1), ("anisotropic", "deviatoric"): (2, 2),
+         ("hybrid", "spectral"): (0, 1)}
+CT = {"triangle": 0, "quadrilateral": 1, "tetrahedron": 2}
+
+
+def dp(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(PD)
+
+
+def sym_store(A):
+    if A.shape[-1] == 2:
+        return np.stack([A[..., 0, 0], A[..., 1, 1], A[..., 0, 1]], -1)
+    return np.stack([A[..., 0, 0], A[..., 1, 1], A[..., 2, 2], A[..., 0, 1], A[..., 0, 2], A[..., 1, 2]], -1)
+
+
+@pytest.mark.parametrize("d", [2, 3])
+@pytest.mark.parametrize("scale", [1e-2, 1e-4, 1e-6])
+@pytest.mark.parametrize("deg,sp", MODELS)
+def test_pointwise_split_and_tangent(hostcheck, d, scale, deg, sp):
+    rng = np.random.default_rng(10 * d)
+    n = 40
+    G = rng.normal(size=(n, d, d)) * scale
+    A = 0.5 * (G + G.transpose(0, 2, 1))
+    A[0] = np.diag([1.0, 0.0, 0.0][:d]) * scale
+    if d == 3:
+        A[1] = np.diag([1.0, -0.3, -0.3001]) * scale
+    G = rng.normal(size=(n, d, d))
+    dA = 0.5 * (G + G.transpose(0, 2, 1))
+    lam, mu = 121.15, 80.77
+    r = cons.split_torch(A, lam, mu, deg, sp)
+    ns = 3 if d == 2 else 6
+    e, de = np.ascontiguousarray(sym_store(A)), np.ascontiguousarray(sym_store(dA))
+    mat = np.array([lam, mu, 0.0027, 0.015, 0.0])
+    sm, em = CODES[(deg, sp)]
+    for fn in (hostcheck.hc_split, hostcheck.hc_split_dual):
+        sa, sb, dsa, dsb = (np.zeros((n, ns)) for _ in range(4))
+        pa, pb = np.zeros(n), np.zeros(n)
+        fn(d, dp(mat), sm, em, ctypes.c_int64(n), dp(e), dp(de), dp(sa), dp(sb), dp(pa), dp(pb), dp(dsa), dp(dsb))
+        tol = 1e-11
+        assert rel(sa, sym_store(r["sig_a"])) < tol and rel(pa, r["psi_a"]) < tol
+        if np.abs(r["psi_b"]).max() > 0:
+            assert rel(pb, r["psi_b"]) < tol and rel(sb, sym_store(r["sig_b"])) < tol
+        assert rel(dsa, sym_store(np.einsum("nijkl,nkl->nij", r["C_a"], dA))) < 1e-9
+        ref_b = np.einsum("nijkl,nkl->nij", r["C_b"], dA)
+        if np.abs(ref_b).max() > 0:
+            assert rel(dsb, sym_store(ref_b)) < 1e-9
+
+
+@pytest.mark.parametrize("deg,sp", MODELS)
+@pytest.mark.parametrize("fat", [False, True])
+def test_element_integrals_match_oracle(hostcheck, deg, sp, fat):
+    rng = np.random.default_rng(1)
+    sm, em = CODES[(deg, sp)]
+    for ctype, m in perturbed_meshes(rng):
+        Pm = Params(E=210.0, nu=0.3, Gc=0.0027, l=0.1, degradation=deg, split_energy=sp, irreversibility="miehe",
+                    fatigue=fat, k=1e-3)
+        o = Oracle(m.geometry.x, m.cells, m.cell_type, Pm)
+        nn, d = o.nn, o.d
+        o.u = rng.normal(size=nn * d) * 1e-3
+        o.phi, o.H = rng.uniform(0, 1, nn), rng.uniform(0, 2, nn)
+        o.Fatigue = rng.uniform(0.2, 1, nn) if fat else np.ones(nn)
+        o.V_c, o.abar_c, o.phi_old = rng.uniform(0, 1, nn), rng.uniform(0, 1, nn), rng.uniform(0, 1, nn)
+        v, p = rng.normal(size=nn * d), rng.normal(size=nn)
+        mat = np.array([Pm.lambda_, Pm.mu, Pm.Gc, Pm.l, Pm.k])
+        cells = np.ascontiguousarray(m.cells, dtype=np.int32)
+        X = np.ascontiguousarray(m.geometry.x)
+
+        def asm(op, f0=None, f1=None, f2=None, f3=None, n=nn):
+            out = np.zeros(n)
+            hostcheck.hc_assemble(op, CT[ctype], dp(mat), sm, em, int(fat), 3, ctypes.c_int64(len(cells)), dp(X),
+                                  cells.ctypes.data_as(PI), dp(f0), dp(f1), dp(f2), dp(f3), dp(out))
+            return out
+        F = o.Fatigue
+        cm, cg = 2 * o.H + F * Pm.Gc / Pm.l, F * Pm.Gc * Pm.l
+        J, K = o.J_u(o.u, o.phi), o.K_phi(o.H, o.Fatigue)
+        tol = 1e-11
+        assert rel(asm(0, o.phi, o.u, v, n=nn * d), J @ v) < tol
+        assert rel(asm(1, o.phi, o.u, n=nn * d), o.F_int_u(o.u, o.phi)) < tol
+        assert rel(asm(2, o.phi, o.u, n=nn * d), J.diagonal()) < tol
+        assert rel(asm(3, cm, cg, p), K @ p) < tol
+        assert rel(asm(4, cm, cg, o.H, o.phi), K @ o.phi - o.b_phi(o.H)) < tol
+        assert rel(asm(5, cm, cg), K.diagonal()) < tol
+        assert rel(asm(6, p), o.M @ p) < tol
+        assert rel(asm(7), o.M.diagonal()) < tol
+        assert rel(asm(8, o.u), o.rhs_psi(o.u)) < tol
+        gq = cons.g_quadratic(o.at_qp(o.phi_old))
+        fe = np.einsum("eq,eq,qa->ea", o.t.W, gq * o.at_qp(o.V_c), o.t.N)
+        assert rel(asm(9, o.phi_old, o.V_c), o._vec(fe, o.edof_s, nn)) < tol
+        a, b = rng.normal(size=nn * d), rng.normal(size=nn * d)
+        s = asm(11, a, b, n=2)
+        assert abs(np.sqrt(s[0] / s[1]) - o.l2_error_normalized(a, b, True)) < 1e-12
+        s = asm(12, o.u, o.phi, F, o.abar_c, n=8)
+        en = o.energies()
+        assert abs(s[0] + s[2] - en["E"]) < tol * abs(en["E"]) and abs(s[1] - en["PSI_a"]) < tol * en["PSI_a"]
+        assert abs(s[3] / (2 * Pm.l) + s[4] * Pm.l / 2 - en["gamma"]) < tol * en["gamma"]
+        if fat:
+            assert abs(s[5] * Pm.Gc / (2 * Pm.l) - en["W_phi"]) < tol * en["W_phi"]
+            assert abs(s[7] - en["alpha_acum"]) < tol * en["alpha_acum"]
+
+
+def test_block_builder_drives_scatter_logic(hostcheck):
+    """pfx_blocks.cpp (RCB tiles, halo lists, 16-bit local connectivity, padded incidence lists)
+    through a CPU mirror of scatter_kernel: result equals the assembled operator, every cell is
+    primary in exactly one block."""
+    from phasefieldx_b200 import mesh as M
+    rng = np.random.default_rng(2)
+    cases = [("triangle", M.create_rectangle(None, [[0, 0], [1, 1]], [31, 27])),
+             ("quadrilateral", M.create_rectangle(None, [[0, 0], [1, 1]], [23, 19], M.CellType.quadrilateral)),
+             ("tetrahedron", M.create_box(None, [[0, 0, 0], [1, 1, 1]], [9, 8, 7]))]
+    m0 = cases[0][1]
+    cases.append(("triangle", M.cut_slit(m0, lambda x: np.isclose(x[1], 13 / 27) & (x[0] < 0.5), lambda c: c[1] > 13 / 27)))
+    for ctype, m in cases:
+        Pm = Params(degradation="anisotropic", split_energy="spectral", k=1e-4)
+        o = Oracle(m.geometry.x, m.cells, m.cell_type, Pm)
+        nn, d = o.nn, o.d
+        o.u, o.phi = rng.normal(size=nn * d) * 1e-3, rng.uniform(0, 1, nn)
+        v = rng.normal(size=nn * d)
+        ref = o.J_u(o.u, o.phi) @ v
+        mat = np.array([Pm.lambda_, Pm.mu, Pm.Gc, Pm.l, Pm.k])
+        cells = np.ascontiguousarray(m.cells, dtype=np.int32)
+        X = np.ascontiguousarray(m.geometry.x)
+        for max_own, chunk in [(64, 32), (100, 64), (240, 512)]:
+            y, dot, st = np.zeros(nn * d), ctypes.c_double(), np.zeros(6, dtype=np.int64)
+            rc = hostcheck.hc_blocks_apply_u(CT[ctype], dp(mat), 1, 3, ctypes.c_int64(nn), ctypes.c_int64(nn),
+                                             ctypes.c_int64(len(cells)), dp(X), cells.ctypes.data_as(PI), None, max_own,
+                                             chunk, dp(o.phi), dp(o.u), dp(v), dp(y), ctypes.byref(dot),
+                                             st.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+            assert rc == 0
+            assert rel(y, ref) < 1e-12
+            assert abs(dot.value - v @ ref) < 1e-11 * abs(v @ ref)
+            assert st[1] <= max_own and st[5] == len(cells)

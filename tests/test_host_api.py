@@ -1,0 +1,180 @@
+"""Host-side drop-in surface: file utilities (mirrors reference test/test_file_utilities.py),
+Input, AllResults, boundary-condition factories on the dolfinx stand-ins, gmsh reader, VTU
+writer, and the `phasefieldx` import aliasing."""
+import os
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture
+def setup_directory(tmp_path):
+    folder = tmp_path / "test_folder"
+    folder.mkdir()
+    (folder / "file1.txt").write_text("This is file 1.")
+    (folder / "file2.txt").write_text("This is file 2.")
+    (folder / "file3.log").write_text("This is a log file.")
+    (folder / "subfolder").mkdir()
+    return str(folder)
+
+
+def test_file_utilities(setup_directory, tmp_path):
+    import phasefieldx_b200.compat as compat
+    compat.install()
+    from phasefieldx import (append_results_to_file, delete_folder, delete_folders_with_contents, delete_specific_files,
+                             find_files_with_extension, get_filenames_in_folder, get_foldernames_in_folder,
+                             prepare_simulation, read_last_line, read_last_lines, replace_text)
+    d = setup_directory
+    assert sorted(get_filenames_in_folder(d)) == ["file1.txt", "file2.txt", "file3.log"]
+    assert get_foldernames_in_folder(d) == ["subfolder"]
+    assert sorted(find_files_with_extension(d, ".txt")) == sorted([os.path.join(d, "file1.txt"), os.path.join(d, "file2.txt")])
+    assert read_last_line(os.path.join(d, "file1.txt")) == "This is file 1."
+    assert read_last_lines(os.path.join(d, "file1.txt"), 1) == ["This is file 1."]
+    assert replace_text(os.path.join(d, "file1.txt"), os.path.join(d, "r.txt"), [("file 1", "replaced file 1")])
+    assert "replaced file 1." in open(os.path.join(d, "r.txt")).read()
+    delete_specific_files(d, [".log"])
+    assert not os.path.exists(os.path.join(d, "file3.log"))
+    delete_folders_with_contents(d, ["subfolder"])
+    assert not os.path.exists(os.path.join(d, "subfolder"))
+    prepare_simulation(d, "results")
+    assert os.path.exists(os.path.join(d, "results"))
+    os.mkdir(os.path.join(d, "temp_folder"))
+    open(os.path.join(d, "temp_folder", "t.txt"), "w").write("x")
+    delete_folder(os.path.join(d, "temp_folder"))
+    assert not os.path.exists(os.path.join(d, "temp_folder"))
+    out = str(tmp_path / "results.txt")
+    append_results_to_file(out, "Step\tValue1\tValue2", 1, 0.5, 1.2)
+    append_results_to_file(out, "Step\tValue1\tValue2", 2, 0.6, 1.3)
+    lines = open(out).read().splitlines()
+    assert lines == ["Step\tValue1\tValue2", "1\t0.5\t1.2", "2\t0.6\t1.3"]
+
+
+def test_input_and_allresults(tmp_path):
+    from phasefieldx_b200.Element.Phase_Field_Fracture.Input import Input
+    from phasefieldx_b200.PostProcessing.ReferenceResult import AllResults
+    from phasefieldx_b200.files import append_results_to_file
+    D = Input(E=210.0, nu=0.3, degradation="anisotropic", split_energy="spectral", results_folder_name=str(tmp_path))
+    assert abs(D.lambda_ - 121.15384615384615) < 1e-12 and abs(D.mu - 80.76923076923077) < 1e-12
+    D.save_parameters_to_csv(str(tmp_path / "parameters.input"))
+    rows = open(tmp_path / "parameters.input").read().splitlines()
+    assert rows[0] == "E\t210.0" and rows[5].startswith("lambda\t121.15") and rows[-1].startswith("results_folder_name\t")
+    append_results_to_file(str(tmp_path / "top.reaction"), "#step\tRx\tRy\tRz", 0, 0.0, -1.5, 0.0)
+    S = AllResults(str(tmp_path))
+    assert S.reaction_files["top.reaction"]["Ry"][0] == -1.5
+    assert S.input["parameters.input"]["degradation"] == "anisotropic"
+    with pytest.raises(ValueError):
+        Input(nu=0.5)
+
+
+def test_boundary_factories_and_value_semantics():
+    """`bc.g.value[...]` mutation as in the reference callbacks (plot_1711.py:236-243,
+    plot_1718.py:286-290) is re-read per dof; later BCs win on shared dofs downstream."""
+    import phasefieldx_b200.compat as compat
+    compat.install()
+    import dolfinx
+    import mpi4py
+    import petsc4py
+    from phasefieldx.Boundary.boundary_conditions import bc_x, bc_xy, bc_y, bc_phi, get_ds_bound_from_marker
+    from phasefieldx_b200 import fem
+    msh = dolfinx.mesh.create_rectangle(mpi4py.MPI.COMM_WORLD, [np.array([0, 0]), np.array([1, 1])], [4, 3],
+                                        cell_type=dolfinx.mesh.CellType.quadrilateral)
+    fdim = msh.topology.dim - 1
+    top = dolfinx.mesh.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[1], 1))
+    assert len(top) == 4
+    V_u = dolfinx.fem.functionspace(msh, ("Lagrange", 1, (msh.geometry.dim,)))
+    V_phi = dolfinx.fem.functionspace(msh, ("Lagrange", 1))
+    b = bc_xy(top, V_u, fdim)
+    b.g.value[1] = petsc4py.PETSc.ScalarType(0.3)
+    dofs, vals = fem.extract_bc(b)
+    assert len(dofs) == 10 and np.all(vals[1::2] == 0.3) and np.all(vals[0::2] == 0.0)
+    by = bc_y(top, V_u, fdim)
+    by.g.value[...] = -0.7
+    dofs, vals = fem.extract_bc(by)
+    assert np.all(dofs % 2 == 1) and np.all(vals == -0.7)
+    assert np.all(fem.extract_bc(bc_x(top, V_u, fdim, 2.0))[1] == 2.0)
+    assert len(fem.extract_bc(bc_phi(top, V_phi, fdim, 1.0))[0]) == 5
+    nodes, w = get_ds_bound_from_marker(top, msh, fdim).nodal_weights()
+    assert abs(w.sum() - 1.0) < 1e-14 and len(nodes) == 5
+
+
+MSH = """$MeshFormat
+4.1 0 8
+$EndMeshFormat
+$PhysicalNames
+2
+1 9 "bottom"
+2 8 "surface"
+$EndPhysicalNames
+$Entities
+4 4 1 0
+1 0 0 0 0
+2 1 0 0 0
+3 1 1 0 0
+4 0 1 0 0
+1 0 0 0 1 0 0 1 9 2 1 -2
+2 1 0 0 1 1 0 0 2 2 -3
+3 0 1 0 1 1 0 0 2 3 -4
+4 0 0 0 0 1 0 0 2 4 -1
+1 0 0 0 1 1 0 1 8 4 1 2 3 4
+$EndEntities
+$Nodes
+5 5 1 5
+0 1 0 1
+1
+0 0 0
+0 2 0 1
+2
+1 0 0
+0 3 0 1
+3
+1 1 0
+0 4 0 1
+4
+0 1 0
+2 1 0 1
+5
+0.5 0.5 0
+$EndNodes
+$Elements
+2 5 1 5
+1 1 1 1
+1 1 2
+2 1 2 4
+2 1 2 5
+3 2 3 5
+4 3 4 5
+5 4 1 5
+$EndElements
+"""
+
+
+def test_gmsh_reader_and_vtu_writer(tmp_path):
+    from phasefieldx_b200 import io_vtk, mesh as M
+    p = tmp_path / "m.msh"
+    p.write_text(MSH)
+    md = M.read_from_msh(str(p), None, 0, 2)
+    msh = md.mesh
+    assert msh.num_nodes == 5 and msh.num_cells == 4 and msh.cell_type == "triangle"
+    assert sorted(M.facet_nodes(msh, md.facet_tags.find(9)).tolist()) == [0, 1]
+    assert md.facet_tags.find(11).size == 0                      # plot_1711.py queries absent tags
+    vt = io_vtk.VTKFile(None, str(tmp_path / "out" / "phasefieldx.pvd"), "w")
+    phi = np.linspace(0, 1, 5)
+    u = np.arange(10.0).reshape(5, 2)
+    vt.write_function(msh, {"phi": phi, "u": u}, 3)
+    vt.close()
+    f = tmp_path / "out" / "phasefieldx_p0_000003.vtu"
+    txt = f.read_text()
+    assert 'VTKFile type="UnstructuredGrid" version="2.2"' in txt and 'Name="vtkOriginalPointIds"' in txt
+    back = io_vtk.read_vtu_points_cells(str(f))
+    assert np.allclose(back["phi"], phi) and np.allclose(back["u"][:, :2], u) and np.all(back["u"][:, 2] == 0)
+    assert np.array_equal(back["cells"], msh.cells)
+    assert "phasefieldx_p0_000003.vtu" in (tmp_path / "out" / "phasefieldx.pvd").read_text()
+
+
+def test_workloads_are_deterministic():
+    from phasefieldx_b200 import workloads as W
+    a, b = W.sen_shear(16), W.sen_shear(16)
+    assert np.array_equal(a.msh.cells, b.msh.cells) and a.msh.num_nodes == 17 * 17 + 8
+    w = W.notched_beam_3d(12, 4, 2)
+    assert w.msh.cell_type == "tetrahedron" and all(len(d) > 0 for _, d in w.bc_sets)
+    assert w.bc_values(3.0)[0][0] == -0.03
