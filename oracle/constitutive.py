@@ -240,7 +240,9 @@ def split_torch(A_np, lam, mu, degradation, split_energy, want_tangent=True):
                sig_a=sig_a.detach().numpy(), sig_b=sig_b.detach().numpy())
     if want_tangent:
         out["C_a"] = tangent(sig_a)
-        out["C_b"] = tangent(sig_b)
+        # σ_b = σ − σ_a with σ linear in A, so its tangent is the constant elastic one minus C_a
+        Ce = lam * torch.einsum("ij,kl->ijkl", I, I) + 2 * mu * torch.einsum("ik,jl->ijkl", I, I)
+        out["C_b"] = Ce.numpy() - out["C_a"] if degradation != "isotropic" else np.zeros_like(out["C_a"])
     return out
 
 

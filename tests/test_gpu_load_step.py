@@ -29,19 +29,21 @@ _SCALE = {}
 
 
 def _compare_step(o, e, bcs, step, names=("u", "phi", "H")):
-    """relative L2 per step; the denominator is floored at 1e-6 x the largest norm seen so far in
-    this run, so load reversals through zero (fatigue cycles) do not divide noise by ~0."""
+    """||gpu - oracle|| <= 1e-8 ||oracle|| + 1e-10 x (largest ||oracle|| seen so far in this run):
+    the absolute term only matters at load reversals through zero (fatigue cycles), where the field
+    itself is ~1e-19 and a pure relative measure divides solver noise by ~0."""
     fields = {"u": o.u, "phi": o.phi, "H": o.H, "V_c": o.V_c, "fatigue": o.Fatigue, "alpha_cum_bar_c": o.abar_c}
     for nm in names:
         ref = fields[nm]
         key = (id(o), nm)
         _SCALE[key] = max(_SCALE.get(key, 0.0), np.linalg.norm(ref))
-        den = max(np.linalg.norm(ref), 1e-6 * _SCALE[key], 1e-300)
-        err = np.linalg.norm(e.get_field(nm) - ref) / den
-        assert err < TOL_FIELD, (step, nm, err)
+        diff = np.linalg.norm(e.get_field(nm) - ref)
+        assert diff <= TOL_FIELD * np.linalg.norm(ref) + 1e-10 * _SCALE[key], (step, nm, diff, np.linalg.norm(ref))
     for i, bc in enumerate(bcs):
         Rg, Ro = e.reaction(i), o.reaction(bc)
-        assert np.all(np.abs(Rg - Ro) <= TOL_REACTION * np.abs(Ro).max() + 1e-12), (step, i, Rg, Ro)
+        key = (id(o), "R")
+        _SCALE[key] = max(_SCALE.get(key, 0.0), np.abs(Ro).max())
+        assert np.all(np.abs(Rg - Ro) <= TOL_REACTION * np.abs(Ro).max() + 1e-10 * _SCALE[key] + 1e-14), (step, i, Rg, Ro)
 
 
 def test_one_element_isotropic_reference_test():
@@ -162,7 +164,7 @@ def test_tet_spectral_vs_oracle():
     """Config-5-like at oracle size: notched beam of P1 tets, spectral split."""
     from phasefieldx_b200 import mesh as M
     from oracle.solver import BC
-    msh = M.create_box(None, [[0, 0, 0], [3.0, 1.0, 0.5]], [9, 4, 2])
+    msh = M.create_box(None, [[0, 0, 0], [3.0, 1.0, 0.5]], [6, 3, 2])
     o, e, P = _pair(msh, "tetrahedron", "anisotropic", "spectral", E=0.6, nu=0.2, Gc=0.00013, l=0.4)
     x = msh.geometry.x
     left = np.nonzero(np.isclose(x[:, 0], 0.0))[0]
@@ -171,8 +173,8 @@ def test_tet_spectral_vs_oracle():
     for i, bc in enumerate(bcs):
         e.set_bc_u(i, bc.dofs)
         e.set_bc_values_u(i, bc.values)
-    for step in range(1, 4):
-        bcs[1].values[:] = 4e-2 * step
+    for step in range(1, 3):
+        bcs[1].values[:] = 1.5e-2 * step
         e.set_bc_values_u(1, bcs[1].values)
         ro = o.load_step(bcs, [], max_stagger_iter=40)
         rg = e.load_step(max_stagger_iter=40)
