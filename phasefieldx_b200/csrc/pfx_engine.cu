@@ -107,6 +107,8 @@ struct pfx_ctx {
     std::vector<std::vector<int32_t>> tmp_idx;
     bool configuring = false;
     bool generic_apply = false;   // PFX_GENERIC_APPLY=1: use the generic scatter kernel for J_u·v on triangles
+    int apply_variant = 2;        // PFX_APPLY_VARIANT: 2 persistent double-buffered (default), 1 one CTA per block
+    int persist_ctas = 0, num_sms = 148;
 };
 
 namespace {
@@ -170,10 +172,42 @@ int launch_apply_u_tri(pfx_ctx* c, const KArgs& a) {
     return PFX_OK;
 }
 
+// persistent, double-buffered variant (requires the input to be zero on Dirichlet dofs when masked)
+template <int SM>
+int launch_apply_u_tri_persist(pfx_ctx* c, const KArgs& a) {
+    BlockView bv = c->bv;
+    bv.chunk = std::min((c->bm.max_elems + 31) / 32 * 32, 2 * kThreads);
+    size_t ML = (size_t)c->bm.max_loc, MI = ((size_t)c->bv.max_inc + 7) & ~(size_t)7;
+    size_t stage = ML * 16 * (SM != M_ISO ? 3 : 2) + ((ML + 1) & ~(size_t)1) * 8 + MI * 2;
+    size_t smem = 2 * stage + 3 * (size_t)bv.chunk * sizeof(double2);
+    if (c->configuring) {
+        CK(cudaFuncSetAttribute(apply_u_tri_persist_kernel<SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apply_u_tri_persist_kernel<SM>, kThreads, smem));
+        c->persist_ctas = std::max(1, nb) * c->num_sms;
+        return PFX_OK;
+    }
+    int grid = std::min(c->bm.nb, c->persist_ctas);
+    apply_u_tri_persist_kernel<SM><<<grid, kThreads, smem, c->stream>>>(bv, a);
+    c->launches++;
+    CK(cudaGetLastError());
+    return PFX_OK;
+}
+
 template <class Cell>
 int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
     switch (op) {
         case OP_APPLY_U:
+            if (std::is_same<Cell, Tri>::value && c->configuring) {      // opt both triangle variants in
+                int st = (a.m.smodel == M_ISO) ? launch_apply_u_tri_persist<M_ISO>(c, a)
+                         : (a.m.smodel == M_SPECTRAL ? launch_apply_u_tri_persist<M_SPECTRAL>(c, a)
+                                                     : launch_apply_u_tri_persist<M_VOLDEV>(c, a));
+                if (st) return st;
+            } else if (std::is_same<Cell, Tri>::value && c->apply_variant == 2 && (a.mask == nullptr || a.input_masked)) {
+                if (a.m.smodel == M_ISO) return launch_apply_u_tri_persist<M_ISO>(c, a);
+                if (a.m.smodel == M_SPECTRAL) return launch_apply_u_tri_persist<M_SPECTRAL>(c, a);
+                return launch_apply_u_tri_persist<M_VOLDEV>(c, a);
+            }
             if (std::is_same<Cell, Tri>::value && !c->generic_apply) {
                 if (a.m.smodel == M_ISO) return launch_apply_u_tri<M_ISO>(c, a);
                 if (a.m.smodel == M_SPECTRAL) return launch_apply_u_tri<M_SPECTRAL>(c, a);
@@ -333,9 +367,10 @@ __global__ void pcg_setup_kernel(double* S, double rtol2) {
     S[S_DONE] = (rr > 0.0 && rr > S[S_THRESH]) ? 0.0 : 1.0;
 }
 
-int apply_lin(pfx_ctx* c, int kind, const double* v, double* y, const uint8_t* mask, double* result, const double* stop) {
+int apply_lin(pfx_ctx* c, int kind, const double* v, double* y, const uint8_t* mask, double* result, const double* stop,
+              int input_masked = 0) {
     KArgs a = base_args(c);
-    a.v = v; a.y = y; a.mask = mask; a.result = result; a.stop = stop;
+    a.v = v; a.y = y; a.mask = mask; a.result = result; a.stop = stop; a.input_masked = input_masked;
     int op = kind == LIN_U ? OP_APPLY_U : (kind == LIN_PHI ? OP_APPLY_PHI : OP_APPLY_MASS);
     return launch_scatter(c, op, a);
 }
@@ -346,7 +381,7 @@ int pcg_iteration(pfx_ctx* c, int kind, int par, int64_t n, const uint8_t* mask,
     int st = exchange(c, c->w_p, nc);
     if (st) return st;
     bool multi = c->n_ranks > 1;
-    st = apply_lin(c, kind, c->w_p, c->w_Ap, mask, multi ? c->S + S_STAGE : c->S + S_PAP, c->S + S_DONE);
+    st = apply_lin(c, kind, c->w_p, c->w_Ap, mask, multi ? c->S + S_STAGE : c->S + S_PAP, c->S + S_DONE, 1);
     if (st) return st;
     if (multi) {
         // skipped launches leave the stage untouched; the guarded copy below keeps S_PAP sane
@@ -661,6 +696,8 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     c->use_graph = !(ng && ng[0] == '1');
     const char* ga = getenv("PFX_GENERIC_APPLY");
     c->generic_apply = (ga && ga[0] == '1');
+    const char* av = getenv("PFX_APPLY_VARIANT");
+    if (av) c->apply_variant = atoi(av);
 
     // ---- blocks
     int target = prm->block_nodes;
@@ -721,6 +758,7 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     c->vec_grid = prop.multiProcessorCount * 8;
+    c->num_sms = prop.multiProcessorCount;
     if ((st = dev_alloc(c, &c->partial, (size_t)std::max(bm.nb, c->vec_grid) * kMaxRed))) return st;
     if ((st = dev_alloc(c, &c->S, (size_t)S_COUNT))) return st;
     if ((st = dev_alloc(c, &c->red, (size_t)kMaxRed))) return st;
@@ -1042,6 +1080,11 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
+    if (kind == 0) {
+        int64_t nall = c->n_nodes * c->dim;
+        mask_zero_kernel<<<vgrid(c, nall), kThreads, 0, c->stream>>>(nall, c->mask_u, c->w_p);
+        CK(cudaGetLastError());
+    }
     // kind 4: a genuine PCG on J_u with right-hand side = current contents of w_p and a
     // tolerance of zero, so every timed iteration does full work
     if (kind == 4) {
@@ -1063,7 +1106,7 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
         }
         CK(cudaEventRecord(e0, c->stream));
         int st = PFX_OK;
-        if (kind == 0) st = apply_lin(c, LIN_U, c->w_p, c->w_Ap, c->mask_u, c->red, nullptr);
+        if (kind == 0) st = apply_lin(c, LIN_U, c->w_p, c->w_Ap, c->mask_u, c->red, nullptr, 1);   // the launch PCG makes
         else if (kind == 1) st = apply_lin(c, LIN_PHI, c->w_p, c->w_Ap, c->mask_phi, c->red, nullptr);
         else if (kind == 2) st = apply_lin(c, LIN_MASS, c->w_p, c->w_Ap, nullptr, c->red, nullptr);
         else if (kind == 3) { KArgs a = base_args(c); a.y = c->w_t0; st = launch_scatter(c, OP_RESIDUAL_U, a); }

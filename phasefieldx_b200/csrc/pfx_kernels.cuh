@@ -53,6 +53,7 @@ struct KArgs {
     double* result;         // [kMaxRed] final sums (written by the last block)
     unsigned int* counter;
     const double* stop;     // optional sticky DONE flag of the running PCG: skip the launch when set
+    int input_masked;       // caller guarantees v == 0 on Dirichlet dofs (PCG directions)
     int nred;
 };
 
@@ -538,6 +539,192 @@ __global__ void __launch_bounds__(kThreads, 4) apply_u_tri_kernel(BlockView bv, 
     grid_reduce<1>(red, a.partial, a.result, a.counter, s_red);
 }
 
+// ----------------------------------------------------------------------------- async staging helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ============================================================================= hot kernel, persistent
+// Same arithmetic as apply_u_tri_kernel, restructured for Blackwell: a persistent grid (a few CTAs
+// per SM, each walking blocks b, b+grid, ...) with DOUBLE-BUFFERED asynchronous staging — the
+// contiguous owned ranges of X, v, u and the incidence list arrive by 1-D bulk copies (TMA engine,
+// mbarrier complete_tx), phi and the halo nodes by per-thread cp.async — so the loads of block
+// i+1 are in flight while block i is computed.  Contract: when a.mask != null the INPUT is already
+// zero on Dirichlet dofs (true for every PCG direction) and the output rows of those dofs are
+// written as zero; the public pfx_apply_u wrapper restores y = v there.
+struct TriStage {
+    double2 *X, *V, *U;
+    double* P;
+    uint16_t* inc;
+};
+
+template <int SM>
+__global__ void __launch_bounds__(kThreads, 3) apply_u_tri_persist_kernel(BlockView bv, KArgs a) {
+    constexpr bool NL = (SM != M_ISO);
+    extern __shared__ double smem[];
+    __shared__ double s_red[kMaxRed * 32];
+    __shared__ uint64_t s_bar[2];
+    if (a.stop && a.stop[0] != 0.0) return;
+    const int tid = threadIdx.x;
+    const int ML = bv.max_loc, chunk = bv.chunk, MI = (bv.max_inc + 7) & ~7;
+    // ---- shared-memory carve-up (every sub-array 16-byte aligned): [stage 0][stage 1][element buffer]
+    const size_t oV = (size_t)ML * 16, oU = 2 * oV, oP = oV * (NL ? 3 : 2), oI = oP + (size_t)((ML + 1) & ~1) * 8;
+    const size_t stage_bytes = oI + (size_t)MI * 2;
+    char* const sbase = reinterpret_cast<char*>(smem);
+    auto stage = [&](int s_) -> TriStage {
+        char* p = sbase + (size_t)s_ * stage_bytes;
+        TriStage t;
+        t.X = reinterpret_cast<double2*>(p); t.V = reinterpret_cast<double2*>(p + oV);
+        t.U = reinterpret_cast<double2*>(p + oU); t.P = reinterpret_cast<double*>(p + oP);
+        t.inc = reinterpret_cast<uint16_t*>(p + oI);
+        return t;
+    };
+    double2* sE = reinterpret_cast<double2*>(sbase + 2 * stage_bytes);
+    const double2* X2 = reinterpret_cast<const double2*>(a.X);
+    const double2* V2 = reinterpret_cast<const double2*>(a.v);
+    const double2* U2 = reinterpret_cast<const double2*>(a.u);
+    const uchar2* M2 = reinterpret_cast<const uchar2*>(a.mask);
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // issue the asynchronous staging of block `blk` into stage `s`; hidx = this thread's halo node id
+    auto issue = [&](int blk, int s, int hidx) {
+        const TriStage T = stage(s);
+        const int n0 = bv.node0[blk], n_own = bv.node0[blk + 1] - n0;
+        const int n_halo = bv.halo_off[blk + 1] - bv.halo_off[blk];
+        const int i0 = bv.inc_ptr[n0], ninc = bv.inc_ptr[n0 + n_own] - i0;
+        if (tid == 0) {
+            fence_proxy_async();
+            uint32_t bytes = (uint32_t)n_own * 16u * (NL ? 3u : 2u) + (uint32_t)ninc * 2u;
+            mbar_expect_tx(&s_bar[s], bytes);
+            bulk_g2s(T.X, X2 + n0, (uint32_t)n_own * 16u, &s_bar[s]);
+            bulk_g2s(T.V, V2 + n0, (uint32_t)n_own * 16u, &s_bar[s]);
+            if (NL) bulk_g2s(T.U, U2 + n0, (uint32_t)n_own * 16u, &s_bar[s]);
+            bulk_g2s(T.inc, bv.inc + i0, (uint32_t)ninc * 2u, &s_bar[s]);
+        }
+        if (tid < n_own) cp_async8(T.P + tid, a.phi + n0 + tid);
+        for (int i = tid; i < n_halo; i += kThreads) {
+            int g = (i == tid) ? hidx : bv.halo[bv.halo_off[blk] + i];
+            cp_async16(T.X + n_own + i, X2 + g);
+            cp_async16(T.V + n_own + i, V2 + g);
+            if (NL) cp_async16(T.U + n_own + i, U2 + g);
+            cp_async8(T.P + n_own + i, a.phi + g);
+        }
+        cp_async_commit();
+    };
+    auto halo_index = [&](int blk) -> int {
+        if (blk >= bv.nb) return 0;
+        int h0 = bv.halo_off[blk], nh = bv.halo_off[blk + 1] - h0;
+        return tid < nh ? bv.halo[h0 + tid] : 0;
+    };
+
+    const int stride = gridDim.x;
+    int blk = blockIdx.x;
+    double red = 0.0;
+    if (blk < bv.nb) {
+        issue(blk, 0, halo_index(blk));
+    }
+    int hnext = halo_index(blk + stride);
+    uint32_t phases = 0u;              // bit s = parity of stage s' mbarrier
+    for (int it = 0; blk < bv.nb; blk += stride, ++it) {
+        const int s = it & 1;
+        const int n0 = bv.node0[blk], n_own = bv.node0[blk + 1] - n0;
+        const int e0 = bv.elem_off[blk], ne = bv.elem_off[blk + 1] - e0;
+        const int i0 = bv.inc_ptr[n0];
+        // connectivity of this thread's first two cells, mask and incidence range: issued before the wait
+        ushort4 lc0 = make_ushort4(0, 0, 0, 0), lc1 = lc0;
+        if (tid < ne) lc0 = bv.lconn[e0 + tid];
+        if (tid + kThreads < ne) lc1 = bv.lconn[e0 + tid + kThreads];
+        int cur = 0, end = 0;
+        uchar2 mk = make_uchar2(0, 0);
+        if (tid < n_own) {
+            cur = bv.inc_ptr[n0 + tid] - i0; end = bv.inc_ptr[n0 + tid + 1] - i0;
+            if (M2) mk = M2[n0 + tid];
+        }
+        // prefetch the next block of this CTA into the other stage (it was fully consumed one
+        // iteration ago; the __syncthreads at the end of that iteration ordered the reads)
+        const int nblk = blk + stride;
+        if (nblk < bv.nb) {
+            issue(nblk, s ^ 1, hnext);
+            hnext = halo_index(nblk + stride);
+            cp_async_wait<1>();            // everything but the group just committed has landed
+        } else {
+            cp_async_wait<0>();
+        }
+        mbar_wait(&s_bar[s], (phases >> s) & 1u);
+        phases ^= (1u << s);
+        __syncthreads();
+        const TriStage T = stage(s);
+        const double2 *sX = T.X, *sV = T.V, *sU = T.U;
+        const double* sP = T.P;
+        const uint16_t* s_inc = T.inc;
+        double2 acc = make_double2(0.0, 0.0);
+        for (int c0 = 0; c0 < ne; c0 += chunk) {
+            const int nc = min(chunk, ne - c0);
+            for (int j = tid; j < nc; j += kThreads) {
+                const int eid = c0 + j;
+                ushort4 lc = (eid == tid) ? lc0 : ((eid == tid + kThreads) ? lc1 : bv.lconn[e0 + eid]);
+                double2 f0, f1, f2;
+                const double2 z = make_double2(0.0, 0.0);
+                tri_apply_elem<SM>(a.m, sX[lc.x], sX[lc.y], sX[lc.z], sP[lc.x], sP[lc.y], sP[lc.z], sV[lc.x], sV[lc.y],
+                                   sV[lc.z], NL ? sU[lc.x] : z, NL ? sU[lc.y] : z, NL ? sU[lc.z] : z, f0, f1, f2);
+                sE[j] = f0; sE[chunk + j] = f1; sE[2 * chunk + j] = f2;
+            }
+            __syncthreads();
+            if (tid < n_own) {
+                while (cur < end) {
+                    int code = s_inc[cur];
+                    int j = (code >> 2) - c0;
+                    if (j >= nc) break;
+                    double2 f = sE[(code & 3) * chunk + j];
+                    acc.x += f.x; acc.y += f.y;
+                    ++cur;
+                }
+            }
+            if (c0 + chunk < ne) __syncthreads();
+        }
+        if (tid < n_own) {
+            if (mk.x) acc.x = 0.0;
+            if (mk.y) acc.y = 0.0;
+            const double2 vin = sV[tid];
+            reinterpret_cast<double2*>(a.y)[n0 + tid] = acc;
+            red += vin.x * acc.x + vin.y * acc.y;
+        }
+        __syncthreads();                   // stage s and sE are free again
+    }
+    double r1[1] = {red};
+    grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red);
+}
+
 // ============================================================================= element reductions
 // One thread per PRIMARY element of the block; sums NR scalars over the whole mesh.
 enum { RED_L2_U, RED_L2_PHI, RED_ENERGY };
@@ -670,6 +857,11 @@ __global__ void __launch_bounds__(kThreads) pcg_direction_kernel(int64_t n, doub
 __global__ void axpby_kernel(int64_t n, double* out, const double* a, double sa, const double* b, double sb) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = (a ? sa * a[i] : 0.0) + (b ? sb * b[i] : 0.0);
+}
+
+__global__ void mask_zero_kernel(int64_t n, const uint8_t* mask, double* v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (mask[i]) v[i] = 0.0;
 }
 
 __global__ void fill_kernel(int64_t n, double* out, double v) {
