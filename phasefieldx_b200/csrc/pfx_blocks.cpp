@@ -16,6 +16,7 @@ struct Rcb {
     int dim;
     std::vector<int32_t>& ids;
     std::vector<int32_t>& part;
+    bool even = false;   // round split points to even counts (block starts stay 16-byte aligned for 8-byte fields)
     void run(int64_t lo, int64_t hi, int nparts, int base) {
         if (nparts <= 1) {
             for (int64_t i = lo; i < hi; ++i) part[ids[i]] = base;
@@ -24,6 +25,7 @@ struct Rcb {
         int pl = nparts / 2;
         int64_t n = hi - lo;
         int64_t nl = (n * pl + nparts / 2) / nparts;
+        if (even && (nl & 1) && nl < n) ++nl;
         double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
         for (int64_t i = lo; i < hi; ++i)
             for (int a = 0; a < dim; ++a) {
@@ -59,7 +61,7 @@ std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int6
     int nb = (int)((n_owned + max_own - 1) / max_own);
     for (;;) {
         std::iota(ids.begin(), ids.end(), 0);
-        Rcb r{coords, dim, ids, part};
+        Rcb r{coords, dim, ids, part, true};
         r.run(0, n_owned, nb, 0);
         std::vector<int32_t> cnt(nb, 0);
         for (int64_t i = 0; i < n_owned; ++i) cnt[part[i]]++;
@@ -178,6 +180,25 @@ std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int6
                     int l = bm.lconn[4 * (int64_t)e + a];
                     if (l < n_own) bm.inc[cur[bm.node0[b] + l]++] = (uint16_t)(((e - bm.elem_off[b]) << 2) | a);
                 }
+        }
+    }
+    // ---- 6. packed per-block metadata and (triangles) fixed-width incidence ------------------
+    bm.meta.resize(8 * (size_t)nb);
+    for (int b = 0; b < nb; ++b) {
+        int32_t* m = &bm.meta[8 * (size_t)b];
+        m[0] = bm.node0[b]; m[1] = bm.node0[b + 1] - bm.node0[b];
+        m[2] = bm.halo_off[b]; m[3] = bm.halo_off[b + 1] - bm.halo_off[b];
+        m[4] = bm.elem_off[b]; m[5] = bm.elem_off[b + 1] - bm.elem_off[b];
+        m[6] = bm.inc_ptr[bm.node0[b]]; m[7] = bm.inc_ptr[bm.node0[b + 1]] - m[6];
+    }
+    if (nv == 3) {
+        bm.inc8.assign(8 * (size_t)n_owned + 8, (uint16_t)0xFFFF);
+        for (int64_t i = 0; i < n_owned; ++i) {
+            int32_t k0 = bm.inc_ptr[i], k1 = bm.inc_ptr[i + 1];
+            while (k1 > k0 && bm.inc[k1 - 1] == 0xFFFF) --k1;          // strip block padding
+            int cnt = k1 - k0;
+            for (int k = 0; k < std::min(cnt, 8); ++k) bm.inc8[8 * i + k] = bm.inc[k0 + k];
+            if (cnt > 8) bm.inc8[8 * i + 7] = 0xFFFE;                   // entries 7.. continue in inc[]
         }
     }
     return "";

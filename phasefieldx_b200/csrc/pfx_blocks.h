@@ -32,6 +32,9 @@ struct BlockMesh {
     std::vector<int32_t> elem_gid;   // [sum elems] caller cell id (diagnostics/tests)
     std::vector<int32_t> inc_ptr;    // [n_owned+1] into inc
     std::vector<uint16_t> inc;       // per owned node: (local elem << 2 | vertex), ascending
+    std::vector<int32_t> meta;       // [8*nb] {n0, n_own, h0, n_halo, e0, n_elems, inc0, n_inc} per block
+    std::vector<uint16_t> inc8;      // triangles: [8*n_owned] first 8 incidence codes per node (0xFFFF = none,
+                                     // slot 7 = 0xFFFE when the node has more than 8: rest in inc[])
     int max_own = 0, max_loc = 0, max_elems = 0;
     int64_t total_elems = 0;         // with overlap duplicates
 };

@@ -107,8 +107,8 @@ struct pfx_ctx {
     std::vector<std::vector<int32_t>> tmp_idx;
     bool configuring = false;
     bool generic_apply = false;   // PFX_GENERIC_APPLY=1: use the generic scatter kernel for J_u·v on triangles
-    int apply_variant = 2;        // PFX_APPLY_VARIANT: 2 persistent double-buffered (default), 1 one CTA per block
-    int persist_ctas = 0, num_sms = 148;
+    int apply_variant = 3;        // PFX_APPLY_VARIANT: 3 persistent + prefetched indices (default), 2 persistent, 1 one CTA per block
+    int persist_ctas = 0, v3_ctas = 0, num_sms = 148;
 };
 
 namespace {
@@ -194,16 +194,46 @@ int launch_apply_u_tri_persist(pfx_ctx* c, const KArgs& a) {
     return PFX_OK;
 }
 
+template <int SM>
+int launch_apply_u_tri_v3(pfx_ctx* c, const KArgs& a) {
+    BlockView bv = c->bv;
+    bv.chunk = 2 * kThreads;
+    size_t ML = (size_t)c->bm.max_loc, MO = ((size_t)c->bm.max_own + 1) & ~(size_t)1;
+    size_t stage = ML * 16 * (SM != M_ISO ? 3 : 2) + ((ML + 3) & ~(size_t)1) * 8 + MO * 16;
+    size_t smem = 2 * stage + (3 * (size_t)bv.chunk + 1) * sizeof(double2);
+    if (c->configuring) {
+        CK(cudaFuncSetAttribute(apply_u_tri_v3_kernel<SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apply_u_tri_v3_kernel<SM>, kThreads, smem));
+        c->v3_ctas = std::max(1, nb) * c->num_sms;
+        return PFX_OK;
+    }
+    int grid = std::min(c->bm.nb, c->v3_ctas);
+    apply_u_tri_v3_kernel<SM><<<grid, kThreads, smem, c->stream>>>(bv, a);
+    c->launches++;
+    CK(cudaGetLastError());
+    return PFX_OK;
+}
+
 template <class Cell>
 int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
     switch (op) {
         case OP_APPLY_U:
-            if (std::is_same<Cell, Tri>::value && c->configuring) {      // opt both triangle variants in
+            if (std::is_same<Cell, Tri>::value && c->configuring) {      // opt every triangle variant in
                 int st = (a.m.smodel == M_ISO) ? launch_apply_u_tri_persist<M_ISO>(c, a)
                          : (a.m.smodel == M_SPECTRAL ? launch_apply_u_tri_persist<M_SPECTRAL>(c, a)
                                                      : launch_apply_u_tri_persist<M_VOLDEV>(c, a));
                 if (st) return st;
-            } else if (std::is_same<Cell, Tri>::value && c->apply_variant == 2 && (a.mask == nullptr || a.input_masked)) {
+                st = (a.m.smodel == M_ISO) ? launch_apply_u_tri_v3<M_ISO>(c, a)
+                     : (a.m.smodel == M_SPECTRAL ? launch_apply_u_tri_v3<M_SPECTRAL>(c, a)
+                                                 : launch_apply_u_tri_v3<M_VOLDEV>(c, a));
+                if (st) return st;
+            } else if (std::is_same<Cell, Tri>::value && c->apply_variant == 3 && c->bm.max_elems <= 2 * kThreads &&
+                       (a.mask == nullptr || a.input_masked)) {
+                if (a.m.smodel == M_ISO) return launch_apply_u_tri_v3<M_ISO>(c, a);
+                if (a.m.smodel == M_SPECTRAL) return launch_apply_u_tri_v3<M_SPECTRAL>(c, a);
+                return launch_apply_u_tri_v3<M_VOLDEV>(c, a);
+            } else if (std::is_same<Cell, Tri>::value && c->apply_variant >= 2 && (a.mask == nullptr || a.input_masked)) {
                 if (a.m.smodel == M_ISO) return launch_apply_u_tri_persist<M_ISO>(c, a);
                 if (a.m.smodel == M_SPECTRAL) return launch_apply_u_tri_persist<M_SPECTRAL>(c, a);
                 return launch_apply_u_tri_persist<M_VOLDEV>(c, a);
@@ -734,7 +764,13 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     if ((st = dev_upload(c, &d_inc, bm.inc))) return st;
     c->bv.nb = bm.nb; c->bv.node0 = d_node0; c->bv.halo_off = d_hoff; c->bv.halo = d_halo; c->bv.elem_off = d_eoff;
     c->bv.nprim = d_nprim; c->bv.lconn = (const ushort4*)d_lconn; c->bv.inc_ptr = d_incp; c->bv.inc = d_inc;
-    c->bv.max_loc = bm.max_loc; c->bv.chunk = 256;
+    c->bv.max_loc = bm.max_loc; c->bv.chunk = 256; c->bv.max_own = bm.max_own;
+    {
+        int32_t* d_meta; uint16_t* d_inc8;
+        if ((st = dev_upload(c, &d_meta, bm.meta))) return st;
+        if ((st = dev_upload(c, &d_inc8, bm.inc8))) return st;
+        c->bv.meta = (const int4*)d_meta; c->bv.inc8 = (const uint4*)d_inc8;
+    }
     {
         int mi = 0;
         for (int b = 0; b < bm.nb; ++b) mi = std::max(mi, bm.inc_ptr[bm.node0[b + 1]] - bm.inc_ptr[bm.node0[b]]);

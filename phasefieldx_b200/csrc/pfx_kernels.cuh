@@ -33,6 +33,9 @@ struct BlockView {
     const uint16_t* inc;
     int max_loc;      // smem sizing
     int max_inc;      // largest per-block incidence list
+    int max_own;      // largest owned-node count of a block
+    const int4* meta; // [2*nb] packed {n0, n_own, h0, n_halo | e0, n_elems, inc0, n_inc}
+    const uint4* inc8; // triangles: 8 incidence codes per owned node
     int chunk;        // elements per phase-B pass
 };
 
@@ -720,6 +723,166 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_persist_kernel(BlockV
             red += vin.x * acc.x + vin.y * acc.y;
         }
         __syncthreads();                   // stage s and sE are free again
+    }
+    double r1[1] = {red};
+    grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red);
+}
+
+// ============================================================================= hot kernel, v3
+// apply_u_tri_persist_kernel plus: packed block metadata and every per-thread index of the NEXT
+// block prefetched in registers one iteration ahead (no dependent global loads on the critical
+// path), phi by bulk copy, two unrolled cells per thread, and phase C on a fixed-width (8)
+// incidence table staged by bulk copy — eight independent 128-bit shared loads per node instead
+// of a pointer-chasing loop.  Requires every block to list <= 2*kThreads cells (the block
+// builder sizes triangle blocks that way; otherwise the engine falls back to the v2 kernel).
+template <int SM>
+__global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView bv, KArgs a) {
+    constexpr bool NL = (SM != M_ISO);
+    extern __shared__ double smem[];
+    __shared__ double s_red[kMaxRed * 32];
+    __shared__ uint64_t s_bar[2];
+    if (a.stop && a.stop[0] != 0.0) return;
+    const int tid = threadIdx.x;
+    const int ML = bv.max_loc, chunk = bv.chunk, MO = (bv.max_own + 1) & ~1;
+    const size_t oV = (size_t)ML * 16, oU = 2 * oV, oP = oV * (NL ? 3 : 2), oI = oP + (size_t)((ML + 3) & ~1) * 8;
+    const size_t stage_bytes = oI + (size_t)MO * 16;
+    char* const sbase = reinterpret_cast<char*>(smem);
+    double2* sE = reinterpret_cast<double2*>(sbase + 2 * stage_bytes);      // [3*chunk + 1], last = zero slot
+    const int zslot = 3 * chunk;
+    const double2* X2 = reinterpret_cast<const double2*>(a.X);
+    const double2* V2 = reinterpret_cast<const double2*>(a.v);
+    const double2* U2 = reinterpret_cast<const double2*>(a.u);
+    const uchar2* M2 = reinterpret_cast<const uchar2*>(a.mask);
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sE[zslot] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+
+    auto issue = [&](int4 ma, int4 mb, int s_, int hidx) {
+        char* p = sbase + (size_t)s_ * stage_bytes;
+        double2 *tX = reinterpret_cast<double2*>(p), *tV = reinterpret_cast<double2*>(p + oV), *tU = reinterpret_cast<double2*>(p + oU);
+        double* tP = reinterpret_cast<double*>(p + oP);
+        const int n0 = ma.x, n_own = ma.y, h0 = ma.z, n_halo = ma.w;
+        if (tid == 0) {
+            fence_proxy_async();
+            const uint32_t nev = (uint32_t)(n_own & ~1);
+            uint32_t bytes = (uint32_t)n_own * 16u * (NL ? 3u : 2u) + nev * 8u + (uint32_t)n_own * 16u;
+            mbar_expect_tx(&s_bar[s_], bytes);
+            bulk_g2s(tX, X2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
+            bulk_g2s(tV, V2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
+            if (NL) bulk_g2s(tU, U2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
+            if (nev) bulk_g2s(tP, a.phi + n0, nev * 8u, &s_bar[s_]);
+            bulk_g2s(p + oI, bv.inc8 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
+            if (n_own & 1) cp_async8(tP + n_own - 1, a.phi + n0 + n_own - 1);
+        }
+        for (int i = tid; i < n_halo; i += kThreads) {
+            int g = (i == tid) ? hidx : bv.halo[h0 + i];
+            cp_async16(tX + n_own + i, X2 + g);
+            cp_async16(tV + n_own + i, V2 + g);
+            if (NL) cp_async16(tU + n_own + i, U2 + g);
+            cp_async8(tP + n_own + i, a.phi + g);
+        }
+        cp_async_commit();
+        (void)mb;
+    };
+
+    const int stride = gridDim.x, nb = bv.nb;
+    int blk = blockIdx.x;                       // grid <= nb: every CTA owns at least one block
+    int4 ma = bv.meta[2 * blk], mb = bv.meta[2 * blk + 1];
+    int4 na = ma, nbm = mb;
+    bool has_next = blk + stride < nb;
+    if (has_next) { na = bv.meta[2 * (blk + stride)]; nbm = bv.meta[2 * (blk + stride) + 1]; }
+    issue(ma, mb, 0, tid < ma.w ? bv.halo[ma.z + tid] : 0);
+    ushort4 lc0 = make_ushort4(0, 0, 0, 0), lc1 = lc0;
+    if (tid < mb.y) lc0 = bv.lconn[mb.x + tid];
+    if (tid + kThreads < mb.y) lc1 = bv.lconn[mb.x + tid + kThreads];
+    uchar2 mk = make_uchar2(0, 0);
+    if (M2 && tid < ma.y) mk = M2[ma.x + tid];
+    int hnext = (has_next && tid < na.w) ? bv.halo[na.z + tid] : 0;
+    double red = 0.0;
+    uint32_t phases = 0u;
+    for (int it = 0;; ++it) {
+        const int s = it & 1;
+        const int n0 = ma.x, n_own = ma.y, ne = mb.y;
+        // prefetch next block into the other stage; start the metadata of the one after
+        int4 fa = na, fb = nbm;
+        const bool has_nn = blk + 2 * stride < nb;
+        if (has_next) {
+            issue(na, nbm, s ^ 1, hnext);
+            if (has_nn) { fa = bv.meta[2 * (blk + 2 * stride)]; fb = bv.meta[2 * (blk + 2 * stride) + 1]; }
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        mbar_wait(&s_bar[s], (phases >> s) & 1u);
+        phases ^= (1u << s);
+        __syncthreads();
+        const char* p = sbase + (size_t)s * stage_bytes;
+        const double2 *sX = reinterpret_cast<const double2*>(p), *sV = reinterpret_cast<const double2*>(p + oV),
+                      *sU = reinterpret_cast<const double2*>(p + oU);
+        const double* sP = reinterpret_cast<const double*>(p + oP);
+        const uint4* s_inc8 = reinterpret_cast<const uint4*>(p + oI);
+        // ---- phase B: two cells per thread
+        const double2 z = make_double2(0.0, 0.0);
+        if (tid < ne) {
+            double2 f0, f1, f2;
+            tri_apply_elem<SM>(a.m, sX[lc0.x], sX[lc0.y], sX[lc0.z], sP[lc0.x], sP[lc0.y], sP[lc0.z], sV[lc0.x], sV[lc0.y],
+                               sV[lc0.z], NL ? sU[lc0.x] : z, NL ? sU[lc0.y] : z, NL ? sU[lc0.z] : z, f0, f1, f2);
+            sE[tid] = f0; sE[chunk + tid] = f1; sE[2 * chunk + tid] = f2;
+        }
+        if (tid + kThreads < ne) {
+            double2 f0, f1, f2;
+            tri_apply_elem<SM>(a.m, sX[lc1.x], sX[lc1.y], sX[lc1.z], sP[lc1.x], sP[lc1.y], sP[lc1.z], sV[lc1.x], sV[lc1.y],
+                               sV[lc1.z], NL ? sU[lc1.x] : z, NL ? sU[lc1.y] : z, NL ? sU[lc1.z] : z, f0, f1, f2);
+            sE[tid + kThreads] = f0; sE[chunk + tid + kThreads] = f1; sE[2 * chunk + tid + kThreads] = f2;
+        }
+        __syncthreads();
+        // ---- per-thread indices of the NEXT block (consumed one iteration later)
+        ushort4 lc0n = make_ushort4(0, 0, 0, 0), lc1n = lc0n;
+        uchar2 mkn = make_uchar2(0, 0);
+        int hnn = 0;
+        if (has_next) {
+            if (tid < nbm.y) lc0n = bv.lconn[nbm.x + tid];
+            if (tid + kThreads < nbm.y) lc1n = bv.lconn[nbm.x + tid + kThreads];
+            if (M2 && tid < na.y) mkn = M2[na.x + tid];
+            if (has_nn && tid < fa.w) hnn = bv.halo[fa.z + tid];
+        }
+        // ---- phase C: eight independent incident rows per owned node, fixed order
+        if (tid < n_own) {
+            const uint4 c8 = s_inc8[tid];
+            const unsigned cw[4] = {c8.x, c8.y, c8.z, c8.w};
+            double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int code = (int)((cw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
+                const int idx = min((code & 3) * chunk + (code >> 2), zslot);
+                const double2 f = sE[idx];
+                acc.x += f.x; acc.y += f.y;
+            }
+            if ((c8.w >> 16) == 0xFFFEu) {                    // rare: valence > 8, rest from the CSR list
+                int k0 = bv.inc_ptr[n0 + tid] + 7, k1 = bv.inc_ptr[n0 + tid + 1];
+                for (int k = k0; k < k1; ++k) {
+                    const int code = bv.inc[k];
+                    if (code >= 0xFFFE) break;
+                    const double2 f = sE[(code & 3) * chunk + (code >> 2)];
+                    acc.x += f.x; acc.y += f.y;
+                }
+            }
+            if (mk.x) acc.x = 0.0;
+            if (mk.y) acc.y = 0.0;
+            const double2 vin = sV[tid];
+            reinterpret_cast<double2*>(a.y)[n0 + tid] = acc;
+            red += vin.x * acc.x + vin.y * acc.y;
+        }
+        if (!has_next) break;
+        __syncthreads();                         // stage s and sE are free again
+        blk += stride;
+        ma = na; mb = nbm; na = fa; nbm = fb;
+        lc0 = lc0n; lc1 = lc1n; mk = mkn; hnext = hnn;
+        has_next = has_nn;
     }
     double r1[1] = {red};
     grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red);
