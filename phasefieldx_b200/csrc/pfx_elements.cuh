@@ -209,6 +209,49 @@ PFX_HD void elem_apply_u(const Material& m_, int n1d, const double* X, const dou
     }
 }
 
+// ---- cached-tangent path for P1 simplices with a nonlinear split: the element
+// tangent is constant over a simplex, so it is evaluated ONCE per Newton linearisation and the
+// CG-hot apply only contracts it.  T[21] = upper triangle of A[i][j] = w_i·∂s_i/∂e_j
+// (w = 1 for normal, 2 for shear components: A is the symmetric matrix of the bilinear form
+// dε':C:dε in sym storage), already multiplied by vol and with g(φ)+k folded in.
+template <class Cell>
+PFX_HD void elem_tangent_u(const Material& m, const double* X, const double* phi, const double* U, double* T) {
+    constexpr int D = Cell::D, NS = SymN<D>::N;
+    Geo<Cell> geo; geo.init(X, 1);
+    const double gb = gbar_simplex<Cell>(phi) + m.k;
+    double e[NS], de[NS], dsa[NS], dsb[NS];
+    sym_grad<Cell>(geo.G, U, e);
+    int t = 0;
+    double A[NS][NS];
+    for (int j = 0; j < NS; ++j) {
+        for (int i = 0; i < NS; ++i) de[i] = 0.0;
+        de[j] = 1.0;
+        dstress_split<D>(m, m.smodel, e, de, dsa, dsb);
+        for (int i = 0; i < NS; ++i) A[i][j] = ((i < D) ? 1.0 : 2.0) * geo.vol * (gb * dsa[i] + dsb[i]);
+    }
+    for (int i = 0; i < NS; ++i)
+        for (int j = i; j < NS; ++j) T[t++] = 0.5 * (A[i][j] + A[j][i]);
+}
+
+template <class Cell>
+PFX_HD void elem_apply_u_tan(const double* X, const double* V, const double* T, double* out) {
+    constexpr int NV = Cell::NV, D = Cell::D, NS = SymN<D>::N;
+    for (int i = 0; i < NV * D; ++i) out[i] = 0.0;
+    Geo<Cell> geo; geo.init(X, 1);
+    double de[NS], S[NS];
+    sym_grad<Cell>(geo.G, V, de);
+    for (int i = 0; i < NS; ++i) S[i] = 0.0;
+    int t = 0;
+    for (int i = 0; i < NS; ++i)
+        for (int j = i; j < NS; ++j) {
+            const double a = T[t++];
+            S[i] += a * de[j];
+            if (j != i) S[j] += a * de[i];
+        }
+    for (int i = D; i < NS; ++i) S[i] *= 0.5;          // undo the shear weight
+    add_div<Cell>(geo.G, S, 1.0, out);
+}
+
 // out[NV*D] = ∫ ((g(φ)+k) σ_a(u) + σ_b(u)) : ε(N_a e_i)     (F_u, solver.py:173-177)
 template <class Cell>
 PFX_HD void elem_residual_u(const Material& m, int n1d, const double* X, const double* phi,

@@ -106,6 +106,8 @@ struct pfx_ctx {
     int64_t flush_n = 0;
     std::vector<std::vector<int32_t>> tmp_idx;
     bool configuring = false;
+    double* tan = nullptr;        // cached element tangents (tets + nonlinear split)
+    bool use_tan = false;
     bool generic_apply = false;   // PFX_GENERIC_APPLY=1: use the generic scatter kernel for J_u·v on triangles
     int apply_variant = 3;        // PFX_APPLY_VARIANT: 3 persistent + prefetched indices (default), 2 persistent, 1 one CTA per block
     int persist_ctas = 0, v3_ctas = 0, num_sms = 148;
@@ -255,7 +257,14 @@ int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
         case OP_DIAG_MASS: return launch_scatter_op<OpDiagMass<Cell>>(c, a);
         case OP_RHS_PSI: return launch_scatter_op<OpRhsPsi<Cell>>(c, a);
         case OP_RHS_FATIGUE: return launch_scatter_op<OpRhsFatigue<Cell>>(c, a);
+        case OP_TANGENT_U:
+            if constexpr (Cell::simplex) return launch_scatter_op<OpTangentU<Cell>>(c, a);
+            break;
+        case OP_APPLY_U_TAN:
+            if constexpr (Cell::simplex) return launch_scatter_op<OpApplyUTan<Cell>>(c, a);
+            break;
     }
+    if (c->configuring) return PFX_OK;
     c->err = "unknown op";
     return PFX_ERR_BAD_ARG;
 }
@@ -297,6 +306,7 @@ KArgs base_args(pfx_ctx* c) {
     a.n1d = c->prm.quad_points_1d;
     a.X = c->X; a.u = c->u; a.phi = c->phi; a.H = c->H; a.Fat = c->Fat;
     a.partial = c->partial; a.result = c->red; a.counter = c->counter;
+    a.tan = c->tan; a.tan_stride = c->bm.total_elems;
     return a;
 }
 
@@ -401,7 +411,7 @@ int apply_lin(pfx_ctx* c, int kind, const double* v, double* y, const uint8_t* m
               int input_masked = 0) {
     KArgs a = base_args(c);
     a.v = v; a.y = y; a.mask = mask; a.result = result; a.stop = stop; a.input_masked = input_masked;
-    int op = kind == LIN_U ? OP_APPLY_U : (kind == LIN_PHI ? OP_APPLY_PHI : OP_APPLY_MASS);
+    int op = kind == LIN_U ? (c->use_tan ? OP_APPLY_U_TAN : OP_APPLY_U) : (kind == LIN_PHI ? OP_APPLY_PHI : OP_APPLY_MASS);
     return launch_scatter(c, op, a);
 }
 
@@ -518,8 +528,14 @@ int newton(pfx_ctx* c, bool is_u, NewtonOut* out) {
         a.y = c->w_t0;
         st = launch_scatter(c, is_u ? OP_RESIDUAL_U : OP_RESIDUAL_PHI, a);
         if (st) return st;
+        auto refresh_tangent = [&]() -> int {
+            if (!is_u || !c->use_tan) return PFX_OK;
+            KArgs t = base_args(c);
+            return launch_scatter(c, OP_TANGENT_U, t);
+        };
         const double* lift = nullptr;
         if (it == 0) {
+            if ((st = refresh_tangent())) return st;
             // gap on every local dof (ghost entries feed the halo elements of the apply)
             int64_t nall = c->n_nodes * nc;
             bc_gap_kernel<<<vgrid(c, nall), kThreads, 0, c->stream>>>(nall, x, g, mask, c->w_p, c->partial, c->red, c->counter);
@@ -546,6 +562,7 @@ int newton(pfx_ctx* c, bool is_u, NewtonOut* out) {
             if (snorm < c->prm.snes_stol * xnorm) { out->reason = 4; return PFX_OK; }
         }
         if (it >= c->prm.snes_max_it) { out->reason = -5; return PFX_OK; }
+        if (it > 0 && (st = refresh_tangent())) return st;
         // Jacobi data of the current tangent
         KArgs d = base_args(c);
         d.y = c->w_dinv; d.mask = mask;
@@ -804,11 +821,15 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     CK(cudaEventCreate(&c->ev1));
     c->graph_iters = prm->cg_chunk > 0 ? (prm->cg_chunk + 1) / 2 * 2 : 32;
 
+    if (c->cell_type == PFX_CELL_TETRAHEDRON && c->mat.smodel != M_ISO && !getenv("PFX_NO_TANGENT_CACHE")) {
+        if ((st = dev_alloc(c, &c->tan, (size_t)21 * (size_t)bm.total_elems))) return st;
+        c->use_tan = true;
+    }
     // ---- opt every kernel instantiation of this mesh/model in to its shared-memory size
     {
         c->configuring = true;
         KArgs z = base_args(c);
-        for (int op = OP_APPLY_U; op <= OP_RHS_FATIGUE; ++op)
+        for (int op = OP_APPLY_U; op <= OP_APPLY_U_TAN; ++op)
             if ((st = launch_scatter(c, op, z))) return st;
         if ((st = launch_reduce<RED_L2_U>(c, z))) return st;
         if ((st = launch_reduce<RED_L2_PHI>(c, z))) return st;
@@ -1116,6 +1137,11 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
+    if ((kind == 0 || kind == 4) && c->use_tan) {          // linearise at the current state first
+        KArgs t = base_args(c);
+        int st = launch_scatter(c, OP_TANGENT_U, t);
+        if (st) return st;
+    }
     if (kind == 0) {
         int64_t nall = c->n_nodes * c->dim;
         mask_zero_kernel<<<vgrid(c, nall), kThreads, 0, c->stream>>>(nall, c->mask_u, c->w_p);

@@ -57,6 +57,8 @@ struct KArgs {
     unsigned int* counter;
     const double* stop;     // optional sticky DONE flag of the running PCG: skip the launch when set
     int input_masked;       // caller guarantees v == 0 on Dirichlet dofs (PCG directions)
+    double* tan;            // cached element tangents, SoA [21][tan_stride] (tets, nonlinear split)
+    int64_t tan_stride;
     int nred;
 };
 
@@ -122,7 +124,7 @@ __device__ __forceinline__ void grid_reduce(double* vals, double* partial, doubl
 // Each Op: NF staged doubles per local node (odd => conflict-free AoS), NOUT rows per node,
 // NRED partial sums; load(), elem(), store().
 enum { OP_APPLY_U, OP_RESIDUAL_U, OP_DIAG_U, OP_APPLY_PHI, OP_RESIDUAL_PHI, OP_DIAG_PHI, OP_APPLY_MASS,
-       OP_DIAG_MASS, OP_RHS_PSI, OP_RHS_FATIGUE };
+       OP_DIAG_MASS, OP_RHS_PSI, OP_RHS_FATIGUE, OP_TANGENT_U, OP_APPLY_U_TAN };
 
 template <int V> struct odd { static constexpr int value = (V & 1) ? V : V + 1; };
 template <class Op, class = void> struct min_blocks { static constexpr int value = (Op::NV == 3) ? 4 : (Op::D == 2 ? 3 : (Op::NOUT == 1 ? 2 : 1)); };
@@ -144,7 +146,7 @@ struct OpApplyU {          // staged: X[D] phi v[D] (u[D]); SM = compile-time st
         }
         if (NL) for (int i = 0; i < D; ++i) s[2 * D + 1 + i] = a.u[(size_t)g * D + i];
     }
-    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
         double X[NV * D], ph[NV], V[NV * D], U[NV * D];
         for (int k = 0; k < NV; ++k) {
             for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; V[k * D + i] = nd[k][D + 1 + i]; U[k * D + i] = NL ? nd[k][2 * D + 1 + i] : 0.0; }
@@ -170,7 +172,7 @@ struct OpResidualU {       // staged: X phi u
         for (int i = 0; i < D; ++i) { s[i] = a.X[(size_t)g * D + i]; s[D + 1 + i] = a.u[(size_t)g * D + i]; }
         s[D] = a.phi[g];
     }
-    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
         double X[NV * D], ph[NV], U[NV * D];
         for (int k = 0; k < NV; ++k) {
             for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; U[k * D + i] = nd[k][D + 1 + i]; }
@@ -188,7 +190,7 @@ struct OpDiagU {           // writes 1/diag (1 at Dirichlet dofs)
     static constexpr int D = Cell::D, NV = Cell::NV, NOUT = D, NRED = 0;
     static constexpr int NF = odd<D + 1 + D>::value;
     __device__ static void load(const KArgs& a, int g, double* s) { OpResidualU<Cell>::load(a, g, s); }
-    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
         double X[NV * D], ph[NV], U[NV * D];
         for (int k = 0; k < NV; ++k) {
             for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; U[k * D + i] = nd[k][D + 1 + i]; }
@@ -222,7 +224,7 @@ struct OpApplyPhi {        // staged: X cm cg p
         if (a.mask && a.mask[g]) vv = 0.0;
         s[D + 2] = vv;
     }
-    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
         double X[NV * D], cm[NV], cg[NV], p[NV];
         for (int k = 0; k < NV; ++k) {
             for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i];
@@ -248,7 +250,7 @@ struct OpResidualPhi {     // staged: X cm cg H phi
         s[D + 2] = a.H[g];
         s[D + 3] = a.phi[g];
     }
-    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
         double X[NV * D], cm[NV], cg[NV], H[NV], p[NV];
         for (int k = 0; k < NV; ++k) {
             for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i];
@@ -267,7 +269,7 @@ struct OpDiagPhi {
         for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i];
         phi_coeffs(a, g, s[D], s[D + 1]);
     }
-    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
         double X[NV * D], cm[NV], cg[NV];
         for (int k = 0; k < NV; ++k) {
             for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i];
@@ -288,7 +290,7 @@ struct OpApplyMass {       // staged: X p
         for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i];
         s[D] = a.v[g];
     }
-    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
         double X[NV * D], p[NV];
         for (int k = 0; k < NV; ++k) { for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i]; p[k] = nd[k][D]; }
         elem_apply_mass<Cell>(a.n1d, X, p, out);
@@ -304,7 +306,7 @@ struct OpDiagMass {
     static constexpr int D = Cell::D, NV = Cell::NV, NOUT = 1, NRED = 0;
     static constexpr int NF = odd<D>::value;
     __device__ static void load(const KArgs& a, int g, double* s) { for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i]; }
-    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
         double X[NV * D];
         for (int k = 0; k < NV; ++k) for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i];
         elem_diag_mass<Cell>(a.n1d, X, out);
@@ -319,7 +321,7 @@ struct OpRhsPsi {          // staged: X u ; y = ∫ψ_a(u) N
     __device__ static void load(const KArgs& a, int g, double* s) {
         for (int i = 0; i < D; ++i) { s[i] = a.X[(size_t)g * D + i]; s[D + i] = a.u[(size_t)g * D + i]; }
     }
-    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
         double X[NV * D], U[NV * D];
         for (int k = 0; k < NV; ++k) for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; U[k * D + i] = nd[k][D + i]; }
         elem_rhs_psi<Cell>(a.m, a.n1d, X, U, out);
@@ -335,12 +337,55 @@ struct OpRhsFatigue {      // staged: X f1(=phi_old) f2(=V_c)
         for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i];
         s[D] = a.f1[g]; s[D + 1] = a.f2[g];
     }
-    __device__ static void elem(const KArgs& a, const double* const* nd, double* out) {
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
         double X[NV * D], p[NV], v[NV];
         for (int k = 0; k < NV; ++k) { for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i]; p[k] = nd[k][D]; v[k] = nd[k][D + 1]; }
         elem_rhs_fatigue<Cell>(a.n1d, X, p, v, out);
     }
     __device__ static void store(const KArgs& a, int g, const double* acc, double*) { a.y[g] = acc[0]; }
+};
+
+template <class Cell>
+struct OpTangentU {        // staged: X phi u ; writes the cached tangent of every listed cell, no nodal output
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = 1, NRED = 0;
+    static constexpr int NF = odd<D + 1 + D>::value;
+    static constexpr int MINB = 1;
+    __device__ static void load(const KArgs& a, int g, double* s) { OpResidualU<Cell>::load(a, g, s); }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t gid) {
+        double X[NV * D], ph[NV], U[NV * D], T[21];
+        for (int k = 0; k < NV; ++k) {
+            for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; U[k * D + i] = nd[k][D + 1 + i]; }
+            ph[k] = nd[k][D];
+        }
+        elem_tangent_u<Cell>(a.m, X, ph, U, T);
+        constexpr int NT = SymN<D>::N * (SymN<D>::N + 1) / 2;
+        for (int t = 0; t < NT; ++t) a.tan[(size_t)t * a.tan_stride + gid] = T[t];
+        for (int k = 0; k < NV; ++k) out[k] = 0.0;
+    }
+    __device__ static void store(const KArgs&, int, const double*, double*) {}
+};
+
+template <class Cell>
+struct OpApplyUTan {       // staged: X v ; contracts the cached tangent
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = D, NRED = 1;
+    static constexpr int NF = odd<2 * D>::value;
+    static constexpr int MINB = 2;
+    __device__ static void load(const KArgs& a, int g, double* s) {
+        for (int i = 0; i < D; ++i) {
+            s[i] = a.X[(size_t)g * D + i];
+            double vv = a.v[(size_t)g * D + i];
+            if (a.mask && a.mask[(size_t)g * D + i]) vv = 0.0;
+            s[D + i] = vv;
+        }
+    }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t gid) {
+        constexpr int NT = SymN<D>::N * (SymN<D>::N + 1) / 2;
+        double X[NV * D], V[NV * D], T[NT];
+        for (int t = 0; t < NT; ++t) T[t] = __ldg(&a.tan[(size_t)t * a.tan_stride + gid]);
+        for (int k = 0; k < NV; ++k) for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; V[k * D + i] = nd[k][D + i]; }
+        elem_apply_u_tan<Cell>(X, V, T, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double* red) { OpApplyU<Cell, M_ISO>::store(a, g, acc, red); }
 };
 
 template <class Op>
@@ -383,7 +428,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks<Op>::value) scatter_kerne
             const double* nd[4] = {s_nodes + (size_t)lc.x * NF, s_nodes + (size_t)lc.y * NF,
                                    s_nodes + (size_t)lc.z * NF, s_nodes + (size_t)lc.w * NF};
             double out[NV * NOUT];
-            Op::elem(a, nd, out);
+            Op::elem(a, nd, out, (int64_t)e0 + c0 + j);
 #pragma unroll
             for (int k = 0; k < NV * NOUT; ++k) s_ebuf[k * chunk + j] = out[k];
         }

@@ -45,6 +45,15 @@ static void assemble(int op, const Material& m, int n1d, int64_t ne, const doubl
             case 10: gs(f0, a0); gs(f1, a1); elem_l2<Cell, 1>(n1d, X, a0, a1, out); continue;
             case 11: gv(f0, a0); gv(f1, a1); elem_l2<Cell, D>(n1d, X, a0, a1, out); continue;
             case 12: gv(f0, a0); gs(f1, a1); gs(f2, a2); gs(f3, a3); elem_energies<Cell>(m, n1d, X, a0, a1, a2, a3, out); continue;
+            case 13:        // cached-tangent apply (simplices): phi,u,v
+                if constexpr (Cell::simplex) {
+                    double T[21];
+                    gs(f0, a0); gv(f1, a1); gv(f2, a2);
+                    elem_tangent_u<Cell>(m, X, a0, a1, T);
+                    elem_apply_u_tan<Cell>(X, a2, T, o);
+                    nout = D;
+                    break;
+                } else return;
             default: return;
         }
         for (int a = 0; a < NV; ++a) for (int i = 0; i < nout; ++i) out[c[a] * nout + i] += o[a * nout + i];

@@ -144,3 +144,24 @@ def test_block_builder_drives_scatter_logic(hostcheck):
             assert rel(y, ref) < 1e-12
             assert abs(dot.value - v @ ref) < 1e-11 * abs(v @ ref)
             assert st[1] <= max_own and st[5] == len(cells)
+
+
+@pytest.mark.parametrize("sp", ["spectral", "deviatoric"])
+def test_cached_tangent_apply_matches_direct(hostcheck, sp):
+    """SURVEY H4 path: element tangent evaluated once per linearisation, then contracted."""
+    rng = np.random.default_rng(4)
+    sm = CODES[("anisotropic", sp)][0]
+    for ctype, m in perturbed_meshes(rng):
+        if ctype == "quadrilateral":
+            continue
+        Pm = Params(degradation="anisotropic", split_energy=sp, k=1e-3)
+        o = Oracle(m.geometry.x, m.cells, m.cell_type, Pm)
+        nn, d = o.nn, o.d
+        o.u, o.phi = rng.normal(size=nn * d) * 1e-3, rng.uniform(0, 1, nn)
+        v = rng.normal(size=nn * d)
+        mat = np.array([Pm.lambda_, Pm.mu, Pm.Gc, Pm.l, Pm.k])
+        cells = np.ascontiguousarray(m.cells, dtype=np.int32)
+        out = np.zeros(nn * d)
+        hostcheck.hc_assemble(13, CT[ctype], dp(mat), sm, sm, 0, 3, ctypes.c_int64(len(cells)), dp(m.geometry.x),
+                              cells.ctypes.data_as(PI), dp(o.phi), dp(o.u), dp(v), None, dp(out))
+        assert rel(out, o.J_u(o.u, o.phi) @ v) < 1e-10
