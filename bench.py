@@ -169,6 +169,11 @@ def build_rank_engine(w, rank, world, device, opts):
     uid = [_lib.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     e.comm_attach(rank, world, uid[0], R)
+    if os.environ.get("PFX_NO_P2P", "0") != "1":
+        # NVLink peer path: all-gather the CUDA-IPC handles, map the peers' exchange buffers
+        handles = [None] * world
+        dist.all_gather_object(handles, e.p2p_export())
+        e.p2p_import(handles, _lib.peer_ghost_start(P, rank))
     return e, local_sets
 
 
@@ -228,6 +233,7 @@ def main_b200(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device: phasefieldx_b200 has no CPU fallback")
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")        # keep NCCL's version banner off stdout (one JSON line)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     w = W.sen_shear(args.n)
@@ -288,6 +294,8 @@ def main_b200(args, rank, world, local_rank):
             roof["pcg_iteration"] = {"achieved": bi / (ms_it.mean() * 1e-3) / 1e9, "ms": float(ms_it.mean()),
                                      "algorithmic_bytes": bi, "frac": bi / (ms_it.mean() * 1e-3) / 1e9 / peak}
     stats = e.block_stats()
+    if world > 1:
+        dist.barrier()          # peers keep each other's buffers mapped (CUDA IPC): close together
     e.close()
 
     if rank != 0:

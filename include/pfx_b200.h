@@ -194,6 +194,17 @@ int pfx_comm_attach(pfx_ctx* ctx, int rank, int n_ranks, const uint8_t id[128], 
                     const int32_t* neighbors, const int64_t* send_offsets, const int32_t* send_local_idx,
                     const int64_t* recv_offsets);
 
+/* NVLink peer path (optional, after pfx_comm_attach): map the peers' exchange buffers with CUDA
+ * IPC so that halo values are pushed with direct stores into the neighbours' ghost ranges and the
+ * CG scalars are all-reduced through mailboxes — no NCCL call inside the PCG iteration.
+ * pfx_comm_p2p_export fills PFX_P2P_HANDLE_BYTES bytes; the host all-gathers them (rank-major) and
+ * passes the table to pfx_comm_p2p_import together with peer_ghost_start[j] = position (in nodes,
+ * in neighbour j's local numbering) where this rank's values start in neighbour j's ghost range. */
+#define PFX_P2P_HANDLE_BYTES 384
+int pfx_comm_p2p_export(pfx_ctx* ctx, uint8_t* handles /* [PFX_P2P_HANDLE_BYTES] */);
+int pfx_comm_p2p_import(pfx_ctx* ctx, const uint8_t* all_handles /* [n_ranks][PFX_P2P_HANDLE_BYTES] */,
+                        const int64_t* peer_ghost_start /* [n_neighbors] */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,7 +60,7 @@ SYMBOLS = [
     "pfx_l2_error", "pfx_time_operator", "pfx_algorithmic_bytes", "pfx_launch_count", "pfx_block_stats",
     "pfx_partition_create", "pfx_partition_destroy", "pfx_partition_cell_rank", "pfx_partition_node_owner",
     "pfx_partition_rank_sizes", "pfx_partition_rank_maps", "pfx_partition_rank_plan", "pfx_comm_unique_id",
-    "pfx_comm_attach",
+    "pfx_comm_attach", "pfx_comm_p2p_export", "pfx_comm_p2p_import",
 ]
 
 _lib = None
@@ -118,6 +118,8 @@ def load():
     lib.pfx_partition_rank_plan.argtypes = [C.c_void_p, C.c_int, pi, pl, pi, pl]
     lib.pfx_comm_unique_id.argtypes = [p8]
     lib.pfx_comm_attach.argtypes = [C.c_void_p, C.c_int, C.c_int, p8, C.c_int, pi, pl, pi, pl]
+    lib.pfx_comm_p2p_export.argtypes = [C.c_void_p, p8]
+    lib.pfx_comm_p2p_import.argtypes = [C.c_void_p, p8, pl]
     _lib = lib
     return lib
 
@@ -397,6 +399,31 @@ class Engine:
         si = np.ascontiguousarray(plan["send_idx"], dtype=np.int32)
         ro = np.ascontiguousarray(plan["recv_off"], dtype=np.int64)
         self._ck(self.lib.pfx_comm_attach(self.h, rank, n_ranks, _p8(uid), len(nb), _pi(nb), _pl(so), _pi(si), _pl(ro)))
+
+    def p2p_export(self):
+        h = np.zeros(P2P_HANDLE_BYTES, dtype=np.uint8)
+        self._ck(self.lib.pfx_comm_p2p_export(self.h, _p8(h)))
+        return h.tobytes()
+
+    def p2p_import(self, all_handles, ghost_start):
+        a = np.frombuffer(b"".join(all_handles), dtype=np.uint8).copy()
+        g = np.ascontiguousarray(ghost_start, dtype=np.int64)
+        self._ck(self.lib.pfx_comm_p2p_import(self.h, _p8(a), _pl(g)))
+
+
+P2P_HANDLE_BYTES = 384
+
+
+def peer_ghost_start(partition, rank):
+    """For every neighbour q of `rank` (ascending): position, in q's local node numbering, where
+    the values `rank` owns start inside q's ghost range (host-side, from the deterministic partition)."""
+    R = partition.rank(rank)
+    out = []
+    for q in R["neighbors"]:
+        Q = partition.rank(int(q))
+        j = int(np.nonzero(Q["neighbors"] == rank)[0][0])
+        out.append(Q["n_owned"] + int(Q["recv_off"][j]))
+    return np.array(out, dtype=np.int64)
 
 
 def comm_unique_id():

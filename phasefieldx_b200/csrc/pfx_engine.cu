@@ -97,6 +97,14 @@ struct pfx_ctx {
     int32_t* d_send_idx = nullptr;
     double* d_send_buf = nullptr;
     int64_t n_send = 0;
+    // NVLink peer path
+    bool p2p = false;
+    PeerView pv;
+    double* mbox = nullptr;           // mailboxes + halo flags + counters (IPC-exported)
+    uint8_t* d_send_nbr = nullptr;
+    int64_t* d_send_dst = nullptr;
+    double** d_peer_vec[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    std::vector<void*> ipc_opened;
     // misc
     std::vector<void*> allocs;
     std::string err;
@@ -313,14 +321,30 @@ KArgs base_args(pfx_ctx* c) {
 // --------------------------------------------------------------------------- communication
 int allreduce(pfx_ctx* c, double* buf, int n) {
     if (c->n_ranks <= 1) return PFX_OK;
+    if (c->p2p) {
+        p2p_allreduce_kernel<<<1, 32, 0, c->stream>>>(c->pv, c->S, buf, n, 2, 0);
+        c->launches++;
+        CK(cudaGetLastError());
+        return PFX_OK;
+    }
     int r = nccl().AllReduce(buf, buf, (size_t)n, kNcclFloat64, kNcclSum, c->comm, c->stream);
     if (r != 0) { c->err = std::string("ncclAllReduce: ") + nccl().GetErrorString(r); return PFX_ERR_COMM; }
     return PFX_OK;
 }
 
 // forward halo: owners send the values of their boundary nodes, ghosts receive in place
-int exchange(pfx_ctx* c, double* v, int nc) {
+int exchange(pfx_ctx* c, double* v, int nc, const double* stop = nullptr) {
     if (c->n_ranks <= 1 || c->nbrs.empty()) return PFX_OK;
+    if (c->p2p) {
+        int vid = v == c->w_p ? 0 : (v == c->u ? 1 : (v == c->phi ? 2 : (v == c->Vc ? 3 : (v == c->alpha_c ? 4 : -1))));
+        if (vid < 0) { c->err = "exchange: vector is not peer-mapped"; return PFX_ERR_COMM; }
+        halo_push_kernel<<<vgrid(c, std::max<int64_t>(c->n_send * nc, 1)), kThreads, 0, c->stream>>>(
+            c->n_send, c->d_send_idx, c->d_send_nbr, c->d_send_dst, nc, v, c->d_peer_vec[vid], c->pv, c->counter + 1, stop);
+        halo_wait_kernel<<<1, 32, 0, c->stream>>>(c->pv, stop);
+        c->launches += 2;
+        CK(cudaGetLastError());
+        return PFX_OK;
+    }
     if (c->n_send > 0) {
         pack_kernel<<<vgrid(c, c->n_send * nc), kThreads, 0, c->stream>>>(c->n_send, c->d_send_idx, nc, v, c->d_send_buf);
         c->launches++;
@@ -418,12 +442,15 @@ int apply_lin(pfx_ctx* c, int kind, const double* v, double* y, const uint8_t* m
 // one PCG iteration (parity par) enqueued on the stream
 int pcg_iteration(pfx_ctx* c, int kind, int par, int64_t n, const uint8_t* mask, const double* dinv) {
     int nc = (kind == LIN_U) ? c->dim : 1;
-    int st = exchange(c, c->w_p, nc);
+    int st = exchange(c, c->w_p, nc, c->S + S_DONE);
     if (st) return st;
     bool multi = c->n_ranks > 1;
     st = apply_lin(c, kind, c->w_p, c->w_Ap, mask, multi ? c->S + S_STAGE : c->S + S_PAP, c->S + S_DONE, 1);
     if (st) return st;
-    if (multi) {
+    if (multi && c->p2p) {
+        p2p_allreduce_kernel<<<1, 32, 0, c->stream>>>(c->pv, c->S, c->S + S_STAGE, 1, 0, par);
+        c->launches++;
+    } else if (multi) {
         // skipped launches leave the stage untouched; the guarded copy below keeps S_PAP sane
         st = allreduce(c, c->S + S_STAGE, 1);
         if (st) return st;
@@ -434,7 +461,10 @@ int pcg_iteration(pfx_ctx* c, int kind, int par, int64_t n, const uint8_t* mask,
     pcg_update_kernel<<<g, kThreads, 0, c->stream>>>(n, c->w_x, c->w_r, c->w_p, c->w_Ap, dinv, c->S, par, multi ? 0 : 1,
                                                     c->partial, c->counter);
     c->launches++;
-    if (multi) {
+    if (multi && c->p2p) {
+        p2p_allreduce_kernel<<<1, 32, 0, c->stream>>>(c->pv, c->S, c->S + S_STAGE, 2, 1, par);
+        c->launches++;
+    } else if (multi) {
         st = allreduce(c, c->S + S_STAGE, 2);
         if (st) return st;
         pcg_publish_kernel<<<1, 1, 0, c->stream>>>(c->S, par);
@@ -497,6 +527,7 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
         CK(cudaStreamSynchronize(c->stream));
         *iters = (int64_t)c->h_pinned[S_ITERS];
         double rr = c->h_pinned[S_RR];
+        if (c->h_pinned[S_ERR] != 0.0) { c->err = "peer wait timed out (halo/all-reduce)"; return PFX_ERR_COMM; }
         if (!(rr == rr)) { c->err = "NaN in PCG"; return PFX_ERR_NAN; }
         if (c->h_pinned[S_DONE] != 0.0) { *converged = true; break; }
         if (*iters >= max_it) break;
@@ -850,6 +881,7 @@ int pfx_destroy(pfx_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int k = 0; k < 3; ++k)
         if (c->graph[k]) cudaGraphExecDestroy(c->graph[k]);
+    for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->comm) nccl().CommDestroy(c->comm);
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -1283,6 +1315,75 @@ int pfx_comm_attach(pfx_ctx* c, int rank, int n_ranks, const uint8_t id[128], in
     if ((st = dev_upload(c, &c->d_send_idx, idx))) return st;
     if ((st = dev_alloc(c, &c->d_send_buf, (size_t)(c->n_send * c->dim)))) return st;
     // graphs captured before the attach (none normally) would miss the collectives
+    for (int k = 0; k < 3; ++k)
+        if (c->graph[k]) { cudaGraphExecDestroy(c->graph[k]); c->graph[k] = nullptr; }
+    return PFX_OK;
+}
+
+// ------------------------------------------------------------------------------- NVLink peer path
+int pfx_comm_p2p_export(pfx_ctx* c, uint8_t* handles) {
+    if (!c || !handles) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    if (!c->mbox) {
+        int st = dev_alloc(c, &c->mbox, (size_t)4 * kMaxRanks * kMboxStride + 2 * kMaxRanks + 16);
+        if (st) return st;
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    void* vecs[6] = {c->w_p, c->u, c->phi, c->Vc, c->alpha_c, c->mbox};
+    for (int k = 0; k < 6; ++k) {
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, vecs[k]));
+        static_assert(sizeof(h) == 64, "IPC handle size");
+        memcpy(handles + 64 * k, &h, 64);
+    }
+    return PFX_OK;
+}
+
+int pfx_comm_p2p_import(pfx_ctx* c, const uint8_t* all, const int64_t* peer_ghost_start) {
+    if (!c || !all || (c->nbrs.size() && !peer_ghost_start)) return PFX_ERR_BAD_ARG;
+    if (c->n_ranks < 2 || c->n_ranks > kMaxRanks || !c->mbox) { c->err = "p2p import: attach + export first (2..8 ranks)"; return PFX_ERR_BAD_ARG; }
+    CK(cudaSetDevice(c->device));
+    const int R = c->n_ranks, nn = (int)c->nbrs.size();
+    std::vector<std::vector<void*>> peer(R, std::vector<void*>(6, nullptr));
+    void* mine[6] = {c->w_p, c->u, c->phi, c->Vc, c->alpha_c, c->mbox};
+    auto need = [&](int r) { return std::find(c->nbrs.begin(), c->nbrs.end(), r) != c->nbrs.end(); };
+    for (int r = 0; r < R; ++r)
+        for (int k = 0; k < 6; ++k) {
+            if (r == c->rank) { peer[r][k] = mine[k]; continue; }
+            if (k < 5 && !need(r)) continue;                       // vectors only of neighbours, mailbox of everyone
+            cudaIpcMemHandle_t h;
+            memcpy(&h, all + (size_t)r * PFX_P2P_HANDLE_BYTES + 64 * k, 64);
+            CK(cudaIpcOpenMemHandle(&peer[r][k], h, cudaIpcMemLazyEnablePeerAccess));
+            c->ipc_opened.push_back(peer[r][k]);
+        }
+    PeerView& pv = c->pv;
+    memset(&pv, 0, sizeof(pv));
+    pv.rank = c->rank; pv.n_ranks = R; pv.n_nbrs = nn;
+    for (int j = 0; j < nn; ++j) pv.nbr_rank[j] = c->nbrs[j];
+    const size_t flag_off = (size_t)4 * kMaxRanks * kMboxStride;   // in doubles
+    pv.mbox_local = c->mbox;
+    pv.hflag_local = reinterpret_cast<unsigned long long*>(c->mbox + flag_off);
+    pv.seq = reinterpret_cast<unsigned long long*>(c->mbox + flag_off + kMaxRanks);
+    pv.err = c->S + S_ERR;
+    for (int r = 0; r < R; ++r) {
+        pv.mbox_peer[r] = reinterpret_cast<double*>(peer[r][5]);
+        pv.hflag_peer[r] = reinterpret_cast<unsigned long long*>(reinterpret_cast<double*>(peer[r][5]) + flag_off);
+    }
+    // per-entry destination of the send list
+    std::vector<uint8_t> nbr(c->n_send);
+    std::vector<int64_t> dst(c->n_send);
+    for (int j = 0; j < nn; ++j)
+        for (int64_t k = c->send_off[j]; k < c->send_off[j + 1]; ++k) { nbr[k] = (uint8_t)j; dst[k] = peer_ghost_start[j] + (k - c->send_off[j]); }
+    int st;
+    if ((st = dev_upload(c, &c->d_send_nbr, nbr))) return st;
+    if ((st = dev_upload(c, &c->d_send_dst, dst))) return st;
+    for (int v = 0; v < 5; ++v) {
+        std::vector<double*> tab(std::max(nn, 1), nullptr);
+        for (int j = 0; j < nn; ++j) tab[j] = reinterpret_cast<double*>(peer[c->nbrs[j]][v]);
+        if ((st = dev_upload(c, &c->d_peer_vec[v], tab))) return st;
+    }
+    const char* np = getenv("PFX_NO_P2P");
+    c->p2p = !(np && np[0] == '1');
     for (int k = 0; k < 3; ++k)
         if (c->graph[k]) { cudaGraphExecDestroy(c->graph[k]); c->graph[k] = nullptr; }
     return PFX_OK;

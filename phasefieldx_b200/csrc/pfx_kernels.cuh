@@ -991,7 +991,7 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(BlockView bv, KArgs a)
 
 // ============================================================================= vector kernels
 // PCG state scalars (device resident).  Indices into the scalar array S.
-enum { S_PAP = 0, S_RZ0 = 1, S_RZ1 = 2, S_RR = 3, S_THRESH = 4, S_ITERS = 5, S_DONE = 6, S_STAGE = 8, S_COUNT = 16 };
+enum { S_PAP = 0, S_RZ0 = 1, S_RZ1 = 2, S_RR = 3, S_THRESH = 4, S_ITERS = 5, S_DONE = 6, S_STAGE = 8, S_ERR = 15, S_COUNT = 16 };
 
 // Publishes the two sums of an update step: rz_next, rr; bumps the iteration count and sets
 // the sticky DONE flag (all later launches of the captured graph then return immediately).
@@ -1200,6 +1200,120 @@ __global__ void pack_kernel(int64_t n, const int32_t* idx, int nc, const double*
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n * nc; k += (int64_t)gridDim.x * blockDim.x) {
         int64_t j = k / nc; int c = (int)(k - j * nc);
         buf[k] = v[(int64_t)idx[j] * nc + c];
+    }
+}
+
+// ============================================================================= NVLink peer path
+// One process per GPU; peers' buffers are mapped with CUDA IPC (pfx_comm_p2p_import).  Halo values
+// are PUSHED straight into the neighbours' ghost ranges with plain stores over NVLink and the CG
+// scalars are all-reduced through per-rank mailboxes — no NCCL call inside the PCG iteration.
+// Every rank runs the same launch sequence, so sequence counters advance in lock step; waits are
+// bounded (a timeout raises a flag instead of hanging the GPU).
+constexpr int kMaxRanks = 8;
+constexpr int kMboxStride = 16;              // doubles per (slot, rank): 8 payload + sequence word
+constexpr long long kSpinLimit = 20000000LL;   // ~10 s, then S[S_ERR] is raised instead of hanging
+
+struct PeerView {
+    int rank, n_ranks, n_nbrs;
+    int nbr_rank[kMaxRanks];
+    double* mbox_local;                      // [4][n_ranks][kMboxStride]
+    double* mbox_peer[kMaxRanks];            // mailbox base of every rank
+    unsigned long long* hflag_local;         // [n_ranks]: last halo sequence pushed by rank r
+    unsigned long long* hflag_peer[kMaxRanks];
+    unsigned long long* seq;                 // local counters: [0] all-reduce, [1] halo
+    double* err;                             // S[S_ERR]: set on spin timeout
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// values of the send list -> the neighbours' ghost ranges; the last block raises the halo flags
+__global__ void __launch_bounds__(kThreads) halo_push_kernel(int64_t n_send, const int32_t* idx, const uint8_t* nbr,
+                                                             const int64_t* dst, int nc, const double* v,
+                                                             double* const* peer_vec /*[n_nbrs]*/, PeerView pv,
+                                                             unsigned int* counter, const double* stop) {
+    if (stop && stop[0] != 0.0) return;
+    __shared__ bool is_last;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n_send * nc; k += (int64_t)gridDim.x * blockDim.x) {
+        int64_t j = k / nc;
+        int c = (int)(k - j * nc);
+        peer_vec[nbr[j]][dst[j] * nc + c] = v[(int64_t)idx[j] * nc + c];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicInc(counter, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last && threadIdx.x < pv.n_nbrs) {
+        __threadfence_system();
+        unsigned long long sq = pv.seq[1] + 1ull;
+        st_release_sys(pv.hflag_peer[pv.nbr_rank[threadIdx.x]] + pv.rank, sq);
+    }
+    if (is_last) {
+        __syncthreads();
+        if (threadIdx.x == 0) pv.seq[1] = pv.seq[1] + 1ull;
+    }
+}
+
+// blocks the stream until every neighbour's push of the current halo sequence has landed
+__global__ void halo_wait_kernel(PeerView pv, const double* stop) {
+    if (stop && stop[0] != 0.0) return;
+    if ((int)threadIdx.x < pv.n_nbrs) {
+        const unsigned long long want = pv.seq[1];
+        const unsigned long long* f = pv.hflag_local + pv.nbr_rank[threadIdx.x];
+        long long spins = 0;
+        while (ld_acquire_sys(f) < want) {
+            if (++spins > kSpinLimit) { *pv.err = 1.0; break; }
+        }
+    }
+}
+
+// all-reduce (sum) of n <= 8 staged doubles through the mailboxes, then the PCG bookkeeping:
+// mode 0: S[S_PAP] = sum0 ; mode 1: pcg_finalize(par, sum0, sum1) ; mode 2: stage[] = sums
+__global__ void p2p_allreduce_kernel(PeerView pv, double* S, double* stage, int n, int mode, int par) {
+    if (mode != 2 && S[S_DONE] != 0.0) return;
+    const int lane = threadIdx.x;
+    unsigned long long sq = 0;
+    if (lane == 0) { sq = pv.seq[0] + 1ull; pv.seq[0] = sq; }
+    sq = __shfl_sync(0xffffffffu, sq, 0);
+    const int slot = (int)(sq & 3ull);
+    if (lane < pv.n_ranks) {
+        double* dst = pv.mbox_peer[lane] + ((size_t)slot * pv.n_ranks + pv.rank) * kMboxStride;
+        for (int k = 0; k < n; ++k) dst[k] = stage[k];
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long*>(dst + 8), sq);
+    }
+    double vals[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) vals[k] = 0.0;
+    if (lane < pv.n_ranks) {
+        const double* src = pv.mbox_local + ((size_t)slot * pv.n_ranks + lane) * kMboxStride;
+        long long spins = 0;
+        while (ld_acquire_sys(reinterpret_cast<const unsigned long long*>(src + 8)) != sq) {
+            if (++spins > kSpinLimit) { *pv.err = 2.0; break; }
+        }
+        for (int k = 0; k < n; ++k) vals[k] = __ldcv(src + k);
+    }
+    // fixed-order sum over ranks (identical on every rank)
+    double sums[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        double t = 0.0;
+        for (int r = 0; r < pv.n_ranks; ++r) t += __shfl_sync(0xffffffffu, vals[k], r);
+        sums[k] = t;
+    }
+    if (lane == 0) {
+        if (mode == 0) S[S_PAP] = sums[0];
+        else if (mode == 1) pcg_finalize(S, par, sums[0], sums[1]);
+        else for (int k = 0; k < n; ++k) stage[k] = sums[k];
     }
 }
 
