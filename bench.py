@@ -283,9 +283,16 @@ def main_b200(args, rank, world, local_rank):
         ms_nf = e.time_operator(0, reps=13, flush_l2=False)[3:]
         ms_it = e.time_operator(4, reps=13, flush_l2=True)[3:] if world == 1 else None
         bytes_apply = e.algorithmic_bytes(0)
+        traffic = None
+        try:    # DRAM bytes of one launch from the committed `ncu --set full` capture of this kernel/workload
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_apply_u_traffic.json")))
+            if tj.get("workload") == w.name and world == 1:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
         ach = bytes_apply / (ms.mean() * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "apply_u_tri_kernel<spectral> (J_u·v, P1 triangles)", "achieved": ach, "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        roof = {"bound": "hbm", "kernel": "apply_u_tri_v3_kernel<spectral> (J_u·v on P1 triangles; persistent, TMA-staged)", "achieved": ach, "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": bytes_apply, "ms_per_launch": float(ms.mean()),
                 "ms_per_launch_l2_warm": float(ms_nf.mean()),
                 "note": "fp64 ALU work of the spectral split also bounds this kernel (see DESIGN.md)"}
