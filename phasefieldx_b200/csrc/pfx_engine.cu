@@ -114,8 +114,13 @@ struct pfx_ctx {
     int64_t flush_n = 0;
     std::vector<std::vector<int32_t>> tmp_idx;
     bool configuring = false;
+    bool verbose = false;         // PFX_VERBOSE=1: per-Newton-iteration trace on stderr
+    bool cg_adaptive = true;      // PFX_CG_ADAPTIVE=0: every PCG solve to cg_rtol of its own right-hand side
     double* tan = nullptr;        // cached element tangents (tets + nonlinear split)
+    double *cm = nullptr, *cg = nullptr;   // phi-operator nodal coefficients (triangles, v3 path)
+    int phi_v3_ctas = 0;
     bool use_tan = false;
+    bool phi_coeff_fresh = false;
     bool generic_apply = false;   // PFX_GENERIC_APPLY=1: use the generic scatter kernel for J_u·v on triangles
     int apply_variant = 3;        // PFX_APPLY_VARIANT: 3 persistent + prefetched indices (default), 2 persistent, 1 one CTA per block
     int persist_ctas = 0, v3_ctas = 0, num_sms = 148;
@@ -225,8 +230,33 @@ int launch_apply_u_tri_v3(pfx_ctx* c, const KArgs& a) {
     return PFX_OK;
 }
 
+int launch_apply_phi_tri_v3(pfx_ctx* c, const KArgs& a) {
+    BlockView bv = c->bv;
+    bv.chunk = 2 * kThreads;
+    size_t ML = (size_t)c->bm.max_loc, MO = ((size_t)c->bm.max_own + 1) & ~(size_t)1;
+    size_t stage = ML * 16 + 3 * (((ML + 3) & ~(size_t)1) * 8) + MO * 16;
+    size_t smem = 2 * stage + (3 * (size_t)bv.chunk + 2) * sizeof(double);
+    if (c->configuring) {
+        CK(cudaFuncSetAttribute(apply_phi_tri_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apply_phi_tri_v3_kernel, kThreads, smem));
+        c->phi_v3_ctas = std::max(1, nb) * c->num_sms;
+        return PFX_OK;
+    }
+    int grid = std::min(c->bm.nb, c->phi_v3_ctas);
+    apply_phi_tri_v3_kernel<<<grid, kThreads, smem, c->stream>>>(bv, a);
+    c->launches++;
+    CK(cudaGetLastError());
+    return PFX_OK;
+}
+
 template <class Cell>
 int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
+    if (op == OP_APPLY_PHI && std::is_same<Cell, Tri>::value && c->cm) {
+        if (c->configuring) { int st = launch_apply_phi_tri_v3(c, a); if (st) return st; }
+        else if (c->apply_variant == 3 && c->bm.max_elems <= 2 * kThreads && a.input_masked && c->phi_coeff_fresh)
+            return launch_apply_phi_tri_v3(c, a);
+    }
     switch (op) {
         case OP_APPLY_U:
             if (std::is_same<Cell, Tri>::value && c->configuring) {      // opt every triangle variant in
@@ -315,6 +345,7 @@ KArgs base_args(pfx_ctx* c) {
     a.X = c->X; a.u = c->u; a.phi = c->phi; a.H = c->H; a.Fat = c->Fat;
     a.partial = c->partial; a.result = c->red; a.counter = c->counter;
     a.tan = c->tan; a.tan_stride = c->bm.total_elems;
+    a.cm = c->cm; a.cg = c->cg;
     return a;
 }
 
@@ -423,10 +454,20 @@ int rebuild_fext(pfx_ctx* c) {
 }
 
 // --------------------------------------------------------------------------- PCG
-__global__ void pcg_setup_kernel(double* S, double rtol2) {
+// bref_slot >= 0: the stop threshold is floored at rtol^2 * (largest ||b||^2 this operator has seen in
+// the current load step), so later Newton / stagger iterations, whose right-hand sides are orders of
+// magnitude smaller, are solved to the same ABSOLUTE accuracy as the first solve instead of to 11
+// digits of their own tiny residual (the reference's MUMPS solves are exact; what parity needs is the
+// absolute error of u, phi).
+__global__ void pcg_setup_kernel(double* S, double rtol2, int bref_slot) {
     double rz = S[S_STAGE], rr = S[S_STAGE + 1];
     S[S_RZ0] = rz; S[S_RZ1] = 0.0; S[S_RR] = rr; S[S_PAP] = 1.0;
-    S[S_THRESH] = rtol2 * rr;
+    double ref = rr;
+    if (bref_slot >= 0) {
+        ref = fmax(S[bref_slot], rr);
+        S[bref_slot] = ref;
+    }
+    S[S_THRESH] = rtol2 * ref;
     S[S_ITERS] = 0.0;
     S[S_DONE] = (rr > 0.0 && rr > S[S_THRESH]) ? 0.0 : 1.0;
 }
@@ -503,7 +544,7 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
     c->launches++;
     int st = allreduce(c, c->S + S_STAGE, 2);
     if (st) return st;
-    pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, rtol * rtol);
+    pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, rtol * rtol, (c->cg_adaptive && kind != LIN_MASS) ? S_BREF + kind : -1);
     c->launches++;
     CK(cudaGetLastError());
     int64_t max_it = c->prm.cg_max_it;
@@ -553,6 +594,13 @@ int newton(pfx_ctx* c, bool is_u, NewtonOut* out) {
     const int gr = vgrid(c, n);
     double ttol = 0, snorm = 0, xnorm = 0, vals[4];
     int st;
+    c->phi_coeff_fresh = false;
+    if (!is_u && c->cm) {               // H and the fatigue field are fixed during the phi solve
+        int64_t nall = c->n_nodes;
+        phi_coeff_kernel<<<vgrid(c, nall), kThreads, 0, c->stream>>>(nall, c->mat, c->H, c->Fat, c->cm, c->cg);
+        c->launches++;
+        c->phi_coeff_fresh = true;
+    }
     for (int it = 0;; ++it) {
         // residual with lifting (dolfinx assemble_residual idiom)
         KArgs a = base_args(c);
@@ -603,6 +651,9 @@ int newton(pfx_ctx* c, bool is_u, NewtonOut* out) {
         st = pcg_solve(c, kind, c->prm.cg_rtol, &cg, &conv);
         if (st) return st;
         out->cg_its += cg;
+        if (c->verbose)
+            fprintf(stderr, "[pfx] %s newton it %d: |F| %.3e  pcg its %lld  |r|/|b| %.2e\n", is_u ? "u  " : "phi", it, fnorm,
+                    (long long)cg, std::sqrt(c->h_pinned[S_RR]) / std::max(fnorm, 1e-300));
         if (!conv) { out->reason = -3; return PFX_OK; }      // linear solve failed (KSP analogue)
         newton_update_kernel<<<gr, kThreads, 0, c->stream>>>(n, x, c->w_x, c->w_F, mask, c->partial, c->red, c->counter);
         c->launches++;
@@ -774,6 +825,10 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     c->use_graph = !(ng && ng[0] == '1');
     const char* ga = getenv("PFX_GENERIC_APPLY");
     c->generic_apply = (ga && ga[0] == '1');
+    const char* vb = getenv("PFX_VERBOSE");
+    c->verbose = (vb && vb[0] == '1');
+    const char* ca = getenv("PFX_CG_ADAPTIVE");
+    if (ca) c->cg_adaptive = (ca[0] != '0');
     const char* av = getenv("PFX_APPLY_VARIANT");
     if (av) c->apply_variant = atoi(av);
 
@@ -855,6 +910,10 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     if (c->cell_type == PFX_CELL_TETRAHEDRON && c->mat.smodel != M_ISO && !getenv("PFX_NO_TANGENT_CACHE")) {
         if ((st = dev_alloc(c, &c->tan, (size_t)21 * (size_t)bm.total_elems))) return st;
         c->use_tan = true;
+    }
+    if (c->cell_type == PFX_CELL_TRIANGLE) {
+        if ((st = dev_alloc(c, &c->cm, (size_t)N + 2))) return st;
+        if ((st = dev_alloc(c, &c->cg, (size_t)N + 2))) return st;
     }
     // ---- opt every kernel instantiation of this mesh/model in to its shared-memory size
     {
@@ -962,6 +1021,7 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
     double err_phi = 1.0, err_u = 1.0;
     int it = 0, st;
     CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemsetAsync(c->S + S_BREF, 0, 3 * sizeof(double), c->stream));      // per-step PCG reference norms
     const int gN = vgrid(c, N);
     while ((err_phi > o->stagger_tol || err_u > o->stagger_tol || it < o->min_stagger_iter) && it < o->max_stagger_iter) {
         ++it;
@@ -1191,7 +1251,7 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
         pcg_init_kernel<<<vgrid(c, n), kThreads, 0, c->stream>>>(n, c->w_F, c->mask_u, c->w_dinv, nullptr, nullptr, c->w_x, c->w_r,
                                                                c->w_p, c->partial, c->S + S_STAGE, c->counter);
         if ((st = allreduce(c, c->S + S_STAGE, 2))) return st;
-        pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, 0.0);
+        pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, 0.0, -1);
         CK(cudaStreamSynchronize(c->stream));
     }
     for (int r = 0; r < reps; ++r) {

@@ -57,6 +57,8 @@ struct KArgs {
     unsigned int* counter;
     const double* stop;     // optional sticky DONE flag of the running PCG: skip the launch when set
     int input_masked;       // caller guarantees v == 0 on Dirichlet dofs (PCG directions)
+    const double* cm;       // precomputed phi-operator coefficients 2H + F·Gc/l and F·Gc·l (per node)
+    const double* cg;
     double* tan;            // cached element tangents, SoA [21][tan_stride] (tets, nonlinear split)
     int64_t tan_stride;
     int nred;
@@ -797,7 +799,8 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
     const double2* X2 = reinterpret_cast<const double2*>(a.X);
     const double2* V2 = reinterpret_cast<const double2*>(a.v);
     const double2* U2 = reinterpret_cast<const double2*>(a.u);
-    const uchar2* M2 = reinterpret_cast<const uchar2*>(a.mask);
+    const unsigned short* M2 = reinterpret_cast<const unsigned short*>(a.mask);   // 2 flags per node, kept raw
+    const uint2* LC = reinterpret_cast<const uint2*>(bv.lconn);                  // 4 x u16 per cell, kept raw
     if (tid == 0) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -841,10 +844,10 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
     bool has_next = blk + stride < nb;
     if (has_next) { na = bv.meta[2 * (blk + stride)]; nbm = bv.meta[2 * (blk + stride) + 1]; }
     issue(ma, mb, 0, tid < ma.w ? bv.halo[ma.z + tid] : 0);
-    ushort4 lc0 = make_ushort4(0, 0, 0, 0), lc1 = lc0;
-    if (tid < mb.y) lc0 = bv.lconn[mb.x + tid];
-    if (tid + kThreads < mb.y) lc1 = bv.lconn[mb.x + tid + kThreads];
-    uchar2 mk = make_uchar2(0, 0);
+    uint2 lc0 = make_uint2(0u, 0u), lc1 = lc0;
+    if (tid < mb.y) lc0 = LC[mb.x + tid];
+    if (tid + kThreads < mb.y) lc1 = LC[mb.x + tid + kThreads];
+    unsigned int mk = 0u;
     if (M2 && tid < ma.y) mk = M2[ma.x + tid];
     int hnext = (has_next && tid < na.w) ? bv.halo[na.z + tid] : 0;
     double red = 0.0;
@@ -874,24 +877,26 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
         const double2 z = make_double2(0.0, 0.0);
         if (tid < ne) {
             double2 f0, f1, f2;
-            tri_apply_elem<SM>(a.m, sX[lc0.x], sX[lc0.y], sX[lc0.z], sP[lc0.x], sP[lc0.y], sP[lc0.z], sV[lc0.x], sV[lc0.y],
-                               sV[lc0.z], NL ? sU[lc0.x] : z, NL ? sU[lc0.y] : z, NL ? sU[lc0.z] : z, f0, f1, f2);
+            const int vx = lc0.x & 0xFFFF, vy = lc0.x >> 16, vz = lc0.y & 0xFFFF;
+            tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
+                               sV[vz], NL ? sU[vx] : z, NL ? sU[vy] : z, NL ? sU[vz] : z, f0, f1, f2);
             sE[tid] = f0; sE[chunk + tid] = f1; sE[2 * chunk + tid] = f2;
         }
         if (tid + kThreads < ne) {
             double2 f0, f1, f2;
-            tri_apply_elem<SM>(a.m, sX[lc1.x], sX[lc1.y], sX[lc1.z], sP[lc1.x], sP[lc1.y], sP[lc1.z], sV[lc1.x], sV[lc1.y],
-                               sV[lc1.z], NL ? sU[lc1.x] : z, NL ? sU[lc1.y] : z, NL ? sU[lc1.z] : z, f0, f1, f2);
+            const int vx = lc1.x & 0xFFFF, vy = lc1.x >> 16, vz = lc1.y & 0xFFFF;
+            tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
+                               sV[vz], NL ? sU[vx] : z, NL ? sU[vy] : z, NL ? sU[vz] : z, f0, f1, f2);
             sE[tid + kThreads] = f0; sE[chunk + tid + kThreads] = f1; sE[2 * chunk + tid + kThreads] = f2;
         }
         __syncthreads();
         // ---- per-thread indices of the NEXT block (consumed one iteration later)
-        ushort4 lc0n = make_ushort4(0, 0, 0, 0), lc1n = lc0n;
-        uchar2 mkn = make_uchar2(0, 0);
+        uint2 lc0n = make_uint2(0u, 0u), lc1n = lc0n;
+        unsigned int mkn = 0u;
         int hnn = 0;
         if (has_next) {
-            if (tid < nbm.y) lc0n = bv.lconn[nbm.x + tid];
-            if (tid + kThreads < nbm.y) lc1n = bv.lconn[nbm.x + tid + kThreads];
+            if (tid < nbm.y) lc0n = LC[nbm.x + tid];
+            if (tid + kThreads < nbm.y) lc1n = LC[nbm.x + tid + kThreads];
             if (M2 && tid < na.y) mkn = M2[na.x + tid];
             if (has_nn && tid < fa.w) hnn = bv.halo[fa.z + tid];
         }
@@ -916,14 +921,186 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
                     acc.x += f.x; acc.y += f.y;
                 }
             }
-            if (mk.x) acc.x = 0.0;
-            if (mk.y) acc.y = 0.0;
+            if (mk & 0xFFu) acc.x = 0.0;
+            if (mk & 0xFF00u) acc.y = 0.0;
             const double2 vin = sV[tid];
             reinterpret_cast<double2*>(a.y)[n0 + tid] = acc;
             red += vin.x * acc.x + vin.y * acc.y;
         }
         if (!has_next) break;
         __syncthreads();                         // stage s and sE are free again
+        blk += stride;
+        ma = na; mb = nbm; na = fa; nbm = fb;
+        lc0 = lc0n; lc1 = lc1n; mk = mkn; hnext = hnn;
+        has_next = has_nn;
+    }
+    double r1[1] = {red};
+    grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red);
+}
+
+// ============================================================================= phi-apply, v3 pipeline
+// J_phi·p on P1 triangles with the same persistent / TMA double-buffered / prefetched structure as
+// apply_u_tri_v3_kernel; staged fields: X (double2), cm, cg, p (doubles; cm = 2H + F·Gc/l and
+// cg = F·Gc·l are refreshed once per phi-solve by phi_coeff_kernel).  Same input/output contract.
+__global__ void phi_coeff_kernel(int64_t n, Material m, const double* H, const double* Fat, double* cm, double* cg) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double F = m.fatigue ? Fat[i] : 1.0;
+        cm[i] = 2.0 * H[i] + F * m.Gc / m.l;
+        cg[i] = F * m.Gc * m.l;
+    }
+}
+
+__device__ __forceinline__ void tri_apply_phi_elem(double2 x0, double2 x1, double2 x2, double m0, double m1, double m2,
+                                                   double c0, double c1, double c2, double p0, double p1, double p2,
+                                                   double& f0, double& f1, double& f2) {
+    const double ax = x1.x - x0.x, ay = x1.y - x0.y, bx = x2.x - x0.x, by = x2.y - x0.y;
+    const double det = ax * by - ay * bx, inv = __drcp_rn(det);
+    const double g1x = by * inv, g1y = -bx * inv, g2x = -ay * inv, g2y = ax * inv;
+    const double g0x = -(g1x + g2x), g0y = -(g1y + g2y);
+    const double vol = 0.5 * fabs(det);
+    const double C = m0 + m1 + m2, P = p0 + p1 + p2, Q = m0 * p0 + m1 * p1 + m2 * p2;
+    const double cgm = vol * (c0 + c1 + c2) * (1.0 / 3.0);
+    const double gpx = g0x * p0 + g1x * p1 + g2x * p2, gpy = g0y * p0 + g1y * p1 + g2y * p2;
+    const double vb = vol * (1.0 / 60.0), cpq = C * P + Q;
+    f0 = vb * (cpq + C * p0 + m0 * P + 2.0 * m0 * p0) + cgm * (g0x * gpx + g0y * gpy);
+    f1 = vb * (cpq + C * p1 + m1 * P + 2.0 * m1 * p1) + cgm * (g1x * gpx + g1y * gpy);
+    f2 = vb * (cpq + C * p2 + m2 * P + 2.0 * m2 * p2) + cgm * (g2x * gpx + g2y * gpy);
+}
+
+__global__ void __launch_bounds__(kThreads, 4) apply_phi_tri_v3_kernel(BlockView bv, KArgs a) {
+    extern __shared__ double smem[];
+    __shared__ double s_red[kMaxRed * 32];
+    __shared__ uint64_t s_bar[2];
+    if (a.stop && a.stop[0] != 0.0) return;
+    const int tid = threadIdx.x;
+    const int ML = bv.max_loc, chunk = bv.chunk, MO = (bv.max_own + 1) & ~1;
+    const size_t sc = (size_t)((ML + 3) & ~1) * 8;                       // bytes of one scalar array
+    const size_t oM = (size_t)ML * 16, oG = oM + sc, oP = oG + sc, oI = oP + sc;
+    const size_t stage_bytes = oI + (size_t)MO * 16;
+    char* const sbase = reinterpret_cast<char*>(smem);
+    double* sE = reinterpret_cast<double*>(sbase + 2 * stage_bytes);     // [3*chunk + 2], slot 3*chunk = zero
+    const int zslot = 3 * chunk;
+    const double2* X2 = reinterpret_cast<const double2*>(a.X);
+    const uint2* LC = reinterpret_cast<const uint2*>(bv.lconn);
+    if (tid == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sE[zslot] = 0.0;
+    }
+    __syncthreads();
+
+    auto issue = [&](int4 ma, int s_, int hidx) {
+        char* p = sbase + (size_t)s_ * stage_bytes;
+        double2* tX = reinterpret_cast<double2*>(p);
+        double *tM = reinterpret_cast<double*>(p + oM), *tG = reinterpret_cast<double*>(p + oG), *tP = reinterpret_cast<double*>(p + oP);
+        const int n0 = ma.x, n_own = ma.y, h0 = ma.z, n_halo = ma.w;
+        if (tid == 0) {
+            fence_proxy_async();
+            const uint32_t nev = (uint32_t)(n_own & ~1);
+            mbar_expect_tx(&s_bar[s_], (uint32_t)n_own * 32u + 3u * nev * 8u);
+            bulk_g2s(tX, X2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
+            if (nev) {
+                bulk_g2s(tM, a.cm + n0, nev * 8u, &s_bar[s_]);
+                bulk_g2s(tG, a.cg + n0, nev * 8u, &s_bar[s_]);
+                bulk_g2s(tP, a.v + n0, nev * 8u, &s_bar[s_]);
+            }
+            bulk_g2s(p + oI, bv.inc8 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
+            if (n_own & 1) {
+                const int t = n_own - 1;
+                cp_async8(tM + t, a.cm + n0 + t); cp_async8(tG + t, a.cg + n0 + t); cp_async8(tP + t, a.v + n0 + t);
+            }
+        }
+        for (int i = tid; i < n_halo; i += kThreads) {
+            int g = (i == tid) ? hidx : bv.halo[h0 + i];
+            cp_async16(tX + n_own + i, X2 + g);
+            cp_async8(tM + n_own + i, a.cm + g);
+            cp_async8(tG + n_own + i, a.cg + g);
+            cp_async8(tP + n_own + i, a.v + g);
+        }
+        cp_async_commit();
+    };
+
+    const int stride = gridDim.x, nb = bv.nb;
+    int blk = blockIdx.x;
+    int4 ma = bv.meta[2 * blk], mb = bv.meta[2 * blk + 1];
+    int4 na = ma, nbm = mb;
+    bool has_next = blk + stride < nb;
+    if (has_next) { na = bv.meta[2 * (blk + stride)]; nbm = bv.meta[2 * (blk + stride) + 1]; }
+    issue(ma, 0, tid < ma.w ? bv.halo[ma.z + tid] : 0);
+    uint2 lc0 = make_uint2(0u, 0u), lc1 = lc0;
+    if (tid < mb.y) lc0 = LC[mb.x + tid];
+    if (tid + kThreads < mb.y) lc1 = LC[mb.x + tid + kThreads];
+    unsigned int mk = 0u;
+    if (a.mask && tid < ma.y) mk = a.mask[ma.x + tid];
+    int hnext = (has_next && tid < na.w) ? bv.halo[na.z + tid] : 0;
+    double red = 0.0;
+    uint32_t phases = 0u;
+    for (int it = 0;; ++it) {
+        const int s = it & 1;
+        const int n0 = ma.x, n_own = ma.y, ne = mb.y;
+        int4 fa = na, fb = nbm;
+        const bool has_nn = blk + 2 * stride < nb;
+        if (has_next) {
+            issue(na, s ^ 1, hnext);
+            if (has_nn) { fa = bv.meta[2 * (blk + 2 * stride)]; fb = bv.meta[2 * (blk + 2 * stride) + 1]; }
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        mbar_wait(&s_bar[s], (phases >> s) & 1u);
+        phases ^= (1u << s);
+        __syncthreads();
+        const char* p = sbase + (size_t)s * stage_bytes;
+        const double2* sX = reinterpret_cast<const double2*>(p);
+        const double *sM = reinterpret_cast<const double*>(p + oM), *sG = reinterpret_cast<const double*>(p + oG),
+                     *sP = reinterpret_cast<const double*>(p + oP);
+        const uint4* s_inc8 = reinterpret_cast<const uint4*>(p + oI);
+        if (tid < ne) {
+            const int vx = lc0.x & 0xFFFF, vy = lc0.x >> 16, vz = lc0.y & 0xFFFF;
+            double f0, f1, f2;
+            tri_apply_phi_elem(sX[vx], sX[vy], sX[vz], sM[vx], sM[vy], sM[vz], sG[vx], sG[vy], sG[vz], sP[vx], sP[vy], sP[vz], f0, f1, f2);
+            sE[tid] = f0; sE[chunk + tid] = f1; sE[2 * chunk + tid] = f2;
+        }
+        if (tid + kThreads < ne) {
+            const int vx = lc1.x & 0xFFFF, vy = lc1.x >> 16, vz = lc1.y & 0xFFFF;
+            double f0, f1, f2;
+            tri_apply_phi_elem(sX[vx], sX[vy], sX[vz], sM[vx], sM[vy], sM[vz], sG[vx], sG[vy], sG[vz], sP[vx], sP[vy], sP[vz], f0, f1, f2);
+            sE[tid + kThreads] = f0; sE[chunk + tid + kThreads] = f1; sE[2 * chunk + tid + kThreads] = f2;
+        }
+        __syncthreads();
+        uint2 lc0n = make_uint2(0u, 0u), lc1n = lc0n;
+        unsigned int mkn = 0u;
+        int hnn = 0;
+        if (has_next) {
+            if (tid < nbm.y) lc0n = LC[nbm.x + tid];
+            if (tid + kThreads < nbm.y) lc1n = LC[nbm.x + tid + kThreads];
+            if (a.mask && tid < na.y) mkn = a.mask[na.x + tid];
+            if (has_nn && tid < fa.w) hnn = bv.halo[fa.z + tid];
+        }
+        if (tid < n_own) {
+            const uint4 c8 = s_inc8[tid];
+            const unsigned cw[4] = {c8.x, c8.y, c8.z, c8.w};
+            double acc = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int code = (int)((cw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
+                acc += sE[min((code & 3) * chunk + (code >> 2), zslot)];
+            }
+            if ((c8.w >> 16) == 0xFFFEu) {
+                int k0 = bv.inc_ptr[n0 + tid] + 7, k1 = bv.inc_ptr[n0 + tid + 1];
+                for (int k = k0; k < k1; ++k) {
+                    const int code = bv.inc[k];
+                    if (code >= 0xFFFE) break;
+                    acc += sE[(code & 3) * chunk + (code >> 2)];
+                }
+            }
+            if (mk) acc = 0.0;
+            a.y[n0 + tid] = acc;
+            red += sP[tid] * acc;
+        }
+        if (!has_next) break;
+        __syncthreads();
         blk += stride;
         ma = na; mb = nbm; na = fa; nbm = fb;
         lc0 = lc0n; lc1 = lc1n; mk = mkn; hnext = hnn;
@@ -991,7 +1168,7 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(BlockView bv, KArgs a)
 
 // ============================================================================= vector kernels
 // PCG state scalars (device resident).  Indices into the scalar array S.
-enum { S_PAP = 0, S_RZ0 = 1, S_RZ1 = 2, S_RR = 3, S_THRESH = 4, S_ITERS = 5, S_DONE = 6, S_STAGE = 8, S_ERR = 15, S_COUNT = 16 };
+enum { S_PAP = 0, S_RZ0 = 1, S_RZ1 = 2, S_RR = 3, S_THRESH = 4, S_ITERS = 5, S_DONE = 6, S_STAGE = 8, S_BREF = 10 /* ..12: largest ||b||^2 of this load step per operator */, S_ERR = 15, S_COUNT = 16 };
 
 // Publishes the two sums of an update step: rz_next, rr; bumps the iteration count and sets
 // the sticky DONE flag (all later launches of the captured graph then return immediately).
@@ -1014,9 +1191,24 @@ __global__ void __launch_bounds__(kThreads) pcg_update_kernel(int64_t n, double*
     if (S[S_DONE] != 0.0) return;
     const double alpha = S[S_RZ0 + par] / S[S_PAP];
     double vals[2] = {0.0, 0.0};
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        double pi = p[i], ri = r[i] - alpha * Ap[i];
-        x[i] += alpha * pi;
+    const int64_t n2 = n >> 1, gs = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double2* x2 = reinterpret_cast<double2*>(x);
+    double2* r2 = reinterpret_cast<double2*>(r);
+    const double2 *p2 = reinterpret_cast<const double2*>(p), *A2 = reinterpret_cast<const double2*>(Ap),
+                  *d2 = reinterpret_cast<const double2*>(dinv);
+    for (int64_t i = i0; i < n2; i += gs) {                  // 128-bit streams
+        const double2 pv = p2[i], av = A2[i], dv = d2[i];
+        double2 rv = r2[i], xv = x2[i];
+        rv.x -= alpha * av.x; rv.y -= alpha * av.y;
+        xv.x += alpha * pv.x; xv.y += alpha * pv.y;
+        x2[i] = xv; r2[i] = rv;
+        vals[0] += rv.x * dv.x * rv.x + rv.y * dv.y * rv.y;
+        vals[1] += rv.x * rv.x + rv.y * rv.y;
+    }
+    if ((n & 1) && i0 == 0) {                                // odd tail
+        const int64_t i = n - 1;
+        double ri = r[i] - alpha * Ap[i];
+        x[i] += alpha * p[i];
         r[i] = ri;
         vals[0] += ri * dinv[i] * ri;
         vals[1] += ri * ri;
@@ -1056,8 +1248,16 @@ __global__ void __launch_bounds__(kThreads) pcg_direction_kernel(int64_t n, doub
                                                                  const double* __restrict__ dinv, const double* S, int par) {
     if (S[S_DONE] != 0.0) return;
     const double beta = S[S_RZ0 + (par ^ 1)] / S[S_RZ0 + par];
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        p[i] = dinv[i] * r[i] + beta * p[i];
+    const int64_t n2 = n >> 1, gs = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double2* p2 = reinterpret_cast<double2*>(p);
+    const double2 *r2 = reinterpret_cast<const double2*>(r), *d2 = reinterpret_cast<const double2*>(dinv);
+    for (int64_t i = i0; i < n2; i += gs) {
+        const double2 rv = r2[i], dv = d2[i];
+        double2 pv = p2[i];
+        pv.x = dv.x * rv.x + beta * pv.x; pv.y = dv.y * rv.y + beta * pv.y;
+        p2[i] = pv;
+    }
+    if ((n & 1) && i0 == 0) p[n - 1] = dinv[n - 1] * r[n - 1] + beta * p[n - 1];
 }
 
 // generic fused vector helpers -------------------------------------------------------------
