@@ -239,7 +239,15 @@ class Oracle:
                 return x, it, 4, hist
         return x, max_it, -5, hist
 
-    def solve_u(self, bcs_u):
+    def traction_vector(self, nodes, weights, T):
+        """Load vector of reference solver.py:179-184 (∫ T·δu ds) for pre-integrated nodal weights
+        w_i = ∫ N_i ds of the tagged boundary."""
+        f = np.zeros(self.nn * self.d)
+        for c in range(self.d):
+            np.add.at(f, np.asarray(nodes) * self.d + c, np.asarray(weights) * T[c])
+        return f
+
+    def solve_u(self, bcs_u, fext=None):
         mask, g = _bc_vectors(self.nn * self.d, bcs_u)
         cache = {}
 
@@ -248,7 +256,10 @@ class Oracle:
             if cache.get("k") != key:
                 cache["k"], cache["s"] = key, self.split(x, True)
             return cache["s"]
-        res = lambda x: self.F_int_u(x, self.phi, split_at(x))
+        if fext is None:
+            res = lambda x: self.F_int_u(x, self.phi, split_at(x))
+        else:
+            res = lambda x: self.F_int_u(x, self.phi, split_at(x)) - fext       # F_u -= L  (solver.py:184)
         jac = lambda x: self.J_u(x, self.phi, split_at(x))
         self.u, its, reason, hist = self._snes(res, jac, self.u, mask, g)
         return its, reason, hist
@@ -261,7 +272,7 @@ class Oracle:
         return its, reason, hist
 
     # ------------------------------------------------------------------ one load step (solver.py:319-411)
-    def load_step(self, bcs_u, bcs_phi, dt=1.0, min_stagger_iter=2, max_stagger_iter=10000, tol=1e-8):
+    def load_step(self, bcs_u, bcs_phi, dt=1.0, min_stagger_iter=2, max_stagger_iter=10000, tol=1e-8, fext=None):
         p = self.p
         err_phi = err_u = 1.0
         it = 0
@@ -269,7 +280,7 @@ class Oracle:
         u_its = phi_its = 0
         while (err_phi > tol or err_u > tol or it < min_stagger_iter) and it < max_stagger_iter:
             it += 1
-            u_its, reason, hist_u = self.solve_u(bcs_u)
+            u_its, reason, hist_u = self.solve_u(bcs_u, fext)
             err_u = self.l2_error_normalized(self.u, self.u_old, True)
             if reason <= 0:
                 raise RuntimeError(f"Solver did not converge, got {reason}.")

@@ -226,3 +226,37 @@ def test_non_convergence_raises_reference_error():
     with pytest.raises(RuntimeError, match="Solver did not converge, got -3."):
         e.load_step()
     e.close()
+
+
+def test_traction_loading_and_phi_dirichlet_vs_oracle():
+    """Neumann data (T_list_u, reference solver.py:179-184) and a phase-field Dirichlet set
+    (bc_list_phi, seeding a crack as the energy-controlled examples do) against the oracle."""
+    from phasefieldx_b200 import mesh as M, fem
+    from oracle.solver import BC
+    msh = M.create_rectangle(None, [[0, 0], [1.0, 1.0]], [14, 14])
+    o, e, P = _pair(msh, "triangle", "anisotropic", "spectral", l=0.1, Gc=0.0027)
+    x = msh.geometry.x
+    bot = np.nonzero(np.isclose(x[:, 1], 0.0))[0]
+    seed = np.nonzero(np.isclose(x[:, 1], 0.5) & (x[:, 0] < 0.3))[0]
+    top_facets = M.locate_entities_boundary(msh, 1, lambda p: np.isclose(p[1], 1.0))
+    nodes, w = fem.Measure(msh, top_facets).nodal_weights()
+    bcs_u = [BC((bot[:, None] * 2 + np.arange(2)).ravel())]
+    bcs_phi = [BC(seed, np.ones(len(seed)))]
+    e.set_bc_u(0, bcs_u[0].dofs)
+    e.set_bc_values_u(0, bcs_u[0].values)
+    e.set_bc_phi(0, seed)
+    e.set_bc_values_phi(0, bcs_phi[0].values)
+    e.set_traction(0, nodes, w)
+    for step in range(1, 4):
+        T = np.array([0.02 * step, 0.05 * step])
+        e.set_traction_value(0, T)
+        fext = o.traction_vector(nodes, w, T)
+        ro = o.load_step(bcs_u, bcs_phi, max_stagger_iter=80, fext=fext)
+        rg = e.load_step(max_stagger_iter=80)
+        assert rg["stagger"] == ro["stagger"], (step, rg["stagger"], ro["stagger"])
+        _compare_step(o, e, bcs_u, step)
+        assert np.allclose(e.get_field("phi")[seed], 1.0)
+    # total reaction balances the applied traction
+    R = e.reaction(0)
+    assert np.allclose(R[:2], -T * 1.0, rtol=1e-6, atol=1e-10)
+    e.close()

@@ -81,3 +81,50 @@ def test_phase_field_simulation(tmp_path, split_energy_i):
     assert len(S.paraview_filenames) == 201 and "phasefieldx.pvd" in S.paraview_filenames
     assert os.path.exists(os.path.join(Data.results_folder_name, "simulation.log"))
     shutil.rmtree(Data.results_folder_name)
+
+
+def test_config1_through_solve_matches_stored_reference_files(tmp_path, c1_mesh):
+    """Config 1 driven exactly like reference examples/PhaseFieldFracture/plot_1711.py:189-320
+    (bottom bc_xy = 0, top bc_y = 1e-4 t, stagger 2/500/1e-8): the result FILES written by the
+    drop-in solve() reproduce the reference's stored bottom.reaction / total.energy /
+    phasefieldx.conv rows (first load steps; tolerances = oracle-vs-stored agreement)."""
+    import phasefieldx_b200.compat as compat
+    compat.install()
+    import dolfinx
+    from phasefieldx.Element.Phase_Field_Fracture.Input import Input
+    from phasefieldx.Element.Phase_Field_Fracture.solver.solver import solve
+    from phasefieldx.Boundary.boundary_conditions import bc_xy, bc_y
+    from phasefieldx.PostProcessing.ReferenceResult import AllResults
+    from conftest import GOLDEN
+    msh, _, _ = c1_mesh
+    Data = Input(E=210.0, nu=0.3, Gc=0.0027, l=0.015, degradation="isotropic", split_energy="no",
+                 degradation_function="quadratic", irreversibility="miehe", fatigue=False, k=0.0,
+                 save_solution_xdmf=False, save_solution_vtu=True, results_folder_name=str(tmp_path / "1711"))
+    fdim = msh.topology.dim - 1
+    bottom = dolfinx.mesh.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[1], -0.5))
+    top = dolfinx.mesh.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[1], 0.5))
+    V_u = dolfinx.fem.functionspace(msh, ("Lagrange", 1, (msh.geometry.dim,)))
+    V_phi = dolfinx.fem.functionspace(msh, ("Lagrange", 1))
+    bcs = [bc_y(top, V_u, fdim), bc_xy(bottom, V_u, fdim)]
+
+    def update_boundary_conditions(bcs_, time):
+        val = 1e-4 * time if time <= 50 else 5e-3 + 1e-5 * (time - 50)
+        bcs_[0].g.value[...] = val
+        return 0, val, 0
+    solve(Data, msh, 5.0, V_u, V_phi, bcs, [], update_boundary_conditions, None, None, None, None, 1.0,
+          path=str(tmp_path), bcs_list_u_names=["top", "bottom"], min_stagger_iter=2, max_stagger_iter=500,
+          stagger_error_tol=1e-8, vtu_every=4)
+    S = AllResults(Data.results_folder_name)
+    ref = np.load(os.path.join(GOLDEN, "ref_1711.npz"))
+    Ry = S.reaction_files["bottom.reaction"]["Ry"].to_numpy()
+    np.testing.assert_allclose(Ry[1:5], ref["bottom_reaction"][1:5, 2], rtol=2e-9)
+    np.testing.assert_allclose(S.reaction_files["top.reaction"]["Ry"].to_numpy()[1:5], -ref["bottom_reaction"][1:5, 2], rtol=2e-9)
+    en = S.energy_files["total.energy"]
+    np.testing.assert_allclose(en["PSI_a"].to_numpy()[1:5], ref["energy"][1:5, 9], rtol=1e-11)
+    np.testing.assert_allclose(en["E"].to_numpy()[1:5], ref["energy"][1:5, 2], rtol=1e-7)
+    np.testing.assert_allclose(en["gamma_phi"].to_numpy()[1:5], ref["energy"][1:5, 7], rtol=1e-5)   # reference KSP noise (H1)
+    conv = S.convergence_files["phasefieldx.conv"]
+    assert conv["stagger"].tolist() == ref["conv"][:5, 1].astype(int).tolist()
+    assert conv["iterU"].tolist() == [0] * 5 and conv["iterPhi"].tolist() == [0] * 5
+    assert S.dof_files["top.dof"]["Uy"].tolist()[:3] == [0.0, 0.0001, 0.0002]
+    assert sorted(f for f in S.paraview_filenames if f.endswith(".vtu")) == ["phasefieldx_p0_000000.vtu", "phasefieldx_p0_000004.vtu"]
