@@ -102,6 +102,8 @@ struct pfx_ctx {
     PeerView pv;
     double* mbox = nullptr;           // mailboxes + halo flags + counters (IPC-exported)
     uint8_t* d_send_nbr = nullptr;
+    PeerView* d_pv = nullptr;          // device copy of pv (fused waits / mailbox pushes inside the big kernels)
+    bool p2p_fused = true;             // PFX_P2P_FUSED=0: separate wait / all-reduce kernels
     int64_t* d_send_dst = nullptr;
     double** d_peer_vec[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     std::vector<void*> ipc_opened;
@@ -364,14 +366,14 @@ int allreduce(pfx_ctx* c, double* buf, int n) {
 }
 
 // forward halo: owners send the values of their boundary nodes, ghosts receive in place
-int exchange(pfx_ctx* c, double* v, int nc, const double* stop = nullptr) {
+int exchange(pfx_ctx* c, double* v, int nc, const double* stop = nullptr, bool consumer_waits = false) {
     if (c->n_ranks <= 1 || c->nbrs.empty()) return PFX_OK;
     if (c->p2p) {
         int vid = v == c->w_p ? 0 : (v == c->u ? 1 : (v == c->phi ? 2 : (v == c->Vc ? 3 : (v == c->alpha_c ? 4 : -1))));
         if (vid < 0) { c->err = "exchange: vector is not peer-mapped"; return PFX_ERR_COMM; }
         halo_push_kernel<<<vgrid(c, std::max<int64_t>(c->n_send * nc, 1)), kThreads, 0, c->stream>>>(
             c->n_send, c->d_send_idx, c->d_send_nbr, c->d_send_dst, nc, v, c->d_peer_vec[vid], c->pv, c->counter + 1, stop);
-        halo_wait_kernel<<<1, 32, 0, c->stream>>>(c->pv, stop);
+        if (!consumer_waits) halo_wait_kernel<<<1, 32, 0, c->stream>>>(c->pv, stop);
         c->launches += 2;
         CK(cudaGetLastError());
         return PFX_OK;
@@ -472,10 +474,17 @@ __global__ void pcg_setup_kernel(double* S, double rtol2, int bref_slot) {
     S[S_DONE] = (rr > 0.0 && rr > S[S_THRESH]) ? 0.0 : 1.0;
 }
 
+// does the apply of this operator run on a kernel that waits for the halo in its own prologue?
+bool apply_waits_for_halo(const pfx_ctx* c, int kind) {
+    if (c->cell_type != PFX_CELL_TRIANGLE || c->apply_variant != 3 || c->bm.max_elems > 2 * kThreads) return false;
+    return kind == LIN_U || (kind == LIN_PHI && c->cm && c->phi_coeff_fresh);
+}
+
 int apply_lin(pfx_ctx* c, int kind, const double* v, double* y, const uint8_t* mask, double* result, const double* stop,
-              int input_masked = 0) {
+              int input_masked = 0, const PeerView* pv = nullptr, int wait_halo = 0) {
     KArgs a = base_args(c);
     a.v = v; a.y = y; a.mask = mask; a.result = result; a.stop = stop; a.input_masked = input_masked;
+    a.pv = pv; a.wait_halo = wait_halo;
     int op = kind == LIN_U ? (c->use_tan ? OP_APPLY_U_TAN : OP_APPLY_U) : (kind == LIN_PHI ? OP_APPLY_PHI : OP_APPLY_MASS);
     return launch_scatter(c, op, a);
 }
@@ -483,9 +492,26 @@ int apply_lin(pfx_ctx* c, int kind, const double* v, double* y, const uint8_t* m
 // one PCG iteration (parity par) enqueued on the stream
 int pcg_iteration(pfx_ctx* c, int kind, int par, int64_t n, const uint8_t* mask, const double* dinv) {
     int nc = (kind == LIN_U) ? c->dim : 1;
+    bool multi = c->n_ranks > 1;
+    if (multi && c->p2p && c->p2p_fused) {
+        // fused NVLink path: 4 launches, no collective call — halo push | apply (waits for the halo in its
+        // prologue, pushes p.Ap to the peers' mailboxes in its epilogue) | update (sums p.Ap from the
+        // mailboxes, pushes r.z, r.r) | direction (sums them, publishes the PCG state)
+        const bool cw = apply_waits_for_halo(c, kind);
+        int st = exchange(c, c->w_p, nc, c->S + S_DONE, cw);
+        if (st) return st;
+        st = apply_lin(c, kind, c->w_p, c->w_Ap, mask, c->S + S_STAGE, c->S + S_DONE, 1, c->d_pv, cw ? 1 : 0);
+        if (st) return st;
+        int g = vgrid(c, n);
+        pcg_update_kernel<<<g, kThreads, 0, c->stream>>>(n, c->w_x, c->w_r, c->w_p, c->w_Ap, dinv, c->S, par, 0, c->partial,
+                                                        c->counter, c->d_pv);
+        pcg_direction_kernel<<<g, kThreads, 0, c->stream>>>(n, c->w_p, c->w_r, dinv, c->S, par, c->d_pv);
+        c->launches += 2;
+        CK(cudaGetLastError());
+        return PFX_OK;
+    }
     int st = exchange(c, c->w_p, nc, c->S + S_DONE);
     if (st) return st;
-    bool multi = c->n_ranks > 1;
     st = apply_lin(c, kind, c->w_p, c->w_Ap, mask, multi ? c->S + S_STAGE : c->S + S_PAP, c->S + S_DONE, 1);
     if (st) return st;
     if (multi && c->p2p) {
@@ -1442,8 +1468,14 @@ int pfx_comm_p2p_import(pfx_ctx* c, const uint8_t* all, const int64_t* peer_ghos
         for (int j = 0; j < nn; ++j) tab[j] = reinterpret_cast<double*>(peer[c->nbrs[j]][v]);
         if ((st = dev_upload(c, &c->d_peer_vec[v], tab))) return st;
     }
+    {
+        std::vector<PeerView> one(1, pv);
+        if ((st = dev_upload(c, &c->d_pv, one))) return st;
+    }
     const char* np = getenv("PFX_NO_P2P");
     c->p2p = !(np && np[0] == '1');
+    const char* pf = getenv("PFX_P2P_FUSED");
+    if (pf) c->p2p_fused = (pf[0] != '0');
     for (int k = 0; k < 3; ++k)
         if (c->graph[k]) { cudaGraphExecDestroy(c->graph[k]); c->graph[k] = nullptr; }
     return PFX_OK;

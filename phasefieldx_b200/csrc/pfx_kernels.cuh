@@ -39,6 +39,8 @@ struct BlockView {
     int chunk;        // elements per phase-B pass
 };
 
+struct PeerView;
+
 struct KArgs {
     Material m;
     int n1d;
@@ -57,12 +59,90 @@ struct KArgs {
     unsigned int* counter;
     const double* stop;     // optional sticky DONE flag of the running PCG: skip the launch when set
     int input_masked;       // caller guarantees v == 0 on Dirichlet dofs (PCG directions)
+    int wait_halo;          // kernel waits for the halo itself (no separate halo_wait_kernel)
+    const PeerView* pv;     // multi-GPU fused path: wait for the halo in the prologue, push the partial
+                            // dot product to the peers' mailboxes in the epilogue (null otherwise)
     const double* cm;       // precomputed phi-operator coefficients 2H + F·Gc/l and F·Gc·l (per node)
     const double* cg;
     double* tan;            // cached element tangents, SoA [21][tan_stride] (tets, nonlinear split)
     int64_t tan_stride;
     int nred;
 };
+
+constexpr int kMaxRanks = 8;
+constexpr int kMboxStride = 16;              // doubles per (slot, rank): 8 payload + sequence word
+constexpr long long kSpinLimit = 20000000LL;   // ~10 s, then S[S_ERR] is raised instead of hanging
+
+struct PeerView {
+    int rank, n_ranks, n_nbrs;
+    int nbr_rank[kMaxRanks];
+    double* mbox_local;                      // [4][n_ranks][kMboxStride]
+    double* mbox_peer[kMaxRanks];            // mailbox base of every rank
+    unsigned long long* hflag_local;         // [n_ranks]: last halo sequence pushed by rank r
+    unsigned long long* hflag_peer[kMaxRanks];
+    unsigned long long* seq;                 // local counters: [0] all-reduce, [1] halo
+    double* err;                             // S[S_ERR]: set on spin timeout
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// S-array slots of the PCG (device-resident scalars)
+enum { S_PAP = 0, S_RZ0 = 1, S_RZ1 = 2, S_RR = 3, S_THRESH = 4, S_ITERS = 5, S_DONE = 6, S_STAGE = 8, S_BREF = 10 /* ..12: largest ||b||^2 of this load step per operator */, S_ERR = 15, S_COUNT = 16 };
+
+// warp 0, all 32 lanes: publish n <= 8 partial sums of this rank to every rank's mailbox
+__device__ __forceinline__ void mbox_push(const PeerView* pv, const double* vals, int n) {
+    const int lane = threadIdx.x & 31;
+    unsigned long long sq = 0;
+    if (lane == 0) { sq = pv->seq[0] + 1ull; pv->seq[0] = sq; }
+    sq = __shfl_sync(0xffffffffu, sq, 0);
+    if (lane < pv->n_ranks) {
+        double* dst = pv->mbox_peer[lane] + ((size_t)(sq & 3ull) * pv->n_ranks + pv->rank) * kMboxStride;
+        for (int k = 0; k < n; ++k) dst[k] = vals[k];          // every lane holds the warp-reduced sums
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned long long*>(dst + 8), sq);
+    }
+}
+
+// warp 0, all 32 lanes: wait for the current all-reduce sequence and return the rank-ordered sums
+// (identical on every rank and in every CTA); valid in every lane of the warp
+__device__ __forceinline__ void mbox_sum(const PeerView* pv, double* sums, int n) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long sq = pv->seq[0];
+    double v[2] = {0.0, 0.0};
+    if (lane < pv->n_ranks) {
+        const double* src = pv->mbox_local + ((size_t)(sq & 3ull) * pv->n_ranks + lane) * kMboxStride;
+        long long spins = 0;
+        while (ld_acquire_sys(reinterpret_cast<const unsigned long long*>(src + 8)) != sq) {
+            if (++spins > kSpinLimit) { *pv->err = 2.0; break; }
+        }
+        for (int k = 0; k < n; ++k) v[k] = __ldcv(src + k);
+    }
+    for (int k = 0; k < n; ++k) {
+        double t = 0.0;
+        for (int r = 0; r < pv->n_ranks; ++r) t += __shfl_sync(0xffffffffu, v[k], r);
+        sums[k] = t;
+    }
+}
+
+// every thread of the CTA: wait until all neighbours pushed the current halo sequence
+__device__ __forceinline__ void halo_wait_cta(const PeerView* pv) {
+    if ((int)threadIdx.x < pv->n_nbrs) {
+        const unsigned long long want = pv->seq[1];
+        const unsigned long long* f = pv->hflag_local + pv->nbr_rank[threadIdx.x];
+        long long spins = 0;
+        while (ld_acquire_sys(f) < want) {
+            if (++spins > kSpinLimit) { *pv->err = 1.0; break; }
+        }
+    }
+    __syncthreads();
+}
 
 // ----------------------------------------------------------------------------- reductions
 __device__ __forceinline__ double warp_sum(double v) {
@@ -95,7 +175,7 @@ __device__ __forceinline__ void block_sum(double* vals, double* s_red /*[NR*32]*
 // last block's warp 0 adds the partials in a fixed order (deterministic result).
 template <int NR>
 __device__ __forceinline__ void grid_reduce(double* vals, double* partial, double* result, unsigned int* counter,
-                                            double* s_red) {
+                                            double* s_red, const PeerView* pv = nullptr) {
     block_sum<NR>(vals, s_red);
     if (threadIdx.x >= 32) return;
     unsigned int last = 0;
@@ -117,6 +197,7 @@ __device__ __forceinline__ void grid_reduce(double* vals, double* partial, doubl
         for (int k = 0; k < NR; ++k) acc[k] += __ldcg(&partial[(size_t)b * kMaxRed + k]);
 #pragma unroll
     for (int k = 0; k < NR; ++k) acc[k] = warp_sum(acc[k]);
+    if (pv) { mbox_push(pv, acc, NR); return; }            // fused all-reduce: straight to the peers' mailboxes
     if (threadIdx.x == 0)
 #pragma unroll
         for (int k = 0; k < NR; ++k) result[k] = acc[k];
@@ -453,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks<Op>::value) scatter_kerne
 #pragma unroll
     for (int k = 0; k < (Op::NRED > 0 ? Op::NRED : 1); ++k) red[k] = 0.0;
     if (tid < n_own) Op::store(a, n0 + tid, acc, red);
-    if (Op::NRED > 0) grid_reduce<(Op::NRED > 0 ? Op::NRED : 1)>(red, a.partial, a.result, a.counter, s_red);
+    if (Op::NRED > 0) grid_reduce<(Op::NRED > 0 ? Op::NRED : 1)>(red, a.partial, a.result, a.counter, s_red, a.pv);
 }
 
 // ============================================================================= hot kernel
@@ -586,7 +667,7 @@ __global__ void __launch_bounds__(kThreads, 4) apply_u_tri_kernel(BlockView bv, 
         reinterpret_cast<double2*>(a.y)[g] = acc;
         red[0] = vin.x * acc.x + vin.y * acc.y;
     }
-    grid_reduce<1>(red, a.partial, a.result, a.counter, s_red);
+    grid_reduce<1>(red, a.partial, a.result, a.counter, s_red, a.pv);
 }
 
 // ----------------------------------------------------------------------------- async staging helpers
@@ -772,7 +853,7 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_persist_kernel(BlockV
         __syncthreads();                   // stage s and sE are free again
     }
     double r1[1] = {red};
-    grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red);
+    grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red, a.pv);
 }
 
 // ============================================================================= hot kernel, v3
@@ -808,6 +889,7 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
         sE[zslot] = make_double2(0.0, 0.0);
     }
     __syncthreads();
+    if (a.pv && a.wait_halo) halo_wait_cta(a.pv);          // neighbours' pushes of this direction have landed
 
     auto issue = [&](int4 ma, int4 mb, int s_, int hidx) {
         char* p = sbase + (size_t)s_ * stage_bytes;
@@ -935,7 +1017,7 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
         has_next = has_nn;
     }
     double r1[1] = {red};
-    grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red);
+    grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red, a.pv);
 }
 
 // ============================================================================= phi-apply, v3 pipeline
@@ -989,6 +1071,7 @@ __global__ void __launch_bounds__(kThreads, 4) apply_phi_tri_v3_kernel(BlockView
         sE[zslot] = 0.0;
     }
     __syncthreads();
+    if (a.pv && a.wait_halo) halo_wait_cta(a.pv);
 
     auto issue = [&](int4 ma, int s_, int hidx) {
         char* p = sbase + (size_t)s_ * stage_bytes;
@@ -1107,7 +1190,7 @@ __global__ void __launch_bounds__(kThreads, 4) apply_phi_tri_v3_kernel(BlockView
         has_next = has_nn;
     }
     double r1[1] = {red};
-    grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red);
+    grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red, a.pv);
 }
 
 // ============================================================================= element reductions
@@ -1168,7 +1251,7 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(BlockView bv, KArgs a)
 
 // ============================================================================= vector kernels
 // PCG state scalars (device resident).  Indices into the scalar array S.
-enum { S_PAP = 0, S_RZ0 = 1, S_RZ1 = 2, S_RR = 3, S_THRESH = 4, S_ITERS = 5, S_DONE = 6, S_STAGE = 8, S_BREF = 10 /* ..12: largest ||b||^2 of this load step per operator */, S_ERR = 15, S_COUNT = 16 };
+
 
 // Publishes the two sums of an update step: rz_next, rr; bumps the iteration count and sets
 // the sticky DONE flag (all later launches of the captured graph then return immediately).
@@ -1185,11 +1268,23 @@ __device__ __forceinline__ void pcg_finalize(double* S, int par, double rz_new, 
 __global__ void __launch_bounds__(kThreads) pcg_update_kernel(int64_t n, double* __restrict__ x, double* __restrict__ r,
                                                               const double* __restrict__ p, const double* __restrict__ Ap,
                                                               const double* __restrict__ dinv, double* S, int par,
-                                                              int finalize, double* partial, unsigned int* counter) {
+                                                              int finalize, double* partial, unsigned int* counter,
+                                                              const PeerView* pv = nullptr) {
     __shared__ double s_red[kMaxRed * 32];
     __shared__ bool is_last;
+    __shared__ double s_pap;
     if (S[S_DONE] != 0.0) return;
-    const double alpha = S[S_RZ0 + par] / S[S_PAP];
+    double pap = S[S_PAP];
+    if (pv) {                                   // fused all-reduce: p.Ap of all ranks from the mailboxes
+        if (threadIdx.x < 32) {
+            double sm[1];
+            mbox_sum(pv, sm, 1);
+            if (threadIdx.x == 0) s_pap = sm[0];
+        }
+        __syncthreads();
+        pap = s_pap;
+    }
+    const double alpha = S[S_RZ0 + par] / pap;
     double vals[2] = {0.0, 0.0};
     const int64_t n2 = n >> 1, gs = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double2* x2 = reinterpret_cast<double2*>(x);
@@ -1230,7 +1325,13 @@ __global__ void __launch_bounds__(kThreads) pcg_update_kernel(int64_t n, double*
             acc[1] += __ldcg(&partial[(size_t)b * kMaxRed + 1]);
         }
         block_sum<2>(acc, s_red);
-        if (threadIdx.x == 0) {
+        if (pv) {
+            if (threadIdx.x < 32) {
+                acc[0] = __shfl_sync(0xffffffffu, acc[0], 0);
+                acc[1] = __shfl_sync(0xffffffffu, acc[1], 0);
+                mbox_push(pv, acc, 2);
+            }
+        } else if (threadIdx.x == 0) {
             if (finalize) pcg_finalize(S, par, acc[0], acc[1]);
             else { S[S_STAGE] = acc[0]; S[S_STAGE + 1] = acc[1]; }
         }
@@ -1245,9 +1346,21 @@ __global__ void pcg_publish_kernel(double* S, int par) {
 
 // p = Dinv r + β p   (β = rz[par^1]/rz[par])
 __global__ void __launch_bounds__(kThreads) pcg_direction_kernel(int64_t n, double* __restrict__ p, const double* __restrict__ r,
-                                                                 const double* __restrict__ dinv, const double* S, int par) {
+                                                                 const double* __restrict__ dinv, double* S, int par,
+                                                                 const PeerView* pv = nullptr) {
+    __shared__ double s_sum[2];
     if (S[S_DONE] != 0.0) return;
-    const double beta = S[S_RZ0 + (par ^ 1)] / S[S_RZ0 + par];
+    double rz_new = S[S_RZ0 + (par ^ 1)];
+    if (pv) {                                   // fused all-reduce of (r.z, r.r); block 0 publishes them at its end
+        if (threadIdx.x < 32) {
+            double sm[2];
+            mbox_sum(pv, sm, 2);
+            if (threadIdx.x == 0) { s_sum[0] = sm[0]; s_sum[1] = sm[1]; }
+        }
+        __syncthreads();
+        rz_new = s_sum[0];
+    }
+    const double beta = rz_new / S[S_RZ0 + par];
     const int64_t n2 = n >> 1, gs = (int64_t)gridDim.x * blockDim.x, i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     double2* p2 = reinterpret_cast<double2*>(p);
     const double2 *r2 = reinterpret_cast<const double2*>(r), *d2 = reinterpret_cast<const double2*>(dinv);
@@ -1258,6 +1371,10 @@ __global__ void __launch_bounds__(kThreads) pcg_direction_kernel(int64_t n, doub
         p2[i] = pv;
     }
     if ((n & 1) && i0 == 0) p[n - 1] = dinv[n - 1] * r[n - 1] + beta * p[n - 1];
+    if (pv && blockIdx.x == 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) pcg_finalize(S, par, s_sum[0], s_sum[1]);
+    }
 }
 
 // generic fused vector helpers -------------------------------------------------------------
@@ -1409,30 +1526,6 @@ __global__ void pack_kernel(int64_t n, const int32_t* idx, int nc, const double*
 // scalars are all-reduced through per-rank mailboxes — no NCCL call inside the PCG iteration.
 // Every rank runs the same launch sequence, so sequence counters advance in lock step; waits are
 // bounded (a timeout raises a flag instead of hanging the GPU).
-constexpr int kMaxRanks = 8;
-constexpr int kMboxStride = 16;              // doubles per (slot, rank): 8 payload + sequence word
-constexpr long long kSpinLimit = 20000000LL;   // ~10 s, then S[S_ERR] is raised instead of hanging
-
-struct PeerView {
-    int rank, n_ranks, n_nbrs;
-    int nbr_rank[kMaxRanks];
-    double* mbox_local;                      // [4][n_ranks][kMboxStride]
-    double* mbox_peer[kMaxRanks];            // mailbox base of every rank
-    unsigned long long* hflag_local;         // [n_ranks]: last halo sequence pushed by rank r
-    unsigned long long* hflag_peer[kMaxRanks];
-    unsigned long long* seq;                 // local counters: [0] all-reduce, [1] halo
-    double* err;                             // S[S_ERR]: set on spin timeout
-};
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // values of the send list -> the neighbours' ghost ranges; the last block raises the halo flags
 __global__ void __launch_bounds__(kThreads) halo_push_kernel(int64_t n_send, const int32_t* idx, const uint8_t* nbr,
                                                              const int64_t* dst, int nc, const double* v,

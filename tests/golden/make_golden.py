@@ -7,6 +7,7 @@ container only; the GPU box has no /root/reference).
                      total.energy, phasefieldx.conv, top.dof)
   ref_1713.npz       same for example 1713 (structured 200x100 Q1 mesh, no mesh file needed)
   ref_1712.npz       same for example 1712 (shear, spectral)
+  ref_1800.npz       first 40 rows of the fatigue example 1800 (total.energy incl. alpha_acum, conv, dof)
   ref_constitutive.npz  outputs of the reference's own constitutive layer
                      (Math/invariants.py, Math/tensor_decomposition.py, Materials/elastic_isotropic.py,
                      split_energy_stress_tangent_functions.py) executed UNMODIFIED under the torch-fp64
@@ -45,6 +46,9 @@ def main():
                             energy=table(os.path.join(d, "total.energy"), n),
                             conv=table(os.path.join(d, "phasefieldx.conv"), n),
                             dof=table(os.path.join(d, "top.dof"), n))
+    fat = os.path.join(REF, "examples", "Fatigue", "1800_Fatigue_Single_Edge_Notched_Tension_Test")
+    np.savez_compressed(os.path.join(HERE, "ref_1800.npz"), energy=table(os.path.join(fat, "total.energy"), 40),
+                        conv=table(os.path.join(fat, "phasefieldx.conv"), 40), dof=table(os.path.join(fat, "top.dof"), 40))
     from ufl_shim import reference_constitutive
     np.savez_compressed(os.path.join(HERE, "ref_constitutive.npz"), **reference_constitutive())
     print("fixtures written to", HERE)

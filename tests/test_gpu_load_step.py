@@ -260,3 +260,27 @@ def test_traction_loading_and_phi_dirichlet_vs_oracle():
     R = e.reaction(0)
     assert np.allclose(R[:2], -T * 1.0, rtol=1e-6, atol=1e-10)
     e.close()
+
+
+def test_config3_fatigue_vs_stored_reference_energy(c1_mesh):
+    """Config 3 on the GPU, 1.5 load cycles (13 steps), against the reference's stored
+    examples/Fatigue/1800_*/total.energy: alpha_acum within 5e-6 (reference projection noise,
+    SURVEY V9), PSI_a within 1e-8, stagger counts equal."""
+    import os
+    from conftest import GOLDEN
+    from phasefieldx_b200 import workloads as W
+    msh, bot, top = c1_mesh
+    w = W.sen_tension(msh, bot, top, fatigue=True)
+    e = W.make_engine(w)
+    ref = np.load(os.path.join(GOLDEN, "ref_1800.npz"))
+    for step in range(13):
+        for i, v in enumerate(w.bc_values(float(step))):
+            e.set_bc_values_u(i, v)
+        r = e.load_step(dt=1.0, max_stagger_iter=500)
+        en = e.energies()
+        assert r["stagger"] == int(ref["conv"][step, 1]), (step, r["stagger"], ref["conv"][step, 1])
+        if step:
+            assert abs(en["alpha_acum"] - ref["energy"][step, 11]) < 5e-6 * ref["energy"][step, 11], step
+            if ref["energy"][step, 9] > 1e-12:
+                assert abs(en["PSI_a"] - ref["energy"][step, 9]) < 1e-7 * ref["energy"][step, 9] + 1e-16, step
+    e.close()

@@ -105,3 +105,27 @@ def test_oracle_l2_projection_modes_agree_to_solver_noise(c1_mesh):
     a, b = o1.project(o1.split(u, False)["psi_a"]), o2.project(o2.split(u, False)["psi_a"])
     err = np.linalg.norm(a - b) / np.linalg.norm(a)
     assert 0 < err < 1e-3
+
+
+def test_stored_fatigue_example_1800_first_steps(c1_mesh):
+    """Config 3 (reference examples/Fatigue/plot_1800.py:102-116, 223-264): the fatigue bookkeeping
+    (alpha_c projection, heaviside(.,1), per-step carry-over, Fatigue field inside the phi form)
+    against the stored total.energy: alpha_acum to ~2e-6 (the reference's own
+    projection-solver noise), PSI_a to 1e-9.  (The 1800 *.reaction files predate the current
+    reaction routine and are not pins.)"""
+    from phasefieldx_b200 import workloads as W
+    msh, bot, top = c1_mesh
+    w = W.sen_tension(msh, bot, top, fatigue=True)
+    o = Oracle(msh.geometry.x, msh.cells, msh.cell_type, Params(**w.params))
+    bcs = [BC(d) for _, d in w.bc_sets]
+    ref = np.load(os.path.join(GOLDEN, "ref_1800.npz"))
+    for step in range(4):
+        for bc, v in zip(bcs, w.bc_values(float(step))):
+            bc.values = v
+        assert abs(bcs[0].values[0] - ref["dof"][step, 2]) < 1e-15
+        r = o.load_step(bcs, [], dt=1.0, max_stagger_iter=500)
+        e = o.energies()
+        assert r["stagger"] == int(ref["conv"][step, 1])
+        if step:
+            assert abs(e["alpha_acum"] - ref["energy"][step, 11]) < 5e-6 * ref["energy"][step, 11]
+            assert abs(e["PSI_a"] - ref["energy"][step, 9]) < 1e-9 * ref["energy"][step, 9]
