@@ -122,6 +122,8 @@ struct pfx_ctx {
     double *cm = nullptr, *cg = nullptr;   // phi-operator nodal coefficients (triangles, v3 path)
     int phi_v3_ctas = 0;
     bool use_tan = false;
+    int coop_capacity = 0;        // co-resident CTAs of the whole-PCG cooperative kernel (0: unavailable)
+    unsigned long long* coop_bar = nullptr;
     bool phi_coeff_fresh = false;
     bool generic_apply = false;   // PFX_GENERIC_APPLY=1: use the generic scatter kernel for J_u·v on triangles
     int apply_variant = 3;        // PFX_APPLY_VARIANT: 3 persistent + prefetched indices (default), 2 persistent, 1 one CTA per block
@@ -250,6 +252,34 @@ int launch_apply_phi_tri_v3(pfx_ctx* c, const KArgs& a) {
     c->launches++;
     CK(cudaGetLastError());
     return PFX_OK;
+}
+
+// whole-PCG cooperative kernel (small triangle meshes, one GPU)
+template <int SM>
+int coop_u_tri(pfx_ctx* c, const KArgs& a, CoopArgs ca, bool configure) {
+    size_t ML = (size_t)c->bm.max_loc, MO = ((size_t)c->bm.max_own + 1) & ~(size_t)1;
+    size_t smem = 4 * ML * 16 + (3 * (size_t)(2 * kThreads) + 1) * 16 + ((ML + 1) & ~(size_t)1) * 8 +
+                  ((ML + 3) & ~(size_t)3) * 4 + MO * 16;
+    if (configure) {
+        CK(cudaFuncSetAttribute(pcg_coop_u_tri_kernel<SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0, coop = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_coop_u_tri_kernel<SM>, kThreads, smem));
+        CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+        c->coop_capacity = coop ? per_sm * c->num_sms : 0;
+        return PFX_OK;
+    }
+    BlockView bv = c->bv;
+    KArgs aa = a;
+    void* args[] = {(void*)&bv, (void*)&aa, (void*)&ca};
+    CK(cudaLaunchCooperativeKernel((void*)pcg_coop_u_tri_kernel<SM>, dim3(c->bm.nb), dim3(kThreads), args, smem, c->stream));
+    c->launches++;
+    return PFX_OK;
+}
+
+int coop_u(pfx_ctx* c, const KArgs& a, const CoopArgs& ca, bool configure) {
+    if (c->mat.smodel == M_ISO) return coop_u_tri<M_ISO>(c, a, ca, configure);
+    if (c->mat.smodel == M_SPECTRAL) return coop_u_tri<M_SPECTRAL>(c, a, ca, configure);
+    return coop_u_tri<M_VOLDEV>(c, a, ca, configure);
 }
 
 template <class Cell>
@@ -564,6 +594,33 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
     int64_t n = c->n_owned * nc;
     const uint8_t* mask = kind == LIN_U ? c->mask_u : (kind == LIN_PHI ? c->mask_phi : nullptr);
     const double* dinv = kind == LIN_MASS ? c->dinv_mass : c->w_dinv;
+    *converged = false;
+    *iters = 0;
+    if (kind == LIN_U && c->n_ranks == 1 && c->coop_capacity >= c->bm.nb && c->coop_bar) {
+        // small mesh: the whole solve in one cooperative launch (re-launched only if max_iters runs out)
+        KArgs a = base_args(c);
+        a.mask = mask;
+        CoopArgs ca;
+        ca.F = c->w_F; ca.dinv = dinv; ca.x = c->w_x; ca.r = c->w_r; ca.p = c->w_p; ca.partial = c->partial;
+        ca.bar = c->coop_bar; ca.S = c->S; ca.rtol2 = rtol * rtol;
+        ca.bref_slot = c->cg_adaptive ? S_BREF + kind : -1;
+        ca.resume = 0;
+        for (;;) {
+            ca.max_iters = (int)std::min<int64_t>(4096, (int64_t)c->prm.cg_max_it - *iters);
+            CK(cudaMemsetAsync(c->coop_bar, 0, sizeof(unsigned long long), c->stream));
+            int st = coop_u(c, a, ca, false);
+            if (st) return st;
+            CK(cudaMemcpyAsync(c->h_pinned, c->S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            *iters = (int64_t)c->h_pinned[S_ITERS];
+            double rr = c->h_pinned[S_RR];
+            if (!(rr == rr)) { c->err = "NaN in PCG"; return PFX_ERR_NAN; }
+            if (c->h_pinned[S_DONE] != 0.0) { *converged = true; break; }
+            if (*iters >= c->prm.cg_max_it) break;
+            ca.resume = 1;
+        }
+        return PFX_OK;
+    }
     int g = vgrid(c, n);
     pcg_init_kernel<<<g, kThreads, 0, c->stream>>>(n, c->w_F, mask, dinv, nullptr, nullptr, c->w_x, c->w_r, c->w_p,
                                                   c->partial, c->S + S_STAGE, c->counter);
@@ -574,8 +631,6 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
     c->launches++;
     CK(cudaGetLastError());
     int64_t max_it = c->prm.cg_max_it;
-    *converged = false;
-    *iters = 0;
     for (;;) {
         if (c->use_graph) {
             if (!c->graph[kind]) {
@@ -950,6 +1005,10 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
         if ((st = launch_reduce<RED_L2_U>(c, z))) return st;
         if ((st = launch_reduce<RED_L2_PHI>(c, z))) return st;
         if ((st = launch_reduce<RED_ENERGY>(c, z))) return st;
+        if (c->cell_type == PFX_CELL_TRIANGLE && bm.max_elems <= 2 * kThreads && !getenv("PFX_NO_COOP")) {
+            if ((st = coop_u(c, z, CoopArgs(), true))) return st;
+            if ((st = dev_alloc(c, &c->coop_bar, (size_t)2))) return st;
+        }
         c->configuring = false;
     }
     // ---- constant data: 1/diag(M)

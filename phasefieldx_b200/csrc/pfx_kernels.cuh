@@ -571,12 +571,14 @@ __device__ __forceinline__ void tri_apply_elem(const Material& m, double2 x0, do
             const double l0 = 0.5 * (tr - s), l1 = 0.5 * (tr + s);
             const double m0 = amc * is, m1 = 2.0 * b * is;
             const double ds = m0 * dd + 2.0 * m1 * de[2];
-            const double w0 = (l0 > 0.0 ? 0.5 : (l0 < 0.0 ? 0.0 : 0.25)) * (dtr - ds);
-            const double w1 = (l1 > 0.0 ? 0.5 : (l1 < 0.0 ? 0.0 : 0.25)) * (dtr + ds);
+            // ½·H(λ) with H = ½(1 + sign λ); copysign form (differs from sign() only at λ == 0 exactly,
+            // which the eps-regularised eigenvalues never hit; tangent only, the residual is unaffected)
+            const double w0 = (0.25 + copysign(0.25, l0)) * (dtr - ds);
+            const double w1 = (0.25 + copysign(0.25, l1)) * (dtr + ds);
             const double pd = 0.5 * (fmax(l1, 0.0) - fmax(l0, 0.0)) * is;
             const double dm0 = dd - m0 * ds, dm1 = 2.0 * de[2] - m1 * ds;
             const double e1x = 0.5 * (1.0 + m0), e1y = 0.5 * (1.0 - m0), e1s = 0.5 * m1;
-            const double lt = m.lam * (tr > 0.0 ? 1.0 : (tr < 0.0 ? 0.0 : 0.5)) * dtr, mu2 = 2.0 * m.mu;
+            const double lt = m.lam * (tr > 0.0 ? 1.0 : (tr < 0.0 ? 0.0 : 0.5)) * dtr, mu2 = 2.0 * m.mu;   // tr == 0 at u = 0
             dsa[0] = lt + mu2 * (w0 * (1.0 - e1x) + w1 * e1x + pd * dm0);
             dsa[1] = lt + mu2 * (w0 * (1.0 - e1y) + w1 * e1y - pd * dm0);
             dsa[2] = mu2 * ((w1 - w0) * e1s + pd * dm1);
@@ -1191,6 +1193,216 @@ __global__ void __launch_bounds__(kThreads, 4) apply_phi_tri_v3_kernel(BlockView
     }
     double r1[1] = {red};
     grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red, a.pv);
+}
+
+// ============================================================================= small meshes: whole PCG in one kernel
+// Configs 1 and 3 (5 089 nodes, 80 blocks) are launch-latency bound: three launches per CG iteration
+// cost ~13 µs while the arithmetic is ~1 µs.  Here the ENTIRE Jacobi-PCG solve of J_u δ = b runs in one
+// cooperative launch, one CTA per mesh block: coordinates, phi, u, the incidence table and the
+// connectivities are staged ONCE and stay in shared memory / registers for the whole solve; per
+// iteration a CTA only (i) recomputes p on its halo from the neighbours' r (written to global before
+// the reduction barrier), (ii) runs phases B/C, and (iii) takes part in two grid barriers that also
+// carry the two dot products (per-block partials, summed by every CTA in the same fixed order, so
+// all CTAs take identical decisions and the result is bit-reproducible).
+struct CoopArgs {
+    const double* F;          // right-hand side (Dirichlet entries ignored)
+    const double* dinv;       // Jacobi data
+    double* x;                // solution (w_x)
+    double* r;                // residual, also the halo exchange buffer (w_r)
+    double* p;                // direction, saved on exit / reloaded on resume (w_p)
+    double* partial;          // [2][nb][2]
+    unsigned long long* bar;  // grid barrier counter (monotonic, zeroed by the host before the launch)
+    double* S;                // PCG scalars (S_RR, S_ITERS, S_DONE, S_THRESH, S_RZ0)
+    double rtol2;
+    int bref_slot;            // >= 0: per-load-step absolute floor (see pcg_setup_kernel)
+    int max_iters;            // iterations in this launch
+    int resume;               // 0: start from x = 0; 1: continue from the saved x, r, p
+};
+
+__device__ __forceinline__ void coop_barrier(unsigned long long* bar, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1ull);
+        long long spins = 0;
+        while (ld_acquire_sys(bar) < target) {
+            if (++spins > kSpinLimit) break;
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int SM>
+__global__ void __launch_bounds__(kThreads, 1) pcg_coop_u_tri_kernel(BlockView bv, KArgs a, CoopArgs ca) {
+    constexpr bool NL = (SM != M_ISO);
+    extern __shared__ double smem[];
+    __shared__ double s_red[kMaxRed * 32];
+    __shared__ double s_tot[2];
+    const int tid = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
+    const int4 ma = bv.meta[2 * b], mb = bv.meta[2 * b + 1];
+    const int n0 = ma.x, n_own = ma.y, h0 = ma.z, n_halo = ma.w, n_loc = n_own + n_halo, e0 = mb.x, ne = mb.y;
+    const int ML = bv.max_loc, chunk = 2 * kThreads, MO = (bv.max_own + 1) & ~1;
+    double2* sX = reinterpret_cast<double2*>(smem);
+    double2* sU = sX + ML;
+    double2* sV = sU + ML;                   // p on every local node
+    double2* sD = sV + ML;                   // Jacobi data on every local node
+    double2* sE = sD + ML;                   // [3*chunk + 1]
+    double* sP = reinterpret_cast<double*>(sE + 3 * chunk + 1);
+    int* sH = reinterpret_cast<int*>(sP + ((ML + 1) & ~1));
+    uint4* sI = reinterpret_cast<uint4*>(sH + ((ML + 3) & ~3));
+    const int zslot = 3 * chunk;
+    const double2* X2 = reinterpret_cast<const double2*>(a.X);
+    const double2* U2 = reinterpret_cast<const double2*>(a.u);
+    const double2* D2 = reinterpret_cast<const double2*>(ca.dinv);
+    const unsigned short* M2 = reinterpret_cast<const unsigned short*>(a.mask);
+    const uint2* LC = reinterpret_cast<const uint2*>(bv.lconn);
+    // ---- one-time staging
+    for (int i = tid; i < n_loc; i += kThreads) {
+        const int g = (i < n_own) ? n0 + i : bv.halo[h0 + i - n_own];
+        sX[i] = X2[g]; sP[i] = a.phi[g]; sD[i] = D2[g]; sH[i] = g;
+        if (NL) sU[i] = U2[g];
+    }
+    if (tid < n_own) sI[tid] = bv.inc8[n0 + tid];
+    if (tid == 0) sE[zslot] = make_double2(0.0, 0.0);
+    uint2 lc0 = make_uint2(0u, 0u), lc1 = lc0;
+    if (tid < ne) lc0 = LC[e0 + tid];
+    if (tid + kThreads < ne) lc1 = LC[e0 + tid + kThreads];
+    unsigned int mk = 0u;
+    double2 x = make_double2(0.0, 0.0), r = x, dv = x;
+    const bool own = tid < n_own;
+    double2* Xg = reinterpret_cast<double2*>(ca.x);
+    double2* Rg = reinterpret_cast<double2*>(ca.r);
+    double2* Pg = reinterpret_cast<double2*>(ca.p);
+    const double2* Fg = reinterpret_cast<const double2*>(ca.F);
+    if (own) {
+        if (M2) mk = M2[n0 + tid];
+        dv = D2[n0 + tid];
+        if (ca.resume) { x = Xg[n0 + tid]; r = Rg[n0 + tid]; }
+        else {
+            r = Fg[n0 + tid];
+            if (mk & 0xFFu) r.x = 0.0;
+            if (mk & 0xFF00u) r.y = 0.0;
+            Rg[n0 + tid] = r;
+        }
+    }
+    unsigned long long gen = 0;
+    int red_par = 0;
+    // grid-wide sums of two per-thread values; every CTA obtains bit-identical totals
+    auto grid_sum2 = [&](double v0, double v1, double& t0, double& t1) {
+        double vals[2] = {v0, v1};
+        block_sum<2>(vals, s_red);
+        double* part = ca.partial + (size_t)red_par * nb * 2;
+        if (tid == 0) { part[2 * b] = vals[0]; part[2 * b + 1] = vals[1]; }
+        ++gen;
+        coop_barrier(ca.bar, gen * (unsigned long long)nb);
+        if (tid < 32) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int k = tid; k < nb; k += 32) { s0 += __ldcg(part + 2 * k); s1 += __ldcg(part + 2 * k + 1); }
+            s0 = warp_sum(s0); s1 = warp_sum(s1);
+            if (tid == 0) { s_tot[0] = s0; s_tot[1] = s1; }
+        }
+        __syncthreads();
+        t0 = s_tot[0]; t1 = s_tot[1];
+        red_par ^= 1;
+        __syncthreads();
+    };
+    // ---- start-up: z = D^-1 r, p = z (or the saved p), rz, rr
+    double rz, rr;
+    {
+        double2 z = make_double2(dv.x * r.x, dv.y * r.y);
+        grid_sum2(own ? r.x * z.x + r.y * z.y : 0.0, own ? r.x * r.x + r.y * r.y : 0.0, rz, rr);
+        // (the barrier inside grid_sum2 also published every block's r for the halo reads below)
+        for (int i = tid; i < n_loc; i += kThreads) {
+            const int g = sH[i];
+            if (ca.resume) sV[i] = Pg[g];
+            else { const double2 rg = __ldcg(Rg + g); const double2 d = sD[i]; sV[i] = make_double2(d.x * rg.x, d.y * rg.y); }
+        }
+        __syncthreads();
+    }
+    double thresh = ca.S[S_THRESH];
+    if (!ca.resume) {
+        double ref = rr;
+        if (ca.bref_slot >= 0) ref = fmax(ca.S[ca.bref_slot], rr);
+        thresh = ca.rtol2 * ref;
+        if (b == 0 && tid == 0) { if (ca.bref_slot >= 0) ca.S[ca.bref_slot] = ref; ca.S[S_THRESH] = thresh; ca.S[S_ITERS] = 0.0; }
+    }
+    int it = 0;
+    const double2 zz = make_double2(0.0, 0.0);
+    while (it < ca.max_iters && rr > thresh && rr > 0.0) {
+        // ---- phase B / C: Ap on the owned nodes
+        if (tid < ne) {
+            const int vx = lc0.x & 0xFFFF, vy = lc0.x >> 16, vz = lc0.y & 0xFFFF;
+            double2 f0, f1, f2;
+            tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy], sV[vz],
+                               NL ? sU[vx] : zz, NL ? sU[vy] : zz, NL ? sU[vz] : zz, f0, f1, f2);
+            sE[tid] = f0; sE[chunk + tid] = f1; sE[2 * chunk + tid] = f2;
+        }
+        if (tid + kThreads < ne) {
+            const int vx = lc1.x & 0xFFFF, vy = lc1.x >> 16, vz = lc1.y & 0xFFFF;
+            double2 f0, f1, f2;
+            tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy], sV[vz],
+                               NL ? sU[vx] : zz, NL ? sU[vy] : zz, NL ? sU[vz] : zz, f0, f1, f2);
+            sE[tid + kThreads] = f0; sE[chunk + tid + kThreads] = f1; sE[2 * chunk + tid + kThreads] = f2;
+        }
+        __syncthreads();
+        double2 Ap = zz, pv = zz;
+        if (own) {
+            const uint4 c8 = sI[tid];
+            const unsigned cw[4] = {c8.x, c8.y, c8.z, c8.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int code = (int)((cw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
+                const double2 f = sE[min((code & 3) * chunk + (code >> 2), zslot)];
+                Ap.x += f.x; Ap.y += f.y;
+            }
+            if ((c8.w >> 16) == 0xFFFEu) {
+                int k0 = bv.inc_ptr[n0 + tid] + 7, k1 = bv.inc_ptr[n0 + tid + 1];
+                for (int k = k0; k < k1; ++k) {
+                    const int code = bv.inc[k];
+                    if (code >= 0xFFFE) break;
+                    const double2 f = sE[(code & 3) * chunk + (code >> 2)];
+                    Ap.x += f.x; Ap.y += f.y;
+                }
+            }
+            if (mk & 0xFFu) Ap.x = 0.0;
+            if (mk & 0xFF00u) Ap.y = 0.0;
+            pv = sV[tid];
+        }
+        double pAp, dummy;
+        grid_sum2(own ? pv.x * Ap.x + pv.y * Ap.y : 0.0, 0.0, pAp, dummy);
+        const double alpha = rz / pAp;
+        double lz = 0.0, lr = 0.0;
+        if (own) {
+            x.x += alpha * pv.x; x.y += alpha * pv.y;
+            r.x -= alpha * Ap.x; r.y -= alpha * Ap.y;
+            Rg[n0 + tid] = r;                                   // neighbours read their halo r after the barrier
+            lz = r.x * dv.x * r.x + r.y * dv.y * r.y;
+            lr = r.x * r.x + r.y * r.y;
+        }
+        double rz_new, rr_new;
+        grid_sum2(lz, lr, rz_new, rr_new);
+        const double beta = rz_new / rz;
+        rz = rz_new; rr = rr_new;
+        ++it;
+        // ---- p = D^-1 r + beta p on every local node (halo r from the neighbours)
+        for (int i = tid; i < n_loc; i += kThreads) {
+            const double2 rg = (i < n_own) ? ((i == tid) ? r : __ldcg(Rg + n0 + i)) : __ldcg(Rg + sH[i]);
+            const double2 d = sD[i];
+            double2 pp = sV[i];
+            pp.x = d.x * rg.x + beta * pp.x; pp.y = d.y * rg.y + beta * pp.y;
+            sV[i] = pp;
+        }
+        __syncthreads();
+        // the next write of Rg happens after the next grid barrier (p.Ap), so these reads are safe
+    }
+    // ---- save state and publish the PCG bookkeeping
+    if (own) { Xg[n0 + tid] = x; Pg[n0 + tid] = sV[tid]; }
+    if (b == 0 && tid == 0) {
+        ca.S[S_RR] = rr; ca.S[S_RZ0] = rz;
+        ca.S[S_ITERS] += (double)it;
+        ca.S[S_DONE] = (!(rr > thresh) || !(rr > 0.0)) ? 1.0 : 0.0;
+    }
 }
 
 // ============================================================================= element reductions
