@@ -276,6 +276,24 @@ int coop_u_tri(pfx_ctx* c, const KArgs& a, CoopArgs ca, bool configure) {
     return PFX_OK;
 }
 
+int coop_phi(pfx_ctx* c, const KArgs& a, CoopArgs ca, bool configure) {
+    size_t ML = (size_t)c->bm.max_loc, MO = ((size_t)c->bm.max_own + 1) & ~(size_t)1, MLe = (ML + 1) & ~(size_t)1;
+    size_t smem = ML * 16 + 4 * MLe * 8 + (3 * (size_t)(2 * kThreads) + 2) * 8 + ((ML + 3) & ~(size_t)3) * 4 + MO * 16 + 16;
+    if (configure) {
+        CK(cudaFuncSetAttribute(pcg_coop_phi_tri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pcg_coop_phi_tri_kernel, kThreads, smem));
+        c->coop_capacity = std::min(c->coop_capacity, per_sm * c->num_sms);
+        return PFX_OK;
+    }
+    BlockView bv = c->bv;
+    KArgs aa = a;
+    void* args[] = {(void*)&bv, (void*)&aa, (void*)&ca};
+    CK(cudaLaunchCooperativeKernel((void*)pcg_coop_phi_tri_kernel, dim3(c->bm.nb), dim3(kThreads), args, smem, c->stream));
+    c->launches++;
+    return PFX_OK;
+}
+
 int coop_u(pfx_ctx* c, const KArgs& a, const CoopArgs& ca, bool configure) {
     if (c->mat.smodel == M_ISO) return coop_u_tri<M_ISO>(c, a, ca, configure);
     if (c->mat.smodel == M_SPECTRAL) return coop_u_tri<M_SPECTRAL>(c, a, ca, configure);
@@ -596,7 +614,8 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
     const double* dinv = kind == LIN_MASS ? c->dinv_mass : c->w_dinv;
     *converged = false;
     *iters = 0;
-    if (kind == LIN_U && c->n_ranks == 1 && c->coop_capacity >= c->bm.nb && c->coop_bar) {
+    if ((kind == LIN_U || (kind == LIN_PHI && c->cm && c->phi_coeff_fresh)) && c->n_ranks == 1 &&
+        c->coop_capacity >= c->bm.nb && c->coop_bar) {
         // small mesh: the whole solve in one cooperative launch (re-launched only if max_iters runs out)
         KArgs a = base_args(c);
         a.mask = mask;
@@ -608,7 +627,7 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
         for (;;) {
             ca.max_iters = (int)std::min<int64_t>(4096, (int64_t)c->prm.cg_max_it - *iters);
             CK(cudaMemsetAsync(c->coop_bar, 0, sizeof(unsigned long long), c->stream));
-            int st = coop_u(c, a, ca, false);
+            int st = (kind == LIN_U) ? coop_u(c, a, ca, false) : coop_phi(c, a, ca, false);
             if (st) return st;
             CK(cudaMemcpyAsync(c->h_pinned, c->S, S_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
@@ -1007,6 +1026,7 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
         if ((st = launch_reduce<RED_ENERGY>(c, z))) return st;
         if (c->cell_type == PFX_CELL_TRIANGLE && bm.max_elems <= 2 * kThreads && !getenv("PFX_NO_COOP")) {
             if ((st = coop_u(c, z, CoopArgs(), true))) return st;
+            if ((st = coop_phi(c, z, CoopArgs(), true))) return st;
             if ((st = dev_alloc(c, &c->coop_bar, (size_t)2))) return st;
         }
         c->configuring = false;

@@ -1219,16 +1219,20 @@ struct CoopArgs {
     int resume;               // 0: start from x = 0; 1: continue from the saved x, r, p
 };
 
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void coop_barrier(unsigned long long* bar, unsigned long long target) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1ull);
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar), "l"(1ull) : "memory");
         long long spins = 0;
-        while (ld_acquire_sys(bar) < target) {
+        while (ld_acquire_gpu(bar) < target) {
             if (++spins > kSpinLimit) break;
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -1398,6 +1402,142 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_coop_u_tri_kernel(BlockView b
     }
     // ---- save state and publish the PCG bookkeeping
     if (own) { Xg[n0 + tid] = x; Pg[n0 + tid] = sV[tid]; }
+    if (b == 0 && tid == 0) {
+        ca.S[S_RR] = rr; ca.S[S_RZ0] = rz;
+        ca.S[S_ITERS] += (double)it;
+        ca.S[S_DONE] = (!(rr > thresh) || !(rr > 0.0)) ? 1.0 : 0.0;
+    }
+}
+
+// same structure for the phase-field operator J_phi (scalar unknown; coefficients cm, cg per node)
+__global__ void __launch_bounds__(kThreads, 1) pcg_coop_phi_tri_kernel(BlockView bv, KArgs a, CoopArgs ca) {
+    extern __shared__ double smem[];
+    __shared__ double s_red[kMaxRed * 32];
+    __shared__ double s_tot[2];
+    const int tid = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
+    const int4 ma = bv.meta[2 * b], mb = bv.meta[2 * b + 1];
+    const int n0 = ma.x, n_own = ma.y, h0 = ma.z, n_halo = ma.w, n_loc = n_own + n_halo, e0 = mb.x, ne = mb.y;
+    const int ML = bv.max_loc, chunk = 2 * kThreads, MO = (bv.max_own + 1) & ~1, MLe = (ML + 1) & ~1;
+    double2* sX = reinterpret_cast<double2*>(smem);
+    double* sM = reinterpret_cast<double*>(sX + ML);     // cm
+    double* sG = sM + MLe;                               // cg
+    double* sV = sG + MLe;                               // p on every local node
+    double* sD = sV + MLe;                               // Jacobi data
+    double* sE = sD + MLe;                               // [3*chunk + 2]
+    int* sH = reinterpret_cast<int*>(sE + 3 * chunk + 2);
+    uint4* sI = reinterpret_cast<uint4*>(sH + ((ML + 3) & ~3));
+    const int zslot = 3 * chunk;
+    const double2* X2 = reinterpret_cast<const double2*>(a.X);
+    const uint2* LC = reinterpret_cast<const uint2*>(bv.lconn);
+    for (int i = tid; i < n_loc; i += kThreads) {
+        const int g = (i < n_own) ? n0 + i : bv.halo[h0 + i - n_own];
+        sX[i] = X2[g]; sM[i] = a.cm[g]; sG[i] = a.cg[g]; sD[i] = ca.dinv[g]; sH[i] = g;
+    }
+    if (tid < n_own) sI[tid] = bv.inc8[n0 + tid];
+    if (tid == 0) sE[zslot] = 0.0;
+    uint2 lc0 = make_uint2(0u, 0u), lc1 = lc0;
+    if (tid < ne) lc0 = LC[e0 + tid];
+    if (tid + kThreads < ne) lc1 = LC[e0 + tid + kThreads];
+    unsigned int mk = 0u;
+    double x = 0.0, r = 0.0, dv = 0.0;
+    const bool own = tid < n_own;
+    if (own) {
+        if (a.mask) mk = a.mask[n0 + tid];
+        dv = ca.dinv[n0 + tid];
+        if (ca.resume) { x = ca.x[n0 + tid]; r = ca.r[n0 + tid]; }
+        else { r = mk ? 0.0 : ca.F[n0 + tid]; ca.r[n0 + tid] = r; }
+    }
+    unsigned long long gen = 0;
+    int red_par = 0;
+    auto grid_sum2 = [&](double v0, double v1, double& t0, double& t1) {
+        double vals[2] = {v0, v1};
+        block_sum<2>(vals, s_red);
+        double* part = ca.partial + (size_t)red_par * nb * 2;
+        if (tid == 0) { part[2 * b] = vals[0]; part[2 * b + 1] = vals[1]; }
+        ++gen;
+        coop_barrier(ca.bar, gen * (unsigned long long)nb);
+        if (tid < 32) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int k = tid; k < nb; k += 32) { s0 += __ldcg(part + 2 * k); s1 += __ldcg(part + 2 * k + 1); }
+            s0 = warp_sum(s0); s1 = warp_sum(s1);
+            if (tid == 0) { s_tot[0] = s0; s_tot[1] = s1; }
+        }
+        __syncthreads();
+        t0 = s_tot[0]; t1 = s_tot[1];
+        red_par ^= 1;
+        __syncthreads();
+    };
+    double rz, rr;
+    grid_sum2(own ? r * dv * r : 0.0, own ? r * r : 0.0, rz, rr);
+    for (int i = tid; i < n_loc; i += kThreads) {
+        const int g = sH[i];
+        sV[i] = ca.resume ? ca.p[g] : sD[i] * __ldcg(ca.r + g);
+    }
+    __syncthreads();
+    double thresh = ca.S[S_THRESH];
+    if (!ca.resume) {
+        double ref = rr;
+        if (ca.bref_slot >= 0) ref = fmax(ca.S[ca.bref_slot], rr);
+        thresh = ca.rtol2 * ref;
+        if (b == 0 && tid == 0) { if (ca.bref_slot >= 0) ca.S[ca.bref_slot] = ref; ca.S[S_THRESH] = thresh; ca.S[S_ITERS] = 0.0; }
+    }
+    int it = 0;
+    while (it < ca.max_iters && rr > thresh && rr > 0.0) {
+        if (tid < ne) {
+            const int vx = lc0.x & 0xFFFF, vy = lc0.x >> 16, vz = lc0.y & 0xFFFF;
+            double f0, f1, f2;
+            tri_apply_phi_elem(sX[vx], sX[vy], sX[vz], sM[vx], sM[vy], sM[vz], sG[vx], sG[vy], sG[vz], sV[vx], sV[vy], sV[vz], f0, f1, f2);
+            sE[tid] = f0; sE[chunk + tid] = f1; sE[2 * chunk + tid] = f2;
+        }
+        if (tid + kThreads < ne) {
+            const int vx = lc1.x & 0xFFFF, vy = lc1.x >> 16, vz = lc1.y & 0xFFFF;
+            double f0, f1, f2;
+            tri_apply_phi_elem(sX[vx], sX[vy], sX[vz], sM[vx], sM[vy], sM[vz], sG[vx], sG[vy], sG[vz], sV[vx], sV[vy], sV[vz], f0, f1, f2);
+            sE[tid + kThreads] = f0; sE[chunk + tid + kThreads] = f1; sE[2 * chunk + tid + kThreads] = f2;
+        }
+        __syncthreads();
+        double Ap = 0.0, pv = 0.0;
+        if (own) {
+            const uint4 c8 = sI[tid];
+            const unsigned cw[4] = {c8.x, c8.y, c8.z, c8.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int code = (int)((cw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
+                Ap += sE[min((code & 3) * chunk + (code >> 2), zslot)];
+            }
+            if ((c8.w >> 16) == 0xFFFEu) {
+                int k0 = bv.inc_ptr[n0 + tid] + 7, k1 = bv.inc_ptr[n0 + tid + 1];
+                for (int k = k0; k < k1; ++k) {
+                    const int code = bv.inc[k];
+                    if (code >= 0xFFFE) break;
+                    Ap += sE[(code & 3) * chunk + (code >> 2)];
+                }
+            }
+            if (mk) Ap = 0.0;
+            pv = sV[tid];
+        }
+        double pAp, dummy;
+        grid_sum2(own ? pv * Ap : 0.0, 0.0, pAp, dummy);
+        const double alpha = rz / pAp;
+        double lz = 0.0, lr = 0.0;
+        if (own) {
+            x += alpha * pv;
+            r -= alpha * Ap;
+            ca.r[n0 + tid] = r;
+            lz = r * dv * r; lr = r * r;
+        }
+        double rz_new, rr_new;
+        grid_sum2(lz, lr, rz_new, rr_new);
+        const double beta = rz_new / rz;
+        rz = rz_new; rr = rr_new;
+        ++it;
+        for (int i = tid; i < n_loc; i += kThreads) {
+            const double rg = (i < n_own) ? ((i == tid) ? r : __ldcg(ca.r + n0 + i)) : __ldcg(ca.r + sH[i]);
+            sV[i] = sD[i] * rg + beta * sV[i];
+        }
+        __syncthreads();
+    }
+    if (own) { ca.x[n0 + tid] = x; ca.p[n0 + tid] = sV[tid]; }
     if (b == 0 && tid == 0) {
         ca.S[S_RR] = rr; ca.S[S_RZ0] = rz;
         ca.S[S_ITERS] += (double)it;
