@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "staggered_load_steps_per_second"
 UNIT = "steps/s"
-SAMPLE_N = 128           # CPU sample: same workload on a SAMPLE_N x SAMPLE_N grid
+SAMPLE_N = 160           # CPU sample: same workload on a SAMPLE_N x SAMPLE_N grid
 
 
 def measured_peak():

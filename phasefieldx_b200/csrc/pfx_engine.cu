@@ -51,10 +51,6 @@ struct Traction {
     double T[3] = {0, 0, 0};
 };
 
-struct DevBuf {
-    void* p = nullptr;
-};
-
 }  // namespace
 
 struct pfx_ctx {
@@ -77,7 +73,6 @@ struct pfx_ctx {
     bool has_fext = false;
     std::vector<BCSet> bcs_u, bcs_phi;
     std::vector<Traction> tractions;
-    bool bc_dirty_u = true, bc_dirty_phi = true;
     // reductions
     double* partial = nullptr;
     double* S = nullptr;          // PCG scalars
@@ -114,7 +109,6 @@ struct pfx_ctx {
     double* flush_buf = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t flush_n = 0;
-    std::vector<std::vector<int32_t>> tmp_idx;
     bool configuring = false;
     bool verbose = false;         // PFX_VERBOSE=1: per-Newton-iteration trace on stderr
     bool cg_adaptive = true;      // PFX_CG_ADAPTIVE=0: every PCG solve to cg_rtol of its own right-hand side

@@ -66,7 +66,6 @@ struct KArgs {
     const double* cg;
     double* tan;            // cached element tangents, SoA [21][tan_stride] (tets, nonlinear split)
     int64_t tan_stride;
-    int nred;
 };
 
 constexpr int kMaxRanks = 8;
@@ -1739,23 +1738,6 @@ __global__ void axpby_kernel(int64_t n, double* out, const double* a, double sa,
 __global__ void mask_zero_kernel(int64_t n, const uint8_t* mask, double* v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         if (mask[i]) v[i] = 0.0;
-}
-
-__global__ void fill_kernel(int64_t n, double* out, double v) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
-}
-
-// dots: res[0] = Σ a·b, res[1] = Σ a·a·w (optional w), deterministic two-stage
-__global__ void __launch_bounds__(kThreads) dot2_kernel(int64_t n, const double* a, const double* b, const double* c,
-                                                        const double* d, double* partial, double* result,
-                                                        unsigned int* counter) {
-    __shared__ double s_red[kMaxRed * 32];
-    double vals[2] = {0.0, 0.0};
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        vals[0] += a[i] * b[i];
-        if (c) vals[1] += c[i] * d[i];
-    }
-    grid_reduce<2>(vals, partial, result, counter, s_red);
 }
 
 // SNES residual assembly (dolfinx NonlinearProblem idiom):
