@@ -141,39 +141,26 @@ def main_reference(args, rank):
 
 # ------------------------------------------------------------------------------- GPU leg
 def build_rank_engine(w, rank, world, device, opts):
-    """Engine of this rank: whole mesh (world == 1) or its partition + NCCL attach."""
+    """Engine of this rank: whole mesh (world == 1) or its partition + NCCL / NVLink peer attach."""
     from phasefieldx_b200 import _lib, workloads as W
     if world == 1:
         return W.make_engine(w, device=device, **opts), None
     import torch.distributed as dist
-    P = _lib.Partition(w.cell_type, w.msh.geometry.x, w.msh.cells, world)
-    R = P.rank(rank)
-    l2g = R["l2g"]
-    g2l = np.full(w.msh.num_nodes, -1, dtype=np.int64)
-    g2l[l2g] = np.arange(len(l2g))
-    cells = g2l[w.msh.cells[R["cell_gid"]]].astype(np.int32)
+    from phasefieldx_b200.distributed import RankMesh, attach
     from phasefieldx_b200.Materials.conversion import get_lambda_lame, get_mu_lame
+    rm = RankMesh(w.msh.geometry.x, w.msh.cells, w.cell_type, world, rank)
     p = w.params
-    e = _lib.Engine(w.msh.geometry.x[l2g], cells, w.cell_type, get_lambda_lame(p["E"], p["nu"]), get_mu_lame(p["E"], p["nu"]),
+    e = _lib.Engine(rm.coords, rm.cells, w.cell_type, get_lambda_lame(p["E"], p["nu"]), get_mu_lame(p["E"], p["nu"]),
                     p["Gc"], p["l"], k=p["k"], model=_lib.model_code(p["degradation"], None if p["split_energy"] == "no" else p["split_energy"]),
                     irreversibility=(p["irreversibility"] == "miehe"), fatigue=p["fatigue"],
-                    fatigue_val=p.get("fatigue_val", 0.05625), device=device, n_owned=R["n_owned"],
-                    cell_primary=R["cell_primary"], **opts)
-    d = w.msh.geometry.dim
+                    fatigue_val=p.get("fatigue_val", 0.05625), device=device, n_owned=rm.n_owned,
+                    cell_primary=rm.cell_primary, **opts)
     local_sets = []
     for i, (_, dofs) in enumerate(w.bc_sets):
-        node, comp = dofs // d, dofs % d
-        keep = g2l[node] >= 0
+        keep, ldofs = rm.local_dofs(dofs, w.msh.geometry.dim)
         local_sets.append(keep)
-        e.set_bc_u(i, (g2l[node[keep]] * d + comp[keep]).astype(np.int32))
-    uid = [_lib.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(uid, src=0)
-    e.comm_attach(rank, world, uid[0], R)
-    if os.environ.get("PFX_NO_P2P", "0") != "1":
-        # NVLink peer path: all-gather the CUDA-IPC handles, map the peers' exchange buffers
-        handles = [None] * world
-        dist.all_gather_object(handles, e.p2p_export())
-        e.p2p_import(handles, _lib.peer_ghost_start(P, rank))
+        e.set_bc_u(i, ldofs)
+    attach(e, rm, dist)
     return e, local_sets
 
 

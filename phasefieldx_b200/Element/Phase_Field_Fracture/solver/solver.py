@@ -21,6 +21,13 @@ from phasefieldx_b200.Logger.library_versions import (log_end_analysis, log_libr
                                                       log_system_info, set_logger)
 
 
+class _NullLogger:
+    def info(self, *a, **k):
+        pass
+
+    error = info
+
+
 def _traction_sets(T_list_u):
     sets = []
     for T, ds in (T_list_u or []):
@@ -42,12 +49,25 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     if path is None:
         path = os.getcwd()
     result_folder_name = Data.results_folder_name
-    prepare_simulation(path, result_folder_name)
-    logger = set_logger(result_folder_name)
+    # one process per GPU under torchrun (the reference's `mpirun`): rank 0 owns the files
+    dist, rank, world = None, 0, 1
+    try:
+        import torch.distributed as _dist
+        if _dist.is_available() and _dist.is_initialized() and _dist.get_world_size() > 1:
+            dist, rank, world = _dist, _dist.get_rank(), _dist.get_world_size()
+            device = int(os.environ.get("LOCAL_RANK", device))
+    except ImportError:
+        pass
+    if rank == 0:
+        prepare_simulation(path, result_folder_name)
+    if dist is not None:
+        dist.barrier()
+    logger = set_logger(result_folder_name) if rank == 0 else _NullLogger()
     log_system_info(logger)
     log_library_versions(logger)
     Data.save_log_info(logger)
-    Data.save_parameters_to_csv(os.path.join(result_folder_name, "parameters.input"))
+    if rank == 0:
+        Data.save_parameters_to_csv(os.path.join(result_folder_name, "parameters.input"))
     log_model_information(msh, logger)
     logger.info("========== Stagger settings ===========")
     logger.info(f"  minimum stagger iterations: {min_stagger_iter}")
@@ -64,17 +84,38 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     # ---- device context (replaces the form / NonlinearProblem construction, solver.py:148-245)
     points, cells, ctype = fem.extract_mesh(msh)
     split = None if Data.split_energy == "no" else Data.split_energy
-    eng = _lib.Engine(points, cells, ctype, Data.lambda_, Data.mu, Data.Gc, Data.l, k=float(Data.k),
-                      model=_lib.model_code(Data.degradation, split),
-                      irreversibility=(Data.irreversibility == "miehe"), fatigue=bool(Data.fatigue),
-                      fatigue_val=float(Data.fatigue_val), device=device, **(solver_options or {}))
+    gdim = 3 if ctype == "tetrahedron" else 2
+    rmesh, keep_u, keep_phi = None, [], []
+    engine_kw = dict(k=float(Data.k), model=_lib.model_code(Data.degradation, split),
+                     irreversibility=(Data.irreversibility == "miehe"), fatigue=bool(Data.fatigue),
+                     fatigue_val=float(Data.fatigue_val), device=device, **(solver_options or {}))
+    if dist is None:
+        eng = _lib.Engine(points, cells, ctype, Data.lambda_, Data.mu, Data.Gc, Data.l, **engine_kw)
+    else:
+        from phasefieldx_b200.distributed import RankMesh, attach, gather_field
+        rmesh = RankMesh(points, cells, ctype, world, rank)
+        eng = _lib.Engine(rmesh.coords, rmesh.cells, ctype, Data.lambda_, Data.mu, Data.Gc, Data.l,
+                          n_owned=rmesh.n_owned, cell_primary=rmesh.cell_primary, **engine_kw)
     for i, bc in enumerate(bc_list_u):
-        eng.set_bc_u(i, fem.extract_bc(bc)[0])
+        dofs = fem.extract_bc(bc)[0]
+        if rmesh is not None:
+            keep, dofs = rmesh.local_dofs(dofs, gdim)
+            keep_u.append(keep)
+        eng.set_bc_u(i, dofs)
     for i, bc in enumerate(bc_list_phi):
-        eng.set_bc_phi(i, fem.extract_bc(bc)[0])
+        dofs = fem.extract_bc(bc)[0]
+        if rmesh is not None:
+            keep, dofs = rmesh.local_dofs(dofs, 1)
+            keep_phi.append(keep)
+        eng.set_bc_phi(i, dofs)
     tractions = _traction_sets(T_list_u)
     for i, (_, nodes, w) in enumerate(tractions):
+        if rmesh is not None:
+            keep, nodes = rmesh.local_nodes(nodes)
+            w = np.asarray(w)[keep]
         eng.set_traction(i, nodes, w)
+    if rmesh is not None:
+        attach(eng, rmesh, dist)
     for key, val in (("ksp_type", "pcg (Jacobi), matrix-free on GPU"), ("snes_linesearch_type", "none"),
                      ("snes_max_it", eng.params.snes_max_it), ("snes_rtol", eng.params.snes_rtol),
                      ("snes_atol", eng.params.snes_atol), ("cg_rtol", eng.params.cg_rtol)):
@@ -83,7 +124,7 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     start = time.perf_counter()
     logger.info(f" start time: {start}")
     vtk_sol = None
-    if Data.save_solution_vtu:
+    if Data.save_solution_vtu and rank == 0:
         vtk_sol = VTKFile(None, os.path.join(result_folder_name, "paraview-solutions_vtu", "phasefieldx.pvd"), "w")
     logger.info(" S t a r t i n g    A n a l y s i s ")
     logger.info(" ---------------------------------- ")
@@ -103,9 +144,11 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
                 update_loading(T_list_u, t)
             # re-read every mutable value after the callbacks (solver.py:306-312)
             for i, bc in enumerate(bc_list_u):
-                eng.set_bc_values_u(i, fem.extract_bc(bc)[1])
+                vals = fem.extract_bc(bc)[1]
+                eng.set_bc_values_u(i, vals if rmesh is None else vals[keep_u[i]])
             for i, bc in enumerate(bc_list_phi):
-                eng.set_bc_values_phi(i, fem.extract_bc(bc)[1])
+                vals = fem.extract_bc(bc)[1]
+                eng.set_bc_values_phi(i, vals if rmesh is None else vals[keep_phi[i]])
             for i, (T, _, _) in enumerate(tractions):
                 eng.set_traction_value(i, np.asarray(T.value, dtype=np.float64).reshape(-1))
 
@@ -130,24 +173,37 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
             logger.info(f" PCG iterations (u, Φ, projection): {rep['cg_its_u']}, {rep['cg_its_phi']}, {rep['cg_its_proj']}")
 
             logger.info("\n\n Saving results: ")
-            append_results_to_file(os.path.join(result_folder_name, "phasefieldx.conv"),
-                                   '#step\tstagger\titerPhi\titerU', step, rep["stagger"], rep["phi_its"], rep["u_its"])
-            append_results_to_file(os.path.join(result_folder_name, "top.dof"),
-                                   '#step\tUx\tUy\tUz\tphi', step, bc_ux, bc_uy, bc_uz, 0.0)
+            if rank == 0:
+                append_results_to_file(os.path.join(result_folder_name, "phasefieldx.conv"),
+                                       '#step\tstagger\titerPhi\titerU', step, rep["stagger"], rep["phi_its"], rep["u_its"])
+                append_results_to_file(os.path.join(result_folder_name, "top.dof"),
+                                       '#step\tUx\tUy\tUz\tphi', step, bc_ux, bc_uy, bc_uz, 0.0)
+            # reactions and energies are collective (global values on every rank); unlike the reference
+            # (solver.py:427) the reaction files are also written in multi-rank runs
             for i in range(len(bc_list_u)):
                 R = eng.reaction(i)
-                append_results_to_file(os.path.join(result_folder_name, bcs_list_u_names[i] + ".reaction"),
-                                       '#step\tRx\tRy\tRz', step, float(R[0]), float(R[1]), float(R[2]))
+                if rank == 0:
+                    append_results_to_file(os.path.join(result_folder_name, bcs_list_u_names[i] + ".reaction"),
+                                           '#step\tRx\tRy\tRz', step, float(R[0]), float(R[1]), float(R[2]))
             en = eng.energies()
             header = '#step\tEplusW\tE\tW\tW_phi\tW_gradphi\tgamma\tgamma_phi\tgamma_gradphi\tPSI_a\tPSI_b\talpha_acum'
-            append_results_to_file(os.path.join(result_folder_name, "total.energy"), header, step,
-                                   *[en[c] for c in _lib.ENERGY_COLUMNS])
-            if vtk_sol is not None and (step % max(1, int(vtu_every)) == 0):
-                vtk_sol.write_function(msh, {"phi": eng.get_field("phi"), "u": eng.get_field("u").reshape(-1, d)}, step)
+            if rank == 0:
+                append_results_to_file(os.path.join(result_folder_name, "total.energy"), header, step,
+                                       *[en[c] for c in _lib.ENERGY_COLUMNS])
+            if Data.save_solution_vtu and (step % max(1, int(vtu_every)) == 0):
+                if rmesh is None:
+                    phi_out, u_out = eng.get_field("phi"), eng.get_field("u").reshape(-1, d)
+                else:
+                    dev = f"cuda:{device}"
+                    phi_out, u_out = gather_field(eng, rmesh, "phi", dist, dev), gather_field(eng, rmesh, "u", dist, dev)
+                if vtk_sol is not None:
+                    vtk_sol.write_function(msh, {"phi": phi_out, "u": u_out}, step)
             t += dt
             step += 1
     finally:
         if vtk_sol is not None:
             vtk_sol.close()
+        if dist is not None:
+            dist.barrier()          # peers keep each other's buffers mapped: close together
         eng.close()
     log_end_analysis(logger, time.perf_counter() - start)
