@@ -67,3 +67,28 @@ def test_partition_and_ghost_maps_bit_exact(n_ranks):
         # replay of an external partition
         P2 = _lib.Partition(m.cell_type, m.geometry.x, m.cells, n_ranks, cell_rank=cr[::-1].copy())
         assert np.array_equal(P2.cell_rank(), cr[::-1])
+
+
+def test_rank_mesh_local_views_cover_the_mesh():
+    """distributed.RankMesh: local meshes, Dirichlet dof maps and peer ghost offsets (host logic)."""
+    from phasefieldx_b200 import _lib, mesh as M
+    from phasefieldx_b200.distributed import RankMesh
+    m = M.create_rectangle(None, [[0, 0], [1, 1]], [12, 9])
+    world = 3
+    top = np.nonzero(np.isclose(m.geometry.x[:, 1], 1.0))[0]
+    dofs = (top[:, None] * 2 + np.arange(2)).ravel()
+    owned_seen = np.zeros(m.num_nodes, dtype=int)
+    for r in range(world):
+        rm = RankMesh(m.geometry.x, m.cells, m.cell_type, world, r)
+        owned_seen[rm.l2g[: rm.n_owned]] += 1
+        assert np.array_equal(rm.coords, m.geometry.x[rm.l2g])
+        assert rm.cells.min() >= 0 and rm.cells.max() < len(rm.l2g)
+        keep, ld = rm.local_dofs(dofs, 2)
+        assert np.array_equal(rm.l2g[ld // 2] * 2 + ld % 2, dofs[keep])
+        gs = _lib.peer_ghost_start(rm.partition, r)
+        for j, q in enumerate(rm.plan["neighbors"]):
+            Q = rm.partition.rank(int(q))
+            n_send = int(rm.plan["send_off"][j + 1] - rm.plan["send_off"][j])
+            sent_global = rm.l2g[rm.plan["send_idx"][rm.plan["send_off"][j]: rm.plan["send_off"][j + 1]]]
+            assert np.array_equal(Q["l2g"][gs[j]: gs[j] + n_send], sent_global)     # lands on the right ghosts
+    assert np.all(owned_seen == 1)
