@@ -162,6 +162,15 @@ int pfx_algorithmic_bytes(pfx_ctx* ctx, int kind, double* bytes);
 int pfx_launch_count(pfx_ctx* ctx, int64_t* n);
 int pfx_block_stats(pfx_ctx* ctx, int64_t out[8]);
 
+/* ---- output formatting (host only; replaces the ASCII conversion inside dolfinx
+ * VTKFile.write_function as called by reference solver.py:476-477) -------------------------
+ * Write n_rows rows of ncomp_in doubles as shortest round-trip decimal text, each number
+ * followed by one blank, rows padded with "0 " to ncomp_out components (dolfinx pads vectors
+ * to 3).  Returns the bytes written, or -1 when cap < n_rows*ncomp_out*25 (i64: n*21). */
+int64_t pfx_format_f64(const double* v, int64_t n_rows, int32_t ncomp_in, int32_t ncomp_out, char* out,
+                       int64_t cap);
+int64_t pfx_format_i64(const int64_t* v, int64_t n, char* out, int64_t cap);
+
 /* ---- multi-GPU: partition + ghost maps (dolfinx IndexMap/Scatterer + graph partitioner) ---
  * Host-only, deterministic.  cell_rank_in may supply an external partition (replay of a
  * dolfinx partition) or be NULL (recursive coordinate bisection of cell centroids).

@@ -197,7 +197,7 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
                     dev = f"cuda:{device}"
                     phi_out, u_out = gather_field(eng, rmesh, "phi", dist, dev), gather_field(eng, rmesh, "u", dist, dev)
                 if vtk_sol is not None:
-                    vtk_sol.write_function(msh, {"phi": phi_out, "u": u_out}, step)
+                    vtk_sol.write_function(msh, {"phi": phi_out, "u": u_out}, step, background=True)
             t += dt
             step += 1
     finally:

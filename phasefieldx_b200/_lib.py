@@ -60,7 +60,7 @@ SYMBOLS = [
     "pfx_l2_error", "pfx_time_operator", "pfx_algorithmic_bytes", "pfx_launch_count", "pfx_block_stats",
     "pfx_partition_create", "pfx_partition_destroy", "pfx_partition_cell_rank", "pfx_partition_node_owner",
     "pfx_partition_rank_sizes", "pfx_partition_rank_maps", "pfx_partition_rank_plan", "pfx_comm_unique_id",
-    "pfx_comm_attach", "pfx_comm_p2p_export", "pfx_comm_p2p_import",
+    "pfx_comm_attach", "pfx_comm_p2p_export", "pfx_comm_p2p_import", "pfx_format_f64", "pfx_format_i64",
 ]
 
 _lib = None
@@ -120,6 +120,10 @@ def load():
     lib.pfx_comm_attach.argtypes = [C.c_void_p, C.c_int, C.c_int, p8, C.c_int, pi, pl, pi, pl]
     lib.pfx_comm_p2p_export.argtypes = [C.c_void_p, p8]
     lib.pfx_comm_p2p_import.argtypes = [C.c_void_p, p8, pl]
+    lib.pfx_format_f64.restype = C.c_int64
+    lib.pfx_format_f64.argtypes = [pd, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
+    lib.pfx_format_i64.restype = C.c_int64
+    lib.pfx_format_i64.argtypes = [pl, C.c_int64, C.c_void_p, C.c_int64]
     _lib = lib
     return lib
 
@@ -433,6 +437,29 @@ def comm_unique_id():
     if st:
         raise PfxError(st, "pfx_comm_unique_id failed (NCCL not loadable?)")
     return uid.tobytes()
+
+
+def format_f64(values, ncomp_out=None):
+    """Shortest round-trip ASCII of a [N] or [N, ncomp] float64 array (blank separated, rows
+    padded with zeros to ncomp_out) as bytes — the VTU writer's number formatting."""
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    n = v.shape[0]
+    nc = 1 if v.ndim == 1 else v.shape[1]
+    nco = nc if ncomp_out is None else int(ncomp_out)
+    buf = np.empty(max(1, n * nco * 25), dtype=np.uint8)
+    m = load().pfx_format_f64(_pd(v), n, nc, nco, buf.ctypes.data, buf.size)
+    if m < 0:
+        raise PfxError(2, "pfx_format_f64: bad arguments")
+    return buf[:max(0, m - 1)].tobytes()
+
+
+def format_i64(values):
+    v = np.ascontiguousarray(values, dtype=np.int64).ravel()
+    buf = np.empty(max(1, v.size * 21), dtype=np.uint8)
+    m = load().pfx_format_i64(_pl(v), v.size, buf.ctypes.data, buf.size)
+    if m < 0:
+        raise PfxError(2, "pfx_format_i64: bad arguments")
+    return buf[:max(0, m - 1)].tobytes()
 
 
 def device_count():

@@ -46,7 +46,7 @@ def build(force=False, verbose=False, ptxas_log=None):
     bdir = os.path.join(ROOT, "build")
     os.makedirs(bdir, exist_ok=True)
     objs, procs = [], []
-    for src in ("pfx_engine.cu", "pfx_blocks.cpp"):
+    for src in ("pfx_engine.cu", "pfx_blocks.cpp", "pfx_format.cpp"):
         obj = os.path.join(bdir, src.rsplit(".", 1)[0] + ".o")
         cmd = [nv] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_log else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:

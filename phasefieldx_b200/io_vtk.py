@@ -15,49 +15,103 @@ _VTK_TYPE = {"triangle": 69, "quadrilateral": 70, "tetrahedron": 71}
 _VTK_PERM = {"triangle": [0, 1, 2], "quadrilateral": [0, 1, 3, 2], "tetrahedron": [0, 1, 2, 3]}
 
 
-def _arr(a, fmt):
-    return " ".join(fmt % v for v in np.asarray(a).ravel())
+def _f64(a, ncomp_out=None):
+    from phasefieldx_b200._lib import format_f64
+    return format_f64(a, ncomp_out)
+
+
+def _i64(a):
+    from phasefieldx_b200._lib import format_i64
+    return format_i64(a)
+
+
+def _da(attrs, payload):
+    return b'        <DataArray ' + attrs.encode() + b' format="ascii">' + payload + b"</DataArray>"
 
 
 class VTKFile:
+    """Numbers are formatted natively (pfx_format_f64/_i64 in libpfx_b200.so: shortest text
+    that reads back bit-exactly); everything that does not change between load steps —
+    points, cells, id arrays — is formatted once and reused."""
+
     def __init__(self, comm, filename, mode="w"):
         self.pvd = filename
         self.dir = os.path.dirname(filename)
         self.stem = os.path.splitext(os.path.basename(filename))[0]
         self.records = []
+        self._static = None
+        self._pending = None
+        self._error = None
         os.makedirs(self.dir, exist_ok=True)
 
-    def write_function(self, msh, fields, t):
-        """fields: dict name -> array [N] or [N, ncomp<=3] in mesh node order."""
-        x = msh.geometry.x
+    def _static_part(self, msh):
+        key = (id(msh), msh.geometry.x.shape, msh.cells.shape)
+        if self._static is not None and self._static[0] == key:
+            return self._static[1]
+        x = np.asarray(msh.geometry.x, dtype=np.float64)
+        if x.shape[1] < 3:
+            x = np.hstack([x, np.zeros((len(x), 3 - x.shape[1]))])
         cells = msh.cells[:, _VTK_PERM[msh.cell_type]]
         nn, ne, nv = len(x), len(cells), cells.shape[1]
+        L = [b'<?xml version="1.0"?>', b'<VTKFile type="UnstructuredGrid" version="2.2">', b"  <UnstructuredGrid>",
+             f'    <Piece NumberOfPoints="{nn}" NumberOfCells="{ne}">'.encode(), b"      <Points>",
+             _da('type="Float64" NumberOfComponents="3"', _f64(x)),
+             b"      </Points>", b"      <Cells>",
+             _da('type="Int32" Name="connectivity"', _i64(cells)),
+             _da('type="Int32" Name="offsets"', _i64(np.arange(1, ne + 1) * nv)),
+             _da('type="Int8" Name="types"', _i64(np.full(ne, _VTK_TYPE[msh.cell_type]))),
+             b"      </Cells>", b"      <CellData>",
+             _da('type="UInt8" Name="vtkGhostType"', _i64(np.zeros(ne, int))),
+             _da('type="Int64" Name="vtkOriginalCellIds"', _i64(np.arange(ne))),
+             b"      </CellData>", b"      <PointData>",
+             _da('type="Int64" Name="vtkOriginalPointIds"', _i64(np.arange(nn))),
+             _da('type="UInt8" Name="vtkGhostType"', _i64(np.zeros(nn, int)))]
+        head = b"\n".join(L) + b"\n"
+        self._static = (key, head)
+        return head
+
+    def write_function(self, msh, fields, t, background=False):
+        """fields: dict name -> array [N] or [N, ncomp<=3] in mesh node order.  With
+        background=True the file is formatted and written by a helper thread while the caller
+        goes on with the next load step (at most one file in flight; the arrays must not be
+        modified by the caller afterwards; close() waits for the last one)."""
+        self._join()
+        if background:
+            import threading
+
+            def run():
+                try:
+                    self._write(msh, fields, t)
+                except BaseException as exc:      # surfaced by the next call / close()
+                    self._error = exc
+            self._pending = threading.Thread(target=run, daemon=True)
+            self._pending.start()
+        else:
+            self._write(msh, fields, t)
+
+    def _join(self):
+        if self._pending is not None:
+            self._pending.join()
+            self._pending = None
+        if self._error is not None:
+            err, self._error = self._error, None
+            raise err
+
+    def _write(self, msh, fields, t):
+        head = self._static_part(msh)
         step = int(t)
         name = f"{self.stem}_p0_{step:06d}.vtu"
-        L = ['<?xml version="1.0"?>', '<VTKFile type="UnstructuredGrid" version="2.2">', "  <UnstructuredGrid>",
-             f'    <Piece NumberOfPoints="{nn}" NumberOfCells="{ne}">', "      <Points>",
-             '        <DataArray type="Float64" NumberOfComponents="3" format="ascii">' + _arr(x, "%.16g") + "</DataArray>",
-             "      </Points>", "      <Cells>",
-             '        <DataArray type="Int32" Name="connectivity" format="ascii">' + _arr(cells, "%d") + "</DataArray>",
-             '        <DataArray type="Int32" Name="offsets" format="ascii">' + _arr(np.arange(1, ne + 1) * nv, "%d") + "</DataArray>",
-             '        <DataArray type="Int8" Name="types" format="ascii">' + _arr(np.full(ne, _VTK_TYPE[msh.cell_type]), "%d") + "</DataArray>",
-             "      </Cells>", "      <CellData>",
-             '        <DataArray type="UInt8" Name="vtkGhostType" format="ascii">' + _arr(np.zeros(ne, int), "%d") + "</DataArray>",
-             '        <DataArray type="Int64" Name="vtkOriginalCellIds" format="ascii">' + _arr(np.arange(ne), "%d") + "</DataArray>",
-             "      </CellData>", "      <PointData>",
-             '        <DataArray type="Int64" Name="vtkOriginalPointIds" format="ascii">' + _arr(np.arange(nn), "%d") + "</DataArray>",
-             '        <DataArray type="UInt8" Name="vtkGhostType" format="ascii">' + _arr(np.zeros(nn, int), "%d") + "</DataArray>"]
+        L = []
         for fname, vals in fields.items():
             v = np.asarray(vals, dtype=np.float64)
             if v.ndim == 2:
-                pad = np.zeros((nn, 3))
-                pad[:, : v.shape[1]] = v
-                L.append(f'        <DataArray type="Float64" Name="{fname}" NumberOfComponents="3" format="ascii">' + _arr(pad, "%.16g") + "</DataArray>")
+                L.append(_da(f'type="Float64" Name="{fname}" NumberOfComponents="3"', _f64(v, 3)))
             else:
-                L.append(f'        <DataArray type="Float64" Name="{fname}" format="ascii">' + _arr(v, "%.16g") + "</DataArray>")
-        L += ["      </PointData>", "    </Piece>", "  </UnstructuredGrid>", "</VTKFile>"]
-        with open(os.path.join(self.dir, name), "w") as fh:
-            fh.write("\n".join(L) + "\n")
+                L.append(_da(f'type="Float64" Name="{fname}"', _f64(v)))
+        L += [b"      </PointData>", b"    </Piece>", b"  </UnstructuredGrid>", b"</VTKFile>"]
+        with open(os.path.join(self.dir, name), "wb") as fh:
+            fh.write(head)
+            fh.write(b"\n".join(L) + b"\n")
         self.records.append((t, name))
         self._write_pvd()
 
@@ -69,6 +123,7 @@ class VTKFile:
             fh.write("\n".join(L) + "\n")
 
     def close(self):
+        self._join()
         self._write_pvd()
 
 

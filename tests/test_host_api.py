@@ -178,3 +178,25 @@ def test_workloads_are_deterministic():
     w = W.notched_beam_3d(12, 4, 2)
     assert w.msh.cell_type == "tetrahedron" and all(len(d) > 0 for _, d in w.bc_sets)
     assert w.bc_values(3.0)[0][0] == -0.03
+
+
+def test_native_number_formatting_round_trips_bit_exactly():
+    """pfx_format_f64/_i64 (the VTU writer's ASCII conversion): text parses back to the same
+    bits, vectors are zero-padded like dolfinx pads u to 3 components, and the threaded path
+    (> 65536 rows) gives the same bytes as formatting the pieces one by one."""
+    from phasefieldx_b200 import _lib
+    rng = np.random.default_rng(5)
+    special = np.array([0.0, -0.0, 1.0, -1.0, 5e-324, 1.7976931348623157e308, 1e-5, 0.1, 1 / 3, 2.5e-7, 123456789.125])
+    txt = _lib.format_f64(special).decode()
+    back = np.array(txt.split(), dtype=np.float64)
+    assert np.array_equal(back.view(np.int64), special.view(np.int64))
+    assert txt.split()[:3] == ["0", "-0", "1"]
+    v = rng.standard_normal((200001, 2)) * 10.0 ** rng.integers(-12, 6, size=(200001, 1))
+    txt = _lib.format_f64(v, 3)
+    back = np.array(txt.split(), dtype=np.float64).reshape(-1, 3)
+    assert np.array_equal(back[:, :2], v) and not back[:, 2].any()
+    pieces = b" ".join(_lib.format_f64(v[a:a + 50000], 3) for a in range(0, len(v), 50000))
+    assert pieces == txt
+    ints = rng.integers(-2**62, 2**62, size=150000)
+    assert np.array_equal(np.array(_lib.format_i64(ints).split(), dtype=np.int64), ints)
+    assert _lib.format_f64(np.zeros((0, 2)), 3) == b"" and _lib.format_i64(np.zeros(0, int)) == b""
