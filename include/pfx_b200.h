@@ -161,6 +161,10 @@ int pfx_algorithmic_bytes(pfx_ctx* ctx, int kind, double* bytes);
 /* kernels launched by this context since creation (bench `gpu_launches`) */
 int pfx_launch_count(pfx_ctx* ctx, int64_t* n);
 int pfx_block_stats(pfx_ctx* ctx, int64_t out[8]);
+/* aggregate coarse space of the PCG (the stand-in for the reference's MUMPS factorisation,
+ * solver.py:198-205): out = {active (0/1), aggregates, colours of the probing set-up,
+ * set-ups done so far}.  Inactive on meshes of fewer than 32 blocks or with PFX_NO_COARSE=1. */
+int pfx_coarse_stats(pfx_ctx* ctx, int64_t out[4]);
 
 /* ---- output formatting (host only; replaces the ASCII conversion inside dolfinx
  * VTKFile.write_function as called by reference solver.py:476-477) -------------------------

@@ -57,7 +57,7 @@ SYMBOLS = [
     "pfx_default_params", "pfx_set_bc_u", "pfx_set_bc_values_u", "pfx_set_bc_phi", "pfx_set_bc_values_phi",
     "pfx_set_traction", "pfx_set_traction_value", "pfx_load_step", "pfx_reaction", "pfx_energies", "pfx_get_field",
     "pfx_set_field", "pfx_apply_u", "pfx_apply_phi", "pfx_apply_mass", "pfx_residual_u", "pfx_diag_u", "pfx_rhs_psi",
-    "pfx_l2_error", "pfx_time_operator", "pfx_algorithmic_bytes", "pfx_launch_count", "pfx_block_stats",
+    "pfx_l2_error", "pfx_time_operator", "pfx_algorithmic_bytes", "pfx_launch_count", "pfx_block_stats", "pfx_coarse_stats",
     "pfx_partition_create", "pfx_partition_destroy", "pfx_partition_cell_rank", "pfx_partition_node_owner",
     "pfx_partition_rank_sizes", "pfx_partition_rank_maps", "pfx_partition_rank_plan", "pfx_comm_unique_id",
     "pfx_comm_attach", "pfx_comm_p2p_export", "pfx_comm_p2p_import", "pfx_format_f64", "pfx_format_i64",
@@ -120,6 +120,7 @@ def load():
     lib.pfx_comm_attach.argtypes = [C.c_void_p, C.c_int, C.c_int, p8, C.c_int, pi, pl, pi, pl]
     lib.pfx_comm_p2p_export.argtypes = [C.c_void_p, p8]
     lib.pfx_comm_p2p_import.argtypes = [C.c_void_p, p8, pl]
+    lib.pfx_coarse_stats.argtypes = [C.c_void_p, pl]
     lib.pfx_format_f64.restype = C.c_int64
     lib.pfx_format_f64.argtypes = [pd, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
     lib.pfx_format_i64.restype = C.c_int64
@@ -394,6 +395,11 @@ class Engine:
         self._ck(self.lib.pfx_block_stats(self.h, _pl(s)))
         return dict(zip(("n_blocks", "max_owned", "max_local", "max_elems", "elems_with_overlap", "n_cells",
                          "halo_entries", "n_owned"), (int(v) for v in s)))
+
+    def coarse_stats(self):
+        s = np.zeros(4, dtype=np.int64)
+        self._ck(self.lib.pfx_coarse_stats(self.h, _pl(s)))
+        return dict(zip(("active", "aggregates", "colours", "setups"), (int(v) for v in s)))
 
     # ---------------------------------------------------------------- multi-GPU
     def comm_attach(self, rank, n_ranks, unique_id, plan):

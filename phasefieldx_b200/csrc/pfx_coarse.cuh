@@ -1,0 +1,364 @@
+// pfx_coarse.cuh — aggregate coarse space for the PCG: M^-1 = D^-1 + Z (Z^T A Z)^-1 Z^T.
+//
+// The reference factorises J_u and J_phi with MUMPS (solver.py:198-205, 237-244); the matrix-free
+// PCG that replaces it needs O(1/h) iterations with a Jacobi preconditioner, which is what a
+// 10^6-node load step spends its time on.  Aggregates are runs of consecutive CTA blocks of the
+// RCB tree (spatially compact, contiguous node ranges); every aggregate carries its rigid-body
+// modes (u: translations + rotations, phi: the constant).  The coarse matrix is small enough
+// (<= kCoarseMax rows) that its inverse is kept explicitly, in fp32 (36 MB: L2 resident), and
+// the coarse solve is one dense mat-vec spread over the SMs.  Additive combination keeps M^-1
+// symmetric positive definite for ANY symmetric positive definite coarse matrix, so Z^T A Z may
+// lag behind the current tangent (it is refreshed once per load step / when iterations grow).
+//
+// Per PCG iteration the Jacobi path's update / direction kernels are replaced by
+//   pcg_update_coarse_kernel    x += a p ; r -= a Ap ; sums r.D^-1 r, r.r ; w = Z^T r per chunk
+//   coarse_solve_kernel         y = Ainv w ; r.z = r.D^-1 r + w.y ; publishes the PCG scalars
+//   pcg_direction_coarse_kernel p = D^-1 r + Z y + b p
+// All sums have a fixed order (no atomics on data): results are run-to-run reproducible.
+#pragma once
+#include "pfx_kernels.cuh"
+
+namespace pfx {
+
+constexpr int kCoarseMax = 3072;     // coarse dofs of one operator
+
+struct CoarseView {
+    int n_agg, n_chunks, S, ld;       // S chunks (CTAs) per aggregate; ld: row stride of Ainv (multiple of 4)
+    const int32_t* chunk_node0;       // [n_chunks+1] owned-node range of every chunk
+    const float* rel;                 // [n_owned*GD] (x - centroid(aggregate)) / size(aggregate)
+    double* wpart;                    // [n_chunks*M] per-chunk pieces of Z^T r
+    double* y;                        // [n_agg*M]
+    const float* Ainv;                // [n_agg*M][ld]
+};
+
+template <int NC, int GD> struct Modes { static constexpr int M = NC == 1 ? 1 : (GD == 2 ? 3 : 6); };
+
+// w += Z_node^T v   (modes: translations, then rotations about x, y, z / about z in 2D)
+template <int NC, int GD>
+__device__ __forceinline__ void restrict_add(const float* rl, const double* v, double* w) {
+    if constexpr (NC == 1) {
+        w[0] += v[0];
+    } else if constexpr (GD == 2) {
+        w[0] += v[0]; w[1] += v[1];
+        w[2] += (double)rl[0] * v[1] - (double)rl[1] * v[0];
+    } else {
+        w[0] += v[0]; w[1] += v[1]; w[2] += v[2];
+        w[3] += (double)rl[1] * v[2] - (double)rl[2] * v[1];
+        w[4] += (double)rl[2] * v[0] - (double)rl[0] * v[2];
+        w[5] += (double)rl[0] * v[1] - (double)rl[1] * v[0];
+    }
+}
+
+// z = Z_node y
+template <int NC, int GD>
+__device__ __forceinline__ void prolong(const float* rl, const double* y, double* z) {
+    if constexpr (NC == 1) {
+        z[0] = y[0];
+    } else if constexpr (GD == 2) {
+        z[0] = y[0] - (double)rl[1] * y[2];
+        z[1] = y[1] + (double)rl[0] * y[2];
+    } else {
+        z[0] = y[0] + (double)rl[2] * y[4] - (double)rl[1] * y[5];
+        z[1] = y[1] - (double)rl[2] * y[3] + (double)rl[0] * y[5];
+        z[2] = y[2] + (double)rl[1] * y[3] - (double)rl[0] * y[4];
+    }
+}
+
+template <int NC, int GD>
+__device__ __forceinline__ void load_rel(const CoarseView& cv, int nd, float* rl) {
+    if constexpr (NC > 1) {
+        if constexpr (GD == 2) {
+            const float2 t = reinterpret_cast<const float2*>(cv.rel)[nd];
+            rl[0] = t.x; rl[1] = t.y;
+        } else {
+            for (int k = 0; k < GD; ++k) rl[k] = cv.rel[(size_t)nd * GD + k];
+        }
+    }
+}
+
+template <int NC>
+__device__ __forceinline__ void load_vec(const double* v, int nd, double* out) {
+    if constexpr (NC == 2) {
+        const double2 t = reinterpret_cast<const double2*>(v)[nd];
+        out[0] = t.x; out[1] = t.y;
+    } else {
+        for (int k = 0; k < NC; ++k) out[k] = v[(size_t)nd * NC + k];
+    }
+}
+template <int NC>
+__device__ __forceinline__ void store_vec(double* v, int nd, const double* in) {
+    if constexpr (NC == 2) {
+        reinterpret_cast<double2*>(v)[nd] = make_double2(in[0], in[1]);
+    } else {
+        for (int k = 0; k < NC; ++k) v[(size_t)nd * NC + k] = in[k];
+    }
+}
+
+// x += alpha p ; r -= alpha Ap ; per-chunk Z^T r ; grid sums r.D^-1 r, r.r -> S[S_STAGE..+1]
+// init != 0: r is only read (start of a solve; also ignores a stale DONE flag)
+template <int NC, int GD>
+__global__ void __launch_bounds__(kThreads) pcg_update_coarse_kernel(CoarseView cv, double* __restrict__ x, double* __restrict__ r,
+                                                                     const double* __restrict__ p, const double* __restrict__ Ap,
+                                                                     const double* __restrict__ dinv, double* S, int par,
+                                                                     int init, double* partial, unsigned int* counter) {
+    constexpr int M = Modes<NC, GD>::M;
+    __shared__ double s_red[kMaxRed * 32];
+    __shared__ bool is_last;
+    if (!init && S[S_DONE] != 0.0) return;
+    const int ch = blockIdx.x;
+    const int n0 = cv.chunk_node0[ch], n1 = cv.chunk_node0[ch + 1];
+    const double alpha = init ? 0.0 : S[S_RZ0 + par] / S[S_PAP];
+    double vals[M + 2];
+#pragma unroll
+    for (int k = 0; k < M + 2; ++k) vals[k] = 0.0;
+    for (int nd = n0 + (int)threadIdx.x; nd < n1; nd += kThreads) {
+        double rv[NC], dv[NC];
+        float rl[GD];
+        load_vec<NC>(r, nd, rv);
+        load_vec<NC>(dinv, nd, dv);
+        load_rel<NC, GD>(cv, nd, rl);
+        if (!init) {
+            double pv[NC], av[NC], xv[NC];
+            load_vec<NC>(p, nd, pv);
+            load_vec<NC>(Ap, nd, av);
+            load_vec<NC>(x, nd, xv);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) { rv[k] -= alpha * av[k]; xv[k] += alpha * pv[k]; }
+            store_vec<NC>(r, nd, rv);
+            store_vec<NC>(x, nd, xv);
+        }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) { vals[0] += rv[k] * dv[k] * rv[k]; vals[1] += rv[k] * rv[k]; }
+        restrict_add<NC, GD>(rl, rv, vals + 2);
+    }
+    block_sum<M + 2>(vals, s_red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < M; ++k) cv.wpart[(size_t)ch * M + k] = vals[2 + k];
+        partial[(size_t)ch * 2 + 0] = vals[0];
+        partial[(size_t)ch * 2 + 1] = vals[1];
+        __threadfence();
+        unsigned int t = atomicInc(counter, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double acc[2] = {0.0, 0.0};
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            acc[0] += __ldcg(&partial[(size_t)b * 2 + 0]);
+            acc[1] += __ldcg(&partial[(size_t)b * 2 + 1]);
+        }
+        block_sum<2>(acc, s_red);
+        if (threadIdx.x == 0) { S[S_STAGE] = acc[0]; S[S_STAGE + 1] = acc[1]; }
+    }
+}
+
+// 128-bit read of the coarse inverse with an L2 evict-last policy: the 36 MB matrix is re-read every
+// iteration while ~300 MB of vectors stream past it
+__device__ __forceinline__ float4 ld_keep(const float4* p, unsigned long long pol) {
+    float4 v;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(pol));
+    return v;
+}
+
+// y = Ainv w (fp32 matrix, fp64 accumulation), r.z = S[S_STAGE] + w.y.  One row per warp; a lane's
+// whole slice of the row (<= kCoarseMax/128 float4) is requested before w is staged in shared memory.
+// init: the sum goes back to S[S_STAGE] for pcg_setup_kernel; else the PCG scalars are published.
+template <int M>
+__global__ void __launch_bounds__(kThreads, 3) coarse_solve_kernel(CoarseView cv, double* S, int par, int init, double* partial,
+                                                                unsigned int* counter) {
+    constexpr int kSlice = kCoarseMax / 128;      // float4 per lane and row
+    constexpr int kFly = 8;                       // of which in flight at a time
+    extern __shared__ __align__(16) double s_w[];          // [ld]
+    __shared__ double s_red[kMaxRed * 32];
+    __shared__ bool is_last;
+    if (!init && S[S_DONE] != 0.0) return;
+    const int nc = cv.n_agg * M;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int ld4 = cv.ld >> 2;
+    const int row = blockIdx.x * nw + warp;
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    const float4* A4 = reinterpret_cast<const float4*>(cv.Ainv + (size_t)(row < nc ? row : 0) * cv.ld);
+    float4 a[kFly];
+#pragma unroll
+    for (int q = 0; q < kFly; ++q) {              // first batch flies while w is staged
+        const int j4 = lane + 32 * q;
+        a[q] = (row < nc && j4 < ld4) ? ld_keep(A4 + j4, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = threadIdx.x; i < cv.ld; i += blockDim.x) {
+        double t = 0.0;
+        if (i < nc) {
+            const int ag = i / M, k = i - ag * M;
+            for (int s = 0; s < cv.S; ++s) t += __ldcg(&cv.wpart[((size_t)ag * cv.S + s) * M + k]);
+        }
+        s_w[i] = t;
+    }
+    __syncthreads();
+    double wy[1] = {0.0};
+    if (row < nc) {
+        const double2* w2 = reinterpret_cast<const double2*>(s_w);
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 1
+        for (int q0 = 0; q0 < kSlice; q0 += kFly) {
+            float4 nx[kFly];
+            if (q0 + kFly < kSlice) {
+#pragma unroll
+                for (int q = 0; q < kFly; ++q) {
+                    const int j4 = lane + 32 * (q0 + kFly + q);
+                    nx[q] = (j4 < ld4) ? ld_keep(A4 + j4, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kFly; ++q) {
+                const int j4 = lane + 32 * (q0 + q);
+                if (j4 < ld4) {
+                    const double2 u0 = w2[2 * j4], u1 = w2[2 * j4 + 1];
+                    acc0 += (double)a[q].x * u0.x + (double)a[q].y * u0.y;
+                    acc1 += (double)a[q].z * u1.x + (double)a[q].w * u1.y;
+                }
+            }
+            if (q0 + kFly < kSlice) {
+#pragma unroll
+                for (int q = 0; q < kFly; ++q) a[q] = nx[q];
+            }
+        }
+        const double acc = warp_sum(acc0 + acc1);
+        if (lane == 0) { cv.y[row] = acc; wy[0] = acc * s_w[row]; }
+    }
+    block_sum<1>(wy, s_red);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = wy[0];
+        __threadfence();
+        unsigned int t = atomicInc(counter, gridDim.x - 1);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double acc[1] = {0.0};
+        for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) acc[0] += __ldcg(&partial[b]);
+        block_sum<1>(acc, s_red);
+        if (threadIdx.x == 0) {
+            const double rz = S[S_STAGE] + acc[0];
+            if (init) S[S_STAGE] = rz;
+            else pcg_finalize(S, par, rz, S[S_STAGE + 1]);
+        }
+    }
+}
+
+// p = D^-1 r + Z y + beta p   (Dirichlet dofs stay zero)
+template <int NC, int GD>
+__global__ void __launch_bounds__(kThreads) pcg_direction_coarse_kernel(CoarseView cv, double* __restrict__ p,
+                                                                        const double* __restrict__ r,
+                                                                        const double* __restrict__ dinv,
+                                                                        const uint8_t* __restrict__ mask, double* S, int par,
+                                                                        int init) {
+    constexpr int M = Modes<NC, GD>::M;
+    if (!init && S[S_DONE] != 0.0) return;
+    const int ch = blockIdx.x, ag = ch / cv.S;
+    const int n0 = cv.chunk_node0[ch], n1 = cv.chunk_node0[ch + 1];
+    double y[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) y[k] = cv.y[(size_t)ag * M + k];
+    const double beta = init ? 0.0 : S[S_RZ0 + (par ^ 1)] / S[S_RZ0 + par];
+    for (int nd = n0 + (int)threadIdx.x; nd < n1; nd += kThreads) {
+        double rv[NC], dv[NC], z[NC], pv[NC];
+        float rl[GD];
+        load_vec<NC>(r, nd, rv);
+        load_vec<NC>(dinv, nd, dv);
+        load_rel<NC, GD>(cv, nd, rl);
+        prolong<NC, GD>(rl, y, z);
+        if (init) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) pv[k] = 0.0;
+        } else {
+            load_vec<NC>(p, nd, pv);
+        }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            const bool fixed = mask && mask[(size_t)nd * NC + k];
+            pv[k] = fixed ? 0.0 : dv[k] * rv[k] + z[k] + beta * pv[k];
+        }
+        store_vec<NC>(p, nd, pv);
+    }
+}
+
+// ---- set-up of Z^T A Z by probing: one apply per (colour, mode) ---------------------------------
+// v = sum over the aggregates of one colour of their mode `mode` (zero on Dirichlet dofs)
+template <int NC, int GD>
+__global__ void __launch_bounds__(kThreads) coarse_probe_kernel(CoarseView cv, const int32_t* agg_colour, int colour, int mode,
+                                                                const uint8_t* mask, double* v) {
+    constexpr int M = Modes<NC, GD>::M;
+    const int ch = blockIdx.x, ag = ch / cv.S;
+    const int n0 = cv.chunk_node0[ch], n1 = cv.chunk_node0[ch + 1];
+    double y[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) y[k] = (k == mode && agg_colour[ag] == colour) ? 1.0 : 0.0;
+    for (int nd = n0 + (int)threadIdx.x; nd < n1; nd += kThreads) {
+        double z[NC];
+        float rl[GD];
+        load_rel<NC, GD>(cv, nd, rl);
+        prolong<NC, GD>(rl, y, z);
+#pragma unroll
+        for (int k = 0; k < NC; ++k)
+            if (mask && mask[(size_t)nd * NC + k]) z[k] = 0.0;
+        store_vec<NC>(v, nd, z);
+    }
+}
+
+template <int NC, int GD>
+__global__ void __launch_bounds__(kThreads) coarse_restrict_kernel(CoarseView cv, const double* __restrict__ v) {
+    constexpr int M = Modes<NC, GD>::M;
+    __shared__ double s_red[kMaxRed * 32];
+    const int ch = blockIdx.x;
+    const int n0 = cv.chunk_node0[ch], n1 = cv.chunk_node0[ch + 1];
+    double vals[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) vals[k] = 0.0;
+    for (int nd = n0 + (int)threadIdx.x; nd < n1; nd += kThreads) {
+        double vv[NC];
+        float rl[GD];
+        load_vec<NC>(v, nd, vv);
+        load_rel<NC, GD>(cv, nd, rl);
+        restrict_add<NC, GD>(rl, vv, vals);
+    }
+    block_sum<M>(vals, s_red);
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int k = 0; k < M; ++k) cv.wpart[(size_t)ch * M + k] = vals[k];
+}
+
+// column (j, mode) of Z^T A Z from the restricted probe: rows of aggregate i belong to the one
+// aggregate j of this colour within distance one of i (distance-2 colouring => unique)
+template <int M>
+__global__ void coarse_fill_kernel(CoarseView cv, const int32_t* nbrcol, int n_col, int colour, int mode, double* Ac, int ldc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cv.n_agg * M) return;
+    const int a = i / M, k = i - a * M;
+    const int j = nbrcol[(size_t)a * n_col + colour];
+    if (j < 0) return;
+    double t = 0.0;
+    for (int s = 0; s < cv.S; ++s) t += cv.wpart[((size_t)a * cv.S + s) * M + k];
+    Ac[(size_t)(j * M + mode) * ldc + i] = t;
+}
+
+// aggregates without a free dof in some mode leave an empty row/column: decouple them
+__global__ void coarse_fixdiag_kernel(int nc, double* Ac, int ldc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nc && !(Ac[(size_t)i * ldc + i] > 0.0)) Ac[(size_t)i * ldc + i] = 1.0;
+}
+
+// fp32 full symmetric copy of the inverse held in the lower triangle (column-major) of Ac
+__global__ void coarse_convert_kernel(int nc, const double* Ac, int ldc, float* Ainv, int ld) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+    if (col >= ld) return;
+    float v = 0.f;
+    if (col < nc) v = (float)(row >= col ? Ac[(size_t)col * ldc + row] : Ac[(size_t)row * ldc + col]);
+    Ainv[(size_t)row * ld + col] = v;
+}
+
+}  // namespace pfx

@@ -5,8 +5,10 @@
 // place of the MUMPS factorisation.  All arithmetic on fields runs in the kernels of
 // pfx_kernels.cuh; there is no CPU compute path.
 #include <cuda_runtime.h>
+#include <cusolverDn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -19,6 +21,7 @@
 #include "pfx_blocks.h"
 #include "pfx_comm.h"
 #include "pfx_kernels.cuh"
+#include "pfx_coarse.cuh"
 
 using namespace pfx;
 
@@ -49,6 +52,29 @@ struct Traction {
     double* d_w = nullptr;
     int64_t n = 0;
     double T[3] = {0, 0, 0};
+};
+
+// aggregate coarse space of the PCG (pfx_coarse.cuh); op 0 = J_u, op 1 = J_phi
+struct CoarseOp {
+    float* Ainv = nullptr;
+    int nc = 0, ld = 0;
+    bool valid = false, stale = true;
+    int64_t ref_its = -1;           // PCG iterations of the first solve after the last refresh
+    cudaGraphExec_t graph = nullptr;
+};
+
+struct Coarse {
+    bool enabled = false;
+    int n_agg = 0, S = 1, n_chunks = 0, n_col = 0, solve_ctas = 0;
+    int32_t *chunk_node0 = nullptr, *colour = nullptr, *nbrcol = nullptr;
+    float* rel = nullptr;
+    double *wpart = nullptr, *y = nullptr, *Ac = nullptr, *partial = nullptr, *work = nullptr;
+    int lwork = 0, ldc = 0;
+    int* info = nullptr;
+    cusolverDnHandle_t solver = nullptr;
+    CoarseOp op[2];
+    bool refresh_every_step = true;
+    int64_t setups = 0;
 };
 
 }  // namespace
@@ -122,6 +148,7 @@ struct pfx_ctx {
     bool generic_apply = false;   // PFX_GENERIC_APPLY=1: use the generic scatter kernel for J_u·v on triangles
     int apply_variant = 3;        // PFX_APPLY_VARIANT: 3 persistent + prefetched indices (default), 2 persistent, 1 one CTA per block
     int persist_ctas = 0, v3_ctas = 0, num_sms = 148;
+    Coarse coarse;
 };
 
 namespace {
@@ -458,6 +485,7 @@ int rebuild_bc(pfx_ctx* c, bool is_u) {
     CK(cudaMemcpyAsync(mask, hm.data(), n, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     (void)g;
+    c->coarse.op[is_u ? 0 : 1].stale = true;      // the masked modes changed
     return PFX_OK;
 }
 
@@ -531,6 +559,234 @@ int apply_lin(pfx_ctx* c, int kind, const double* v, double* y, const uint8_t* m
     return launch_scatter(c, op, a);
 }
 
+// --------------------------------------------------------------------------- coarse space
+// Aggregates = runs of consecutive blocks; distance-2 colouring of the aggregate graph for the
+// probing set-up.  Host work, once per mesh.
+int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
+    const BlockMesh& bm = c->bm;
+    Coarse& cs = c->coarse;
+    const char* nc_env = getenv("PFX_NO_COARSE");
+    if ((nc_env && nc_env[0] == '1') || bm.nb < 32) return PFX_OK;
+    const char* rf = getenv("PFX_COARSE_REFRESH");
+    if (rf && rf[0] == 'a') cs.refresh_every_step = false;        // "adaptive": only when iterations grow
+    const int D = c->dim, m_u = D == 2 ? 3 : 6;
+    const int max_agg = kCoarseMax / m_u;
+    const int g = (bm.nb + max_agg - 1) / max_agg;
+    const int n_agg = (bm.nb + g - 1) / g;
+    cs.n_agg = n_agg;
+    cs.S = std::max(1, (4 * c->num_sms + n_agg - 1) / n_agg);
+    cs.n_chunks = n_agg * cs.S;
+    std::vector<int32_t> agg0(n_agg + 1), chunk0(cs.n_chunks + 1);
+    for (int a = 0; a <= n_agg; ++a) agg0[a] = bm.node0[std::min(bm.nb, a * g)];
+    for (int a = 0; a < n_agg; ++a)
+        for (int s = 0; s < cs.S; ++s)
+            chunk0[a * cs.S + s] = agg0[a] + (int32_t)((int64_t)(agg0[a + 1] - agg0[a]) * s / cs.S);
+    chunk0[cs.n_chunks] = agg0[n_agg];
+    // geometry of the modes: coordinates relative to the aggregate centroid, scaled by its size
+    std::vector<int32_t> node_agg(c->n_owned);
+    std::vector<float> rel((size_t)c->n_owned * D);
+    for (int a = 0; a < n_agg; ++a) {
+        double cen[3] = {0, 0, 0}, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        const int n0 = agg0[a], n1 = agg0[a + 1];
+        for (int i = n0; i < n1; ++i)
+            for (int k = 0; k < D; ++k) {
+                double x = mesh->coords[3 * (int64_t)bm.perm[i] + k];
+                cen[k] += x; lo[k] = std::min(lo[k], x); hi[k] = std::max(hi[k], x);
+            }
+        double size = 0;
+        for (int k = 0; k < D; ++k) { cen[k] /= std::max(1, n1 - n0); size = std::max(size, 0.5 * (hi[k] - lo[k])); }
+        const double sc = size > 0 ? 1.0 / size : 1.0;
+        for (int i = n0; i < n1; ++i) {
+            node_agg[i] = a;
+            for (int k = 0; k < D; ++k) rel[(size_t)i * D + k] = (float)((mesh->coords[3 * (int64_t)bm.perm[i] + k] - cen[k]) * sc);
+        }
+    }
+    // aggregate graph: i ~ j when a cell has owned vertices in both
+    std::vector<std::vector<int32_t>> adj(n_agg);
+    for (int64_t e = 0; e < mesh->n_cells; ++e) {
+        int32_t ag[4]; int na = 0;
+        for (int k = 0; k < c->nv; ++k) {
+            int32_t nid = bm.iperm[mesh->cells[e * c->nv + k]];
+            if (nid >= c->n_owned) continue;
+            int32_t a = node_agg[nid];
+            bool seen = false;
+            for (int q = 0; q < na; ++q) seen |= (ag[q] == a);
+            if (!seen) ag[na++] = a;
+        }
+        for (int p = 0; p < na; ++p)
+            for (int q = 0; q < na; ++q)
+                if (p != q) adj[ag[p]].push_back(ag[q]);
+    }
+    for (auto& v : adj) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+    std::vector<int32_t> colour(n_agg, -1);
+    int n_col = 0;
+    std::vector<char> used;
+    for (int a = 0; a < n_agg; ++a) {
+        used.assign(n_col + 1, 0);
+        for (int32_t j : adj[a]) {
+            if (colour[j] >= 0) used[colour[j]] = 1;
+            for (int32_t k : adj[j]) if (k != a && colour[k] >= 0) used[colour[k]] = 1;
+        }
+        int col = 0;
+        while (col < n_col && used[col]) ++col;
+        colour[a] = col;
+        n_col = std::max(n_col, col + 1);
+    }
+    cs.n_col = n_col;
+    std::vector<int32_t> nbrcol((size_t)n_agg * n_col, -1);
+    for (int a = 0; a < n_agg; ++a) {
+        nbrcol[(size_t)a * n_col + colour[a]] = a;
+        for (int32_t j : adj[a]) {
+            int32_t& slot = nbrcol[(size_t)a * n_col + colour[j]];
+            if (slot >= 0 && slot != j) { c->err = "coarse space: colouring is not distance-2"; return PFX_ERR_BAD_ARG; }
+            slot = j;
+        }
+    }
+    int st;
+    if ((st = dev_upload(c, &cs.chunk_node0, chunk0))) return st;
+    if ((st = dev_upload(c, &cs.colour, colour))) return st;
+    if ((st = dev_upload(c, &cs.nbrcol, nbrcol))) return st;
+    if ((st = dev_upload(c, &cs.rel, rel))) return st;
+    const int nc_u = n_agg * m_u, nc_p = n_agg;
+    cs.ldc = nc_u;
+    cs.op[0].nc = nc_u; cs.op[0].ld = (nc_u + 3) / 4 * 4;
+    cs.op[1].nc = nc_p; cs.op[1].ld = (nc_p + 3) / 4 * 4;
+    if ((st = dev_alloc(c, &cs.wpart, (size_t)cs.n_chunks * m_u))) return st;
+    if ((st = dev_alloc(c, &cs.y, (size_t)nc_u))) return st;
+    if ((st = dev_alloc(c, &cs.Ac, (size_t)nc_u * nc_u))) return st;
+    cs.solve_ctas = (nc_u + kThreads / 32 - 1) / (kThreads / 32);      // one row of the inverse per warp
+    if ((st = dev_alloc(c, &cs.partial, (size_t)std::max(2 * cs.n_chunks, cs.solve_ctas)))) return st;
+    for (int k = 0; k < 2; ++k)
+        if ((st = dev_alloc(c, &cs.op[k].Ainv, (size_t)cs.op[k].nc * cs.op[k].ld))) return st;
+    if ((st = dev_alloc(c, &cs.info, (size_t)1))) return st;
+    if (cusolverDnCreate(&cs.solver) != CUSOLVER_STATUS_SUCCESS) { c->err = "cusolverDnCreate failed"; return PFX_ERR_CUDA; }
+    cusolverDnSetStream(cs.solver, c->stream);
+    int l1 = 0, l2 = 0;
+    if (cusolverDnDpotrf_bufferSize(cs.solver, CUBLAS_FILL_MODE_LOWER, nc_u, cs.Ac, cs.ldc, &l1) != CUSOLVER_STATUS_SUCCESS ||
+        cusolverDnDpotri_bufferSize(cs.solver, CUBLAS_FILL_MODE_LOWER, nc_u, cs.Ac, cs.ldc, &l2) != CUSOLVER_STATUS_SUCCESS) {
+        c->err = "cusolver workspace query failed";
+        return PFX_ERR_CUDA;
+    }
+    cs.lwork = std::max(l1, l2);
+    if ((st = dev_alloc(c, &cs.work, (size_t)std::max(1, cs.lwork)))) return st;
+    cs.enabled = true;
+    return PFX_OK;
+}
+
+CoarseView coarse_view(const pfx_ctx* c, int kind) {
+    const Coarse& cs = c->coarse;
+    CoarseView v;
+    v.n_agg = cs.n_agg; v.n_chunks = cs.n_chunks; v.S = cs.S; v.ld = cs.op[kind].ld;
+    v.chunk_node0 = cs.chunk_node0; v.rel = cs.rel; v.wpart = cs.wpart; v.y = cs.y; v.Ainv = cs.op[kind].Ainv;
+    return v;
+}
+
+bool coarse_active(const pfx_ctx* c, int kind) {
+    return c->coarse.enabled && kind != LIN_MASS && c->n_ranks == 1;
+}
+
+template <int NC, int GD>
+int coarse_setup_t(pfx_ctx* c, int kind, const uint8_t* mask) {
+    constexpr int M = Modes<NC, GD>::M;
+    Coarse& cs = c->coarse;
+    CoarseOp& op = cs.op[kind];
+    CoarseView cv = coarse_view(c, kind);
+    const int nc = op.nc, ldc = nc;
+    auto now = [&]() { cudaStreamSynchronize(c->stream); return std::chrono::steady_clock::now(); };
+    std::chrono::steady_clock::time_point t0, t1, t2;
+    if (c->verbose) t0 = now();
+    CK(cudaMemsetAsync(cs.Ac, 0, (size_t)nc * ldc * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->w_p, 0, (size_t)c->n_nodes * NC * sizeof(double), c->stream));
+    for (int col = 0; col < cs.n_col; ++col)
+        for (int mode = 0; mode < M; ++mode) {
+            coarse_probe_kernel<NC, GD><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, cs.colour, col, mode, mask, c->w_p);
+            int st = apply_lin(c, kind, c->w_p, c->w_Ap, mask, c->red, nullptr, 1);
+            if (st) return st;
+            coarse_restrict_kernel<NC, GD><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, c->w_Ap);
+            coarse_fill_kernel<M><<<(nc + 127) / 128, 128, 0, c->stream>>>(cv, cs.nbrcol, cs.n_col, col, mode, cs.Ac, ldc);
+            c->launches += 3;
+        }
+    coarse_fixdiag_kernel<<<(nc + 127) / 128, 128, 0, c->stream>>>(nc, cs.Ac, ldc);
+    CK(cudaGetLastError());
+    if (c->verbose) t1 = now();
+    op.valid = false;
+    int h_info[2] = {0, 0};
+    if (cusolverDnDpotrf(cs.solver, CUBLAS_FILL_MODE_LOWER, nc, cs.Ac, ldc, cs.work, cs.lwork, cs.info) != CUSOLVER_STATUS_SUCCESS) {
+        c->err = "cusolverDnDpotrf failed"; return PFX_ERR_CUDA;
+    }
+    CK(cudaMemcpyAsync(&h_info[0], cs.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (h_info[0] == 0) {
+        if (cusolverDnDpotri(cs.solver, CUBLAS_FILL_MODE_LOWER, nc, cs.Ac, ldc, cs.work, cs.lwork, cs.info) != CUSOLVER_STATUS_SUCCESS) {
+            c->err = "cusolverDnDpotri failed"; return PFX_ERR_CUDA;
+        }
+        CK(cudaMemcpyAsync(&h_info[1], cs.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    if (h_info[0] == 0 && h_info[1] == 0) {
+        dim3 grid((op.ld + 127) / 128, nc);
+        coarse_convert_kernel<<<grid, 128, 0, c->stream>>>(nc, cs.Ac, ldc, op.Ainv, op.ld);
+        CK(cudaGetLastError());
+        op.valid = true;
+    } else if (c->verbose) {
+        fprintf(stderr, "[pfx] coarse matrix of operator %d is not positive definite (potrf %d, potri %d): Jacobi only\n", kind,
+                h_info[0], h_info[1]);
+    }
+    if (c->verbose) {
+        t2 = now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[pfx] coarse set-up op %d: %d aggregates x %d modes, %d colours: probing %.2f ms, inverse %.2f ms\n", kind,
+                cs.n_agg, M, cs.n_col, ms(t0, t1), ms(t1, t2));
+    }
+    c->launches += 4;
+    op.stale = false;
+    op.ref_its = -1;
+    cs.setups++;
+    return PFX_OK;
+}
+
+int coarse_setup(pfx_ctx* c, int kind, const uint8_t* mask) {
+    if (kind == LIN_PHI) return c->dim == 2 ? coarse_setup_t<1, 2>(c, kind, mask) : coarse_setup_t<1, 3>(c, kind, mask);
+    return c->dim == 2 ? coarse_setup_t<2, 2>(c, kind, mask) : coarse_setup_t<3, 3>(c, kind, mask);
+}
+
+// tail of one PCG iteration / start of a solve (init) with the coarse space: update, coarse solve, direction
+template <int NC, int GD>
+int coarse_tail_t(pfx_ctx* c, int kind, int par, int init, const uint8_t* mask, const double* dinv, double rtol2, int bref_slot) {
+    constexpr int M = Modes<NC, GD>::M;
+    Coarse& cs = c->coarse;
+    CoarseView cv = coarse_view(c, kind);
+    pcg_update_coarse_kernel<NC, GD><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, c->w_x, c->w_r, c->w_p, c->w_Ap, dinv, c->S, par, init,
+                                                                             cs.partial, c->counter);
+    const int solve_ctas = (cs.op[kind].nc + kThreads / 32 - 1) / (kThreads / 32);
+    coarse_solve_kernel<M><<<solve_ctas, kThreads, (size_t)cv.ld * sizeof(double), c->stream>>>(cv, c->S, par, init, cs.partial,
+                                                                                              c->counter);
+    c->launches += 2;
+    if (init) {
+        pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, rtol2, bref_slot);
+        c->launches++;
+    }
+    pcg_direction_coarse_kernel<NC, GD><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, c->w_p, c->w_r, dinv, mask, c->S, par, init);
+    c->launches++;
+    CK(cudaGetLastError());
+    return PFX_OK;
+}
+
+int coarse_tail(pfx_ctx* c, int kind, int par, int init, const uint8_t* mask, const double* dinv, double rtol2 = 0.0,
+                int bref_slot = -1) {
+    if (kind == LIN_PHI)
+        return c->dim == 2 ? coarse_tail_t<1, 2>(c, kind, par, init, mask, dinv, rtol2, bref_slot)
+                           : coarse_tail_t<1, 3>(c, kind, par, init, mask, dinv, rtol2, bref_slot);
+    return c->dim == 2 ? coarse_tail_t<2, 2>(c, kind, par, init, mask, dinv, rtol2, bref_slot)
+                       : coarse_tail_t<3, 3>(c, kind, par, init, mask, dinv, rtol2, bref_slot);
+}
+
+int pcg_iteration_coarse(pfx_ctx* c, int kind, int par, const uint8_t* mask, const double* dinv) {
+    int st = apply_lin(c, kind, c->w_p, c->w_Ap, mask, c->S + S_PAP, c->S + S_DONE, 1);
+    if (st) return st;
+    return coarse_tail(c, kind, par, 0, mask, dinv);
+}
+
 // one PCG iteration (parity par) enqueued on the stream
 int pcg_iteration(pfx_ctx* c, int kind, int par, int64_t n, const uint8_t* mask, const double* dinv) {
     int nc = (kind == LIN_U) ? c->dim : 1;
@@ -585,16 +841,17 @@ int pcg_iteration(pfx_ctx* c, int kind, int par, int64_t n, const uint8_t* mask,
     return PFX_OK;
 }
 
-int build_graph(pfx_ctx* c, int kind, int64_t n, const uint8_t* mask, const double* dinv) {
+int build_graph(pfx_ctx* c, int kind, int64_t n, const uint8_t* mask, const double* dinv, bool coarse_on = false) {
     int iters = c->graph_iters;
     cudaGraph_t g;
     CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int st = PFX_OK;
-    for (int k = 0; k < iters && st == PFX_OK; ++k) st = pcg_iteration(c, kind, k & 1, n, mask, dinv);
+    for (int k = 0; k < iters && st == PFX_OK; ++k)
+        st = coarse_on ? pcg_iteration_coarse(c, kind, k & 1, mask, dinv) : pcg_iteration(c, kind, k & 1, n, mask, dinv);
     cudaError_t e = cudaStreamEndCapture(c->stream, &g);
     if (st) return st;
     CK(e);
-    CK(cudaGraphInstantiate(&c->graph[kind], g, 0));
+    CK(cudaGraphInstantiate(coarse_on ? &c->coarse.op[kind].graph : &c->graph[kind], g, 0));
     CK(cudaGraphDestroy(g));
     return PFX_OK;
 }
@@ -635,26 +892,38 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
         return PFX_OK;
     }
     int g = vgrid(c, n);
+    int st;
+    bool coarse_on = false;
+    if (coarse_active(c, kind)) {
+        if (c->coarse.op[kind].stale && (st = coarse_setup(c, kind, mask))) return st;
+        coarse_on = c->coarse.op[kind].valid;
+    }
+    const int bref_slot = (c->cg_adaptive && kind != LIN_MASS) ? S_BREF + kind : -1;
     pcg_init_kernel<<<g, kThreads, 0, c->stream>>>(n, c->w_F, mask, dinv, nullptr, nullptr, c->w_x, c->w_r, c->w_p,
                                                   c->partial, c->S + S_STAGE, c->counter);
     c->launches++;
-    int st = allreduce(c, c->S + S_STAGE, 2);
-    if (st) return st;
-    pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, rtol * rtol, (c->cg_adaptive && kind != LIN_MASS) ? S_BREF + kind : -1);
-    c->launches++;
+    if (coarse_on) {
+        // z0 = (D^-1 + Z Ainv Z^T) r0: the init pass of the coarse kernels redoes the sums and the direction
+        if ((st = coarse_tail(c, kind, 0, 1, mask, dinv, rtol * rtol, bref_slot))) return st;
+    } else {
+        if ((st = allreduce(c, c->S + S_STAGE, 2))) return st;
+        pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, rtol * rtol, bref_slot);
+        c->launches++;
+    }
     CK(cudaGetLastError());
     int64_t max_it = c->prm.cg_max_it;
     for (;;) {
         if (c->use_graph) {
-            if (!c->graph[kind]) {
-                st = build_graph(c, kind, n, mask, dinv);
+            cudaGraphExec_t& gx = coarse_on ? c->coarse.op[kind].graph : c->graph[kind];
+            if (!gx) {
+                st = build_graph(c, kind, n, mask, dinv, coarse_on);
                 if (st) return st;
             }
-            CK(cudaGraphLaunch(c->graph[kind], c->stream));
-            c->launches += (int64_t)c->graph_iters * 3;
+            CK(cudaGraphLaunch(gx, c->stream));
+            c->launches += (int64_t)c->graph_iters * (coarse_on ? 4 : 3);
         } else {
             for (int k = 0; k < c->graph_iters; ++k) {
-                st = pcg_iteration(c, kind, k & 1, n, mask, dinv);
+                st = coarse_on ? pcg_iteration_coarse(c, kind, k & 1, mask, dinv) : pcg_iteration(c, kind, k & 1, n, mask, dinv);
                 if (st) return st;
             }
         }
@@ -666,6 +935,11 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
         if (!(rr == rr)) { c->err = "NaN in PCG"; return PFX_ERR_NAN; }
         if (c->h_pinned[S_DONE] != 0.0) { *converged = true; break; }
         if (*iters >= max_it) break;
+    }
+    if (coarse_on) {                 // lagged coarse matrix: refresh when it stops paying
+        CoarseOp& op = c->coarse.op[kind];
+        if (op.ref_its < 0) op.ref_its = *iters;
+        else if (*iters > op.ref_its * 3 / 2 + 10) op.stale = true;
     }
     return PFX_OK;
 }
@@ -1030,7 +1304,7 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     a.y = c->dinv_mass;
     if ((st = launch_scatter(c, OP_DIAG_MASS, a))) return st;
     CK(cudaStreamSynchronize(c->stream));
-    return PFX_OK;
+    return build_coarse(c, mesh);
 }
 
 int pfx_destroy(pfx_ctx* c) {
@@ -1039,6 +1313,9 @@ int pfx_destroy(pfx_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int k = 0; k < 3; ++k)
         if (c->graph[k]) cudaGraphExecDestroy(c->graph[k]);
+    for (int k = 0; k < 2; ++k)
+        if (c->coarse.op[k].graph) cudaGraphExecDestroy(c->coarse.op[k].graph);
+    if (c->coarse.solver) cusolverDnDestroy(c->coarse.solver);
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->comm) nccl().CommDestroy(c->comm);
     for (void* p : c->allocs) cudaFree(p);
@@ -1103,6 +1380,7 @@ int pfx_set_field(pfx_ctx* c, int field, const double* host, int64_t n) {
         for (int k = 0; k < nc; ++k) tmp[i * nc + k] = host[(int64_t)c->bm.perm[i] * nc + k];
     CK(cudaMemcpyAsync(d, tmp.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    c->coarse.op[0].stale = c->coarse.op[1].stale = true;
     return PFX_OK;
 }
 
@@ -1121,6 +1399,7 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
     int it = 0, st;
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(c->S + S_BREF, 0, 3 * sizeof(double), c->stream));      // per-step PCG reference norms
+    if (c->coarse.enabled && c->coarse.refresh_every_step) c->coarse.op[0].stale = c->coarse.op[1].stale = true;
     const int gN = vgrid(c, N);
     while ((err_phi > o->stagger_tol || err_u > o->stagger_tol || it < o->min_stagger_iter) && it < o->max_stagger_iter) {
         ++it;
@@ -1328,6 +1607,7 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
+    bool timed_coarse = false;
     if ((kind == 0 || kind == 4) && c->use_tan) {          // linearise at the current state first
         KArgs t = base_args(c);
         int st = launch_scatter(c, OP_TANGENT_U, t);
@@ -1349,8 +1629,16 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
         CK(cudaMemcpyAsync(c->w_F, c->w_p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         pcg_init_kernel<<<vgrid(c, n), kThreads, 0, c->stream>>>(n, c->w_F, c->mask_u, c->w_dinv, nullptr, nullptr, c->w_x, c->w_r,
                                                                c->w_p, c->partial, c->S + S_STAGE, c->counter);
-        if ((st = allreduce(c, c->S + S_STAGE, 2))) return st;
-        pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, 0.0, -1);
+        if (coarse_active(c, LIN_U)) {
+            if ((st = coarse_setup(c, LIN_U, c->mask_u))) return st;
+            timed_coarse = c->coarse.op[LIN_U].valid;
+        }
+        if (timed_coarse) {
+            if ((st = coarse_tail(c, LIN_U, 0, 1, c->mask_u, c->w_dinv, 0.0, -1))) return st;
+        } else {
+            if ((st = allreduce(c, c->S + S_STAGE, 2))) return st;
+            pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, 0.0, -1);
+        }
         CK(cudaStreamSynchronize(c->stream));
     }
     for (int r = 0; r < reps; ++r) {
@@ -1364,7 +1652,8 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
         else if (kind == 2) st = apply_lin(c, LIN_MASS, c->w_p, c->w_Ap, nullptr, c->red, nullptr);
         else if (kind == 3) { KArgs a = base_args(c); a.y = c->w_t0; st = launch_scatter(c, OP_RESIDUAL_U, a); }
         else if (kind == 4) {
-            st = pcg_iteration(c, LIN_U, r & 1, c->n_owned * c->dim, c->mask_u, c->w_dinv);
+            st = timed_coarse ? pcg_iteration_coarse(c, LIN_U, r & 1, c->mask_u, c->w_dinv)
+                              : pcg_iteration(c, LIN_U, r & 1, c->n_owned * c->dim, c->mask_u, c->w_dinv);
         } else st = PFX_ERR_BAD_ARG;
         if (st) return st;
         CK(cudaEventRecord(e1, c->stream));
@@ -1379,6 +1668,12 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
 int pfx_launch_count(pfx_ctx* c, int64_t* n) {
     if (!c || !n) return PFX_ERR_BAD_ARG;
     *n = c->launches;
+    return PFX_OK;
+}
+
+int pfx_coarse_stats(pfx_ctx* c, int64_t out[4]) {
+    if (!c || !out) return PFX_ERR_BAD_ARG;
+    out[0] = c->coarse.enabled ? 1 : 0; out[1] = c->coarse.n_agg; out[2] = c->coarse.n_col; out[3] = c->coarse.setups;
     return PFX_OK;
 }
 

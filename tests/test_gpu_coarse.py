@@ -1,0 +1,104 @@
+"""GPU tests of the aggregate coarse space of the PCG (pfx_coarse.cuh): it only changes how fast
+the linear solves converge, never what they converge to — load steps with it agree with the CPU
+oracle (direct solves) and with the Jacobi-only PCG to the same 1e-8 / 1e-6 bars as every other
+parity test, on every cell type, while needing several times fewer iterations."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+from test_gpu_load_step import _compare_step, _pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def no_coop(monkeypatch):
+    # small test meshes would otherwise take the single-launch cooperative PCG (Jacobi)
+    monkeypatch.setenv("PFX_NO_COOP", "1")
+    return monkeypatch
+
+
+def _shear_mesh(n):
+    from phasefieldx_b200 import mesh as M
+    msh = M.create_rectangle(None, [[-0.5, -0.5], [0.5, 0.5]], [n, n])
+    return M.cut_slit(msh, lambda x: np.isclose(x[1], 0.0) & (x[0] < -1e-9), lambda c: c[1] > 0)
+
+
+def test_coarse_space_load_steps_vs_oracle(no_coop):
+    """Config-2-like slit square (reference plot_1712.py), spectral split, coarse space active."""
+    from oracle.solver import BC
+    msh = _shear_mesh(56)
+    o, e, P = _pair(msh, "triangle", "anisotropic", "spectral", l=0.06, block_nodes=64)
+    st = e.coarse_stats()
+    assert st["active"] == 1 and st["aggregates"] >= 32
+    x = msh.geometry.x
+    top = np.nonzero(np.isclose(x[:, 1], 0.5))[0]
+    bot = np.nonzero(np.isclose(x[:, 1], -0.5))[0]
+    side = np.nonzero((np.isclose(x[:, 0], -0.5) | np.isclose(x[:, 0], 0.5)) & (np.abs(x[:, 1]) < 0.5 - 1e-9))[0]
+    bcs = [BC((top[:, None] * 2 + np.arange(2)).ravel()), BC((bot[:, None] * 2 + np.arange(2)).ravel()), BC(side * 2 + 1)]
+    for i, bc in enumerate(bcs):
+        e.set_bc_u(i, bc.dofs)
+        e.set_bc_values_u(i, bc.values)
+    for step in range(1, 4):
+        bcs[0].values = np.tile([2e-3 * step, 0.0], len(top))
+        e.set_bc_values_u(0, bcs[0].values)
+        ro = o.load_step(bcs, [], max_stagger_iter=60)
+        rg = e.load_step(max_stagger_iter=60)
+        assert rg["stagger"] == ro["stagger"], (step, rg["stagger"], ro["stagger"])
+        _compare_step(o, e, bcs, step)
+    assert e.coarse_stats()["setups"] >= 3
+    e.close()
+
+
+def _run(msh, ctype, deg, sp, bc_sets, load, steps, monkeypatch, coarse, **kw):
+    from phasefieldx_b200 import _lib
+    from oracle.solver import Params
+    monkeypatch.setenv("PFX_NO_COARSE", "0" if coarse else "1")
+    P = Params(degradation=deg, split_energy=sp, **kw)
+    e = _lib.Engine(msh.geometry.x, msh.cells, ctype, P.lambda_, P.mu, P.Gc, P.l, k=P.k,
+                    model=_lib.model_code(deg, None if sp == "no" else sp), block_nodes=64)
+    assert e.coarse_stats()["active"] == (1 if coarse else 0)
+    for i, dofs in enumerate(bc_sets):
+        e.set_bc_u(i, dofs)
+    its = 0
+    for s in range(1, steps + 1):
+        for i, vals in enumerate(load(s)):
+            e.set_bc_values_u(i, vals)
+        r = e.load_step(max_stagger_iter=60)
+        its += r["cg_its_u"] + r["cg_its_phi"]
+    out = dict(u=e.get_field("u"), phi=e.get_field("phi"), H=e.get_field("H"), R=e.reaction(0), its=its)
+    e.close()
+    return out
+
+
+@pytest.mark.parametrize("ctype", ["quadrilateral", "tetrahedron", "triangle_isotropic"])
+def test_coarse_space_matches_jacobi_on_every_cell_type(ctype, no_coop):
+    from phasefieldx_b200 import mesh as M
+    if ctype == "tetrahedron":
+        msh = M.create_box(None, [[0, 0, 0], [3.0, 1.0, 0.8]], [20, 10, 8])
+        x = msh.geometry.x
+        left = np.nonzero(np.isclose(x[:, 0], 0.0))[0]
+        right = np.nonzero(np.isclose(x[:, 0], 3.0))[0]
+        sets = [right * 3 + 1, (left[:, None] * 3 + np.arange(3)).ravel()]
+        load = lambda s: [np.full(len(right), 4e-3 * s), np.zeros(3 * len(left))]
+        args = ("tetrahedron", "anisotropic", "spectral")
+        kw = dict(E=0.6, nu=0.2, Gc=0.00013, l=0.3)
+    else:
+        if ctype == "quadrilateral":
+            msh = M.create_rectangle(None, [[0, 0], [1, 1]], [60, 60], M.CellType.quadrilateral)
+            args = ("quadrilateral", "anisotropic", "deviatoric")
+        else:
+            msh = _shear_mesh(60)
+            args = ("triangle", "isotropic", "no")
+        x = msh.geometry.x
+        top = np.nonzero(np.isclose(x[:, 1], x[:, 1].max()))[0]
+        bot = np.nonzero(np.isclose(x[:, 1], x[:, 1].min()))[0]
+        sets = [(top[:, None] * 2 + np.arange(2)).ravel(), (bot[:, None] * 2 + np.arange(2)).ravel()]
+        load = lambda s: [np.tile([1e-3 * s, 1.5e-3 * s], len(top)), np.zeros(2 * len(bot))]
+        kw = dict(l=0.05)
+    a = _run(msh, *args, sets, load, 2, no_coop, True, **kw)
+    b = _run(msh, *args, sets, load, 2, no_coop, False, **kw)
+    for f in ("u", "phi", "H"):
+        assert rel_l2(a[f], b[f]) < 1e-8, (f, rel_l2(a[f], b[f]))
+    assert np.all(np.abs(a["R"] - b["R"]) <= 1e-6 * np.abs(b["R"]).max())
+    assert a["its"] * 2 < b["its"], (a["its"], b["its"])
