@@ -11,6 +11,7 @@
 // lag behind the current tangent (it is refreshed once per load step / when iterations grow).
 //
 // Per PCG iteration the Jacobi path's update / direction kernels are replaced by
+// (D = diagonal of A for phi, the nodal d x d diagonal blocks of A for u: block-Jacobi smoother)
 //   pcg_update_coarse_kernel    x += a p ; r -= a Ap ; sums r.D^-1 r, r.r ; w = Z^T r per chunk
 //   coarse_solve_kernel         y = Ainv w ; r.z = r.D^-1 r + w.y ; publishes the PCG scalars
 //   pcg_direction_coarse_kernel p = D^-1 r + Z y + b p
@@ -94,41 +95,76 @@ __device__ __forceinline__ void store_vec(double* v, int nd, const double* in) {
     }
 }
 
+// z = D^-1 r: diagonal (BLK = false, dinv[n*NC]) or nodal-block (BLK = true, inverse blocks
+// [n*NC(NC+1)/2] in the order (00, 11[, 22], 01[, 02, 12])) Jacobi smoother
+template <int NC, bool BLK>
+__device__ __forceinline__ void smooth(const double* __restrict__ dinv, int nd, const double* rv, double* z) {
+    if constexpr (!BLK) {
+        double dv[NC];
+        load_vec<NC>(dinv, nd, dv);
+#pragma unroll
+        for (int k = 0; k < NC; ++k) z[k] = dv[k] * rv[k];
+    } else if constexpr (NC == 2) {
+        const double* b = dinv + (size_t)nd * 3;
+        const double b00 = b[0], b11 = b[1], b01 = b[2];
+        z[0] = b00 * rv[0] + b01 * rv[1];
+        z[1] = b01 * rv[0] + b11 * rv[1];
+    } else {
+        const double* b = dinv + (size_t)nd * 6;
+        const double b00 = b[0], b11 = b[1], b22 = b[2], b01 = b[3], b02 = b[4], b12 = b[5];
+        z[0] = b00 * rv[0] + b01 * rv[1] + b02 * rv[2];
+        z[1] = b01 * rv[0] + b11 * rv[1] + b12 * rv[2];
+        z[2] = b02 * rv[0] + b12 * rv[1] + b22 * rv[2];
+    }
+}
+
 // x += alpha p ; r -= alpha Ap ; per-chunk Z^T r ; grid sums r.D^-1 r, r.r -> S[S_STAGE..+1]
 // init != 0: r is only read (start of a solve; also ignores a stale DONE flag)
-template <int NC, int GD>
+template <int NC, int GD, bool BLK>
 __global__ void __launch_bounds__(kThreads) pcg_update_coarse_kernel(CoarseView cv, double* __restrict__ x, double* __restrict__ r,
                                                                      const double* __restrict__ p, const double* __restrict__ Ap,
                                                                      const double* __restrict__ dinv, double* S, int par,
-                                                                     int init, double* partial, unsigned int* counter) {
+                                                                     int init, double* partial, unsigned int* counter,
+                                                                     const PeerView* pv = nullptr) {
     constexpr int M = Modes<NC, GD>::M;
     __shared__ double s_red[kMaxRed * 32];
     __shared__ bool is_last;
+    __shared__ double s_pap;
     if (!init && S[S_DONE] != 0.0) return;
     const int ch = blockIdx.x;
     const int n0 = cv.chunk_node0[ch], n1 = cv.chunk_node0[ch + 1];
-    const double alpha = init ? 0.0 : S[S_RZ0 + par] / S[S_PAP];
+    double pap = S[S_PAP];
+    if (pv && !init) {                          // fused all-reduce: p.Ap of all ranks from the mailboxes
+        if (threadIdx.x < 32) {
+            double sm[1];
+            mbox_sum(pv, sm, 1);
+            if (threadIdx.x == 0) s_pap = sm[0];
+        }
+        __syncthreads();
+        pap = s_pap;
+    }
+    const double alpha = init ? 0.0 : S[S_RZ0 + par] / pap;
     double vals[M + 2];
 #pragma unroll
     for (int k = 0; k < M + 2; ++k) vals[k] = 0.0;
     for (int nd = n0 + (int)threadIdx.x; nd < n1; nd += kThreads) {
-        double rv[NC], dv[NC];
+        double rv[NC], zv[NC];
         float rl[GD];
         load_vec<NC>(r, nd, rv);
-        load_vec<NC>(dinv, nd, dv);
         load_rel<NC, GD>(cv, nd, rl);
         if (!init) {
-            double pv[NC], av[NC], xv[NC];
-            load_vec<NC>(p, nd, pv);
+            double pk[NC], av[NC], xv[NC];
+            load_vec<NC>(p, nd, pk);
             load_vec<NC>(Ap, nd, av);
             load_vec<NC>(x, nd, xv);
 #pragma unroll
-            for (int k = 0; k < NC; ++k) { rv[k] -= alpha * av[k]; xv[k] += alpha * pv[k]; }
+            for (int k = 0; k < NC; ++k) { rv[k] -= alpha * av[k]; xv[k] += alpha * pk[k]; }
             store_vec<NC>(r, nd, rv);
             store_vec<NC>(x, nd, xv);
         }
+        smooth<NC, BLK>(dinv, nd, rv, zv);
 #pragma unroll
-        for (int k = 0; k < NC; ++k) { vals[0] += rv[k] * dv[k] * rv[k]; vals[1] += rv[k] * rv[k]; }
+        for (int k = 0; k < NC; ++k) { vals[0] += rv[k] * zv[k]; vals[1] += rv[k] * rv[k]; }
         restrict_add<NC, GD>(rl, rv, vals + 2);
     }
     block_sum<M + 2>(vals, s_red);
@@ -166,16 +202,18 @@ __device__ __forceinline__ float4 ld_keep(const float4* p, unsigned long long po
 
 // y = Ainv w (fp32 matrix, fp64 accumulation), r.z = S[S_STAGE] + w.y.  One row per warp; a lane's
 // whole slice of the row (<= kCoarseMax/128 float4) is requested before w is staged in shared memory.
-// init: the sum goes back to S[S_STAGE] for pcg_setup_kernel; else the PCG scalars are published.
+// mode bit 0: start of a solve (ignore a stale DONE flag); bit 1: only add w.y to S[S_STAGE] (an
+// all-reduce / pcg_setup_kernel follows); mode 0: publish the PCG scalars, or with pv (fused
+// multi-GPU path) push (r.z, r.r) of this rank to every rank's mailbox.
 template <int M>
-__global__ void __launch_bounds__(kThreads, 3) coarse_solve_kernel(CoarseView cv, double* S, int par, int init, double* partial,
-                                                                unsigned int* counter) {
+__global__ void __launch_bounds__(kThreads, 3) coarse_solve_kernel(CoarseView cv, double* S, int par, int mode, double* partial,
+                                                                   unsigned int* counter, const PeerView* pv = nullptr) {
     constexpr int kSlice = kCoarseMax / 128;      // float4 per lane and row
     constexpr int kFly = 8;                       // of which in flight at a time
     extern __shared__ __align__(16) double s_w[];          // [ld]
     __shared__ double s_red[kMaxRed * 32];
     __shared__ bool is_last;
-    if (!init && S[S_DONE] != 0.0) return;
+    if (!(mode & 1) && S[S_DONE] != 0.0) return;
     const int nc = cv.n_agg * M;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     const int ld4 = cv.ld >> 2;
@@ -242,48 +280,70 @@ __global__ void __launch_bounds__(kThreads, 3) coarse_solve_kernel(CoarseView cv
         double acc[1] = {0.0};
         for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) acc[0] += __ldcg(&partial[b]);
         block_sum<1>(acc, s_red);
-        if (threadIdx.x == 0) {
+        if (pv && mode == 0) {
+            if (threadIdx.x < 32) {
+                double v[2];
+                v[0] = S[S_STAGE] + __shfl_sync(0xffffffffu, acc[0], 0);
+                v[1] = S[S_STAGE + 1];
+                mbox_push(pv, v, 2);
+            }
+        } else if (threadIdx.x == 0) {
             const double rz = S[S_STAGE] + acc[0];
-            if (init) S[S_STAGE] = rz;
+            if (mode & 2) S[S_STAGE] = rz;
             else pcg_finalize(S, par, rz, S[S_STAGE + 1]);
         }
     }
 }
 
 // p = D^-1 r + Z y + beta p   (Dirichlet dofs stay zero)
-template <int NC, int GD>
+template <int NC, int GD, bool BLK>
 __global__ void __launch_bounds__(kThreads) pcg_direction_coarse_kernel(CoarseView cv, double* __restrict__ p,
                                                                         const double* __restrict__ r,
                                                                         const double* __restrict__ dinv,
                                                                         const uint8_t* __restrict__ mask, double* S, int par,
-                                                                        int init) {
+                                                                        int init, const PeerView* pv = nullptr) {
     constexpr int M = Modes<NC, GD>::M;
+    __shared__ double s_sum[2];
     if (!init && S[S_DONE] != 0.0) return;
     const int ch = blockIdx.x, ag = ch / cv.S;
     const int n0 = cv.chunk_node0[ch], n1 = cv.chunk_node0[ch + 1];
     double y[M];
 #pragma unroll
     for (int k = 0; k < M; ++k) y[k] = cv.y[(size_t)ag * M + k];
-    const double beta = init ? 0.0 : S[S_RZ0 + (par ^ 1)] / S[S_RZ0 + par];
+    double rz_new = S[S_RZ0 + (par ^ 1)];
+    if (pv && !init) {                          // fused all-reduce of (r.z, r.r); block 0 publishes them at its end
+        if (threadIdx.x < 32) {
+            double sm[2];
+            mbox_sum(pv, sm, 2);
+            if (threadIdx.x == 0) { s_sum[0] = sm[0]; s_sum[1] = sm[1]; }
+        }
+        __syncthreads();
+        rz_new = s_sum[0];
+    }
+    const double beta = init ? 0.0 : rz_new / S[S_RZ0 + par];
     for (int nd = n0 + (int)threadIdx.x; nd < n1; nd += kThreads) {
-        double rv[NC], dv[NC], z[NC], pv[NC];
+        double rv[NC], zv[NC], z[NC], pk[NC];
         float rl[GD];
         load_vec<NC>(r, nd, rv);
-        load_vec<NC>(dinv, nd, dv);
+        smooth<NC, BLK>(dinv, nd, rv, zv);
         load_rel<NC, GD>(cv, nd, rl);
         prolong<NC, GD>(rl, y, z);
         if (init) {
 #pragma unroll
-            for (int k = 0; k < NC; ++k) pv[k] = 0.0;
+            for (int k = 0; k < NC; ++k) pk[k] = 0.0;
         } else {
-            load_vec<NC>(p, nd, pv);
+            load_vec<NC>(p, nd, pk);
         }
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
             const bool fixed = mask && mask[(size_t)nd * NC + k];
-            pv[k] = fixed ? 0.0 : dv[k] * rv[k] + z[k] + beta * pv[k];
+            pk[k] = fixed ? 0.0 : zv[k] + z[k] + beta * pk[k];
         }
-        store_vec<NC>(p, nd, pv);
+        store_vec<NC>(p, nd, pk);
+    }
+    if (pv && !init && blockIdx.x == 0) {
+        __syncthreads();
+        if (threadIdx.x == 0) pcg_finalize(S, par, s_sum[0], s_sum[1]);
     }
 }
 

@@ -316,6 +316,49 @@ PFX_HD void elem_diag_u(const Material& m, int n1d, const double* X, const doubl
     }
 }
 
+// out[NV*NB] = nodal diagonal blocks K_aa of the element tangent, NB = D(D+1)/2 values per vertex in
+// the order (00, 11[, 22], 01[, 02, 12]) — block-Jacobi smoother of the two-level PCG
+template <class Cell>
+PFX_HD void elem_diagblk_u(const Material& m, int n1d, const double* X, const double* phi,
+                           const double* U, double* out) {
+    constexpr int NV = Cell::NV, D = Cell::D, NS = SymN<D>::N, NB = D * (D + 1) / 2;
+    for (int i = 0; i < NV * NB; ++i) out[i] = 0.0;
+    Geo<Cell> geo; geo.init(X, n1d);
+    double e[NS], de[D][NS], dsa[NS], dsb[NS], S[D][NS];
+    double N[NV], G[NV][D];
+    int nq = Cell::simplex ? 1 : geo.nq;
+    for (int q = 0; q < nq; ++q) {
+        double w, gq;
+        if constexpr (Cell::simplex) {
+            geo.eval(0, N, G); w = geo.vol; gq = gbar_simplex<Cell>(phi) + m.k;
+        } else {
+            w = geo.eval(q, N, G);
+            double ph = interp<NV>(N, phi); gq = (1.0 - ph) * (1.0 - ph) + m.k;
+        }
+        if (m.smodel != M_ISO) sym_grad<Cell>(G, U, e);
+        for (int a = 0; a < NV; ++a) {
+            for (int i = 0; i < D; ++i) {
+                for (int s = 0; s < NS; ++s) de[i][s] = 0.0;
+                de[i][i] = G[a][i];
+                if (D == 2) { de[i][2] = 0.5 * G[a][1 - i]; }
+                else {
+                    if (i == 0) { de[i][3] = 0.5 * G[a][1]; de[i][4] = 0.5 * G[a][2]; }
+                    if (i == 1) { de[i][3] = 0.5 * G[a][0]; de[i][5] = 0.5 * G[a][2]; }
+                    if (i == 2) { de[i][4] = 0.5 * G[a][0]; de[i][5] = 0.5 * G[a][1]; }
+                }
+                dstress_split<D>(m, m.smodel, e, de[i], dsa, dsb);
+                for (int s = 0; s < NS; ++s) S[i][s] = gq * dsa[s] + dsb[s];
+            }
+            for (int i = 0; i < D; ++i) out[a * NB + i] += w * ddot<D, double>(S[i], de[i]);
+            out[a * NB + D] += w * ddot<D, double>(S[0], de[1]);
+            if (D == 3) {
+                out[a * NB + 4] += w * ddot<D, double>(S[0], de[2]);
+                out[a * NB + 5] += w * ddot<D, double>(S[1], de[2]);
+            }
+        }
+    }
+}
+
 // ============================================================================= φ-space
 // cm = 2H + F·Gc/l, cg = F·Gc·l as nodal (P1/Q1) coefficients.
 // out[a] = Σ_b ∫ (cm N_a N_b + cg ∇N_a·∇N_b) p_b   (J_phi·p, solver.py:214-223)

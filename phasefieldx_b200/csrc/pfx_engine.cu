@@ -69,11 +69,13 @@ struct Coarse {
     int32_t *chunk_node0 = nullptr, *colour = nullptr, *nbrcol = nullptr;
     float* rel = nullptr;
     double *wpart = nullptr, *y = nullptr, *Ac = nullptr, *partial = nullptr, *work = nullptr;
+    double* dblk = nullptr;          // inverse nodal diagonal blocks of J_u (block-Jacobi smoother)
     int lwork = 0, ldc = 0;
     int* info = nullptr;
     cusolverDnHandle_t solver = nullptr;
     CoarseOp op[2];
     bool refresh_every_step = true;
+    bool block_jacobi = true;        // PFX_BLOCK_JACOBI=0: plain diagonal smoother for J_u
     int64_t setups = 0;
 };
 
@@ -372,6 +374,7 @@ int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
         case OP_APPLY_U_TAN:
             if constexpr (Cell::simplex) return launch_scatter_op<OpApplyUTan<Cell>>(c, a);
             break;
+        case OP_DIAGBLK_U: return launch_scatter_op<OpDiagBlkU<Cell>>(c, a);
     }
     if (c->configuring) return PFX_OK;
     c->err = "unknown op";
@@ -569,6 +572,8 @@ int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
     if ((nc_env && nc_env[0] == '1') || bm.nb < 32) return PFX_OK;
     const char* rf = getenv("PFX_COARSE_REFRESH");
     if (rf && rf[0] == 'a') cs.refresh_every_step = false;        // "adaptive": only when iterations grow
+    const char* bj = getenv("PFX_BLOCK_JACOBI");
+    if (bj && bj[0] == '0') cs.block_jacobi = false;
     const int D = c->dim, m_u = D == 2 ? 3 : 6;
     const int max_agg = kCoarseMax / m_u;
     const int g = (bm.nb + max_agg - 1) / max_agg;
@@ -659,6 +664,7 @@ int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
     for (int k = 0; k < 2; ++k)
         if ((st = dev_alloc(c, &cs.op[k].Ainv, (size_t)cs.op[k].nc * cs.op[k].ld))) return st;
     if ((st = dev_alloc(c, &cs.info, (size_t)1))) return st;
+    if ((st = dev_alloc(c, &cs.dblk, (size_t)c->n_nodes * (D * (D + 1) / 2)))) return st;
     if (cusolverDnCreate(&cs.solver) != CUSOLVER_STATUS_SUCCESS) { c->err = "cusolverDnCreate failed"; return PFX_ERR_CUDA; }
     cusolverDnSetStream(cs.solver, c->stream);
     int l1 = 0, l2 = 0;
@@ -682,7 +688,7 @@ CoarseView coarse_view(const pfx_ctx* c, int kind) {
 }
 
 bool coarse_active(const pfx_ctx* c, int kind) {
-    return c->coarse.enabled && kind != LIN_MASS && c->n_ranks == 1;
+    return c->coarse.enabled && kind != LIN_MASS;
 }
 
 template <int NC, int GD>
@@ -723,7 +729,15 @@ int coarse_setup_t(pfx_ctx* c, int kind, const uint8_t* mask) {
         CK(cudaMemcpyAsync(&h_info[1], cs.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
     }
-    if (h_info[0] == 0 && h_info[1] == 0) {
+    bool ok = h_info[0] == 0 && h_info[1] == 0;
+    if (c->n_ranks > 1) {          // every rank must take the same PCG path: all or none
+        double bad = ok ? 0.0 : 1.0, tot = 0.0;
+        CK(cudaMemcpyAsync(c->S + S_STAGE, &bad, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        int st = fetch(c, c->S + S_STAGE, 1, &tot);
+        if (st) return st;
+        ok = tot == 0.0;
+    }
+    if (ok) {
         dim3 grid((op.ld + 127) / 128, nc);
         coarse_convert_kernel<<<grid, 128, 0, c->stream>>>(nc, cs.Ac, ldc, op.Ainv, op.ld);
         CK(cudaGetLastError());
@@ -751,39 +765,78 @@ int coarse_setup(pfx_ctx* c, int kind, const uint8_t* mask) {
 }
 
 // tail of one PCG iteration / start of a solve (init) with the coarse space: update, coarse solve, direction
-template <int NC, int GD>
-int coarse_tail_t(pfx_ctx* c, int kind, int par, int init, const uint8_t* mask, const double* dinv, double rtol2, int bref_slot) {
+// fused != 0 (multi-GPU NVLink path): the three kernels do their all-reduces through the peers' mailboxes
+template <int NC, int GD, bool BLK>
+int coarse_tail_t(pfx_ctx* c, int kind, int par, int init, const uint8_t* mask, const double* dinv, double rtol2, int bref_slot,
+                  int fused) {
     constexpr int M = Modes<NC, GD>::M;
     Coarse& cs = c->coarse;
     CoarseView cv = coarse_view(c, kind);
-    pcg_update_coarse_kernel<NC, GD><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, c->w_x, c->w_r, c->w_p, c->w_Ap, dinv, c->S, par, init,
-                                                                             cs.partial, c->counter);
+    const bool multi = c->n_ranks > 1;
+    const PeerView* pv = (fused && !init) ? c->d_pv : nullptr;
+    int st;
+    if (BLK) dinv = cs.dblk;
+    pcg_update_coarse_kernel<NC, GD, BLK><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, c->w_x, c->w_r, c->w_p, c->w_Ap, dinv, c->S, par, init,
+                                                                             cs.partial, c->counter, pv);
     const int solve_ctas = (cs.op[kind].nc + kThreads / 32 - 1) / (kThreads / 32);
-    coarse_solve_kernel<M><<<solve_ctas, kThreads, (size_t)cv.ld * sizeof(double), c->stream>>>(cv, c->S, par, init, cs.partial,
-                                                                                              c->counter);
+    const int mode = init ? 3 : ((multi && !pv) ? 2 : 0);
+    coarse_solve_kernel<M><<<solve_ctas, kThreads, (size_t)cv.ld * sizeof(double), c->stream>>>(cv, c->S, par, mode, cs.partial,
+                                                                                              c->counter, pv);
     c->launches += 2;
     if (init) {
+        if ((st = allreduce(c, c->S + S_STAGE, 2))) return st;
         pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, rtol2, bref_slot);
         c->launches++;
+    } else if (multi && !pv) {
+        if (c->p2p) {
+            p2p_allreduce_kernel<<<1, 32, 0, c->stream>>>(c->pv, c->S, c->S + S_STAGE, 2, 1, par);
+        } else {
+            if ((st = allreduce(c, c->S + S_STAGE, 2))) return st;
+            pcg_publish_kernel<<<1, 1, 0, c->stream>>>(c->S, par);
+        }
+        c->launches++;
     }
-    pcg_direction_coarse_kernel<NC, GD><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, c->w_p, c->w_r, dinv, mask, c->S, par, init);
+    pcg_direction_coarse_kernel<NC, GD, BLK><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, c->w_p, c->w_r, dinv, mask, c->S, par, init, pv);
     c->launches++;
     CK(cudaGetLastError());
     return PFX_OK;
 }
 
 int coarse_tail(pfx_ctx* c, int kind, int par, int init, const uint8_t* mask, const double* dinv, double rtol2 = 0.0,
-                int bref_slot = -1) {
+                int bref_slot = -1, int fused = 0) {
     if (kind == LIN_PHI)
-        return c->dim == 2 ? coarse_tail_t<1, 2>(c, kind, par, init, mask, dinv, rtol2, bref_slot)
-                           : coarse_tail_t<1, 3>(c, kind, par, init, mask, dinv, rtol2, bref_slot);
-    return c->dim == 2 ? coarse_tail_t<2, 2>(c, kind, par, init, mask, dinv, rtol2, bref_slot)
-                       : coarse_tail_t<3, 3>(c, kind, par, init, mask, dinv, rtol2, bref_slot);
+        return c->dim == 2 ? coarse_tail_t<1, 2, false>(c, kind, par, init, mask, dinv, rtol2, bref_slot, fused)
+                           : coarse_tail_t<1, 3, false>(c, kind, par, init, mask, dinv, rtol2, bref_slot, fused);
+    if (!c->coarse.block_jacobi)
+        return c->dim == 2 ? coarse_tail_t<2, 2, false>(c, kind, par, init, mask, dinv, rtol2, bref_slot, fused)
+                           : coarse_tail_t<3, 3, false>(c, kind, par, init, mask, dinv, rtol2, bref_slot, fused);
+    return c->dim == 2 ? coarse_tail_t<2, 2, true>(c, kind, par, init, mask, dinv, rtol2, bref_slot, fused)
+                       : coarse_tail_t<3, 3, true>(c, kind, par, init, mask, dinv, rtol2, bref_slot, fused);
 }
 
+// one PCG iteration with the coarse space.  Multi-GPU: every rank keeps the coarse space of its own
+// aggregates (block-diagonal coarse matrix, no coarse-level communication); the scalars are reduced
+// exactly as on the Jacobi path.
 int pcg_iteration_coarse(pfx_ctx* c, int kind, int par, const uint8_t* mask, const double* dinv) {
-    int st = apply_lin(c, kind, c->w_p, c->w_Ap, mask, c->S + S_PAP, c->S + S_DONE, 1);
-    if (st) return st;
+    const int nc = (kind == LIN_U) ? c->dim : 1;
+    const bool multi = c->n_ranks > 1;
+    int st;
+    if (multi && c->p2p && c->p2p_fused) {
+        const bool cw = apply_waits_for_halo(c, kind);
+        if ((st = exchange(c, c->w_p, nc, c->S + S_DONE, cw))) return st;
+        if ((st = apply_lin(c, kind, c->w_p, c->w_Ap, mask, c->S + S_STAGE, c->S + S_DONE, 1, c->d_pv, cw ? 1 : 0))) return st;
+        return coarse_tail(c, kind, par, 0, mask, dinv, 0.0, -1, 1);
+    }
+    if ((st = exchange(c, c->w_p, nc, c->S + S_DONE))) return st;
+    if ((st = apply_lin(c, kind, c->w_p, c->w_Ap, mask, multi ? c->S + S_STAGE : c->S + S_PAP, c->S + S_DONE, 1))) return st;
+    if (multi && c->p2p) {
+        p2p_allreduce_kernel<<<1, 32, 0, c->stream>>>(c->pv, c->S, c->S + S_STAGE, 1, 0, par);
+        c->launches++;
+    } else if (multi) {
+        if ((st = allreduce(c, c->S + S_STAGE, 1))) return st;
+        axpby_kernel<<<1, 1, 0, c->stream>>>(1, c->S + S_PAP, c->S + S_STAGE, 1.0, nullptr, 0.0);
+        c->launches++;
+    }
     return coarse_tail(c, kind, par, 0, mask, dinv);
 }
 
@@ -944,6 +997,14 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
     return PFX_OK;
 }
 
+// inverse nodal diagonal blocks of the current J_u (smoother of the two-level PCG)
+int block_diag(pfx_ctx* c) {
+    if (!coarse_active(c, LIN_U) || !c->coarse.block_jacobi) return PFX_OK;
+    KArgs d = base_args(c);
+    d.y = c->coarse.dblk; d.mask = c->mask_u;
+    return launch_scatter(c, OP_DIAGBLK_U, d);
+}
+
 // --------------------------------------------------------------------------- SNES-like Newton
 struct NewtonOut {
     int its = 0, reason = 0;
@@ -1015,6 +1076,7 @@ int newton(pfx_ctx* c, bool is_u, NewtonOut* out) {
         d.y = c->w_dinv; d.mask = mask;
         st = launch_scatter(c, is_u ? OP_DIAG_U : OP_DIAG_PHI, d);
         if (st) return st;
+        if (is_u && (st = block_diag(c))) return st;
         int64_t cg = 0; bool conv = false;
         st = pcg_solve(c, kind, c->prm.cg_rtol, &cg, &conv);
         if (st) return st;
@@ -1287,7 +1349,7 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     {
         c->configuring = true;
         KArgs z = base_args(c);
-        for (int op = OP_APPLY_U; op <= OP_APPLY_U_TAN; ++op)
+        for (int op = OP_APPLY_U; op <= OP_DIAGBLK_U; ++op)
             if ((st = launch_scatter(c, op, z))) return st;
         if ((st = launch_reduce<RED_L2_U>(c, z))) return st;
         if ((st = launch_reduce<RED_L2_PHI>(c, z))) return st;
@@ -1625,6 +1687,7 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
         d.y = c->w_dinv; d.mask = c->mask_u;
         int st = launch_scatter(c, OP_DIAG_U, d);
         if (st) return st;
+        if ((st = block_diag(c))) return st;
         int64_t n = c->n_owned * c->dim;
         CK(cudaMemcpyAsync(c->w_F, c->w_p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         pcg_init_kernel<<<vgrid(c, n), kThreads, 0, c->stream>>>(n, c->w_F, c->mask_u, c->w_dinv, nullptr, nullptr, c->w_x, c->w_r,
@@ -1771,6 +1834,15 @@ int pfx_comm_attach(pfx_ctx* c, int rank, int n_ranks, const uint8_t id[128], in
     // graphs captured before the attach (none normally) would miss the collectives
     for (int k = 0; k < 3; ++k)
         if (c->graph[k]) { cudaGraphExecDestroy(c->graph[k]); c->graph[k] = nullptr; }
+    for (int k = 0; k < 2; ++k)
+        if (c->coarse.op[k].graph) { cudaGraphExecDestroy(c->coarse.op[k].graph); c->coarse.op[k].graph = nullptr; }
+    // the coarse space is used by all ranks or by none (a rank with a tiny part has none)
+    if (n_ranks > 1) {
+        double mine = c->coarse.enabled ? 1.0 : 0.0, tot = 0.0;
+        CK(cudaMemcpyAsync(c->S + S_STAGE, &mine, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        if ((st = fetch(c, c->S + S_STAGE, 1, &tot))) return st;
+        if (tot != (double)n_ranks) c->coarse.enabled = false;
+    }
     return PFX_OK;
 }
 

@@ -206,7 +206,7 @@ __device__ __forceinline__ void grid_reduce(double* vals, double* partial, doubl
 // Each Op: NF staged doubles per local node (odd => conflict-free AoS), NOUT rows per node,
 // NRED partial sums; load(), elem(), store().
 enum { OP_APPLY_U, OP_RESIDUAL_U, OP_DIAG_U, OP_APPLY_PHI, OP_RESIDUAL_PHI, OP_DIAG_PHI, OP_APPLY_MASS,
-       OP_DIAG_MASS, OP_RHS_PSI, OP_RHS_FATIGUE, OP_TANGENT_U, OP_APPLY_U_TAN };
+       OP_DIAG_MASS, OP_RHS_PSI, OP_RHS_FATIGUE, OP_TANGENT_U, OP_APPLY_U_TAN, OP_DIAGBLK_U };
 
 template <int V> struct odd { static constexpr int value = (V & 1) ? V : V + 1; };
 template <class Op, class = void> struct min_blocks { static constexpr int value = (Op::NV == 3) ? 4 : (Op::D == 2 ? 3 : (Op::NOUT == 1 ? 2 : 1)); };
@@ -285,6 +285,47 @@ struct OpDiagU {           // writes 1/diag (1 at Dirichlet dofs)
             bool bc = a.mask && a.mask[(size_t)g * D + i];
             a.y[(size_t)g * D + i] = bc ? 1.0 : 1.0 / acc[i];
         }
+    }
+};
+
+// inverse of a symmetric D x D block stored (00, 11[, 22], 01[, 02, 12]); Dirichlet dofs are decoupled first
+template <int D>
+__device__ __forceinline__ void inv_sym_block(const double* b, const bool* fixed, double* out) {
+    if constexpr (D == 2) {
+        double a00 = fixed[0] ? 1.0 : b[0], a11 = fixed[1] ? 1.0 : b[1], a01 = (fixed[0] || fixed[1]) ? 0.0 : b[2];
+        const double id = 1.0 / (a00 * a11 - a01 * a01);
+        out[0] = a11 * id; out[1] = a00 * id; out[2] = -a01 * id;
+    } else {
+        double a00 = fixed[0] ? 1.0 : b[0], a11 = fixed[1] ? 1.0 : b[1], a22 = fixed[2] ? 1.0 : b[2];
+        double a01 = (fixed[0] || fixed[1]) ? 0.0 : b[3], a02 = (fixed[0] || fixed[2]) ? 0.0 : b[4],
+               a12 = (fixed[1] || fixed[2]) ? 0.0 : b[5];
+        const double c00 = a11 * a22 - a12 * a12, c01 = a02 * a12 - a01 * a22, c02 = a01 * a12 - a02 * a11;
+        const double id = 1.0 / (a00 * c00 + a01 * c01 + a02 * c02);
+        out[0] = c00 * id; out[1] = (a00 * a22 - a02 * a02) * id; out[2] = (a00 * a11 - a01 * a01) * id;
+        out[3] = c01 * id; out[4] = c02 * id; out[5] = (a01 * a02 - a00 * a12) * id;
+    }
+}
+
+template <class Cell>
+struct OpDiagBlkU {        // writes the inverse nodal diagonal blocks (block-Jacobi smoother of the two-level PCG)
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = D * (D + 1) / 2, NRED = 0;
+    static constexpr int NF = odd<D + 1 + D>::value;
+    static constexpr int MINB = (NV == 3) ? 3 : (D == 2 ? 2 : 1);
+    __device__ static void load(const KArgs& a, int g, double* s) { OpResidualU<Cell>::load(a, g, s); }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
+        double X[NV * D], ph[NV], U[NV * D];
+        for (int k = 0; k < NV; ++k) {
+            for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; U[k * D + i] = nd[k][D + 1 + i]; }
+            ph[k] = nd[k][D];
+        }
+        elem_diagblk_u<Cell>(a.m, a.n1d, X, ph, U, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double*) {
+        bool fixed[D];
+        double inv[NOUT];
+        for (int i = 0; i < D; ++i) fixed[i] = a.mask && a.mask[(size_t)g * D + i];
+        inv_sym_block<D>(acc, fixed, inv);
+        for (int i = 0; i < NOUT; ++i) a.y[(size_t)g * NOUT + i] = inv[i];
     }
 };
 

@@ -26,7 +26,7 @@ static void assemble(int op, const Material& m, int n1d, int64_t ne, const doubl
     constexpr int NV = Cell::NV, D = Cell::D;
     for (int64_t e = 0; e < ne; ++e) {
         const int32_t* c = cells + e * NV;
-        double X[NV * D], a0[NV * D], a1[NV * D], a2[NV * D], a3[NV * D], o[NV * D];
+        double X[NV * D], a0[NV * D], a1[NV * D], a2[NV * D], a3[NV * D], o[NV * 6];
         auto gs = [&](const double* f, double* dst) { if (f) for (int a = 0; a < NV; ++a) dst[a] = f[c[a]]; };
         auto gv = [&](const double* f, double* dst) { if (f) for (int a = 0; a < NV; ++a) for (int i = 0; i < D; ++i) dst[a * D + i] = f[c[a] * D + i]; };
         for (int a = 0; a < NV; ++a) for (int i = 0; i < D; ++i) X[a * D + i] = coords[c[a] * 3 + i];
@@ -54,6 +54,7 @@ static void assemble(int op, const Material& m, int n1d, int64_t ne, const doubl
                     nout = D;
                     break;
                 } else return;
+            case 14: gs(f0, a0); gv(f1, a1); elem_diagblk_u<Cell>(m, n1d, X, a0, a1, o); nout = D * (D + 1) / 2; break;  // nodal blocks
             default: return;
         }
         for (int a = 0; a < NV; ++a) for (int i = 0; i < nout; ++i) out[c[a] * nout + i] += o[a * nout + i];

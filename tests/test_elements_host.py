@@ -92,6 +92,12 @@ def test_element_integrals_match_oracle(hostcheck, deg, sp, fat):
         assert rel(asm(0, o.phi, o.u, v, n=nn * d), J @ v) < tol
         assert rel(asm(1, o.phi, o.u, n=nn * d), o.F_int_u(o.u, o.phi)) < tol
         assert rel(asm(2, o.phi, o.u, n=nn * d), J.diagonal()) < tol
+        # nodal d x d diagonal blocks (block-Jacobi smoother), stored (00, 11[, 22], 01[, 02, 12])
+        Jd = J.tocsr()
+        pairs = [(i, i) for i in range(d)] + [(0, 1)] + ([(0, 2), (1, 2)] if d == 3 else [])
+        nodes = np.arange(nn)
+        blk = np.stack([np.asarray(Jd[nodes * d + i, nodes * d + j]).ravel() for i, j in pairs], 1)
+        assert rel(asm(14, o.phi, o.u, n=nn * len(pairs)), blk.ravel()) < tol
         assert rel(asm(3, cm, cg, p), K @ p) < tol
         assert rel(asm(4, cm, cg, o.H, o.phi), K @ o.phi - o.b_phi(o.H)) < tol
         assert rel(asm(5, cm, cg), K.diagonal()) < tol
