@@ -147,7 +147,33 @@ __global__ void __launch_bounds__(kThreads) pcg_update_coarse_kernel(CoarseView 
     double vals[M + 2];
 #pragma unroll
     for (int k = 0; k < M + 2; ++k) vals[k] = 0.0;
-    for (int nd = n0 + (int)threadIdx.x; nd < n1; nd += kThreads) {
+    int nbeg = n0;
+    if constexpr (NC == 1) {
+        // scalar field: two nodes per thread through 128-bit accesses (chunks start on even nodes)
+        if ((n0 & 1) == 0) {
+            const int np2 = (n1 - n0) >> 1;
+            double2* r2 = reinterpret_cast<double2*>(r + n0);
+            double2* x2 = reinterpret_cast<double2*>(x + n0);
+            const double2 *p2 = reinterpret_cast<const double2*>(p + n0), *A2 = reinterpret_cast<const double2*>(Ap + n0),
+                          *d2 = reinterpret_cast<const double2*>(dinv + n0);
+            for (int i = threadIdx.x; i < np2; i += kThreads) {
+                double2 rv = r2[i];
+                const double2 dv = d2[i];
+                if (!init) {
+                    const double2 pk = p2[i], av = A2[i];
+                    double2 xv = x2[i];
+                    rv.x -= alpha * av.x; rv.y -= alpha * av.y;
+                    xv.x += alpha * pk.x; xv.y += alpha * pk.y;
+                    r2[i] = rv; x2[i] = xv;
+                }
+                vals[0] += rv.x * dv.x * rv.x + rv.y * dv.y * rv.y;
+                vals[1] += rv.x * rv.x + rv.y * rv.y;
+                vals[2] += rv.x + rv.y;
+            }
+            nbeg = n0 + 2 * np2;
+        }
+    }
+    for (int nd = nbeg + (int)threadIdx.x; nd < n1; nd += kThreads) {
         double rv[NC], zv[NC];
         float rl[GD];
         load_vec<NC>(r, nd, rv);
@@ -321,7 +347,26 @@ __global__ void __launch_bounds__(kThreads) pcg_direction_coarse_kernel(CoarseVi
         rz_new = s_sum[0];
     }
     const double beta = init ? 0.0 : rz_new / S[S_RZ0 + par];
-    for (int nd = n0 + (int)threadIdx.x; nd < n1; nd += kThreads) {
+    int nbeg = n0;
+    if constexpr (NC == 1) {
+        if ((n0 & 1) == 0) {
+            const int np2 = (n1 - n0) >> 1;
+            double2* p2 = reinterpret_cast<double2*>(p + n0);
+            const double2 *r2 = reinterpret_cast<const double2*>(r + n0), *d2 = reinterpret_cast<const double2*>(dinv + n0);
+            const uchar2* m2 = reinterpret_cast<const uchar2*>(mask ? mask + n0 : nullptr);
+            for (int i = threadIdx.x; i < np2; i += kThreads) {
+                const double2 rv = r2[i], dv = d2[i];
+                double2 pk = init ? make_double2(0.0, 0.0) : p2[i];
+                uchar2 fx = make_uchar2(0, 0);
+                if (mask) fx = m2[i];
+                pk.x = fx.x ? 0.0 : dv.x * rv.x + y[0] + beta * pk.x;
+                pk.y = fx.y ? 0.0 : dv.y * rv.y + y[0] + beta * pk.y;
+                p2[i] = pk;
+            }
+            nbeg = n0 + 2 * np2;
+        }
+    }
+    for (int nd = nbeg + (int)threadIdx.x; nd < n1; nd += kThreads) {
         double rv[NC], zv[NC], z[NC], pk[NC];
         float rl[GD];
         load_vec<NC>(r, nd, rv);

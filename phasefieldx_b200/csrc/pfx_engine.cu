@@ -142,6 +142,7 @@ struct pfx_ctx {
     bool cg_adaptive = true;      // PFX_CG_ADAPTIVE=0: every PCG solve to cg_rtol of its own right-hand side
     double* tan = nullptr;        // cached element tangents (tets + nonlinear split)
     double *cm = nullptr, *cg = nullptr;   // phi-operator nodal coefficients (triangles, v3 path)
+    double *ones = nullptr, *zeros = nullptr;   // coefficients that turn the phi operator into the mass matrix
     int phi_v3_ctas = 0;
     bool use_tan = false;
     int coop_capacity = 0;        // co-resident CTAs of the whole-PCG cooperative kernel (0: unavailable)
@@ -325,6 +326,12 @@ int coop_u(pfx_ctx* c, const KArgs& a, const CoopArgs& ca, bool configure) {
 
 template <class Cell>
 int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
+    if (op == OP_APPLY_MASS && std::is_same<Cell, Tri>::value && c->ones && !c->configuring && c->apply_variant == 3 &&
+        c->bm.max_elems <= 2 * kThreads && a.mask == nullptr) {
+        KArgs m = a;                      // M = the phi operator with coefficients (1, 0)
+        m.cm = c->ones; m.cg = c->zeros;
+        return launch_apply_phi_tri_v3(c, m);
+    }
     if (op == OP_APPLY_PHI && std::is_same<Cell, Tri>::value && c->cm) {
         if (c->configuring) { int st = launch_apply_phi_tri_v3(c, a); if (st) return st; }
         else if (c->apply_variant == 3 && c->bm.max_elems <= 2 * kThreads && a.input_masked && c->phi_coeff_fresh)
@@ -585,7 +592,7 @@ int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
     for (int a = 0; a <= n_agg; ++a) agg0[a] = bm.node0[std::min(bm.nb, a * g)];
     for (int a = 0; a < n_agg; ++a)
         for (int s = 0; s < cs.S; ++s)
-            chunk0[a * cs.S + s] = agg0[a] + (int32_t)((int64_t)(agg0[a + 1] - agg0[a]) * s / cs.S);
+            chunk0[a * cs.S + s] = agg0[a] + ((int32_t)((int64_t)(agg0[a + 1] - agg0[a]) * s / cs.S) & ~1);   // even starts
     chunk0[cs.n_chunks] = agg0[n_agg];
     // geometry of the modes: coordinates relative to the aggregate centroid, scaled by its size
     std::vector<int32_t> node_agg(c->n_owned);
@@ -777,7 +784,7 @@ int coarse_tail_t(pfx_ctx* c, int kind, int par, int init, const uint8_t* mask, 
     int st;
     if (BLK) dinv = cs.dblk;
     pcg_update_coarse_kernel<NC, GD, BLK><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, c->w_x, c->w_r, c->w_p, c->w_Ap, dinv, c->S, par, init,
-                                                                             cs.partial, c->counter, pv);
+                                                                                  cs.partial, c->counter, pv);
     const int solve_ctas = (cs.op[kind].nc + kThreads / 32 - 1) / (kThreads / 32);
     const int mode = init ? 3 : ((multi && !pv) ? 2 : 0);
     coarse_solve_kernel<M><<<solve_ctas, kThreads, (size_t)cv.ld * sizeof(double), c->stream>>>(cv, c->S, par, mode, cs.partial,
@@ -1078,12 +1085,16 @@ int newton(pfx_ctx* c, bool is_u, NewtonOut* out) {
         if (st) return st;
         if (is_u && (st = block_diag(c))) return st;
         int64_t cg = 0; bool conv = false;
+        std::chrono::steady_clock::time_point tp0;
+        if (c->verbose) { cudaStreamSynchronize(c->stream); tp0 = std::chrono::steady_clock::now(); }
         st = pcg_solve(c, kind, c->prm.cg_rtol, &cg, &conv);
         if (st) return st;
         out->cg_its += cg;
-        if (c->verbose)
-            fprintf(stderr, "[pfx] %s newton it %d: |F| %.3e  pcg its %lld  |r|/|b| %.2e\n", is_u ? "u  " : "phi", it, fnorm,
-                    (long long)cg, std::sqrt(c->h_pinned[S_RR]) / std::max(fnorm, 1e-300));
+        if (c->verbose) {
+            double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp0).count();
+            fprintf(stderr, "[pfx] %s newton it %d: |F| %.3e  pcg its %lld  |r|/|b| %.2e  %.2f ms (%.1f us/it)\n", is_u ? "u  " : "phi",
+                    it, fnorm, (long long)cg, std::sqrt(c->h_pinned[S_RR]) / std::max(fnorm, 1e-300), ms, 1e3 * ms / std::max<int64_t>(cg, 1));
+        }
         if (!conv) { out->reason = -3; return PFX_OK; }      // linear solve failed (KSP analogue)
         newton_update_kernel<<<gr, kThreads, 0, c->stream>>>(n, x, c->w_x, c->w_F, mask, c->partial, c->red, c->counter);
         c->launches++;
@@ -1344,6 +1355,9 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     if (c->cell_type == PFX_CELL_TRIANGLE) {
         if ((st = dev_alloc(c, &c->cm, (size_t)N + 2))) return st;
         if ((st = dev_alloc(c, &c->cg, (size_t)N + 2))) return st;
+        if ((st = dev_alloc(c, &c->zeros, (size_t)N + 2))) return st;
+        std::vector<double> one((size_t)N + 2, 1.0);
+        if ((st = dev_upload(c, &c->ones, one))) return st;
     }
     // ---- opt every kernel instantiation of this mesh/model in to its shared-memory size
     {
@@ -1652,7 +1666,16 @@ int pfx_algorithmic_bytes(pfx_ctx* c, int kind, double* bytes) {
         case 1: *bytes = conn + Nn * (8 * d + 24 + (c->mat.fatigue ? 8 : 0)); break;             // phi-apply
         case 2: *bytes = conn + Nn * (8 * d + 16); break;                                        // mass-apply
         case 3: *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d); break;                         // residual_u
-        case 4: *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d + (nl ? 8 * d : 0)) + 11.0 * 8.0 * d * Nn; break;  // u-PCG iteration
+        case 4:                                                                                  // u-PCG iteration
+            *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d + (nl ? 8 * d : 0)) + 11.0 * 8.0 * d * Nn;
+            if (coarse_active(c, LIN_U)) {
+                // two-level iteration: inverse diagonal blocks instead of the diagonal (read twice), the mode
+                // geometry (fp32, read twice), the Dirichlet flags, and the fp32 coarse inverse
+                const CoarseOp& op = c->coarse.op[LIN_U];
+                if (c->coarse.block_jacobi) *bytes += 2.0 * 8.0 * Nn * (d * (d + 1) / 2 - d);
+                *bytes += Nn * (2.0 * 4.0 * d + d) + 4.0 * (double)op.nc * op.ld;
+            }
+            break;
         default: return PFX_ERR_BAD_ARG;
     }
     return PFX_OK;
