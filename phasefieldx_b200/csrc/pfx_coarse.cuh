@@ -21,15 +21,28 @@
 
 namespace pfx {
 
-constexpr int kCoarseMax = 3072;     // coarse dofs of one operator
+constexpr int kCoarseMax = 3072;     // most coarse dofs of one region (one dense inverse)
+constexpr int kCoarseRegion = 1792;  // default region size (coarse u-dofs)
+constexpr int kCoarseTotal = 16384;  // default cap of the whole coarse space (coarse u-dofs)
+constexpr int kCoarseRowsPerWarp = 4;                              // coarse solve: consecutive rows per warp
+constexpr int kCoarseRowsPerCta = kCoarseRowsPerWarp * (kThreads / 32);
+constexpr int kCoarseChunkNodes = 256;                             // update / direction kernels: one warp per chunk of <= this many nodes
+constexpr int kCoarseChunksPerCta = kThreads / 32;
 
+// Regions: contiguous runs of aggregates.  The coarse matrix keeps only the couplings inside a
+// region (block-diagonal Z^T A Z: still symmetric positive definite), so the inverse is one dense
+// block per region and the coarse space can be several times larger than one dense inverse allows.
 struct CoarseView {
-    int n_agg, n_chunks, S, ld;       // S chunks (CTAs) per aggregate; ld: row stride of Ainv (multiple of 4)
+    int n_agg, n_chunks, S, ld;       // S chunks (<= kCoarseChunkNodes nodes, one warp each) per aggregate; ld: largest row stride of a region
     const int32_t* chunk_node0;       // [n_chunks+1] owned-node range of every chunk
     const float* rel;                 // [n_owned*GD] (x - centroid(aggregate)) / size(aggregate)
     double* wpart;                    // [n_chunks*M] per-chunk pieces of Z^T r
     double* y;                        // [n_agg*M]
-    const float* Ainv;                // [n_agg*M][ld]
+    const float* Ainv;                // per region r: [n_r*M][ld_r] at float offset reg_tab[r].z
+    const int32_t* agg_reg;           // [n_agg] region of every aggregate
+    const int4* reg_tab;              // [n_regions] {first aggregate, aggregates, float offset of the inverse, ld_r}
+    const int2* cta_tab;              // coarse solve: [CTAs] {region, first row of the region handled by the CTA}
+    const long long* ac_off;          // [n_regions] offset (doubles) of the region's block in the fp64 work matrix
 };
 
 template <int NC, int GD> struct Modes { static constexpr int M = NC == 1 ? 1 : (GD == 2 ? 3 : 6); };
@@ -131,8 +144,6 @@ __global__ void __launch_bounds__(kThreads) pcg_update_coarse_kernel(CoarseView 
     __shared__ bool is_last;
     __shared__ double s_pap;
     if (!init && S[S_DONE] != 0.0) return;
-    const int ch = blockIdx.x;
-    const int n0 = cv.chunk_node0[ch], n1 = cv.chunk_node0[ch + 1];
     double pap = S[S_PAP];
     if (pv && !init) {                          // fused all-reduce: p.Ap of all ranks from the mailboxes
         if (threadIdx.x < 32) {
@@ -144,61 +155,72 @@ __global__ void __launch_bounds__(kThreads) pcg_update_coarse_kernel(CoarseView 
         pap = s_pap;
     }
     const double alpha = init ? 0.0 : S[S_RZ0 + par] / pap;
-    double vals[M + 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double sums[2] = {0.0, 0.0};
+    // one warp per chunk (<= ~256 nodes): the restriction sums need only shuffles
+    const int c1 = min(cv.n_chunks, (int)(blockIdx.x + 1) * kCoarseChunksPerCta);
+    for (int ch = blockIdx.x * kCoarseChunksPerCta + warp; ch < c1; ch += kThreads / 32) {
+        const int n0 = cv.chunk_node0[ch], n1 = cv.chunk_node0[ch + 1];
+        double w[M];
 #pragma unroll
-    for (int k = 0; k < M + 2; ++k) vals[k] = 0.0;
-    int nbeg = n0;
-    if constexpr (NC == 1) {
-        // scalar field: two nodes per thread through 128-bit accesses (chunks start on even nodes)
-        if ((n0 & 1) == 0) {
-            const int np2 = (n1 - n0) >> 1;
-            double2* r2 = reinterpret_cast<double2*>(r + n0);
-            double2* x2 = reinterpret_cast<double2*>(x + n0);
-            const double2 *p2 = reinterpret_cast<const double2*>(p + n0), *A2 = reinterpret_cast<const double2*>(Ap + n0),
-                          *d2 = reinterpret_cast<const double2*>(dinv + n0);
-            for (int i = threadIdx.x; i < np2; i += kThreads) {
-                double2 rv = r2[i];
-                const double2 dv = d2[i];
-                if (!init) {
-                    const double2 pk = p2[i], av = A2[i];
-                    double2 xv = x2[i];
-                    rv.x -= alpha * av.x; rv.y -= alpha * av.y;
-                    xv.x += alpha * pk.x; xv.y += alpha * pk.y;
-                    r2[i] = rv; x2[i] = xv;
+        for (int k = 0; k < M; ++k) w[k] = 0.0;
+        int nbeg = n0;
+        if constexpr (NC == 1) {
+            // scalar field: two nodes per lane through 128-bit accesses (chunks start on even nodes)
+            if ((n0 & 1) == 0) {
+                const int np2 = (n1 - n0) >> 1;
+                double2* r2 = reinterpret_cast<double2*>(r + n0);
+                double2* x2 = reinterpret_cast<double2*>(x + n0);
+                const double2 *p2 = reinterpret_cast<const double2*>(p + n0), *A2 = reinterpret_cast<const double2*>(Ap + n0),
+                              *d2 = reinterpret_cast<const double2*>(dinv + n0);
+                for (int i = lane; i < np2; i += 32) {
+                    double2 rv = r2[i];
+                    const double2 dv = d2[i];
+                    if (!init) {
+                        const double2 pk = p2[i], av = A2[i];
+                        double2 xv = x2[i];
+                        rv.x -= alpha * av.x; rv.y -= alpha * av.y;
+                        xv.x += alpha * pk.x; xv.y += alpha * pk.y;
+                        r2[i] = rv; x2[i] = xv;
+                    }
+                    sums[0] += rv.x * dv.x * rv.x + rv.y * dv.y * rv.y;
+                    sums[1] += rv.x * rv.x + rv.y * rv.y;
+                    w[0] += rv.x + rv.y;
                 }
-                vals[0] += rv.x * dv.x * rv.x + rv.y * dv.y * rv.y;
-                vals[1] += rv.x * rv.x + rv.y * rv.y;
-                vals[2] += rv.x + rv.y;
+                nbeg = n0 + 2 * np2;
             }
-            nbeg = n0 + 2 * np2;
+        }
+#pragma unroll 2
+        for (int nd = nbeg + lane; nd < n1; nd += 32) {
+            double rv[NC], zv[NC];
+            float rl[GD];
+            load_vec<NC>(r, nd, rv);
+            load_rel<NC, GD>(cv, nd, rl);
+            if (!init) {
+                double pk[NC], av[NC], xv[NC];
+                load_vec<NC>(p, nd, pk);
+                load_vec<NC>(Ap, nd, av);
+                load_vec<NC>(x, nd, xv);
+#pragma unroll
+                for (int k = 0; k < NC; ++k) { rv[k] -= alpha * av[k]; xv[k] += alpha * pk[k]; }
+                store_vec<NC>(r, nd, rv);
+                store_vec<NC>(x, nd, xv);
+            }
+            smooth<NC, BLK>(dinv, nd, rv, zv);
+#pragma unroll
+            for (int k = 0; k < NC; ++k) { sums[0] += rv[k] * zv[k]; sums[1] += rv[k] * rv[k]; }
+            restrict_add<NC, GD>(rl, rv, w);
+        }
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            const double t = warp_sum(w[k]);
+            if (lane == 0) cv.wpart[(size_t)ch * M + k] = t;
         }
     }
-    for (int nd = nbeg + (int)threadIdx.x; nd < n1; nd += kThreads) {
-        double rv[NC], zv[NC];
-        float rl[GD];
-        load_vec<NC>(r, nd, rv);
-        load_rel<NC, GD>(cv, nd, rl);
-        if (!init) {
-            double pk[NC], av[NC], xv[NC];
-            load_vec<NC>(p, nd, pk);
-            load_vec<NC>(Ap, nd, av);
-            load_vec<NC>(x, nd, xv);
-#pragma unroll
-            for (int k = 0; k < NC; ++k) { rv[k] -= alpha * av[k]; xv[k] += alpha * pk[k]; }
-            store_vec<NC>(r, nd, rv);
-            store_vec<NC>(x, nd, xv);
-        }
-        smooth<NC, BLK>(dinv, nd, rv, zv);
-#pragma unroll
-        for (int k = 0; k < NC; ++k) { vals[0] += rv[k] * zv[k]; vals[1] += rv[k] * rv[k]; }
-        restrict_add<NC, GD>(rl, rv, vals + 2);
-    }
-    block_sum<M + 2>(vals, s_red);
+    block_sum<2>(sums, s_red);
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < M; ++k) cv.wpart[(size_t)ch * M + k] = vals[2 + k];
-        partial[(size_t)ch * 2 + 0] = vals[0];
-        partial[(size_t)ch * 2 + 1] = vals[1];
+        partial[(size_t)blockIdx.x * 2 + 0] = sums[0];
+        partial[(size_t)blockIdx.x * 2 + 1] = sums[1];
         __threadfence();
         unsigned int t = atomicInc(counter, gridDim.x - 1);
         is_last = (t == gridDim.x - 1);
@@ -226,72 +248,82 @@ __device__ __forceinline__ float4 ld_keep(const float4* p, unsigned long long po
     return v;
 }
 
-// y = Ainv w (fp32 matrix, fp64 accumulation), r.z = S[S_STAGE] + w.y.  One row per warp; a lane's
-// whole slice of the row (<= kCoarseMax/128 float4) is requested before w is staged in shared memory.
+// y = Ainv w (fp32 matrix, fp64 accumulation), r.z = S[S_STAGE] + w.y.  A warp handles
+// kCoarseRowsPerWarp consecutive rows of one region's inverse at once (each w entry read from shared
+// memory once per kCoarseRowsPerWarp matrix entries), 2 x kCoarseRowsPerWarp 128-bit loads in flight per lane.
 // mode bit 0: start of a solve (ignore a stale DONE flag); bit 1: only add w.y to S[S_STAGE] (an
 // all-reduce / pcg_setup_kernel follows); mode 0: publish the PCG scalars, or with pv (fused
 // multi-GPU path) push (r.z, r.r) of this rank to every rank's mailbox.
 template <int M>
 __global__ void __launch_bounds__(kThreads, 3) coarse_solve_kernel(CoarseView cv, double* S, int par, int mode, double* partial,
                                                                    unsigned int* counter, const PeerView* pv = nullptr) {
-    constexpr int kSlice = kCoarseMax / 128;      // float4 per lane and row
-    constexpr int kFly = 8;                       // of which in flight at a time
+    constexpr int R = kCoarseRowsPerWarp;
     extern __shared__ __align__(16) double s_w[];          // [ld]
     __shared__ double s_red[kMaxRed * 32];
     __shared__ bool is_last;
     if (!(mode & 1) && S[S_DONE] != 0.0) return;
-    const int nc = cv.n_agg * M;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int ld4 = cv.ld >> 2;
-    const int row = blockIdx.x * nw + warp;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int2 ct = cv.cta_tab[blockIdx.x];
+    const int4 rt = cv.reg_tab[ct.x];             // {first aggregate, aggregates, inverse offset, ld}
+    const int nc = rt.y * M, ld4 = rt.w >> 2;
+    const int row0 = ct.y + warp * R;             // this warp's R consecutive rows of the region
     unsigned long long pol;
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    const float4* A4 = reinterpret_cast<const float4*>(cv.Ainv + (size_t)(row < nc ? row : 0) * cv.ld);
-    float4 a[kFly];
+    const float4* A4[R];
 #pragma unroll
-    for (int q = 0; q < kFly; ++q) {              // first batch flies while w is staged
-        const int j4 = lane + 32 * q;
-        a[q] = (row < nc && j4 < ld4) ? ld_keep(A4 + j4, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < R; ++r) A4[r] = reinterpret_cast<const float4*>(cv.Ainv + (size_t)rt.z + (size_t)min(row0 + r, nc - 1) * rt.w);
+    // two column blocks (2 x R loads of 128 bits) in flight per lane; the first pair is requested
+    // before w is staged in shared memory
+    float4 a0[R], a1[R];
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        a0[r] = (lane < ld4) ? ld_keep(A4[r] + lane, pol) : zero4;
+        a1[r] = (lane + 32 < ld4) ? ld_keep(A4[r] + lane + 32, pol) : zero4;
     }
-    for (int i = threadIdx.x; i < cv.ld; i += blockDim.x) {
+    for (int i = threadIdx.x; i < rt.w; i += blockDim.x) {
         double t = 0.0;
         if (i < nc) {
-            const int ag = i / M, k = i - ag * M;
+            const int ag = rt.x + i / M, k = i % M;
             for (int s = 0; s < cv.S; ++s) t += __ldcg(&cv.wpart[((size_t)ag * cv.S + s) * M + k]);
         }
         s_w[i] = t;
     }
     __syncthreads();
     double wy[1] = {0.0};
-    if (row < nc) {
+    if (row0 < nc) {
         const double2* w2 = reinterpret_cast<const double2*>(s_w);
-        double acc0 = 0.0, acc1 = 0.0;
+        double acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.0;
 #pragma unroll 1
-        for (int q0 = 0; q0 < kSlice; q0 += kFly) {
-            float4 nx[kFly];
-            if (q0 + kFly < kSlice) {
+        for (int j4 = lane; j4 < ld4; j4 += 64) {
+            float4 n0[R], n1[R];
 #pragma unroll
-                for (int q = 0; q < kFly; ++q) {
-                    const int j4 = lane + 32 * (q0 + kFly + q);
-                    nx[q] = (j4 < ld4) ? ld_keep(A4 + j4, pol) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            for (int r = 0; r < R; ++r) {
+                n0[r] = (j4 + 64 < ld4) ? ld_keep(A4[r] + j4 + 64, pol) : zero4;
+                n1[r] = (j4 + 96 < ld4) ? ld_keep(A4[r] + j4 + 96, pol) : zero4;
+            }
+            {
+                const double2 u0 = w2[2 * j4], u1 = w2[2 * j4 + 1];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    acc[r] += (double)a0[r].x * u0.x + (double)a0[r].y * u0.y + (double)a0[r].z * u1.x + (double)a0[r].w * u1.y;
+            }
+            if (j4 + 32 < ld4) {
+                const double2 u0 = w2[2 * (j4 + 32)], u1 = w2[2 * (j4 + 32) + 1];
+#pragma unroll
+                for (int r = 0; r < R; ++r)
+                    acc[r] += (double)a1[r].x * u0.x + (double)a1[r].y * u0.y + (double)a1[r].z * u1.x + (double)a1[r].w * u1.y;
             }
 #pragma unroll
-            for (int q = 0; q < kFly; ++q) {
-                const int j4 = lane + 32 * (q0 + q);
-                if (j4 < ld4) {
-                    const double2 u0 = w2[2 * j4], u1 = w2[2 * j4 + 1];
-                    acc0 += (double)a[q].x * u0.x + (double)a[q].y * u0.y;
-                    acc1 += (double)a[q].z * u1.x + (double)a[q].w * u1.y;
-                }
-            }
-            if (q0 + kFly < kSlice) {
-#pragma unroll
-                for (int q = 0; q < kFly; ++q) a[q] = nx[q];
-            }
+            for (int r = 0; r < R; ++r) { a0[r] = n0[r]; a1[r] = n1[r]; }
         }
-        const double acc = warp_sum(acc0 + acc1);
-        if (lane == 0) { cv.y[row] = acc; wy[0] = acc * s_w[row]; }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double v = warp_sum(acc[r]);
+            if (lane == 0 && row0 + r < nc) { cv.y[(size_t)rt.x * M + row0 + r] = v; wy[0] += v * s_w[row0 + r]; }
+        }
     }
     block_sum<1>(wy, s_red);
     if (threadIdx.x == 0) {
@@ -331,11 +363,6 @@ __global__ void __launch_bounds__(kThreads) pcg_direction_coarse_kernel(CoarseVi
     constexpr int M = Modes<NC, GD>::M;
     __shared__ double s_sum[2];
     if (!init && S[S_DONE] != 0.0) return;
-    const int ch = blockIdx.x, ag = ch / cv.S;
-    const int n0 = cv.chunk_node0[ch], n1 = cv.chunk_node0[ch + 1];
-    double y[M];
-#pragma unroll
-    for (int k = 0; k < M; ++k) y[k] = cv.y[(size_t)ag * M + k];
     double rz_new = S[S_RZ0 + (par ^ 1)];
     if (pv && !init) {                          // fused all-reduce of (r.z, r.r); block 0 publishes them at its end
         if (threadIdx.x < 32) {
@@ -347,44 +374,51 @@ __global__ void __launch_bounds__(kThreads) pcg_direction_coarse_kernel(CoarseVi
         rz_new = s_sum[0];
     }
     const double beta = init ? 0.0 : rz_new / S[S_RZ0 + par];
-    int nbeg = n0;
-    if constexpr (NC == 1) {
-        if ((n0 & 1) == 0) {
-            const int np2 = (n1 - n0) >> 1;
-            double2* p2 = reinterpret_cast<double2*>(p + n0);
-            const double2 *r2 = reinterpret_cast<const double2*>(r + n0), *d2 = reinterpret_cast<const double2*>(dinv + n0);
-            const uchar2* m2 = reinterpret_cast<const uchar2*>(mask ? mask + n0 : nullptr);
-            for (int i = threadIdx.x; i < np2; i += kThreads) {
-                const double2 rv = r2[i], dv = d2[i];
-                double2 pk = init ? make_double2(0.0, 0.0) : p2[i];
-                uchar2 fx = make_uchar2(0, 0);
-                if (mask) fx = m2[i];
-                pk.x = fx.x ? 0.0 : dv.x * rv.x + y[0] + beta * pk.x;
-                pk.y = fx.y ? 0.0 : dv.y * rv.y + y[0] + beta * pk.y;
-                p2[i] = pk;
+    {                                            // one CTA per chunk (<= kCoarseChunkNodes nodes: one node per thread)
+        const int ch = blockIdx.x, ag = ch / cv.S;
+        const int n0 = cv.chunk_node0[ch], n1 = cv.chunk_node0[ch + 1];
+        double y[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) y[k] = cv.y[(size_t)ag * M + k];
+        int nbeg = n0;
+        if constexpr (NC == 1) {
+            if ((n0 & 1) == 0) {
+                const int np2 = (n1 - n0) >> 1;
+                double2* p2 = reinterpret_cast<double2*>(p + n0);
+                const double2 *r2 = reinterpret_cast<const double2*>(r + n0), *d2 = reinterpret_cast<const double2*>(dinv + n0);
+                const uchar2* m2 = reinterpret_cast<const uchar2*>(mask ? mask + n0 : nullptr);
+                for (int i = threadIdx.x; i < np2; i += kThreads) {
+                    const double2 rv = r2[i], dv = d2[i];
+                    double2 pk = init ? make_double2(0.0, 0.0) : p2[i];
+                    uchar2 fx = make_uchar2(0, 0);
+                    if (mask) fx = m2[i];
+                    pk.x = fx.x ? 0.0 : dv.x * rv.x + y[0] + beta * pk.x;
+                    pk.y = fx.y ? 0.0 : dv.y * rv.y + y[0] + beta * pk.y;
+                    p2[i] = pk;
+                }
+                nbeg = n0 + 2 * np2;
             }
-            nbeg = n0 + 2 * np2;
         }
-    }
-    for (int nd = nbeg + (int)threadIdx.x; nd < n1; nd += kThreads) {
-        double rv[NC], zv[NC], z[NC], pk[NC];
-        float rl[GD];
-        load_vec<NC>(r, nd, rv);
-        smooth<NC, BLK>(dinv, nd, rv, zv);
-        load_rel<NC, GD>(cv, nd, rl);
-        prolong<NC, GD>(rl, y, z);
-        if (init) {
+        for (int nd = nbeg + (int)threadIdx.x; nd < n1; nd += kThreads) {
+            double rv[NC], zv[NC], z[NC], pk[NC];
+            float rl[GD];
+            load_vec<NC>(r, nd, rv);
+            smooth<NC, BLK>(dinv, nd, rv, zv);
+            load_rel<NC, GD>(cv, nd, rl);
+            prolong<NC, GD>(rl, y, z);
+            if (init) {
 #pragma unroll
-            for (int k = 0; k < NC; ++k) pk[k] = 0.0;
-        } else {
-            load_vec<NC>(p, nd, pk);
-        }
+                for (int k = 0; k < NC; ++k) pk[k] = 0.0;
+            } else {
+                load_vec<NC>(p, nd, pk);
+            }
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
-            const bool fixed = mask && mask[(size_t)nd * NC + k];
-            pk[k] = fixed ? 0.0 : zv[k] + z[k] + beta * pk[k];
+            for (int k = 0; k < NC; ++k) {
+                const bool fixed = mask && mask[(size_t)nd * NC + k];
+                pk[k] = fixed ? 0.0 : zv[k] + z[k] + beta * pk[k];
+            }
+            store_vec<NC>(p, nd, pk);
         }
-        store_vec<NC>(p, nd, pk);
     }
     if (pv && !init && blockIdx.x == 0) {
         __syncthreads();
@@ -438,17 +472,22 @@ __global__ void __launch_bounds__(kThreads) coarse_restrict_kernel(CoarseView cv
 }
 
 // column (j, mode) of Z^T A Z from the restricted probe: rows of aggregate i belong to the one
-// aggregate j of this colour within distance one of i (distance-2 colouring => unique)
+// aggregate j of this colour within distance one of i (distance-2 colouring => unique); couplings
+// between different regions are dropped
 template <int M>
-__global__ void coarse_fill_kernel(CoarseView cv, const int32_t* nbrcol, int n_col, int colour, int mode, double* Ac, int ldc) {
+__global__ void coarse_fill_kernel(CoarseView cv, const int32_t* nbrcol, int n_col, int colour, int mode, double* Ac) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= cv.n_agg * M) return;
     const int a = i / M, k = i - a * M;
     const int j = nbrcol[(size_t)a * n_col + colour];
     if (j < 0) return;
+    const int rg = cv.agg_reg[a];
+    if (cv.agg_reg[j] != rg) return;
+    const int4 rt = cv.reg_tab[rg];
     double t = 0.0;
     for (int s = 0; s < cv.S; ++s) t += cv.wpart[((size_t)a * cv.S + s) * M + k];
-    Ac[(size_t)(j * M + mode) * ldc + i] = t;
+    const size_t ncr = (size_t)rt.y * M;
+    Ac[cv.ac_off[rg] + ((size_t)(j - rt.x) * M + mode) * ncr + (size_t)(a - rt.x) * M + k] = t;
 }
 
 // aggregates without a free dof in some mode leave an empty row/column: decouple them

@@ -56,25 +56,34 @@ struct Traction {
 
 // aggregate coarse space of the PCG (pfx_coarse.cuh); op 0 = J_u, op 1 = J_phi
 struct CoarseOp {
-    float* Ainv = nullptr;
-    int nc = 0, ld = 0;
+    float* Ainv = nullptr;          // one dense fp32 inverse per region
+    int m = 0, ld = 0;              // modes per aggregate; largest row stride of a region
+    int n_ctas = 0;                 // coarse solve: one row per warp
+    int4* reg_tab = nullptr;
+    int2* cta_tab = nullptr;
+    long long* ac_off = nullptr;
+    std::vector<int4> h_reg;        // {first aggregate, aggregates, float offset of the inverse, ld}
+    std::vector<long long> h_ac_off;
+    int64_t ainv_floats = 0;
     bool valid = false, stale = true;
-    int64_t ref_its = -1;           // PCG iterations of the first solve after the last refresh
+    int64_t ref_its = -1;           // most PCG iterations of a solve in the load step(s) right after the last refresh
+    bool ref_open = false;
+    int open_steps = 0;
     cudaGraphExec_t graph = nullptr;
 };
 
 struct Coarse {
     bool enabled = false;
-    int n_agg = 0, S = 1, n_chunks = 0, n_col = 0, solve_ctas = 0;
-    int32_t *chunk_node0 = nullptr, *colour = nullptr, *nbrcol = nullptr;
+    int n_agg = 0, S = 1, n_chunks = 0, n_col = 0, n_reg = 1;
+    int32_t *chunk_node0 = nullptr, *colour = nullptr, *nbrcol = nullptr, *agg_reg = nullptr;
     float* rel = nullptr;
     double *wpart = nullptr, *y = nullptr, *Ac = nullptr, *partial = nullptr, *work = nullptr;
     double* dblk = nullptr;          // inverse nodal diagonal blocks of J_u (block-Jacobi smoother)
-    int lwork = 0, ldc = 0;
+    int lwork = 0;
     int* info = nullptr;
     cusolverDnHandle_t solver = nullptr;
     CoarseOp op[2];
-    bool refresh_every_step = true;
+    bool refresh_every_step = false;
     bool block_jacobi = true;        // PFX_BLOCK_JACOBI=0: plain diagonal smoother for J_u
     int64_t setups = 0;
 };
@@ -578,15 +587,32 @@ int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
     const char* nc_env = getenv("PFX_NO_COARSE");
     if ((nc_env && nc_env[0] == '1') || bm.nb < 32) return PFX_OK;
     const char* rf = getenv("PFX_COARSE_REFRESH");
-    if (rf && rf[0] == 'a') cs.refresh_every_step = false;        // "adaptive": only when iterations grow
+    if (rf) cs.refresh_every_step = (rf[0] == 's');               // "step": every load step; default: when iterations grow
     const char* bj = getenv("PFX_BLOCK_JACOBI");
     if (bj && bj[0] == '0') cs.block_jacobi = false;
     const int D = c->dim, m_u = D == 2 ? 3 : 6;
-    const int max_agg = kCoarseMax / m_u;
-    const int g = (bm.nb + max_agg - 1) / max_agg;
+    // aggregates of g consecutive blocks; regions of at most `reg_cap` coarse u-dofs (dense inverse per
+    // region).  Defaults: at most kCoarseTotal coarse dofs in all, regions of <= kCoarseRegion.
+    const char* eg = getenv("PFX_COARSE_AGG_BLOCKS");
+    const char* er = getenv("PFX_COARSE_REGION");
+    const int total_cap = kCoarseTotal, reg_cap = std::min(kCoarseMax, std::max(m_u * 8, er ? atoi(er) : kCoarseRegion));
+    int g = (bm.nb * m_u + total_cap - 1) / total_cap;
+    if (eg && atoi(eg) > 0) g = atoi(eg);
+    g = std::max(g, 1);
     const int n_agg = (bm.nb + g - 1) / g;
+    const int n_reg = std::max(1, (n_agg * m_u + reg_cap - 1) / reg_cap);
+    cs.n_reg = n_reg;
+    std::vector<int32_t> reg_agg0(n_reg + 1), agg_reg(n_agg);
+    for (int r = 0; r <= n_reg; ++r) reg_agg0[r] = (int32_t)((int64_t)n_agg * r / n_reg);
+    for (int r = 0; r < n_reg; ++r)
+        for (int a = reg_agg0[r]; a < reg_agg0[r + 1]; ++a) agg_reg[a] = r;
     cs.n_agg = n_agg;
-    cs.S = std::max(1, (4 * c->num_sms + n_agg - 1) / n_agg);
+    {   // chunks of at most kCoarseChunkNodes nodes: one warp each in the update / direction kernels
+        int max_nodes = 0;
+        for (int a = 0; a < n_agg; ++a)
+            max_nodes = std::max(max_nodes, bm.node0[std::min(bm.nb, (a + 1) * g)] - bm.node0[std::min(bm.nb, a * g)]);
+        cs.S = std::max(1, (max_nodes + kCoarseChunkNodes - 1) / kCoarseChunkNodes);
+    }
     cs.n_chunks = n_agg * cs.S;
     std::vector<int32_t> agg0(n_agg + 1), chunk0(cs.n_chunks + 1);
     for (int a = 0; a <= n_agg; ++a) agg0[a] = bm.node0[std::min(bm.nb, a * g)];
@@ -659,24 +685,44 @@ int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
     if ((st = dev_upload(c, &cs.colour, colour))) return st;
     if ((st = dev_upload(c, &cs.nbrcol, nbrcol))) return st;
     if ((st = dev_upload(c, &cs.rel, rel))) return st;
-    const int nc_u = n_agg * m_u, nc_p = n_agg;
-    cs.ldc = nc_u;
-    cs.op[0].nc = nc_u; cs.op[0].ld = (nc_u + 3) / 4 * 4;
-    cs.op[1].nc = nc_p; cs.op[1].ld = (nc_p + 3) / 4 * 4;
+    if ((st = dev_upload(c, &cs.agg_reg, agg_reg))) return st;
+    int64_t ac_doubles = 0;
+    int nc_max = 0;
+    for (int k = 0; k < 2; ++k) {
+        CoarseOp& op = cs.op[k];
+        op.m = k == 0 ? m_u : 1;
+        std::vector<int2> ctas;
+        int64_t off = 0, aoff = 0;
+        for (int r = 0; r < n_reg; ++r) {
+            const int na = reg_agg0[r + 1] - reg_agg0[r], ncr = na * op.m, ldr = (ncr + 3) / 4 * 4;
+            op.h_reg.push_back(make_int4(reg_agg0[r], na, (int)off, ldr));
+            op.h_ac_off.push_back(aoff);
+            off += (int64_t)ncr * ldr;
+            aoff += (int64_t)ncr * ncr;
+            op.ld = std::max(op.ld, ldr);
+            nc_max = std::max(nc_max, ncr);
+            for (int row = 0; row < ncr; row += kCoarseRowsPerCta) ctas.push_back(make_int2(r, row));
+        }
+        if (off > (int64_t)0x7fffffff) { c->err = "coarse space: inverse too large"; return PFX_ERR_BAD_ARG; }
+        op.ainv_floats = off;
+        op.n_ctas = (int)ctas.size();
+        ac_doubles = std::max(ac_doubles, aoff);
+        if ((st = dev_upload(c, &op.reg_tab, op.h_reg))) return st;
+        if ((st = dev_upload(c, &op.cta_tab, ctas))) return st;
+        if ((st = dev_upload(c, &op.ac_off, op.h_ac_off))) return st;
+        if ((st = dev_alloc(c, &op.Ainv, (size_t)off))) return st;
+    }
     if ((st = dev_alloc(c, &cs.wpart, (size_t)cs.n_chunks * m_u))) return st;
-    if ((st = dev_alloc(c, &cs.y, (size_t)nc_u))) return st;
-    if ((st = dev_alloc(c, &cs.Ac, (size_t)nc_u * nc_u))) return st;
-    cs.solve_ctas = (nc_u + kThreads / 32 - 1) / (kThreads / 32);      // one row of the inverse per warp
-    if ((st = dev_alloc(c, &cs.partial, (size_t)std::max(2 * cs.n_chunks, cs.solve_ctas)))) return st;
-    for (int k = 0; k < 2; ++k)
-        if ((st = dev_alloc(c, &cs.op[k].Ainv, (size_t)cs.op[k].nc * cs.op[k].ld))) return st;
+    if ((st = dev_alloc(c, &cs.y, (size_t)n_agg * m_u))) return st;
+    if ((st = dev_alloc(c, &cs.Ac, (size_t)ac_doubles))) return st;
+    if ((st = dev_alloc(c, &cs.partial, (size_t)std::max(2 * cs.n_chunks, cs.op[0].n_ctas)))) return st;
     if ((st = dev_alloc(c, &cs.info, (size_t)1))) return st;
     if ((st = dev_alloc(c, &cs.dblk, (size_t)c->n_nodes * (D * (D + 1) / 2)))) return st;
     if (cusolverDnCreate(&cs.solver) != CUSOLVER_STATUS_SUCCESS) { c->err = "cusolverDnCreate failed"; return PFX_ERR_CUDA; }
     cusolverDnSetStream(cs.solver, c->stream);
     int l1 = 0, l2 = 0;
-    if (cusolverDnDpotrf_bufferSize(cs.solver, CUBLAS_FILL_MODE_LOWER, nc_u, cs.Ac, cs.ldc, &l1) != CUSOLVER_STATUS_SUCCESS ||
-        cusolverDnDpotri_bufferSize(cs.solver, CUBLAS_FILL_MODE_LOWER, nc_u, cs.Ac, cs.ldc, &l2) != CUSOLVER_STATUS_SUCCESS) {
+    if (cusolverDnDpotrf_bufferSize(cs.solver, CUBLAS_FILL_MODE_LOWER, nc_max, cs.Ac, nc_max, &l1) != CUSOLVER_STATUS_SUCCESS ||
+        cusolverDnDpotri_bufferSize(cs.solver, CUBLAS_FILL_MODE_LOWER, nc_max, cs.Ac, nc_max, &l2) != CUSOLVER_STATUS_SUCCESS) {
         c->err = "cusolver workspace query failed";
         return PFX_ERR_CUDA;
     }
@@ -691,6 +737,7 @@ CoarseView coarse_view(const pfx_ctx* c, int kind) {
     CoarseView v;
     v.n_agg = cs.n_agg; v.n_chunks = cs.n_chunks; v.S = cs.S; v.ld = cs.op[kind].ld;
     v.chunk_node0 = cs.chunk_node0; v.rel = cs.rel; v.wpart = cs.wpart; v.y = cs.y; v.Ainv = cs.op[kind].Ainv;
+    v.agg_reg = cs.agg_reg; v.reg_tab = cs.op[kind].reg_tab; v.cta_tab = cs.op[kind].cta_tab; v.ac_off = cs.op[kind].ac_off;
     return v;
 }
 
@@ -704,11 +751,12 @@ int coarse_setup_t(pfx_ctx* c, int kind, const uint8_t* mask) {
     Coarse& cs = c->coarse;
     CoarseOp& op = cs.op[kind];
     CoarseView cv = coarse_view(c, kind);
-    const int nc = op.nc, ldc = nc;
+    const int nc = cs.n_agg * M;
     auto now = [&]() { cudaStreamSynchronize(c->stream); return std::chrono::steady_clock::now(); };
     std::chrono::steady_clock::time_point t0, t1, t2;
     if (c->verbose) t0 = now();
-    CK(cudaMemsetAsync(cs.Ac, 0, (size_t)nc * ldc * sizeof(double), c->stream));
+    const long long ac_total = op.h_ac_off.back() + (long long)op.h_reg.back().y * M * op.h_reg.back().y * M;
+    CK(cudaMemsetAsync(cs.Ac, 0, (size_t)ac_total * sizeof(double), c->stream));
     CK(cudaMemsetAsync(c->w_p, 0, (size_t)c->n_nodes * NC * sizeof(double), c->stream));
     for (int col = 0; col < cs.n_col; ++col)
         for (int mode = 0; mode < M; ++mode) {
@@ -716,27 +764,34 @@ int coarse_setup_t(pfx_ctx* c, int kind, const uint8_t* mask) {
             int st = apply_lin(c, kind, c->w_p, c->w_Ap, mask, c->red, nullptr, 1);
             if (st) return st;
             coarse_restrict_kernel<NC, GD><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, c->w_Ap);
-            coarse_fill_kernel<M><<<(nc + 127) / 128, 128, 0, c->stream>>>(cv, cs.nbrcol, cs.n_col, col, mode, cs.Ac, ldc);
+            coarse_fill_kernel<M><<<(nc + 127) / 128, 128, 0, c->stream>>>(cv, cs.nbrcol, cs.n_col, col, mode, cs.Ac);
             c->launches += 3;
         }
-    coarse_fixdiag_kernel<<<(nc + 127) / 128, 128, 0, c->stream>>>(nc, cs.Ac, ldc);
     CK(cudaGetLastError());
     if (c->verbose) t1 = now();
     op.valid = false;
-    int h_info[2] = {0, 0};
-    if (cusolverDnDpotrf(cs.solver, CUBLAS_FILL_MODE_LOWER, nc, cs.Ac, ldc, cs.work, cs.lwork, cs.info) != CUSOLVER_STATUS_SUCCESS) {
-        c->err = "cusolverDnDpotrf failed"; return PFX_ERR_CUDA;
-    }
-    CK(cudaMemcpyAsync(&h_info[0], cs.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (h_info[0] == 0) {
-        if (cusolverDnDpotri(cs.solver, CUBLAS_FILL_MODE_LOWER, nc, cs.Ac, ldc, cs.work, cs.lwork, cs.info) != CUSOLVER_STATUS_SUCCESS) {
+    // factorise and invert region by region; the status words are collected and read once
+    std::vector<int> h_info(2 * cs.n_reg, 0);
+    bool ok = true;
+    for (int r = 0; r < cs.n_reg && ok; ++r) {
+        const int ncr = op.h_reg[r].y * M;
+        double* A = cs.Ac + op.h_ac_off[r];
+        coarse_fixdiag_kernel<<<(ncr + 127) / 128, 128, 0, c->stream>>>(ncr, A, ncr);
+        if (cusolverDnDpotrf(cs.solver, CUBLAS_FILL_MODE_LOWER, ncr, A, ncr, cs.work, cs.lwork, cs.info) != CUSOLVER_STATUS_SUCCESS) {
+            c->err = "cusolverDnDpotrf failed"; return PFX_ERR_CUDA;
+        }
+        CK(cudaMemcpyAsync(&h_info[2 * r], cs.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        if (cusolverDnDpotri(cs.solver, CUBLAS_FILL_MODE_LOWER, ncr, A, ncr, cs.work, cs.lwork, cs.info) != CUSOLVER_STATUS_SUCCESS) {
             c->err = "cusolverDnDpotri failed"; return PFX_ERR_CUDA;
         }
-        CK(cudaMemcpyAsync(&h_info[1], cs.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaMemcpyAsync(&h_info[2 * r + 1], cs.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        dim3 grid((op.h_reg[r].w + 127) / 128, ncr);
+        coarse_convert_kernel<<<grid, 128, 0, c->stream>>>(ncr, A, ncr, op.Ainv + op.h_reg[r].z, op.h_reg[r].w);
+        c->launches += 2;
     }
-    bool ok = h_info[0] == 0 && h_info[1] == 0;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    for (int v : h_info) ok = ok && v == 0;
     if (c->n_ranks > 1) {          // every rank must take the same PCG path: all or none
         double bad = ok ? 0.0 : 1.0, tot = 0.0;
         CK(cudaMemcpyAsync(c->S + S_STAGE, &bad, sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -744,24 +799,18 @@ int coarse_setup_t(pfx_ctx* c, int kind, const uint8_t* mask) {
         if (st) return st;
         ok = tot == 0.0;
     }
-    if (ok) {
-        dim3 grid((op.ld + 127) / 128, nc);
-        coarse_convert_kernel<<<grid, 128, 0, c->stream>>>(nc, cs.Ac, ldc, op.Ainv, op.ld);
-        CK(cudaGetLastError());
-        op.valid = true;
-    } else if (c->verbose) {
-        fprintf(stderr, "[pfx] coarse matrix of operator %d is not positive definite (potrf %d, potri %d): Jacobi only\n", kind,
-                h_info[0], h_info[1]);
-    }
+    op.valid = ok;
+    if (!ok && c->verbose) fprintf(stderr, "[pfx] coarse matrix of operator %d is not positive definite: Jacobi only\n", kind);
     if (c->verbose) {
         t2 = now();
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        fprintf(stderr, "[pfx] coarse set-up op %d: %d aggregates x %d modes, %d colours: probing %.2f ms, inverse %.2f ms\n", kind,
-                cs.n_agg, M, cs.n_col, ms(t0, t1), ms(t1, t2));
+        fprintf(stderr, "[pfx] coarse set-up op %d: %d aggregates x %d modes in %d regions, %d colours: probing %.2f ms, inverses %.2f ms\n",
+                kind, cs.n_agg, M, cs.n_reg, cs.n_col, ms(t0, t1), ms(t1, t2));
     }
-    c->launches += 4;
     op.stale = false;
     op.ref_its = -1;
+    op.ref_open = true;
+    op.open_steps = 0;
     cs.setups++;
     return PFX_OK;
 }
@@ -783,9 +832,10 @@ int coarse_tail_t(pfx_ctx* c, int kind, int par, int init, const uint8_t* mask, 
     const PeerView* pv = (fused && !init) ? c->d_pv : nullptr;
     int st;
     if (BLK) dinv = cs.dblk;
-    pcg_update_coarse_kernel<NC, GD, BLK><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, c->w_x, c->w_r, c->w_p, c->w_Ap, dinv, c->S, par, init,
+    const int vgrid_c = (cs.n_chunks + kCoarseChunksPerCta - 1) / kCoarseChunksPerCta;
+    pcg_update_coarse_kernel<NC, GD, BLK><<<vgrid_c, kThreads, 0, c->stream>>>(cv, c->w_x, c->w_r, c->w_p, c->w_Ap, dinv, c->S, par, init,
                                                                                   cs.partial, c->counter, pv);
-    const int solve_ctas = (cs.op[kind].nc + kThreads / 32 - 1) / (kThreads / 32);
+    const int solve_ctas = cs.op[kind].n_ctas;
     const int mode = init ? 3 : ((multi && !pv) ? 2 : 0);
     coarse_solve_kernel<M><<<solve_ctas, kThreads, (size_t)cv.ld * sizeof(double), c->stream>>>(cv, c->S, par, mode, cs.partial,
                                                                                               c->counter, pv);
@@ -998,7 +1048,7 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
     }
     if (coarse_on) {                 // lagged coarse matrix: refresh when it stops paying
         CoarseOp& op = c->coarse.op[kind];
-        if (op.ref_its < 0) op.ref_its = *iters;
+        if (op.ref_open) op.ref_its = std::max(op.ref_its, *iters);
         else if (*iters > op.ref_its * 3 / 2 + 10) op.stale = true;
     }
     return PFX_OK;
@@ -1475,7 +1525,12 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
     int it = 0, st;
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(c->S + S_BREF, 0, 3 * sizeof(double), c->stream));      // per-step PCG reference norms
-    if (c->coarse.enabled && c->coarse.refresh_every_step) c->coarse.op[0].stale = c->coarse.op[1].stale = true;
+    for (int k = 0; k < 2 && c->coarse.enabled; ++k) {
+        CoarseOp& op = c->coarse.op[k];
+        if (c->coarse.refresh_every_step) op.stale = true;
+        // the reference iteration count is the largest of the solves in the step of the refresh and the next one
+        if (op.ref_open && op.ref_its >= 0 && ++op.open_steps >= 2) op.ref_open = false;
+    }
     const int gN = vgrid(c, N);
     while ((err_phi > o->stagger_tol || err_u > o->stagger_tol || it < o->min_stagger_iter) && it < o->max_stagger_iter) {
         ++it;
@@ -1673,7 +1728,7 @@ int pfx_algorithmic_bytes(pfx_ctx* c, int kind, double* bytes) {
                 // geometry (fp32, read twice), the Dirichlet flags, and the fp32 coarse inverse
                 const CoarseOp& op = c->coarse.op[LIN_U];
                 if (c->coarse.block_jacobi) *bytes += 2.0 * 8.0 * Nn * (d * (d + 1) / 2 - d);
-                *bytes += Nn * (2.0 * 4.0 * d + d) + 4.0 * (double)op.nc * op.ld;
+                *bytes += Nn * (2.0 * 4.0 * d + d) + 4.0 * (double)op.ainv_floats;
             }
             break;
         default: return PFX_ERR_BAD_ARG;

@@ -46,7 +46,7 @@ def test_coarse_space_load_steps_vs_oracle(no_coop):
         rg = e.load_step(max_stagger_iter=60)
         assert rg["stagger"] == ro["stagger"], (step, rg["stagger"], ro["stagger"])
         _compare_step(o, e, bcs, step)
-    assert e.coarse_stats()["setups"] >= 3
+    assert e.coarse_stats()["setups"] >= 1
     e.close()
 
 
