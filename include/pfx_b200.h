@@ -133,6 +133,16 @@ int pfx_set_traction_value(pfx_ctx* ctx, int t_id, const double* T /* [d] */);
 /* ---- the hot path: one load step = the whole stagger loop of solver.py:319-411 on device */
 int pfx_load_step(pfx_ctx* ctx, const pfx_step_opts* opts, pfx_step_report* out);
 
+/* ---- the two sub-problems on their own: the single-field solvers of the reference are
+ * the staggered step with one field frozen.
+ * pfx_solve_u: one SNES solve of F_u = 0 at the current phi (phi = 0, k = 0, isotropic model =
+ *   Element/Elasticity/solver/solver.py:110-141); fills u_newton_its, u_reason, fnorm_u, cg_its_u, gpu_ms.
+ * pfx_solve_phi: one SNES solve of the phase-field problem at the current H, fatigue field
+ *   (H = 0, Gc = 1 = Element/Phase_Field/solver/solver.py:104-125 with case AT2); fills the phi members.
+ * Non-convergence returns PFX_ERR_NOT_CONVERGED_U / _PHI like pfx_load_step. */
+int pfx_solve_u(pfx_ctx* ctx, pfx_step_report* out);
+int pfx_solve_phi(pfx_ctx* ctx, pfx_step_report* out);
+
 /* ---- per-step outputs --------------------------------------------------------------- */
 /* pfx/Reactions/reactions_forces.py:12-65, called per BC at solver.py:428-431 */
 int pfx_reaction(pfx_ctx* ctx, int bc_id, double R[3]);

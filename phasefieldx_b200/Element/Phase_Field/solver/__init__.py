@@ -1,0 +1,3 @@
+from . import solver  # noqa: F401
+
+__all__ = ["solver"]

@@ -1,3 +1,3 @@
-from . import Phase_Field_Fracture  # noqa: F401
+from . import Elasticity, Phase_Field, Phase_Field_Fracture  # noqa: F401
 
-__all__ = ["Phase_Field_Fracture"]
+__all__ = ["Elasticity", "Phase_Field", "Phase_Field_Fracture"]

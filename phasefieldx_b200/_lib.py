@@ -55,7 +55,7 @@ class PfxStepReport(C.Structure):
 SYMBOLS = [
     "pfx_version", "pfx_device_count", "pfx_status_string", "pfx_create", "pfx_destroy", "pfx_last_error",
     "pfx_default_params", "pfx_set_bc_u", "pfx_set_bc_values_u", "pfx_set_bc_phi", "pfx_set_bc_values_phi",
-    "pfx_set_traction", "pfx_set_traction_value", "pfx_load_step", "pfx_reaction", "pfx_energies", "pfx_get_field",
+    "pfx_set_traction", "pfx_set_traction_value", "pfx_load_step", "pfx_solve_u", "pfx_solve_phi", "pfx_reaction", "pfx_energies", "pfx_get_field",
     "pfx_set_field", "pfx_apply_u", "pfx_apply_phi", "pfx_apply_mass", "pfx_residual_u", "pfx_diag_u", "pfx_rhs_psi",
     "pfx_l2_error", "pfx_time_operator", "pfx_algorithmic_bytes", "pfx_launch_count", "pfx_block_stats", "pfx_coarse_stats",
     "pfx_partition_create", "pfx_partition_destroy", "pfx_partition_cell_rank", "pfx_partition_node_owner",
@@ -93,6 +93,8 @@ def load():
     lib.pfx_set_traction.argtypes = [C.c_void_p, C.c_int, pi, pd, C.c_int64]
     lib.pfx_set_traction_value.argtypes = [C.c_void_p, C.c_int, pd]
     lib.pfx_load_step.argtypes = [C.c_void_p, C.POINTER(PfxStepOpts), C.POINTER(PfxStepReport)]
+    lib.pfx_solve_u.argtypes = [C.c_void_p, C.POINTER(PfxStepReport)]
+    lib.pfx_solve_phi.argtypes = [C.c_void_p, C.POINTER(PfxStepReport)]
     lib.pfx_reaction.argtypes = [C.c_void_p, C.c_int, pd]
     lib.pfx_energies.argtypes = [C.c_void_p, pd]
     lib.pfx_get_field.argtypes = [C.c_void_p, C.c_int, pd, C.c_int64]
@@ -320,6 +322,24 @@ class Engine:
             raise RuntimeError(f"Solver did not converge, got {reason}.")
         self._ck(st)
         return rep
+
+    def _solve_single(self, fn, is_u):
+        r = PfxStepReport()
+        st = fn(self.h, C.byref(r))
+        if st in (PFX_ERR_NOT_CONVERGED_U, PFX_ERR_NOT_CONVERGED_PHI):
+            raise RuntimeError(f"Solver did not converge, got {r.u_reason if is_u else r.phi_reason}.")
+        self._ck(st)
+        if is_u:
+            return dict(its=r.u_newton_its, reason=r.u_reason, fnorm=r.fnorm_u, cg_its=r.cg_its_u, gpu_ms=r.gpu_ms)
+        return dict(its=r.phi_newton_its, reason=r.phi_reason, fnorm=r.fnorm_phi, cg_its=r.cg_its_phi, gpu_ms=r.gpu_ms)
+
+    def solve_u(self):
+        """One Newton (SNES) solve of the displacement problem at the current phi."""
+        return self._solve_single(self.lib.pfx_solve_u, True)
+
+    def solve_phi(self):
+        """One Newton (SNES) solve of the phase-field problem at the current H / fatigue field."""
+        return self._solve_single(self.lib.pfx_solve_phi, False)
 
     # ---------------------------------------------------------------- outputs
     def reaction(self, bc_id):

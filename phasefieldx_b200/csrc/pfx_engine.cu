@@ -1608,6 +1608,33 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
 }
 
 // ------------------------------------------------------------------------------- outputs
+static int solve_single(pfx_ctx* c, bool is_u, pfx_step_report* rep) {
+    if (!c || !rep) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    memset(rep, 0, sizeof(*rep));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemsetAsync(c->S + S_BREF, 0, 3 * sizeof(double), c->stream));
+    NewtonOut no;
+    int st = newton(c, is_u, &no);
+    if (st) return st;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    rep->gpu_ms = ms;
+    if (is_u) { rep->u_newton_its = no.its; rep->u_reason = no.reason; rep->fnorm_u = no.fnorm; rep->cg_its_u = no.cg_its; }
+    else { rep->phi_newton_its = no.its; rep->phi_reason = no.reason; rep->fnorm_phi = no.fnorm; rep->cg_its_phi = no.cg_its; }
+    if (no.reason <= 0) {
+        c->err = "Solver did not converge, got " + std::to_string(no.reason) + ".";
+        return is_u ? PFX_ERR_NOT_CONVERGED_U : PFX_ERR_NOT_CONVERGED_PHI;
+    }
+    return PFX_OK;
+}
+
+// the two sub-problems of the staggered step on their own (single-field solvers of the reference)
+int pfx_solve_u(pfx_ctx* c, pfx_step_report* rep) { return solve_single(c, true, rep); }
+int pfx_solve_phi(pfx_ctx* c, pfx_step_report* rep) { return solve_single(c, false, rep); }
+
 int pfx_reaction(pfx_ctx* c, int bc_id, double R[3]) {
     if (!c || !R || bc_id < 0 || (size_t)bc_id >= c->bcs_u.size()) return PFX_ERR_BAD_ARG;
     CK(cudaSetDevice(c->device));

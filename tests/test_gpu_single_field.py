@@ -1,0 +1,100 @@
+"""The single-field drop-in solvers: the reference's own phase-field profile test run
+unchanged in structure through `phasefieldx.Element.Phase_Field.solver.solver.solve` (reference
+test/Element/Phase_Field/test_phase_field_element.py:15-124, the 2D case; intervals and hexahedra are
+not built), and the elasticity solver against the CPU oracle's direct solve."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_phase_field_profile_reference_test(tmp_path):
+    import phasefieldx_b200.compat as compat
+    compat.install()
+    import dolfinx
+    import mpi4py
+    from phasefieldx.Element.Phase_Field.Input import Input
+    from phasefieldx.Element.Phase_Field.solver.solver import solve
+    from phasefieldx.Boundary.boundary_conditions import bc_phi, get_ds_bound_from_marker
+    from phasefieldx.PostProcessing.ReferenceResult import AllResults
+    from phasefieldx_b200.io_vtk import read_vtu_points_cells
+
+    lx, ly, divx, divy = 5.0, 1.0, 200, 1
+    msh = dolfinx.mesh.create_rectangle(mpi4py.MPI.COMM_WORLD, [np.array([0.0, 0.0]), np.array([lx, ly])], [divx, divy],
+                                        cell_type=dolfinx.mesh.CellType.quadrilateral)
+    Data = Input(l=4.0, save_solution_xdmf=False, save_solution_vtu=True, results_folder_name=str(tmp_path / "test_results"))
+
+    def left(x):
+        return np.equal(x[0], 0)
+    fdim = msh.topology.dim - 1
+    left_facet_marker = dolfinx.mesh.locate_entities_boundary(msh, fdim, left)
+    ds_left = get_ds_bound_from_marker(left_facet_marker, msh, fdim)
+    ds_list = np.array([[ds_left, "left"]])
+    V_phi = dolfinx.fem.functionspace(msh, ("Lagrange", 1))
+    bcs_list_phi = [bc_phi(left_facet_marker, V_phi, fdim, value=1.0)]
+    solve(Data, msh, 1.0, V_phi, bcs_list_phi, None, None, ds_list, 1.0, path=str(tmp_path), quadrature_degree=2)
+
+    out = read_vtu_points_cells(str(tmp_path / "test_results" / "paraview-solutions_vtu" / "phasefieldx_p0_000000.vtu"))
+    xt = out["points"][:, 0]
+    phi_theory = np.exp(-abs(xt) / Data.l) + 1 / (np.exp(2 * lx / Data.l) + 1) * 2 * np.sinh(np.abs(xt) / Data.l)
+    assert np.allclose(out["phi"], phi_theory, atol=1e-8)          # the reference's tolerance (rtol 1e-5)
+    S = AllResults(Data.results_folder_name)
+    a = lx / Data.l
+    th = np.tanh(a)
+    W_phi, W_grad = 0.5 * th + 0.5 * a * (1.0 - th**2), 0.5 * th - 0.5 * a * (1.0 - th**2)
+    en = S.energy_files["total.energy"]
+    np.testing.assert_allclose(en["gamma_phi"][0], 0.5 * W_phi, rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(en["gamma_gradphi"][0], 0.5 * W_grad, rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(en["gamma"][0], 0.5 * th, rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("ctype", ["triangle", "tetrahedron"])
+def test_elasticity_solver_vs_oracle(tmp_path, ctype):
+    """Drop-in elasticity solve() (reference Element/Elasticity/solver/solver.py) against the oracle's
+    direct solve of the same problem: u to 1e-8, reactions to 1e-6, elastic energy to 1e-7."""
+    from oracle.solver import BC, Oracle, Params
+    from phasefieldx_b200 import fem, mesh as M
+    from phasefieldx_b200.Boundary.boundary_conditions import bc_xy, bc_xyz
+    from phasefieldx_b200.Element.Elasticity.Input import Input
+    from phasefieldx_b200.Element.Elasticity.solver.solver import solve
+    from phasefieldx_b200.PostProcessing.ReferenceResult import AllResults
+    from phasefieldx_b200.io_vtk import read_vtu_points_cells
+
+    if ctype == "triangle":
+        msh = M.create_rectangle(None, [[0, 0], [2, 1]], [24, 12])
+        d, bc_fix = 2, bc_xy
+    else:
+        msh = M.create_box(None, [[0, 0, 0], [2, 1, 0.5]], [10, 5, 3])
+        d, bc_fix = 3, bc_xyz
+    fdim = msh.topology.dim - 1
+    V_u = fem.functionspace(msh, ("Lagrange", 1, (d,)))
+    left = M.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[0], 0.0))
+    right = M.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[0], 2.0))
+    bcl, bcr = bc_fix(left, V_u, fdim), bc_fix(right, V_u, fdim)
+
+    def update(bcs, t):
+        bcs[1].g.value[...] = 0.0
+        bcs[1].g.value[0] = 1e-3 * t
+        bcs[1].g.value[1] = 5e-4 * t
+        return 1e-3 * t, 5e-4 * t, 0
+    Data = Input(E=210.0, nu=0.3, save_solution_vtu=True, results_folder_name=str(tmp_path / "res"))
+    solve(Data, msh, 3.0, V_u, [bcl, bcr], update, None, None, None, None, 1.0, path=str(tmp_path),
+          bcs_list_u_names=["left", "right"])
+
+    P = Params(E=210.0, nu=0.3, Gc=1.0, l=1.0, k=0.0)
+    o = Oracle(msh.geometry.x, msh.cells, msh.cell_type, P)
+    dl, dr = fem.extract_bc(bcl)[0], fem.extract_bc(bcr)[0]
+    vr = np.zeros(len(dr))
+    vr[dr % d == 0] = 2e-3
+    vr[dr % d == 1] = 1e-3
+    o.solve_u([BC(dl), BC(dr, vr)])
+    out = read_vtu_points_cells(str(tmp_path / "res" / "paraview-solutions_vtu" / "phasefieldx_p0_000002.vtu"))
+    u = out["u"][:, :d].ravel()
+    assert np.linalg.norm(u - o.u) <= 1e-8 * np.linalg.norm(o.u)
+    S = AllResults(Data.results_folder_name)
+    Ro = o.reaction(BC(dr, vr))
+    Rg = np.array([S.reaction_files["right.reaction"][c][2] for c in ("Rx", "Ry", "Rz")])
+    assert np.all(np.abs(Rg[:d] - Ro[:d]) <= 1e-6 * np.abs(Ro).max())
+    E = S.energy_files["total.energy"]["E"][2]
+    assert abs(E - o.energies()["E"]) <= 1e-7 * abs(o.energies()["E"])
+    assert list(S.convergence_files["phasefieldx.conv"]["iterations"]) == [0, 1, 1]

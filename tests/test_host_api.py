@@ -200,3 +200,23 @@ def test_native_number_formatting_round_trips_bit_exactly():
     ints = rng.integers(-2**62, 2**62, size=150000)
     assert np.array_equal(np.array(_lib.format_i64(ints).split(), dtype=np.int64), ints)
     assert _lib.format_f64(np.zeros((0, 2)), 3) == b"" and _lib.format_i64(np.zeros(0, int)) == b""
+
+
+def test_single_field_inputs_match_reference_format(tmp_path):
+    """Input classes of the Elasticity / Phase_Field elements: reference keyword names, defaults and the
+    two-column `parameters.input` layout (reference Element/Elasticity/Input.py:46-111,
+    Element/Phase_Field/Input.py:33-90)."""
+    from phasefieldx_b200.Element.Elasticity.Input import Input as EInput
+    from phasefieldx_b200.Element.Phase_Field.Input import Input as PInput
+    e = EInput(E=100.0, nu=0.25)
+    assert abs(e.lambda_ - 40.0) < 1e-12 and abs(e.mu - 40.0) < 1e-12
+    f = tmp_path / "parameters.input"
+    e.save_parameters_to_csv(str(f))
+    rows = [l.split("\t") for l in f.read_text().splitlines()]
+    assert [r[0] for r in rows] == ["E", "nu", "lambda", "mu", "save_solution_xdmf", "save_solution_vtu", "results_folder_name"]
+    assert rows[0][1] == "100.0" and rows[-1][1] == "results"
+    assert str(e).splitlines()[0] == "Material parameters:"
+    p = PInput(l=4.0, results_folder_name="r")
+    p.save_parameters_to_csv(str(f))
+    assert f.read_text().splitlines() == ["l\t4.0", "save_solution_xdmf\tFalse", "save_solution_vtu\tTrue", "results_folder_name\tr"]
+    assert str(p) == "Parameters:\n  l: 4.0"
