@@ -102,3 +102,37 @@ def test_coarse_space_matches_jacobi_on_every_cell_type(ctype, no_coop):
         assert rel_l2(a[f], b[f]) < 1e-8, (f, rel_l2(a[f], b[f]))
     assert np.all(np.abs(a["R"] - b["R"]) <= 1e-6 * np.abs(b["R"]).max())
     assert a["its"] * 2 < b["its"], (a["its"], b["its"])
+
+
+def test_coarse_space_with_tractions_phi_dirichlet_and_fatigue(no_coop):
+    """The less common ingredients together — Neumann load, a phase-field Dirichlet seed (masked
+    constants in the phi coarse space), hybrid split, fatigue degradation in J_phi — against the CPU
+    oracle with the coarse space active (mesh large enough for >= 32 blocks of 64 nodes)."""
+    from phasefieldx_b200 import mesh as M, fem
+    from oracle.solver import BC
+    msh = M.create_rectangle(None, [[0, 0], [1.0, 1.0]], [52, 52])
+    o, e, P = _pair(msh, "triangle", "hybrid", "spectral", l=0.05, Gc=0.0027, fatigue=True, fatigue_val=0.002, block_nodes=64)
+    assert e.coarse_stats()["active"] == 1
+    x = msh.geometry.x
+    bot = np.nonzero(np.isclose(x[:, 1], 0.0))[0]
+    seed = np.nonzero(np.isclose(x[:, 1], 0.5) & (x[:, 0] < 0.3))[0]
+    top_facets = M.locate_entities_boundary(msh, 1, lambda p: np.isclose(p[1], 1.0))
+    nodes, w = fem.Measure(msh, top_facets).nodal_weights()
+    bcs_u = [BC((bot[:, None] * 2 + np.arange(2)).ravel())]
+    bcs_phi = [BC(seed, np.ones(len(seed)))]
+    e.set_bc_u(0, bcs_u[0].dofs)
+    e.set_bc_values_u(0, bcs_u[0].values)
+    e.set_bc_phi(0, seed)
+    e.set_bc_values_phi(0, bcs_phi[0].values)
+    e.set_traction(0, nodes, w)
+    for step in range(1, 4):
+        T = np.array([0.02 * step, 0.05 * step]) * (1 if step != 2 else 0.5)      # load, partial unload, reload
+        e.set_traction_value(0, T)
+        fext = o.traction_vector(nodes, w, T)
+        ro = o.load_step(bcs_u, bcs_phi, max_stagger_iter=80, fext=fext)
+        rg = e.load_step(max_stagger_iter=80)
+        assert rg["stagger"] == ro["stagger"], (step, rg["stagger"], ro["stagger"])
+        _compare_step(o, e, bcs_u, step, names=("u", "phi", "H", "fatigue", "alpha_cum_bar_c"))
+        assert np.allclose(e.get_field("phi")[seed], 1.0)
+    assert np.allclose(e.reaction(0)[:2], -T, rtol=1e-6, atol=1e-10)
+    e.close()
