@@ -159,7 +159,7 @@ struct pfx_ctx {
     bool phi_coeff_fresh = false;
     bool generic_apply = false;   // PFX_GENERIC_APPLY=1: use the generic scatter kernel for J_u·v on triangles
     int apply_variant = 3;        // PFX_APPLY_VARIANT: 3 persistent + prefetched indices (default), 2 persistent, 1 one CTA per block
-    int persist_ctas = 0, v3_ctas = 0, num_sms = 148;
+    int persist_ctas = 0, v3_ctas = 0, v3_tan_ctas = 0, num_sms = 148;
     Coarse coarse;
 };
 
@@ -246,22 +246,23 @@ int launch_apply_u_tri_persist(pfx_ctx* c, const KArgs& a) {
     return PFX_OK;
 }
 
-template <int SM>
+template <int SM, bool TAN = false>
 int launch_apply_u_tri_v3(pfx_ctx* c, const KArgs& a) {
     BlockView bv = c->bv;
     bv.chunk = 2 * kThreads;
     size_t ML = (size_t)c->bm.max_loc, MO = ((size_t)c->bm.max_own + 1) & ~(size_t)1;
-    size_t stage = ML * 16 * (SM != M_ISO ? 3 : 2) + ((ML + 3) & ~(size_t)1) * 8 + MO * 16;
+    size_t stage = ML * 16 * ((SM != M_ISO && !TAN) ? 3 : 2) + ((ML + 3) & ~(size_t)1) * 8 + MO * 16;
     size_t smem = 2 * stage + (3 * (size_t)bv.chunk + 1) * sizeof(double2);
+    int& ctas = TAN ? c->v3_tan_ctas : c->v3_ctas;
     if (c->configuring) {
-        CK(cudaFuncSetAttribute(apply_u_tri_v3_kernel<SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(apply_u_tri_v3_kernel<SM, TAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apply_u_tri_v3_kernel<SM>, kThreads, smem));
-        c->v3_ctas = std::max(1, nb) * c->num_sms;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apply_u_tri_v3_kernel<SM, TAN>, kThreads, smem));
+        ctas = std::max(1, nb) * c->num_sms;
         return PFX_OK;
     }
-    int grid = std::min(c->bm.nb, c->v3_ctas);
-    apply_u_tri_v3_kernel<SM><<<grid, kThreads, smem, c->stream>>>(bv, a);
+    int grid = std::min(c->bm.nb, ctas);
+    apply_u_tri_v3_kernel<SM, TAN><<<grid, kThreads, smem, c->stream>>>(bv, a);
     c->launches++;
     CK(cudaGetLastError());
     return PFX_OK;
@@ -388,6 +389,12 @@ int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
             if constexpr (Cell::simplex) return launch_scatter_op<OpTangentU<Cell>>(c, a);
             break;
         case OP_APPLY_U_TAN:
+            if constexpr (std::is_same<Cell, Tri>::value) {
+                // persistent TMA-staged kernel fed by the cached element tangents (the split model no longer matters)
+                if (c->configuring) { int st = launch_apply_u_tri_v3<M_SPECTRAL, true>(c, a); if (st) return st; }
+                else if (c->apply_variant == 3 && c->bm.max_elems <= 2 * kThreads && (a.mask == nullptr || a.input_masked))
+                    return launch_apply_u_tri_v3<M_SPECTRAL, true>(c, a);
+            }
             if constexpr (Cell::simplex) return launch_scatter_op<OpApplyUTan<Cell>>(c, a);
             break;
         case OP_DIAGBLK_U: return launch_scatter_op<OpDiagBlkU<Cell>>(c, a);
@@ -1398,7 +1405,12 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     CK(cudaEventCreate(&c->ev1));
     c->graph_iters = prm->cg_chunk > 0 ? (prm->cg_chunk + 1) / 2 * 2 : 32;
 
-    if (c->cell_type == PFX_CELL_TETRAHEDRON && c->mat.smodel != M_ISO && !getenv("PFX_NO_TANGENT_CACHE")) {
+    // triangles: the cached-tangent variant of the persistent kernel (PFX_TRI_TANGENT_CACHE=1) measures 50 us
+    // against 54 us for the re-derived spectral tangent at 1.7x the bytes: the kernel is bound by its per-block
+    // pipeline latency, not by fp64 work, so it stays opt-in
+    const char* ttc = getenv("PFX_TRI_TANGENT_CACHE");
+    const bool tan_cells = c->cell_type == PFX_CELL_TETRAHEDRON || (c->cell_type == PFX_CELL_TRIANGLE && ttc && ttc[0] == '1');
+    if (tan_cells && c->mat.smodel != M_ISO && !getenv("PFX_NO_TANGENT_CACHE")) {
         if ((st = dev_alloc(c, &c->tan, (size_t)21 * (size_t)bm.total_elems))) return st;
         c->use_tan = true;
     }
@@ -1744,12 +1756,17 @@ int pfx_algorithmic_bytes(pfx_ctx* c, int kind, double* bytes) {
     double conn = 4.0 * nv * Ne;
     bool nl = c->mat.smodel != M_ISO;
     switch (kind) {
-        case 0: *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d + (nl ? 8 * d : 0)); break;       // u-apply
+        case 0:                                                                                  // u-apply
+            *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d + (nl ? 8 * d : 0));
+            if (c->use_tan)      // cached element tangent instead of u and phi: X, v, y per node + NT doubles per cell
+                *bytes = conn + Nn * (3 * 8 * d) + Ne * 8.0 * (d == 2 ? 6 : 21);
+            break;
         case 1: *bytes = conn + Nn * (8 * d + 24 + (c->mat.fatigue ? 8 : 0)); break;             // phi-apply
         case 2: *bytes = conn + Nn * (8 * d + 16); break;                                        // mass-apply
         case 3: *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d); break;                         // residual_u
         case 4:                                                                                  // u-PCG iteration
             *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d + (nl ? 8 * d : 0)) + 11.0 * 8.0 * d * Nn;
+            if (c->use_tan) *bytes = conn + Nn * (3 * 8 * d) + Ne * 8.0 * (d == 2 ? 6 : 21) + 11.0 * 8.0 * d * Nn;
             if (coarse_active(c, LIN_U)) {
                 // two-level iteration: inverse diagonal blocks instead of the diagonal (read twice), the mode
                 // geometry (fp32, read twice), the Dirichlet flags, and the fp32 coarse inverse

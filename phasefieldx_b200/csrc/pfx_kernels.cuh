@@ -636,6 +636,24 @@ __device__ __forceinline__ void tri_apply_elem(const Material& m, double2 x0, do
     f0 = make_double2(-(f1.x + f2.x), -(f1.y + f2.y));
 }
 
+// Same element action from the cached element tangent T (elem_tangent_u: symmetric 3x3 of the bilinear
+// form de':C:de in sym storage, shear rows weighted by 2, area and g(phi)+k folded in): 33 multiply-adds
+// instead of the eigen-decomposition of the strain.
+__device__ __forceinline__ void tri_apply_elem_tan(double2 x0, double2 x1, double2 x2, double2 v0, double2 v1, double2 v2,
+                                                   const double* T, double2& f0, double2& f1, double2& f2) {
+    const double ax = x1.x - x0.x, ay = x1.y - x0.y, bx = x2.x - x0.x, by = x2.y - x0.y;
+    const double det = ax * by - ay * bx, inv = __drcp_rn(det);
+    const double g1x = by * inv, g1y = -bx * inv, g2x = -ay * inv, g2y = ax * inv;
+    const double g0x = -(g1x + g2x), g0y = -(g1y + g2y);
+    const double de0 = g0x * v0.x + g1x * v1.x + g2x * v2.x, de1 = g0y * v0.y + g1y * v1.y + g2y * v2.y,
+                 de2 = 0.5 * (g0y * v0.x + g1y * v1.x + g2y * v2.x + g0x * v0.y + g1x * v1.y + g2x * v2.y);
+    const double S0 = T[0] * de0 + T[1] * de1 + T[2] * de2, S1 = T[1] * de0 + T[3] * de1 + T[4] * de2,
+                 S2 = 0.5 * (T[2] * de0 + T[4] * de1 + T[5] * de2);
+    f1 = make_double2(S0 * g1x + S2 * g1y, S2 * g1x + S1 * g1y);
+    f2 = make_double2(S0 * g2x + S2 * g2y, S2 * g2x + S1 * g2y);
+    f0 = make_double2(-(f1.x + f2.x), -(f1.y + f2.y));
+}
+
 template <int SM>
 __global__ void __launch_bounds__(kThreads, 4) apply_u_tri_kernel(BlockView bv, KArgs a) {
     constexpr bool NL = (SM != M_ISO);
@@ -905,9 +923,12 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_persist_kernel(BlockV
 // incidence table staged by bulk copy — eight independent 128-bit shared loads per node instead
 // of a pointer-chasing loop.  Requires every block to list <= 2*kThreads cells (the block
 // builder sizes triangle blocks that way; otherwise the engine falls back to the v2 kernel).
-template <int SM>
+// TAN = true: the element action comes from the cached element tangents a.tan (refreshed once per Newton
+// linearisation by OpTangentU) instead of being re-derived from u and phi in every PCG iteration; u and
+// phi are then not staged at all.
+template <int SM, bool TAN = false>
 __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView bv, KArgs a) {
-    constexpr bool NL = (SM != M_ISO);
+    constexpr bool NL = (SM != M_ISO) && !TAN;
     extern __shared__ double smem[];
     __shared__ double s_red[kMaxRed * 32];
     __shared__ uint64_t s_bar[2];
@@ -941,21 +962,21 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
         if (tid == 0) {
             fence_proxy_async();
             const uint32_t nev = (uint32_t)(n_own & ~1);
-            uint32_t bytes = (uint32_t)n_own * 16u * (NL ? 3u : 2u) + nev * 8u + (uint32_t)n_own * 16u;
+            uint32_t bytes = (uint32_t)n_own * 16u * (NL ? 3u : 2u) + (TAN ? 0u : nev * 8u) + (uint32_t)n_own * 16u;
             mbar_expect_tx(&s_bar[s_], bytes);
             bulk_g2s(tX, X2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
             bulk_g2s(tV, V2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
             if (NL) bulk_g2s(tU, U2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
-            if (nev) bulk_g2s(tP, a.phi + n0, nev * 8u, &s_bar[s_]);
+            if (!TAN && nev) bulk_g2s(tP, a.phi + n0, nev * 8u, &s_bar[s_]);
             bulk_g2s(p + oI, bv.inc8 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
-            if (n_own & 1) cp_async8(tP + n_own - 1, a.phi + n0 + n_own - 1);
+            if (!TAN && (n_own & 1)) cp_async8(tP + n_own - 1, a.phi + n0 + n_own - 1);
         }
         for (int i = tid; i < n_halo; i += kThreads) {
             int g = (i == tid) ? hidx : bv.halo[h0 + i];
             cp_async16(tX + n_own + i, X2 + g);
             cp_async16(tV + n_own + i, V2 + g);
             if (NL) cp_async16(tU + n_own + i, U2 + g);
-            cp_async8(tP + n_own + i, a.phi + g);
+            if (!TAN) cp_async8(tP + n_own + i, a.phi + g);
         }
         cp_async_commit();
         (void)mb;
@@ -989,6 +1010,16 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
         } else {
             cp_async_wait<0>();
         }
+        // cached tangents of this thread's two cells: requested before the wait on the staged nodes
+        double T0[6], T1[6];
+        if (TAN) {
+            const double* tp = a.tan + mb.x + tid;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                T0[k] = (tid < ne) ? __ldg(tp + (size_t)k * a.tan_stride) : 0.0;
+                T1[k] = (tid + kThreads < ne) ? __ldg(tp + (size_t)k * a.tan_stride + kThreads) : 0.0;
+            }
+        }
         mbar_wait(&s_bar[s], (phases >> s) & 1u);
         phases ^= (1u << s);
         __syncthreads();
@@ -1002,15 +1033,21 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
         if (tid < ne) {
             double2 f0, f1, f2;
             const int vx = lc0.x & 0xFFFF, vy = lc0.x >> 16, vz = lc0.y & 0xFFFF;
-            tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
-                               sV[vz], NL ? sU[vx] : z, NL ? sU[vy] : z, NL ? sU[vz] : z, f0, f1, f2);
+            if (TAN)
+                tri_apply_elem_tan(sX[vx], sX[vy], sX[vz], sV[vx], sV[vy], sV[vz], T0, f0, f1, f2);
+            else
+                tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
+                                   sV[vz], NL ? sU[vx] : z, NL ? sU[vy] : z, NL ? sU[vz] : z, f0, f1, f2);
             sE[tid] = f0; sE[chunk + tid] = f1; sE[2 * chunk + tid] = f2;
         }
         if (tid + kThreads < ne) {
             double2 f0, f1, f2;
             const int vx = lc1.x & 0xFFFF, vy = lc1.x >> 16, vz = lc1.y & 0xFFFF;
-            tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
-                               sV[vz], NL ? sU[vx] : z, NL ? sU[vy] : z, NL ? sU[vz] : z, f0, f1, f2);
+            if (TAN)
+                tri_apply_elem_tan(sX[vx], sX[vy], sX[vz], sV[vx], sV[vy], sV[vz], T1, f0, f1, f2);
+            else
+                tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
+                                   sV[vz], NL ? sU[vx] : z, NL ? sU[vy] : z, NL ? sU[vz] : z, f0, f1, f2);
             sE[tid + kThreads] = f0; sE[chunk + tid + kThreads] = f1; sE[2 * chunk + tid + kThreads] = f2;
         }
         __syncthreads();

@@ -24,9 +24,12 @@ def _shear_mesh(n):
     return M.cut_slit(msh, lambda x: np.isclose(x[1], 0.0) & (x[0] < -1e-9), lambda c: c[1] > 0)
 
 
-def test_coarse_space_load_steps_vs_oracle(no_coop):
-    """Config-2-like slit square (reference plot_1712.py), spectral split, coarse space active."""
+@pytest.mark.parametrize("tri_tangent_cache", [False, True])
+def test_coarse_space_load_steps_vs_oracle(no_coop, tri_tangent_cache):
+    """Config-2-like slit square (reference plot_1712.py), spectral split, coarse space active; also with
+    the opt-in cached-element-tangent variant of the persistent apply kernel (PFX_TRI_TANGENT_CACHE=1)."""
     from oracle.solver import BC
+    no_coop.setenv("PFX_TRI_TANGENT_CACHE", "1" if tri_tangent_cache else "0")
     msh = _shear_mesh(56)
     o, e, P = _pair(msh, "triangle", "anisotropic", "spectral", l=0.06, block_nodes=64)
     st = e.coarse_stats()
