@@ -297,4 +297,94 @@ std::string build_partition(int nv, int64_t n_nodes, int64_t n_cells, const doub
     return "";
 }
 
+std::string build_aggregates(const BlockMesh& bm, int64_t n_cells, const double* coords, const int32_t* cells, int g,
+                             int reg_aggs, int chunk_nodes, AggregateSet& out) {
+    if (g < 1 || reg_aggs < 1 || chunk_nodes < 2 || bm.nb < 1) return "build_aggregates: bad arguments";
+    const int D = bm.dim, nv = bm.nv;
+    const int n_agg = (bm.nb + g - 1) / g;
+    out = AggregateSet();
+    out.n_agg = n_agg;
+    out.n_reg = std::max(1, (n_agg + reg_aggs - 1) / reg_aggs);
+    out.reg_agg0.resize(out.n_reg + 1);
+    out.agg_reg.resize(n_agg);
+    for (int r = 0; r <= out.n_reg; ++r) out.reg_agg0[r] = (int32_t)((int64_t)n_agg * r / out.n_reg);
+    for (int r = 0; r < out.n_reg; ++r)
+        for (int a = out.reg_agg0[r]; a < out.reg_agg0[r + 1]; ++a) out.agg_reg[a] = r;
+    out.agg_node0.resize(n_agg + 1);
+    int max_nodes = 0;
+    for (int a = 0; a <= n_agg; ++a) out.agg_node0[a] = bm.node0[std::min(bm.nb, a * g)];
+    for (int a = 0; a < n_agg; ++a) max_nodes = std::max(max_nodes, out.agg_node0[a + 1] - out.agg_node0[a]);
+    out.S = std::max(1, (max_nodes + chunk_nodes - 1) / chunk_nodes);
+    out.n_chunks = n_agg * out.S;
+    out.chunk_node0.resize(out.n_chunks + 1);
+    for (int a = 0; a < n_agg; ++a)
+        for (int s = 0; s < out.S; ++s)
+            out.chunk_node0[a * out.S + s] =
+                out.agg_node0[a] + ((int32_t)((int64_t)(out.agg_node0[a + 1] - out.agg_node0[a]) * s / out.S) & ~1);
+    out.chunk_node0[out.n_chunks] = out.agg_node0[n_agg];
+    // geometry of the modes: coordinates relative to the aggregate centroid, scaled by its half extent
+    const int64_t n_owned = bm.n_owned;
+    std::vector<int32_t> node_agg(n_owned);
+    out.rel.resize((size_t)n_owned * D);
+    for (int a = 0; a < n_agg; ++a) {
+        double cen[3] = {0, 0, 0}, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        const int n0 = out.agg_node0[a], n1 = out.agg_node0[a + 1];
+        for (int i = n0; i < n1; ++i)
+            for (int k = 0; k < D; ++k) {
+                double x = coords[3 * (int64_t)bm.perm[i] + k];
+                cen[k] += x; lo[k] = std::min(lo[k], x); hi[k] = std::max(hi[k], x);
+            }
+        double size = 0;
+        for (int k = 0; k < D; ++k) { cen[k] /= std::max(1, n1 - n0); size = std::max(size, 0.5 * (hi[k] - lo[k])); }
+        const double sc = size > 0 ? 1.0 / size : 1.0;
+        for (int i = n0; i < n1; ++i) {
+            node_agg[i] = a;
+            for (int k = 0; k < D; ++k) out.rel[(size_t)i * D + k] = (float)((coords[3 * (int64_t)bm.perm[i] + k] - cen[k]) * sc);
+        }
+    }
+    // aggregate graph
+    std::vector<std::vector<int32_t>> adj(n_agg);
+    for (int64_t e = 0; e < n_cells; ++e) {
+        int32_t ag[4]; int na = 0;
+        for (int k = 0; k < nv; ++k) {
+            int32_t nid = bm.iperm[cells[e * nv + k]];
+            if (nid >= n_owned) continue;
+            int32_t a = node_agg[nid];
+            bool seen = false;
+            for (int q = 0; q < na; ++q) seen |= (ag[q] == a);
+            if (!seen) ag[na++] = a;
+        }
+        for (int p = 0; p < na; ++p)
+            for (int q = 0; q < na; ++q)
+                if (p != q) adj[ag[p]].push_back(ag[q]);
+    }
+    for (auto& v : adj) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
+    // greedy distance-2 colouring
+    out.colour.assign(n_agg, -1);
+    int n_col = 0;
+    std::vector<char> used;
+    for (int a = 0; a < n_agg; ++a) {
+        used.assign(n_col + 1, 0);
+        for (int32_t j : adj[a]) {
+            if (out.colour[j] >= 0) used[out.colour[j]] = 1;
+            for (int32_t k : adj[j]) if (k != a && out.colour[k] >= 0) used[out.colour[k]] = 1;
+        }
+        int col = 0;
+        while (col < n_col && used[col]) ++col;
+        out.colour[a] = col;
+        n_col = std::max(n_col, col + 1);
+    }
+    out.n_col = n_col;
+    out.nbrcol.assign((size_t)n_agg * n_col, -1);
+    for (int a = 0; a < n_agg; ++a) {
+        out.nbrcol[(size_t)a * n_col + out.colour[a]] = a;
+        for (int32_t j : adj[a]) {
+            int32_t& slot = out.nbrcol[(size_t)a * n_col + out.colour[j]];
+            if (slot >= 0 && slot != j) return "coarse space: colouring is not distance-2";
+            slot = j;
+        }
+    }
+    return "";
+}
+
 }  // namespace pfx

@@ -45,6 +45,26 @@ struct BlockMesh {
 std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int64_t n_cells, const double* coords,
                          const int32_t* cells, const uint8_t* cell_primary, int max_own, BlockMesh& out);
 
+// Aggregates of the PCG coarse space (pfx_coarse.cuh): runs of `g` consecutive blocks; chunks = even splits
+// of an aggregate into <= chunk_nodes nodes; regions = contiguous runs of aggregates whose couplings the
+// coarse matrix keeps; distance-2 colouring of the aggregate graph (i ~ j when a cell has owned vertices in
+// both) so that one operator apply probes all aggregates of a colour at once.
+struct AggregateSet {
+    int n_agg = 0, S = 1, n_chunks = 0, n_col = 0, n_reg = 1;
+    std::vector<int32_t> agg_node0;      // [n_agg+1] owned-node range (new ids)
+    std::vector<int32_t> chunk_node0;    // [n_chunks+1], chunk c belongs to aggregate c / S; even starts
+    std::vector<int32_t> reg_agg0;       // [n_reg+1]
+    std::vector<int32_t> agg_reg;        // [n_agg]
+    std::vector<int32_t> colour;         // [n_agg]
+    std::vector<int32_t> nbrcol;         // [n_agg*n_col] the aggregate of that colour within distance one (or -1)
+    std::vector<float> rel;              // [n_owned*dim] (x - centroid(aggregate)) / half extent(aggregate)
+};
+
+// cells / coords in caller ids as given to build_blocks.  g blocks per aggregate, regions of at most
+// reg_aggs aggregates.  Returns "" or an error text.
+std::string build_aggregates(const BlockMesh& bm, int64_t n_cells, const double* coords, const int32_t* cells, int g,
+                             int reg_aggs, int chunk_nodes, AggregateSet& out);
+
 struct RankPart {
     std::vector<int64_t> l2g;            // local -> global node (owned first, then ghosts by owner, by gid)
     int64_t n_owned = 0;

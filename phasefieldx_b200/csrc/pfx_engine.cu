@@ -606,87 +606,15 @@ int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
     int g = (bm.nb * m_u + total_cap - 1) / total_cap;
     if (eg && atoi(eg) > 0) g = atoi(eg);
     g = std::max(g, 1);
-    const int n_agg = (bm.nb + g - 1) / g;
-    const int n_reg = std::max(1, (n_agg * m_u + reg_cap - 1) / reg_cap);
-    cs.n_reg = n_reg;
-    std::vector<int32_t> reg_agg0(n_reg + 1), agg_reg(n_agg);
-    for (int r = 0; r <= n_reg; ++r) reg_agg0[r] = (int32_t)((int64_t)n_agg * r / n_reg);
-    for (int r = 0; r < n_reg; ++r)
-        for (int a = reg_agg0[r]; a < reg_agg0[r + 1]; ++a) agg_reg[a] = r;
-    cs.n_agg = n_agg;
-    {   // chunks of at most kCoarseChunkNodes nodes: one warp each in the update / direction kernels
-        int max_nodes = 0;
-        for (int a = 0; a < n_agg; ++a)
-            max_nodes = std::max(max_nodes, bm.node0[std::min(bm.nb, (a + 1) * g)] - bm.node0[std::min(bm.nb, a * g)]);
-        cs.S = std::max(1, (max_nodes + kCoarseChunkNodes - 1) / kCoarseChunkNodes);
-    }
-    cs.n_chunks = n_agg * cs.S;
-    std::vector<int32_t> agg0(n_agg + 1), chunk0(cs.n_chunks + 1);
-    for (int a = 0; a <= n_agg; ++a) agg0[a] = bm.node0[std::min(bm.nb, a * g)];
-    for (int a = 0; a < n_agg; ++a)
-        for (int s = 0; s < cs.S; ++s)
-            chunk0[a * cs.S + s] = agg0[a] + ((int32_t)((int64_t)(agg0[a + 1] - agg0[a]) * s / cs.S) & ~1);   // even starts
-    chunk0[cs.n_chunks] = agg0[n_agg];
-    // geometry of the modes: coordinates relative to the aggregate centroid, scaled by its size
-    std::vector<int32_t> node_agg(c->n_owned);
-    std::vector<float> rel((size_t)c->n_owned * D);
-    for (int a = 0; a < n_agg; ++a) {
-        double cen[3] = {0, 0, 0}, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-        const int n0 = agg0[a], n1 = agg0[a + 1];
-        for (int i = n0; i < n1; ++i)
-            for (int k = 0; k < D; ++k) {
-                double x = mesh->coords[3 * (int64_t)bm.perm[i] + k];
-                cen[k] += x; lo[k] = std::min(lo[k], x); hi[k] = std::max(hi[k], x);
-            }
-        double size = 0;
-        for (int k = 0; k < D; ++k) { cen[k] /= std::max(1, n1 - n0); size = std::max(size, 0.5 * (hi[k] - lo[k])); }
-        const double sc = size > 0 ? 1.0 / size : 1.0;
-        for (int i = n0; i < n1; ++i) {
-            node_agg[i] = a;
-            for (int k = 0; k < D; ++k) rel[(size_t)i * D + k] = (float)((mesh->coords[3 * (int64_t)bm.perm[i] + k] - cen[k]) * sc);
-        }
-    }
-    // aggregate graph: i ~ j when a cell has owned vertices in both
-    std::vector<std::vector<int32_t>> adj(n_agg);
-    for (int64_t e = 0; e < mesh->n_cells; ++e) {
-        int32_t ag[4]; int na = 0;
-        for (int k = 0; k < c->nv; ++k) {
-            int32_t nid = bm.iperm[mesh->cells[e * c->nv + k]];
-            if (nid >= c->n_owned) continue;
-            int32_t a = node_agg[nid];
-            bool seen = false;
-            for (int q = 0; q < na; ++q) seen |= (ag[q] == a);
-            if (!seen) ag[na++] = a;
-        }
-        for (int p = 0; p < na; ++p)
-            for (int q = 0; q < na; ++q)
-                if (p != q) adj[ag[p]].push_back(ag[q]);
-    }
-    for (auto& v : adj) { std::sort(v.begin(), v.end()); v.erase(std::unique(v.begin(), v.end()), v.end()); }
-    std::vector<int32_t> colour(n_agg, -1);
-    int n_col = 0;
-    std::vector<char> used;
-    for (int a = 0; a < n_agg; ++a) {
-        used.assign(n_col + 1, 0);
-        for (int32_t j : adj[a]) {
-            if (colour[j] >= 0) used[colour[j]] = 1;
-            for (int32_t k : adj[j]) if (k != a && colour[k] >= 0) used[colour[k]] = 1;
-        }
-        int col = 0;
-        while (col < n_col && used[col]) ++col;
-        colour[a] = col;
-        n_col = std::max(n_col, col + 1);
-    }
-    cs.n_col = n_col;
-    std::vector<int32_t> nbrcol((size_t)n_agg * n_col, -1);
-    for (int a = 0; a < n_agg; ++a) {
-        nbrcol[(size_t)a * n_col + colour[a]] = a;
-        for (int32_t j : adj[a]) {
-            int32_t& slot = nbrcol[(size_t)a * n_col + colour[j]];
-            if (slot >= 0 && slot != j) { c->err = "coarse space: colouring is not distance-2"; return PFX_ERR_BAD_ARG; }
-            slot = j;
-        }
-    }
+    const int reg_aggs = std::max(1, reg_cap / m_u);
+    AggregateSet as;
+    std::string er_ = build_aggregates(bm, mesh->n_cells, mesh->coords, mesh->cells, g, reg_aggs, kCoarseChunkNodes, as);
+    if (!er_.empty()) { c->err = er_; return PFX_ERR_BAD_ARG; }
+    const int n_agg = as.n_agg, n_reg = as.n_reg;
+    cs.n_agg = n_agg; cs.n_reg = n_reg; cs.S = as.S; cs.n_chunks = as.n_chunks; cs.n_col = as.n_col;
+    const std::vector<int32_t>&chunk0 = as.chunk_node0, &colour = as.colour, &nbrcol = as.nbrcol, &agg_reg = as.agg_reg,
+                              &reg_agg0 = as.reg_agg0;
+    const std::vector<float>& rel = as.rel;
     int st;
     if ((st = dev_upload(c, &cs.chunk_node0, chunk0))) return st;
     if ((st = dev_upload(c, &cs.colour, colour))) return st;

@@ -158,4 +158,30 @@ int hc_blocks_apply_u(int cell_type, const double* mat, int smodel, int n1d, int
     else emulate_apply_u<Tet>(bm, m, n1d, coords, phi, u, v, chunk, y, dot);
     return 0;
 }
+// aggregates of the PCG coarse space: returns sizes in stats = {n_agg, S, n_chunks, n_col, n_reg}; arrays are
+// filled up to the given capacities: node_agg [n_nodes] in CALLER node ids (-1 for ghosts), chunk_node0,
+// colour, agg_reg, nbrcol [n_agg*n_col], rel [n_nodes*dim] in caller node order
+int hc_aggregates(int cell_type, int64_t n_nodes, int64_t n_owned, int64_t n_cells, const double* coords,
+                  const int32_t* cells, int max_own, int g, int reg_aggs, int chunk_nodes, int64_t* stats, int32_t* node_agg,
+                  int32_t* chunk_node0, int32_t* colour, int32_t* agg_reg, int32_t* nbrcol, int64_t nbrcol_cap, float* rel) {
+    int nv = cell_type == 0 ? 3 : 4, dim = cell_type == 2 ? 3 : 2;
+    BlockMesh bm;
+    std::string er = build_blocks(nv, dim, n_nodes, n_owned, n_cells, coords, cells, nullptr, max_own, bm);
+    if (!er.empty()) return 1;
+    AggregateSet as;
+    er = build_aggregates(bm, n_cells, coords, cells, g, reg_aggs, chunk_nodes, as);
+    if (!er.empty()) return 2;
+    stats[0] = as.n_agg; stats[1] = as.S; stats[2] = as.n_chunks; stats[3] = as.n_col; stats[4] = as.n_reg;
+    if ((int64_t)as.nbrcol.size() > nbrcol_cap) return 3;
+    for (int64_t i = 0; i < n_nodes; ++i) node_agg[i] = -1;
+    for (int a = 0; a < as.n_agg; ++a)
+        for (int i = as.agg_node0[a]; i < as.agg_node0[a + 1]; ++i) {
+            node_agg[bm.perm[i]] = a;
+            for (int k = 0; k < dim; ++k) rel[(int64_t)bm.perm[i] * dim + k] = as.rel[(int64_t)i * dim + k];
+        }
+    for (size_t i = 0; i < as.chunk_node0.size(); ++i) chunk_node0[i] = as.chunk_node0[i];
+    for (int a = 0; a < as.n_agg; ++a) { colour[a] = as.colour[a]; agg_reg[a] = as.agg_reg[a]; }
+    for (size_t i = 0; i < as.nbrcol.size(); ++i) nbrcol[i] = as.nbrcol[i];
+    return 0;
+}
 }

@@ -171,3 +171,66 @@ def test_cached_tangent_apply_matches_direct(hostcheck, sp):
         hostcheck.hc_assemble(13, CT[ctype], dp(mat), sm, sm, 0, 3, ctypes.c_int64(len(cells)), dp(m.geometry.x),
                               cells.ctypes.data_as(PI), dp(o.phi), dp(o.u), dp(v), None, dp(out))
         assert rel(out, o.J_u(o.u, o.phi) @ v) < 1e-10
+
+
+def test_coarse_space_aggregates_colouring_and_regions(hostcheck):
+    """pfx_blocks.cpp::build_aggregates (host side of the two-level PCG): aggregates are runs of blocks
+    with contiguous, even-aligned chunks; regions are contiguous; the colouring is a distance-2 colouring of
+    the aggregate graph (checked against a graph built independently from the cells), which is what makes
+    one probing apply per (colour, mode) valid; mode coordinates are centred and scaled by the aggregate size."""
+    from phasefieldx_b200 import mesh as M
+    m0 = M.create_rectangle(None, [[0, 0], [1, 1]], [60, 45])
+    cases = [("triangle", M.cut_slit(m0, lambda x: np.isclose(x[1], 15 / 45) & (x[0] < 0.5), lambda c: c[1] > 15 / 45), 64, 1, 9),
+             ("quadrilateral", M.create_rectangle(None, [[0, 0], [2, 1]], [50, 30], M.CellType.quadrilateral), 48, 2, 4),
+             ("tetrahedron", M.create_box(None, [[0, 0, 0], [2, 1, 1]], [14, 9, 8]), 64, 1, 7)]
+    PI64 = ctypes.POINTER(ctypes.c_int64)
+    PF = ctypes.POINTER(ctypes.c_float)
+    for ctype, m, max_own, g, reg_aggs in cases:
+        nn, d = m.num_nodes, m.geometry.dim
+        cells = np.ascontiguousarray(m.cells, dtype=np.int32)
+        X = np.ascontiguousarray(m.geometry.x)
+        stats = np.zeros(5, dtype=np.int64)
+        node_agg, colour, agg_reg = (np.zeros(nn, np.int32) for _ in range(3))
+        chunk0, nbrcol, rel = np.zeros(8 * nn, np.int32), np.zeros(nn * 64, np.int32), np.zeros(nn * d, np.float32)
+        rc = hostcheck.hc_aggregates(CT[ctype], ctypes.c_int64(nn), ctypes.c_int64(nn), ctypes.c_int64(len(cells)), dp(X),
+                                     cells.ctypes.data_as(PI), max_own, g, reg_aggs, 32, stats.ctypes.data_as(PI64),
+                                     node_agg.ctypes.data_as(PI), chunk0.ctypes.data_as(PI), colour.ctypes.data_as(PI),
+                                     agg_reg.ctypes.data_as(PI), nbrcol.ctypes.data_as(PI), ctypes.c_int64(nbrcol.size),
+                                     rel.ctypes.data_as(PF))
+        assert rc == 0
+        n_agg, S, n_chunks, n_col, n_reg = (int(v) for v in stats)
+        colour, agg_reg, chunk0 = colour[:n_agg], agg_reg[:n_agg], chunk0[: n_chunks + 1]
+        nbrcol = nbrcol[: n_agg * n_col].reshape(n_agg, n_col)
+        assert n_chunks == n_agg * S and node_agg.min() == 0 and node_agg.max() == n_agg - 1
+        # chunks: monotone cover of the owned nodes, even starts, at most 32 (+1 for the even rounding) nodes
+        assert chunk0[0] == 0 and chunk0[-1] == nn and np.all(np.diff(chunk0) >= 0)
+        assert np.all(chunk0[:-1] % 2 == 0) and np.diff(chunk0).max() <= 33
+        sizes = np.bincount(node_agg, minlength=n_agg)
+        assert np.array_equal(chunk0[::S][:n_agg], np.r_[0, np.cumsum(sizes)[:-1]])
+        # regions: contiguous, non-decreasing, at most reg_aggs aggregates each
+        assert agg_reg[0] == 0 and agg_reg[-1] == n_reg - 1 and np.all(np.diff(agg_reg) >= 0)
+        assert np.bincount(agg_reg).max() <= reg_aggs
+        # independent aggregate graph from the cells
+        A = np.zeros((n_agg, n_agg), bool)
+        ca = node_agg[cells]
+        for i in range(ca.shape[1]):
+            for j in range(ca.shape[1]):
+                A[ca[:, i], ca[:, j]] = True
+        np.fill_diagonal(A, False)
+        A2 = (A.astype(np.int32) @ A.astype(np.int32) > 0) | A
+        np.fill_diagonal(A2, False)
+        same = colour[:, None] == colour[None, :]
+        assert not np.any(A2 & same), "not a distance-2 colouring"
+        assert colour.max() == n_col - 1
+        for a in range(n_agg):
+            expect = np.full(n_col, -1)
+            expect[colour[a]] = a
+            nb = np.nonzero(A[a])[0]
+            expect[colour[nb]] = nb
+            assert np.array_equal(nbrcol[a], expect)
+        # mode geometry: centred per aggregate, scaled by the half extent (so within [-2, 2])
+        r = rel.reshape(nn, d)
+        assert np.abs(r).max() <= 2.0 + 1e-6
+        for k in range(d):
+            means = np.bincount(node_agg, weights=r[:, k], minlength=n_agg) / sizes
+            assert np.abs(means).max() < 1e-5
