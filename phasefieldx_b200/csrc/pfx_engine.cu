@@ -158,8 +158,8 @@ struct pfx_ctx {
     unsigned long long* coop_bar = nullptr;
     bool phi_coeff_fresh = false;
     bool generic_apply = false;   // PFX_GENERIC_APPLY=1: use the generic scatter kernel for J_u·v on triangles
-    int apply_variant = 3;        // PFX_APPLY_VARIANT: 3 persistent + prefetched indices (default), 2 persistent, 1 one CTA per block
-    int persist_ctas = 0, v3_ctas = 0, v3_tan_ctas = 0, num_sms = 148;
+    int apply_variant = 3;        // PFX_APPLY_VARIANT: 3 persistent + prefetched indices (default), 4 three-stage ring (slower: 2 CTAs/SM), 2 persistent, 1 one CTA per block
+    int persist_ctas = 0, v3_ctas = 0, v3_tan_ctas = 0, v4_ctas = 0, num_sms = 148;
     Coarse coarse;
 };
 
@@ -268,6 +268,29 @@ int launch_apply_u_tri_v3(pfx_ctx* c, const KArgs& a) {
     return PFX_OK;
 }
 
+template <int SM>
+int launch_apply_u_tri_v4(pfx_ctx* c, const KArgs& a) {
+    BlockView bv = c->bv;
+    bv.chunk = 2 * kThreads;
+    size_t ML = (size_t)c->bm.max_loc, MO = ((size_t)c->bm.max_own + 1) & ~(size_t)1;
+    size_t stage = ML * 16 * (SM != M_ISO ? 3 : 2) + ((ML + 3) & ~(size_t)1) * 8 + MO * 16;
+    size_t smem = 3 * stage + (3 * (size_t)bv.chunk + 1) * sizeof(double2);
+    if (c->configuring) {
+        c->v4_ctas = 0;
+        if (smem > 110 * 1024) return PFX_OK;          // two CTAs per SM must fit: otherwise stay on v3
+        CK(cudaFuncSetAttribute(apply_u_tri_v4_kernel<SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apply_u_tri_v4_kernel<SM>, kThreads, smem));
+        c->v4_ctas = std::max(1, nb) * c->num_sms;
+        return PFX_OK;
+    }
+    int grid = std::min(c->bm.nb, c->v4_ctas);
+    apply_u_tri_v4_kernel<SM><<<grid, kThreads, smem, c->stream>>>(bv, a);
+    c->launches++;
+    CK(cudaGetLastError());
+    return PFX_OK;
+}
+
 int launch_apply_phi_tri_v3(pfx_ctx* c, const KArgs& a) {
     BlockView bv = c->bv;
     bv.chunk = 2 * kThreads;
@@ -336,7 +359,7 @@ int coop_u(pfx_ctx* c, const KArgs& a, const CoopArgs& ca, bool configure) {
 
 template <class Cell>
 int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
-    if (op == OP_APPLY_MASS && std::is_same<Cell, Tri>::value && c->ones && !c->configuring && c->apply_variant == 3 &&
+    if (op == OP_APPLY_MASS && std::is_same<Cell, Tri>::value && c->ones && !c->configuring && c->apply_variant >= 3 &&
         c->bm.max_elems <= 2 * kThreads && a.mask == nullptr) {
         KArgs m = a;                      // M = the phi operator with coefficients (1, 0)
         m.cm = c->ones; m.cg = c->zeros;
@@ -344,7 +367,7 @@ int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
     }
     if (op == OP_APPLY_PHI && std::is_same<Cell, Tri>::value && c->cm) {
         if (c->configuring) { int st = launch_apply_phi_tri_v3(c, a); if (st) return st; }
-        else if (c->apply_variant == 3 && c->bm.max_elems <= 2 * kThreads && a.input_masked && c->phi_coeff_fresh)
+        else if (c->apply_variant >= 3 && c->bm.max_elems <= 2 * kThreads && a.input_masked && c->phi_coeff_fresh)
             return launch_apply_phi_tri_v3(c, a);
     }
     switch (op) {
@@ -358,7 +381,16 @@ int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
                      : (a.m.smodel == M_SPECTRAL ? launch_apply_u_tri_v3<M_SPECTRAL>(c, a)
                                                  : launch_apply_u_tri_v3<M_VOLDEV>(c, a));
                 if (st) return st;
-            } else if (std::is_same<Cell, Tri>::value && c->apply_variant == 3 && c->bm.max_elems <= 2 * kThreads &&
+                st = (a.m.smodel == M_ISO) ? launch_apply_u_tri_v4<M_ISO>(c, a)
+                     : (a.m.smodel == M_SPECTRAL ? launch_apply_u_tri_v4<M_SPECTRAL>(c, a)
+                                                 : launch_apply_u_tri_v4<M_VOLDEV>(c, a));
+                if (st) return st;
+            } else if (std::is_same<Cell, Tri>::value && c->apply_variant == 4 && c->v4_ctas > 0 && c->bm.max_elems <= 2 * kThreads &&
+                       (a.mask == nullptr || a.input_masked)) {
+                if (a.m.smodel == M_ISO) return launch_apply_u_tri_v4<M_ISO>(c, a);
+                if (a.m.smodel == M_SPECTRAL) return launch_apply_u_tri_v4<M_SPECTRAL>(c, a);
+                return launch_apply_u_tri_v4<M_VOLDEV>(c, a);
+            } else if (std::is_same<Cell, Tri>::value && c->apply_variant >= 3 && c->bm.max_elems <= 2 * kThreads &&
                        (a.mask == nullptr || a.input_masked)) {
                 if (a.m.smodel == M_ISO) return launch_apply_u_tri_v3<M_ISO>(c, a);
                 if (a.m.smodel == M_SPECTRAL) return launch_apply_u_tri_v3<M_SPECTRAL>(c, a);
@@ -392,7 +424,7 @@ int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
             if constexpr (std::is_same<Cell, Tri>::value) {
                 // persistent TMA-staged kernel fed by the cached element tangents (the split model no longer matters)
                 if (c->configuring) { int st = launch_apply_u_tri_v3<M_SPECTRAL, true>(c, a); if (st) return st; }
-                else if (c->apply_variant == 3 && c->bm.max_elems <= 2 * kThreads && (a.mask == nullptr || a.input_masked))
+                else if (c->apply_variant >= 3 && c->bm.max_elems <= 2 * kThreads && (a.mask == nullptr || a.input_masked))
                     return launch_apply_u_tri_v3<M_SPECTRAL, true>(c, a);
             }
             if constexpr (Cell::simplex) return launch_scatter_op<OpApplyUTan<Cell>>(c, a);
@@ -572,7 +604,7 @@ __global__ void pcg_setup_kernel(double* S, double rtol2, int bref_slot) {
 
 // does the apply of this operator run on a kernel that waits for the halo in its own prologue?
 bool apply_waits_for_halo(const pfx_ctx* c, int kind) {
-    if (c->cell_type != PFX_CELL_TRIANGLE || c->apply_variant != 3 || c->bm.max_elems > 2 * kThreads) return false;
+    if (c->cell_type != PFX_CELL_TRIANGLE || c->apply_variant < 3 || c->bm.max_elems > 2 * kThreads) return false;
     return kind == LIN_U || (kind == LIN_PHI && c->cm && c->phi_coeff_fresh);
 }
 

@@ -1099,6 +1099,171 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
     grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red, a.pv);
 }
 
+// ============================================================================= hot kernel, v4 (experiment, opt-in)
+// Same phases as v3 with a THREE-stage ring and a prefetch distance of two blocks (PFX_APPLY_VARIANT=4).
+// Knock-out timings of v3 on the bench mesh (57.6 us): without phase B 40.3, without phase C 53.3,
+// staging only 34.9 — the phases add up instead of overlapping.  Two blocks in flight per CTA do not
+// help: at 84 KB of shared memory only 2 CTAs fit per SM and the kernel slows to 65 us, i.e. the
+// phases themselves are latency-bound and what they need is more resident warps, not deeper
+// prefetching.  Kept as a parity-tested variant for the next round of work on this kernel.
+template <int SM>
+__global__ void __launch_bounds__(kThreads, 2) apply_u_tri_v4_kernel(BlockView bv, KArgs a) {
+    constexpr bool NL = (SM != M_ISO);
+    constexpr int NST = 3, PD = NST - 1;
+    extern __shared__ double smem[];
+    __shared__ double s_red[kMaxRed * 32];
+    __shared__ uint64_t s_bar[NST];
+    if (a.stop && a.stop[0] != 0.0) return;
+    const int tid = threadIdx.x;
+    const int ML = bv.max_loc, chunk = bv.chunk, MO = (bv.max_own + 1) & ~1;
+    const size_t oV = (size_t)ML * 16, oU = 2 * oV, oP = oV * (NL ? 3 : 2), oI = oP + (size_t)((ML + 3) & ~1) * 8;
+    const size_t stage_bytes = oI + (size_t)MO * 16;
+    char* const sbase = reinterpret_cast<char*>(smem);
+    double2* sE = reinterpret_cast<double2*>(sbase + NST * stage_bytes);    // [3*chunk + 1], last = zero slot
+    const int zslot = 3 * chunk;
+    const double2* X2 = reinterpret_cast<const double2*>(a.X);
+    const double2* V2 = reinterpret_cast<const double2*>(a.v);
+    const double2* U2 = reinterpret_cast<const double2*>(a.u);
+    const unsigned short* M2 = reinterpret_cast<const unsigned short*>(a.mask);
+    const uint2* LC = reinterpret_cast<const uint2*>(bv.lconn);
+    if (tid == 0) {
+        for (int k = 0; k < NST; ++k) mbar_init(&s_bar[k], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        sE[zslot] = make_double2(0.0, 0.0);
+    }
+    __syncthreads();
+    if (a.pv && a.wait_halo) halo_wait_cta(a.pv);
+
+    // stage the block described by ma into ring slot s_ (hidx: this thread's first halo node id)
+    auto issue = [&](int4 ma, int s_, int hidx) {
+        char* p = sbase + (size_t)s_ * stage_bytes;
+        double2 *tX = reinterpret_cast<double2*>(p), *tV = reinterpret_cast<double2*>(p + oV), *tU = reinterpret_cast<double2*>(p + oU);
+        double* tP = reinterpret_cast<double*>(p + oP);
+        const int n0 = ma.x, n_own = ma.y, h0 = ma.z, n_halo = ma.w;
+        if (tid == 0) {
+            fence_proxy_async();
+            const uint32_t nev = (uint32_t)(n_own & ~1);
+            uint32_t bytes = (uint32_t)n_own * 16u * (NL ? 3u : 2u) + nev * 8u + (uint32_t)n_own * 16u;
+            mbar_expect_tx(&s_bar[s_], bytes);
+            bulk_g2s(tX, X2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
+            bulk_g2s(tV, V2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
+            if (NL) bulk_g2s(tU, U2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
+            if (nev) bulk_g2s(tP, a.phi + n0, nev * 8u, &s_bar[s_]);
+            bulk_g2s(p + oI, bv.inc8 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
+            if (n_own & 1) cp_async8(tP + n_own - 1, a.phi + n0 + n_own - 1);
+        }
+        for (int i = tid; i < n_halo; i += kThreads) {
+            int g = (i == tid) ? hidx : bv.halo[h0 + i];
+            cp_async16(tX + n_own + i, X2 + g);
+            cp_async16(tV + n_own + i, V2 + g);
+            if (NL) cp_async16(tU + n_own + i, U2 + g);
+            cp_async8(tP + n_own + i, a.phi + g);
+        }
+    };
+
+    const int stride = gridDim.x, nb = bv.nb;
+    int blk = blockIdx.x;                       // grid <= nb: every CTA owns at least one block
+    // metadata ring: A[j] / B[j] describe block blk + j*stride (A: n0, n_own, h0, n_halo; B: e0, n_elems, ..)
+    int4 A0 = bv.meta[2 * blk], B0 = bv.meta[2 * blk + 1];
+    int4 A1 = A0, B1 = B0, A2 = A0, A3 = A0;
+    if (blk + stride < nb) { A1 = bv.meta[2 * (blk + stride)]; B1 = bv.meta[2 * (blk + stride) + 1]; }
+    if (blk + 2 * stride < nb) A2 = bv.meta[2 * (blk + 2 * stride)];
+    if (blk + 3 * stride < nb) A3 = bv.meta[2 * (blk + 3 * stride)];
+    // prologue: blocks 0 and 1 into slots 0 and 1 (one cp.async group each, empty if the block does not exist)
+    issue(A0, 0, tid < A0.w ? bv.halo[A0.z + tid] : 0);
+    cp_async_commit();
+    if (blk + stride < nb) issue(A1, 1, tid < A1.w ? bv.halo[A1.z + tid] : 0);
+    cp_async_commit();
+    uint2 lc0 = make_uint2(0u, 0u), lc1 = lc0;
+    if (tid < B0.y) lc0 = LC[B0.x + tid];
+    if (tid + kThreads < B0.y) lc1 = LC[B0.x + tid + kThreads];
+    unsigned int mk = 0u;
+    if (M2 && tid < A0.y) mk = M2[A0.x + tid];
+    int h2 = (blk + 2 * stride < nb && tid < A2.w) ? bv.halo[A2.z + tid] : 0;     // halo ids of block +2
+    double red = 0.0;
+    for (int it = 0;; ++it) {
+        const int s = it % NST;
+        const int n0 = A0.x, n_own = A0.y, ne = B0.y;
+        const bool v1 = blk + stride < nb, v2 = blk + 2 * stride < nb, v3 = blk + 3 * stride < nb;
+        // block +2 into the slot block -1 has just released; metadata of block +4
+        if (v2) issue(A2, (it + PD) % NST, h2);
+        cp_async_commit();
+        int4 A4 = A3, B2 = B1;
+        if (blk + 4 * stride < nb) A4 = bv.meta[2 * (blk + 4 * stride)];
+        if (v2) B2 = bv.meta[2 * (blk + 2 * stride) + 1];
+        cp_async_wait<PD>();
+        mbar_wait(&s_bar[s], (uint32_t)(it / NST) & 1u);
+        __syncthreads();
+        const char* p = sbase + (size_t)s * stage_bytes;
+        const double2 *sX = reinterpret_cast<const double2*>(p), *sV = reinterpret_cast<const double2*>(p + oV),
+                      *sU = reinterpret_cast<const double2*>(p + oU);
+        const double* sP = reinterpret_cast<const double*>(p + oP);
+        const uint4* s_inc8 = reinterpret_cast<const uint4*>(p + oI);
+        // ---- phase B: two cells per thread
+        const double2 z = make_double2(0.0, 0.0);
+        if (tid < ne) {
+            double2 f0, f1, f2;
+            const int vx = lc0.x & 0xFFFF, vy = lc0.x >> 16, vz = lc0.y & 0xFFFF;
+            tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
+                               sV[vz], NL ? sU[vx] : z, NL ? sU[vy] : z, NL ? sU[vz] : z, f0, f1, f2);
+            sE[tid] = f0; sE[chunk + tid] = f1; sE[2 * chunk + tid] = f2;
+        }
+        if (tid + kThreads < ne) {
+            double2 f0, f1, f2;
+            const int vx = lc1.x & 0xFFFF, vy = lc1.x >> 16, vz = lc1.y & 0xFFFF;
+            tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
+                               sV[vz], NL ? sU[vx] : z, NL ? sU[vy] : z, NL ? sU[vz] : z, f0, f1, f2);
+            sE[tid + kThreads] = f0; sE[chunk + tid + kThreads] = f1; sE[2 * chunk + tid + kThreads] = f2;
+        }
+        __syncthreads();
+        // ---- per-thread indices of later blocks (consumed one iteration later)
+        uint2 lc0n = make_uint2(0u, 0u), lc1n = lc0n;
+        unsigned int mkn = 0u;
+        int h3 = 0;
+        if (v1) {
+            if (tid < B1.y) lc0n = LC[B1.x + tid];
+            if (tid + kThreads < B1.y) lc1n = LC[B1.x + tid + kThreads];
+            if (M2 && tid < A1.y) mkn = M2[A1.x + tid];
+            if (v3 && tid < A3.w) h3 = bv.halo[A3.z + tid];
+        }
+        // ---- phase C: eight independent incident rows per owned node, fixed order
+        if (tid < n_own) {
+            const uint4 c8 = s_inc8[tid];
+            const unsigned cw[4] = {c8.x, c8.y, c8.z, c8.w};
+            double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int code = (int)((cw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
+                const int idx = min((code & 3) * chunk + (code >> 2), zslot);
+                const double2 f = sE[idx];
+                acc.x += f.x; acc.y += f.y;
+            }
+            if ((c8.w >> 16) == 0xFFFEu) {                    // rare: valence > 8, rest from the CSR list
+                int k0 = bv.inc_ptr[n0 + tid] + 7, k1 = bv.inc_ptr[n0 + tid + 1];
+                for (int k = k0; k < k1; ++k) {
+                    const int code = bv.inc[k];
+                    if (code >= 0xFFFE) break;
+                    const double2 f = sE[(code & 3) * chunk + (code >> 2)];
+                    acc.x += f.x; acc.y += f.y;
+                }
+            }
+            if (mk & 0xFFu) acc.x = 0.0;
+            if (mk & 0xFF00u) acc.y = 0.0;
+            const double2 vin = sV[tid];
+            reinterpret_cast<double2*>(a.y)[n0 + tid] = acc;
+            red += vin.x * acc.x + vin.y * acc.y;
+        }
+        if (!v1) break;
+        __syncthreads();                         // slot s and sE are free again
+        blk += stride;
+        A0 = A1; B0 = B1; A1 = A2; B1 = B2; A2 = A3; A3 = A4;
+        lc0 = lc0n; lc1 = lc1n; mk = mkn; h2 = h3;
+    }
+    cp_async_wait<0>();
+    double r1[1] = {red};
+    grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red, a.pv);
+}
+
 // ============================================================================= phi-apply, v3 pipeline
 // J_phi·p on P1 triangles with the same persistent / TMA double-buffered / prefetched structure as
 // apply_u_tri_v3_kernel; staged fields: X (double2), cm, cg, p (doubles; cm = 2H + F·Gc/l and
