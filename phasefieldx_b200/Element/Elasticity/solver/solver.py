@@ -18,12 +18,12 @@ from phasefieldx_b200.files import append_results_to_file
 
 def solve(Data, msh, final_time, V_u, bc_list_u=[], update_boundary_conditions=None, f_list_u=None, T_list_u=None,
           update_loading=None, ds_bound=None, dt=1.0, path=None, quadrature_degree=2, bcs_list_u_names=None,
-          device=0, solver_options=None):
+          device=0, solver_options=None, vtu_format="ascii"):
     """Reference signature; `f_list_u`, `ds_bound` and `quadrature_degree` are accepted and unused (P1/Q1
     elements with a constant tangent are integrated exactly by the kernels' fixed rules)."""
     options = {"ksp_type": "two-level pcg, matrix-free on GPU", "snes_linesearch_type": "none", "snes_max_it": 50,
                "snes_rtol": 1e-8, "snes_atol": 1e-9}
-    run = Run(Data, msh, path, options)
+    run = Run(Data, msh, path, options, vtu_format)
     logger, folder = run.logger, run.folder
     if bcs_list_u_names is None:
         bcs_list_u_names = [f"bc_u_{i}" for i in range(len(bc_list_u))]

@@ -15,7 +15,7 @@ from phasefieldx_b200.files import append_results_to_file
 
 def solve(Data, msh, final_time, V_Φ, bc_list_phi=[], update_boundary_conditions=None, update_loading=None,
           ds_bound=None, dt=1.0, path=None, quadrature_degree=2, case="AT2", V_gradient_Φ=None, device=0,
-          solver_options=None):
+          solver_options=None, vtu_format="ascii"):
     """Reference signature; `update_loading`, `ds_bound`, `quadrature_degree` are accepted and unused."""
     if case != "AT2":
         raise NotImplementedError("only the AT2 geometric crack function is on the GPU path (SURVEY §8f N2)")
@@ -23,7 +23,7 @@ def solve(Data, msh, final_time, V_Φ, bc_list_phi=[], update_boundary_condition
         raise NotImplementedError("gradient output (V_gradient_Φ) is not available")
     options = {"ksp_type": "two-level pcg, matrix-free on GPU", "snes_linesearch_type": "none", "snes_max_it": 50,
                "snes_rtol": 1e-8, "snes_atol": 1e-9}
-    run = Run(Data, msh, path, options)
+    run = Run(Data, msh, path, options, vtu_format)
     logger, folder = run.logger, run.folder
     points, cells, ctype = fem.extract_mesh(msh)
     eng = _lib.Engine(points, cells, ctype, 1.0, 1.0, 1.0, float(Data.l), k=0.0, model=_lib.model_code("isotropic", None),

@@ -41,11 +41,12 @@ def _traction_sets(T_list_u):
 def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update_boundary_conditions=None,
           f_list_u=None, T_list_u=None, update_loading=None, ds_bound=None, dt=1.0, path=None,
           bcs_list_u_names=None, min_stagger_iter=2, max_stagger_iter=10000, stagger_error_tol=1e-8,
-          device=0, solver_options=None, vtu_every=1):
+          device=0, solver_options=None, vtu_every=1, vtu_format="ascii"):
     """Solve the phase-field fracture and fatigue problem (reference signature; `f_list_u` and
     `ds_bound` are accepted and unused exactly as in the reference).
     Extra keyword-only knobs (not in the reference): `device`, `solver_options` (pfx_params
-    overrides such as cg_rtol), `vtu_every` (VTU cadence; default every step as the reference)."""
+    overrides such as cg_rtol), `vtu_every` (VTU cadence; default every step as the reference),
+    `vtu_format` ("ascii" = the reference's layout, "binary" = raw appended data)."""
     if path is None:
         path = os.getcwd()
     result_folder_name = Data.results_folder_name
@@ -125,7 +126,7 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     logger.info(f" start time: {start}")
     vtk_sol = None
     if Data.save_solution_vtu and rank == 0:
-        vtk_sol = VTKFile(None, os.path.join(result_folder_name, "paraview-solutions_vtu", "phasefieldx.pvd"), "w")
+        vtk_sol = VTKFile(None, os.path.join(result_folder_name, "paraview-solutions_vtu", "phasefieldx.pvd"), "w", fmt=vtu_format)
     logger.info(" S t a r t i n g    A n a l y s i s ")
     logger.info(" ---------------------------------- ")
     logger.info(" ---------------------------------- ")

@@ -11,7 +11,7 @@ from phasefieldx_b200.Logger.library_versions import (log_end_analysis, log_libr
 class Run:
     """Set-up shared by reference Elasticity/solver/solver.py:78-107 and Phase_Field/solver/solver.py:84-101."""
 
-    def __init__(self, Data, msh, path, options):
+    def __init__(self, Data, msh, path, options, vtu_format="ascii"):
         self.path = os.getcwd() if path is None else path
         self.folder = Data.results_folder_name
         prepare_simulation(self.path, self.folder)
@@ -28,7 +28,7 @@ class Run:
         self.logger.info(f" start time: {self.start}")
         self.vtk = None
         if Data.save_solution_vtu:
-            self.vtk = VTKFile(None, os.path.join(self.folder, "paraview-solutions_vtu", "phasefieldx.pvd"), "w")
+            self.vtk = VTKFile(None, os.path.join(self.folder, "paraview-solutions_vtu", "phasefieldx.pvd"), "w", fmt=vtu_format)
         self.logger.info(" S t a r t i n g    A n a l y s i s ")
         self.logger.info(" ---------------------------------- ")
         self.logger.info(" ---------------------------------- ")

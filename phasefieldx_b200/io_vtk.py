@@ -34,7 +34,13 @@ class VTKFile:
     that reads back bit-exactly); everything that does not change between load steps —
     points, cells, id arrays — is formatted once and reused."""
 
-    def __init__(self, comm, filename, mode="w"):
+    def __init__(self, comm, filename, mode="w", fmt="ascii"):
+        """fmt "ascii": the reference's layout; "binary": same arrays as raw appended data (VTK
+        `format="appended"`, UInt64 block headers) — a third of the bytes and no number formatting,
+        for meshes where the ASCII file is what a load step waits for."""
+        if fmt not in ("ascii", "binary"):
+            raise ValueError("fmt must be 'ascii' or 'binary'")
+        self.fmt = fmt
         self.pvd = filename
         self.dir = os.path.dirname(filename)
         self.stem = os.path.splitext(os.path.basename(filename))[0]
@@ -97,7 +103,59 @@ class VTKFile:
             err, self._error = self._error, None
             raise err
 
+    def _write_binary(self, msh, fields, t):
+        x = np.asarray(msh.geometry.x, dtype=np.float64)
+        if x.shape[1] < 3:
+            x = np.hstack([x, np.zeros((len(x), 3 - x.shape[1]))])
+        cells = np.ascontiguousarray(msh.cells[:, _VTK_PERM[msh.cell_type]], dtype=np.int32)
+        nn, ne, nv = len(x), len(cells), cells.shape[1]
+        key = (id(msh), x.shape, cells.shape)
+        if self._static is None or self._static[0] != key:
+            self._static = (key, [("Points", None, "Float64", 3, np.ascontiguousarray(x)),
+                                  ("Cells", "connectivity", "Int32", 0, cells),
+                                  ("Cells", "offsets", "Int32", 0, (np.arange(1, ne + 1) * nv).astype(np.int32)),
+                                  ("Cells", "types", "Int8", 0, np.full(ne, _VTK_TYPE[msh.cell_type], np.int8)),
+                                  ("CellData", "vtkGhostType", "UInt8", 0, np.zeros(ne, np.uint8)),
+                                  ("CellData", "vtkOriginalCellIds", "Int64", 0, np.arange(ne, dtype=np.int64)),
+                                  ("PointData", "vtkOriginalPointIds", "Int64", 0, np.arange(nn, dtype=np.int64)),
+                                  ("PointData", "vtkGhostType", "UInt8", 0, np.zeros(nn, np.uint8))])
+        arrays = list(self._static[1])
+        for fname, vals in fields.items():
+            v = np.asarray(vals, dtype=np.float64)
+            if v.ndim == 2:
+                pad = np.zeros((nn, 3))
+                pad[:, : v.shape[1]] = v
+                arrays.append(("PointData", fname, "Float64", 3, pad))
+            else:
+                arrays.append(("PointData", fname, "Float64", 0, np.ascontiguousarray(v)))
+        L = ['<?xml version="1.0"?>',
+             '<VTKFile type="UnstructuredGrid" version="2.2" byte_order="LittleEndian" header_type="UInt64">',
+             "  <UnstructuredGrid>", f'    <Piece NumberOfPoints="{nn}" NumberOfCells="{ne}">']
+        off, section = 0, None
+        for sec, name, typ, ncomp, arr in arrays:
+            if sec != section:
+                if section is not None:
+                    L.append(f"      </{section}>")
+                L.append(f"      <{sec}>")
+                section = sec
+            attrs = f'type="{typ}"' + (f' Name="{name}"' if name else "") + (f' NumberOfComponents="{ncomp}"' if ncomp else "")
+            L.append(f'        <DataArray {attrs} format="appended" offset="{off}"/>')
+            off += 8 + arr.nbytes
+        L += [f"      </{section}>", "    </Piece>", "  </UnstructuredGrid>", '  <AppendedData encoding="raw">']
+        step = int(t)
+        fname_out = f"{self.stem}_p0_{step:06d}.vtu"
+        with open(os.path.join(self.dir, fname_out), "wb") as fh:
+            fh.write(("\n".join(L) + "\n_").encode())
+            for _, _, _, _, arr in arrays:
+                fh.write(np.uint64(arr.nbytes).tobytes())
+                fh.write(arr.tobytes())
+            fh.write(b"\n  </AppendedData>\n</VTKFile>\n")
+        self.records.append((t, fname_out))
+        self._write_pvd()
+
     def _write(self, msh, fields, t):
+        if self.fmt == "binary":
+            return self._write_binary(msh, fields, t)
         head = self._static_part(msh)
         step = int(t)
         name = f"{self.stem}_p0_{step:06d}.vtu"
@@ -128,11 +186,32 @@ class VTKFile:
 
 
 def read_vtu_points_cells(path):
-    """Tiny reader for the ASCII VTUs above (and the reference's stored ones): points, cells."""
+    """Tiny reader for the VTUs above (ASCII, also the reference's stored ones, or raw appended): points,
+    cells, phi, u."""
     import re
-    txt = open(path).read()
+    raw = open(path, "rb").read()
+    cut = raw.find(b"<AppendedData")
+    txt = (raw if cut < 0 else raw[:cut]).decode()
     npts = int(re.search(r'NumberOfPoints="(\d+)"', txt).group(1))
     ncell = int(re.search(r'NumberOfCells="(\d+)"', txt).group(1))
+    if cut >= 0:
+        base = raw.index(b"_", cut) + 1
+        dt = {"Float64": np.float64, "Int32": np.int32, "Int8": np.int8, "UInt8": np.uint8, "Int64": np.int64}
+
+        def block(tag):
+            typ = re.search(r'type="(\w+)"', tag).group(1)
+            off = base + int(re.search(r'offset="(\d+)"', tag).group(1))
+            nbytes = int(np.frombuffer(raw, dtype=np.uint64, count=1, offset=off)[0])
+            return np.frombuffer(raw, dtype=dt[typ], count=nbytes // np.dtype(dt[typ]).itemsize, offset=off + 8)
+        tags = re.findall(r"<DataArray[^>]*/>", txt)
+        named = {re.search(r'Name="(\w+)"', t).group(1): t for t in tags if 'Name="' in t}
+        pts = block(next(t for t in tags if 'Name="' not in t)).astype(np.float64).reshape(npts, 3)
+        out = {"points": pts, "cells": block(named["connectivity"]).astype(np.int64).reshape(ncell, -1)}
+        for nm in ("phi", "u"):
+            if nm in named:
+                a = block(named[nm]).astype(np.float64)
+                out[nm] = a.reshape(npts, -1) if a.size != npts else a
+        return out
 
     def data(pattern):
         m = re.search(pattern + r'[^>]*>([^<]*)</DataArray>', txt)

@@ -220,3 +220,30 @@ def test_single_field_inputs_match_reference_format(tmp_path):
     p.save_parameters_to_csv(str(f))
     assert f.read_text().splitlines() == ["l\t4.0", "save_solution_xdmf\tFalse", "save_solution_vtu\tTrue", "results_folder_name\tr"]
     assert str(p) == "Parameters:\n  l: 4.0"
+
+
+def test_binary_vtu_round_trips_bit_exactly(tmp_path):
+    """`VTKFile(fmt="binary")`: raw appended VTU with the same arrays and cell types as
+    the ASCII layout; fields, points and connectivity read back bit-exactly, for every cell type."""
+    from phasefieldx_b200 import io_vtk, mesh as M
+    rng = np.random.default_rng(11)
+    meshes = [M.create_rectangle(None, [[0, 0], [1, 2]], [7, 5]),
+              M.create_rectangle(None, [[0, 0], [1, 2]], [4, 3], M.CellType.quadrilateral),
+              M.create_box(None, [[0, 0, 0], [1, 1, 1]], [3, 2, 2])]
+    for k, msh in enumerate(meshes):
+        d = msh.geometry.dim
+        phi, u = rng.uniform(size=msh.num_nodes), rng.standard_normal((msh.num_nodes, d)) * 1e-3
+        out = {}
+        for fmt in ("ascii", "binary"):
+            vt = io_vtk.VTKFile(None, str(tmp_path / f"{fmt}{k}" / "phasefieldx.pvd"), "w", fmt=fmt)
+            vt.write_function(msh, {"phi": phi, "u": u}, 2, background=(fmt == "binary"))
+            vt.close()
+            out[fmt] = io_vtk.read_vtu_points_cells(str(tmp_path / f"{fmt}{k}" / "phasefieldx_p0_000002.vtu"))
+            assert "phasefieldx_p0_000002.vtu" in (tmp_path / f"{fmt}{k}" / "phasefieldx.pvd").read_text()
+        for key in ("points", "cells", "phi", "u"):
+            assert np.array_equal(out["ascii"][key], out["binary"][key]), key
+        assert np.array_equal(out["binary"]["phi"], phi) and np.array_equal(out["binary"]["u"][:, :d], u)
+        head = (tmp_path / f"binary{k}" / "phasefieldx_p0_000002.vtu").read_bytes()[:400].decode(errors="ignore")
+        assert 'header_type="UInt64"' in head and 'format="appended"' in head
+    with pytest.raises(ValueError):
+        io_vtk.VTKFile(None, str(tmp_path / "x" / "p.pvd"), "w", fmt="hdf5")
