@@ -192,7 +192,12 @@ template <class Op>
 int launch_scatter_op(pfx_ctx* c, const KArgs& a) {
     BlockView bv = c->bv;
     int per_elem = Op::NV * Op::NOUT;
-    int cap = std::max(32, (32 * 1024 / (per_elem * 8)) / 32 * 32);
+    // element buffer of at most `kb` KB; whole multiples of the CTA width keep phase B balanced (every thread
+    // the same number of cells per chunk).  48 KB: 512 tets per chunk for the vector operators (measured on the
+    // 3D beam: 312 us per PCG iteration with 320-cell chunks, 266 us with 512; 768 and 1024 drop to one CTA per SM)
+    static const int kb = getenv("PFX_CHUNK_KB") ? atoi(getenv("PFX_CHUNK_KB")) : 48;
+    int cap = std::max(32, (kb * 1024 / (per_elem * 8)) / 32 * 32);
+    if (cap >= kThreads) cap = cap / kThreads * kThreads;
     bv.chunk = std::min((c->bm.max_elems + 31) / 32 * 32, cap);
     size_t smem = ((((size_t)c->bm.max_loc * Op::NF + (size_t)per_elem * bv.chunk) + 1) & ~(size_t)1) * sizeof(double) +
                   ((size_t)c->bv.max_inc * sizeof(uint16_t) + 15) / 16 * 16;
