@@ -161,6 +161,9 @@ int pfx_apply_mass(pfx_ctx* ctx, const double* v, double* y);
 int pfx_residual_u(pfx_ctx* ctx, double* f);                 /* F_u_form, solver.py:176-177   */
 int pfx_diag_u(pfx_ctx* ctx, double* diag);                  /* Jacobi preconditioner data    */
 int pfx_rhs_psi(pfx_ctx* ctx, double* b);                    /* ∫ psi_a(u) N_i, projection RHS */
+/* nodal L2 projection of psi_a (which = 0) / psi_b (which = 1) of the current u, host array [n_nodes]
+ * (Math/projection.py:19-59 as used for output by solver_anisotropic.py:236-237); single-GPU contexts */
+int pfx_project_psi(pfx_ctx* ctx, int which, double* host);
 int pfx_l2_error(pfx_ctx* ctx, int field_a, int field_b, double* err); /* errors_functions.py:190-228 */
 /* Device-resident timing of `reps` back-to-back launches of one operator (kind: 0 apply_u,
  * 1 apply_phi, 2 apply_mass, 3 residual_u, 4 one full u-PCG iteration); CUDA events on the

@@ -1,3 +1,3 @@
-from . import solver  # noqa: F401
+from . import solver, solver_anisotropic  # noqa: F401
 
-__all__ = ["solver"]
+__all__ = ["solver", "solver_anisotropic"]

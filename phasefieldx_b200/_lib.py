@@ -56,7 +56,7 @@ SYMBOLS = [
     "pfx_version", "pfx_device_count", "pfx_status_string", "pfx_create", "pfx_destroy", "pfx_last_error",
     "pfx_default_params", "pfx_set_bc_u", "pfx_set_bc_values_u", "pfx_set_bc_phi", "pfx_set_bc_values_phi",
     "pfx_set_traction", "pfx_set_traction_value", "pfx_load_step", "pfx_solve_u", "pfx_solve_phi", "pfx_reaction", "pfx_energies", "pfx_get_field",
-    "pfx_set_field", "pfx_apply_u", "pfx_apply_phi", "pfx_apply_mass", "pfx_residual_u", "pfx_diag_u", "pfx_rhs_psi",
+    "pfx_set_field", "pfx_apply_u", "pfx_apply_phi", "pfx_apply_mass", "pfx_residual_u", "pfx_diag_u", "pfx_rhs_psi", "pfx_project_psi",
     "pfx_l2_error", "pfx_time_operator", "pfx_algorithmic_bytes", "pfx_launch_count", "pfx_block_stats", "pfx_coarse_stats",
     "pfx_partition_create", "pfx_partition_destroy", "pfx_partition_cell_rank", "pfx_partition_node_owner",
     "pfx_partition_rank_sizes", "pfx_partition_rank_maps", "pfx_partition_rank_plan", "pfx_comm_unique_id",
@@ -93,6 +93,7 @@ def load():
     lib.pfx_set_traction.argtypes = [C.c_void_p, C.c_int, pi, pd, C.c_int64]
     lib.pfx_set_traction_value.argtypes = [C.c_void_p, C.c_int, pd]
     lib.pfx_load_step.argtypes = [C.c_void_p, C.POINTER(PfxStepOpts), C.POINTER(PfxStepReport)]
+    lib.pfx_project_psi.argtypes = [C.c_void_p, C.c_int, pd]
     lib.pfx_solve_u.argtypes = [C.c_void_p, C.POINTER(PfxStepReport)]
     lib.pfx_solve_phi.argtypes = [C.c_void_p, C.POINTER(PfxStepReport)]
     lib.pfx_reaction.argtypes = [C.c_void_p, C.c_int, pd]
@@ -332,6 +333,12 @@ class Engine:
         if is_u:
             return dict(its=r.u_newton_its, reason=r.u_reason, fnorm=r.fnorm_u, cg_its=r.cg_its_u, gpu_ms=r.gpu_ms)
         return dict(its=r.phi_newton_its, reason=r.phi_reason, fnorm=r.fnorm_phi, cg_its=r.cg_its_phi, gpu_ms=r.gpu_ms)
+
+    def project_psi(self, which):
+        """Nodal L2 projection of psi_a ("a") or psi_b ("b") of the current displacement field."""
+        out = np.zeros(self.n_nodes)
+        self._ck(self.lib.pfx_project_psi(self.h, {"a": 0, "b": 1}[which], _pd(out)))
+        return out
 
     def solve_u(self):
         """One Newton (SNES) solve of the displacement problem at the current phi."""

@@ -472,9 +472,10 @@ PFX_HD void elem_diag_mass(int n1d, const double* X, double* out) {
     }
 }
 
-// out[a] = ∫ ψ_a(u) N_a     (RHS of project(psi_a(u_new), V_c), solver.py:355)
+// out[a] = ∫ ψ_a(u) N_a     (RHS of project(psi_a(u_new), V_c), solver.py:355); which = 1: ψ_b instead
+// (solver_anisotropic.py:236-237 projects both parts for output)
 template <class Cell>
-PFX_HD void elem_rhs_psi(const Material& m, int n1d, const double* X, const double* U, double* out) {
+PFX_HD void elem_rhs_psi(const Material& m, int n1d, const double* X, const double* U, double* out, int which = 0) {
     constexpr int NV = Cell::NV, D = Cell::D, NS = SymN<D>::N;
     for (int a = 0; a < NV; ++a) out[a] = 0.0;
     Geo<Cell> geo; geo.init(X, n1d);
@@ -482,14 +483,14 @@ PFX_HD void elem_rhs_psi(const Material& m, int n1d, const double* X, const doub
     if constexpr (Cell::simplex) {
         sym_grad<Cell>(geo.G, U, e);
         energy_split<D>(m, m.emodel, e, pa, pb);
-        for (int a = 0; a < NV; ++a) out[a] = geo.vol * pa / NV;
+        for (int a = 0; a < NV; ++a) out[a] = geo.vol * (which ? pb : pa) / NV;
     } else {
         double N[NV], G[NV][D];
         for (int q = 0; q < geo.nq; ++q) {
             double w = geo.eval(q, N, G);
             sym_grad<Cell>(G, U, e);
             energy_split<D>(m, m.emodel, e, pa, pb);
-            for (int a = 0; a < NV; ++a) out[a] += w * pa * N[a];
+            for (int a = 0; a < NV; ++a) out[a] += w * (which ? pb : pa) * N[a];
         }
     }
 }

@@ -1706,6 +1706,26 @@ int pfx_rhs_psi(pfx_ctx* c, double* b) {
     return host_apply(c, OP_RHS_PSI, 1, nullptr, b, nullptr);
 }
 
+// L2 projection of psi_a (which = 0) or psi_b (which = 1) of the current u onto the nodal space, to the host
+// (Math/projection.py:19-59 as called by solver_anisotropic.py:236-237); single GPU
+int pfx_project_psi(pfx_ctx* c, int which, double* host) {
+    if (!c || !host || which < 0 || which > 1) return PFX_ERR_BAD_ARG;
+    if (c->n_ranks > 1) { c->err = "pfx_project_psi: single-GPU contexts only"; return PFX_ERR_BAD_ARG; }
+    CK(cudaSetDevice(c->device));
+    KArgs a = base_args(c);
+    a.y = c->w_F; a.aux = which;
+    int st = launch_scatter(c, OP_RHS_PSI, a);
+    if (st) return st;
+    bool conv = false; int64_t it = 0;
+    if ((st = pcg_solve(c, LIN_MASS, c->prm.proj_rtol, &it, &conv))) return st;
+    if (!conv) { c->err = "projection PCG did not converge"; return PFX_ERR_NOT_CONVERGED_PROJ; }
+    std::vector<double> tmp(c->n_nodes);
+    CK(cudaMemcpyAsync(tmp.data(), c->w_x, c->n_owned * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int64_t i = 0; i < c->n_owned; ++i) host[c->bm.perm[i]] = tmp[i];
+    return PFX_OK;
+}
+
 int pfx_l2_error(pfx_ctx* c, int fa, int fb, double* err) {
     if (!c || !err) return PFX_ERR_BAD_ARG;
     CK(cudaSetDevice(c->device));

@@ -60,6 +60,7 @@ struct KArgs {
     const double* stop;     // optional sticky DONE flag of the running PCG: skip the launch when set
     int input_masked;       // caller guarantees v == 0 on Dirichlet dofs (PCG directions)
     int wait_halo;          // kernel waits for the halo itself (no separate halo_wait_kernel)
+    int aux;                // op-specific selector (OpRhsPsi: 0 = psi_a, 1 = psi_b)
     const PeerView* pv;     // multi-GPU fused path: wait for the halo in the prologue, push the partial
                             // dot product to the peers' mailboxes in the epilogue (null otherwise)
     const double* cm;       // precomputed phi-operator coefficients 2H + F·Gc/l and F·Gc·l (per node)
@@ -447,7 +448,7 @@ struct OpRhsPsi {          // staged: X u ; y = ∫ψ_a(u) N
     __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
         double X[NV * D], U[NV * D];
         for (int k = 0; k < NV; ++k) for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; U[k * D + i] = nd[k][D + i]; }
-        elem_rhs_psi<Cell>(a.m, a.n1d, X, U, out);
+        elem_rhs_psi<Cell>(a.m, a.n1d, X, U, out, a.aux);
     }
     __device__ static void store(const KArgs& a, int g, const double* acc, double*) { a.y[g] = acc[0]; }
 };

@@ -104,3 +104,18 @@ def test_large_mesh_linearity_and_symmetry():
     assert rel(Jvw, 2.0 * Jv - 3.0 * Jw) < 1e-12
     assert abs(w @ Jv - v @ Jw) < 1e-11 * abs(w @ Jv)
     e.close()
+
+
+@pytest.mark.parametrize("deg,sp", [("anisotropic", "spectral"), ("anisotropic", "deviatoric"), ("hybrid", "spectral")])
+def test_projected_energy_parts_match_oracle(deg, sp):
+    """pfx_project_psi: nodal L2 projections of psi_a and psi_b (solver_anisotropic.py:236-237 output fields)
+    against the oracle's exact mass solve, every cell type."""
+    rng = np.random.default_rng(13)
+    for ctype, m in perturbed_meshes(rng):
+        o, e, P = _setup(ctype, m, deg, sp, False, rng, block_nodes=64)
+        s = o.split(o.u, False)
+        for which in ("a", "b"):
+            ref = o.project(s["psi_" + which])
+            got = e.project_psi(which)
+            assert np.linalg.norm(got - ref) <= 1e-9 * max(np.linalg.norm(ref), 1e-30), (ctype, which)
+        e.close()

