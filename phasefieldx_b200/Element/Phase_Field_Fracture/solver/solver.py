@@ -41,12 +41,14 @@ def _traction_sets(T_list_u):
 def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update_boundary_conditions=None,
           f_list_u=None, T_list_u=None, update_loading=None, ds_bound=None, dt=1.0, path=None,
           bcs_list_u_names=None, min_stagger_iter=2, max_stagger_iter=10000, stagger_error_tol=1e-8,
-          device=0, solver_options=None, vtu_every=1, vtu_format="ascii"):
+          device=0, solver_options=None, vtu_every=1, vtu_format="ascii", vtu_parallel=False):
     """Solve the phase-field fracture and fatigue problem (reference signature; `f_list_u` and
     `ds_bound` are accepted and unused exactly as in the reference).
     Extra keyword-only knobs (not in the reference): `device`, `solver_options` (pfx_params
     overrides such as cg_rtol), `vtu_every` (VTU cadence; default every step as the reference),
-    `vtu_format` ("ascii" = the reference's layout, "binary" = raw appended data)."""
+    `vtu_format` ("ascii" = the reference's layout, "binary" = raw appended data), `vtu_parallel` (multi-rank
+    runs: every rank writes its own piece + a .pvtu index, dolfinx's parallel layout, instead of gathering the
+    fields on rank 0)."""
     if path is None:
         path = os.getcwd()
     result_folder_name = Data.results_folder_name
@@ -125,8 +127,10 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     start = time.perf_counter()
     logger.info(f" start time: {start}")
     vtk_sol = None
-    if Data.save_solution_vtu and rank == 0:
-        vtk_sol = VTKFile(None, os.path.join(result_folder_name, "paraview-solutions_vtu", "phasefieldx.pvd"), "w", fmt=vtu_format)
+    pieces = bool(vtu_parallel) and dist is not None
+    if Data.save_solution_vtu and (rank == 0 or pieces):
+        vtk_sol = VTKFile(None, os.path.join(result_folder_name, "paraview-solutions_vtu", "phasefieldx.pvd"), "w", fmt=vtu_format,
+                          rank=rank if pieces else 0, world=world if pieces else 1)
     logger.info(" S t a r t i n g    A n a l y s i s ")
     logger.info(" ---------------------------------- ")
     logger.info(" ---------------------------------- ")
@@ -192,13 +196,13 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
                 append_results_to_file(os.path.join(result_folder_name, "total.energy"), header, step,
                                        *[en[c] for c in _lib.ENERGY_COLUMNS])
             if Data.save_solution_vtu and (step % max(1, int(vtu_every)) == 0):
-                if rmesh is None:
+                if rmesh is None or pieces:
                     phi_out, u_out = eng.get_field("phi"), eng.get_field("u").reshape(-1, d)
                 else:
                     dev = f"cuda:{device}"
                     phi_out, u_out = gather_field(eng, rmesh, "phi", dist, dev), gather_field(eng, rmesh, "u", dist, dev)
                 if vtk_sol is not None:
-                    vtk_sol.write_function(msh, {"phi": phi_out, "u": u_out}, step, background=True)
+                    vtk_sol.write_function(rmesh.piece(ctype) if pieces else msh, {"phi": phi_out, "u": u_out}, step, background=True)
             t += dt
             step += 1
     finally:

@@ -32,6 +32,16 @@ class RankMesh:
         self.cell_primary = R["cell_primary"]
         self.n_global = len(coords)
 
+    def piece(self, cell_type):
+        """Rank-local mesh view for the parallel VTU writer (io_vtk.VTKFile with rank/world): owned + ghost
+        nodes, local cells, global ids, ghost marks (nodes owned elsewhere; cells integrated elsewhere)."""
+        import types
+        ghost_pt = (np.arange(len(self.l2g)) >= self.n_owned).astype(np.uint8)
+        return types.SimpleNamespace(geometry=types.SimpleNamespace(x=self.coords, dim=self.coords.shape[1]), cells=self.cells,
+                                     cell_type=cell_type, num_nodes=len(self.coords), point_gid=self.l2g,
+                                     cell_gid=self.plan["cell_gid"], point_ghost=ghost_pt,
+                                     cell_ghost=(1 - np.asarray(self.cell_primary, dtype=np.uint8)))
+
     def local_dofs(self, dofs, bs):
         """global unrolled dofs -> (keep mask, local unrolled dofs) for the dofs whose node is held here"""
         dofs = np.asarray(dofs, dtype=np.int64)

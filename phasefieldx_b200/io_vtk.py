@@ -5,7 +5,11 @@ examples/PhaseFieldFracture/1711_*/paraview-solutions_vtu/phasefieldx_p0_000149.
 `VTKFile version="2.2"`, Points (3 comps), Cells connectivity/offsets/types (VTK Lagrange
 family: 69 triangle, 70 quadrilateral, 71 tetrahedron; Q1 cells in VTK cyclic order),
 CellData vtkGhostType/vtkOriginalCellIds, PointData vtkOriginalPointIds/vtkGhostType/phi/u
-(u padded to 3 components).
+(u padded to 3 components).  Multi-rank runs (rank, world given) follow dolfinx's parallel layout
+(reference examples/PhaseField/2003_example_mpi/paraview-solutions_vtu/): one piece per rank
+`<stem>_p<rank>_<step>.vtu` holding the rank's owned + ghost nodes and its local cells with
+vtkGhostType = 1 on ghosts and the global ids in vtkOriginal*Ids, plus `<stem><step>.pvtu`
+written by rank 0.
 """
 import os
 
@@ -34,13 +38,14 @@ class VTKFile:
     that reads back bit-exactly); everything that does not change between load steps —
     points, cells, id arrays — is formatted once and reused."""
 
-    def __init__(self, comm, filename, mode="w", fmt="ascii"):
+    def __init__(self, comm, filename, mode="w", fmt="ascii", rank=0, world=1):
         """fmt "ascii": the reference's layout; "binary": same arrays as raw appended data (VTK
         `format="appended"`, UInt64 block headers) — a third of the bytes and no number formatting,
         for meshes where the ASCII file is what a load step waits for."""
         if fmt not in ("ascii", "binary"):
             raise ValueError("fmt must be 'ascii' or 'binary'")
         self.fmt = fmt
+        self.rank, self.world = int(rank), int(world)
         self.pvd = filename
         self.dir = os.path.dirname(filename)
         self.stem = os.path.splitext(os.path.basename(filename))[0]
@@ -49,6 +54,19 @@ class VTKFile:
         self._pending = None
         self._error = None
         os.makedirs(self.dir, exist_ok=True)
+
+    @staticmethod
+    def _ids(msh, nn, ne):
+        """(point ids, cell ids, point ghost flags, cell ghost flags): global numbering and ghost marks of a
+        rank-local piece (attributes point_gid / cell_gid / point_ghost / cell_ghost), else the identity."""
+        pg = getattr(msh, "point_gid", None)
+        cg = getattr(msh, "cell_gid", None)
+        pgh = getattr(msh, "point_ghost", None)
+        cgh = getattr(msh, "cell_ghost", None)
+        return (np.arange(nn) if pg is None else np.asarray(pg, dtype=np.int64),
+                np.arange(ne) if cg is None else np.asarray(cg, dtype=np.int64),
+                np.zeros(nn, np.uint8) if pgh is None else np.asarray(pgh, dtype=np.uint8),
+                np.zeros(ne, np.uint8) if cgh is None else np.asarray(cgh, dtype=np.uint8))
 
     def _static_part(self, msh):
         key = (id(msh), msh.geometry.x.shape, msh.cells.shape)
@@ -59,6 +77,7 @@ class VTKFile:
             x = np.hstack([x, np.zeros((len(x), 3 - x.shape[1]))])
         cells = msh.cells[:, _VTK_PERM[msh.cell_type]]
         nn, ne, nv = len(x), len(cells), cells.shape[1]
+        pid, cid, pgh, cgh = self._ids(msh, nn, ne)
         L = [b'<?xml version="1.0"?>', b'<VTKFile type="UnstructuredGrid" version="2.2">', b"  <UnstructuredGrid>",
              f'    <Piece NumberOfPoints="{nn}" NumberOfCells="{ne}">'.encode(), b"      <Points>",
              _da('type="Float64" NumberOfComponents="3"', _f64(x)),
@@ -67,11 +86,11 @@ class VTKFile:
              _da('type="Int32" Name="offsets"', _i64(np.arange(1, ne + 1) * nv)),
              _da('type="Int8" Name="types"', _i64(np.full(ne, _VTK_TYPE[msh.cell_type]))),
              b"      </Cells>", b"      <CellData>",
-             _da('type="UInt8" Name="vtkGhostType"', _i64(np.zeros(ne, int))),
-             _da('type="Int64" Name="vtkOriginalCellIds"', _i64(np.arange(ne))),
+             _da('type="UInt8" Name="vtkGhostType"', _i64(cgh)),
+             _da('type="Int64" Name="vtkOriginalCellIds"', _i64(cid)),
              b"      </CellData>", b"      <PointData>",
-             _da('type="Int64" Name="vtkOriginalPointIds"', _i64(np.arange(nn))),
-             _da('type="UInt8" Name="vtkGhostType"', _i64(np.zeros(nn, int)))]
+             _da('type="Int64" Name="vtkOriginalPointIds"', _i64(pid)),
+             _da('type="UInt8" Name="vtkGhostType"', _i64(pgh))]
         head = b"\n".join(L) + b"\n"
         self._static = (key, head)
         return head
@@ -111,14 +130,15 @@ class VTKFile:
         nn, ne, nv = len(x), len(cells), cells.shape[1]
         key = (id(msh), x.shape, cells.shape)
         if self._static is None or self._static[0] != key:
+            pid, cid, pgh, cgh = self._ids(msh, nn, ne)
             self._static = (key, [("Points", None, "Float64", 3, np.ascontiguousarray(x)),
                                   ("Cells", "connectivity", "Int32", 0, cells),
                                   ("Cells", "offsets", "Int32", 0, (np.arange(1, ne + 1) * nv).astype(np.int32)),
                                   ("Cells", "types", "Int8", 0, np.full(ne, _VTK_TYPE[msh.cell_type], np.int8)),
-                                  ("CellData", "vtkGhostType", "UInt8", 0, np.zeros(ne, np.uint8)),
-                                  ("CellData", "vtkOriginalCellIds", "Int64", 0, np.arange(ne, dtype=np.int64)),
-                                  ("PointData", "vtkOriginalPointIds", "Int64", 0, np.arange(nn, dtype=np.int64)),
-                                  ("PointData", "vtkGhostType", "UInt8", 0, np.zeros(nn, np.uint8))])
+                                  ("CellData", "vtkGhostType", "UInt8", 0, np.ascontiguousarray(cgh)),
+                                  ("CellData", "vtkOriginalCellIds", "Int64", 0, np.ascontiguousarray(cid)),
+                                  ("PointData", "vtkOriginalPointIds", "Int64", 0, np.ascontiguousarray(pid)),
+                                  ("PointData", "vtkGhostType", "UInt8", 0, np.ascontiguousarray(pgh))])
         arrays = list(self._static[1])
         for fname, vals in fields.items():
             v = np.asarray(vals, dtype=np.float64)
@@ -143,14 +163,36 @@ class VTKFile:
             off += 8 + arr.nbytes
         L += [f"      </{section}>", "    </Piece>", "  </UnstructuredGrid>", '  <AppendedData encoding="raw">']
         step = int(t)
-        fname_out = f"{self.stem}_p0_{step:06d}.vtu"
+        fname_out = f"{self.stem}_p{self.rank}_{step:06d}.vtu"
         with open(os.path.join(self.dir, fname_out), "wb") as fh:
             fh.write(("\n".join(L) + "\n_").encode())
             for _, _, _, _, arr in arrays:
                 fh.write(np.uint64(arr.nbytes).tobytes())
                 fh.write(arr.tobytes())
             fh.write(b"\n  </AppendedData>\n</VTKFile>\n")
-        self.records.append((t, fname_out))
+        self._record(t, step, fname_out, fields)
+
+    def _record(self, t, step, piece_name, fields):
+        """Book-keeping after a piece: rank 0 writes the .pvtu of a multi-rank step and the .pvd index."""
+        if self.rank != 0:
+            return
+        name = piece_name
+        if self.world > 1:
+            name = f"{self.stem}{step:06d}.pvtu"
+            L = ['<?xml version="1.0"?>', '<VTKFile type="PUnstructuredGrid" version="1.0">', '  <PUnstructuredGrid GhostLevel="1">',
+                 "    <PPointData>", '      <PDataArray type="Int64" Name="vtkOriginalPointIds" IdType="1" />',
+                 '      <PDataArray type="UInt8" Name="vtkGhostType" />']
+            for fname, vals in fields.items():
+                nc = 3 if np.ndim(vals) == 2 else 1
+                L.append(f'      <PDataArray type="Float64" Name="{fname}" NumberOfComponents="{nc}" />')
+            L += ["    </PPointData>", "    <PCellData>", '      <PDataArray type="UInt8" Name="vtkGhostType" />',
+                  '      <PDataArray type="Int64" Name="vtkOriginalCellIds" IdType="1" />', "    </PCellData>", "    <PPoints>",
+                  '      <PDataArray type="Float64" NumberOfComponents="3" />', "    </PPoints>"]
+            L += [f'    <Piece Source="{self.stem}_p{r}_{step:06d}.vtu" />' for r in range(self.world)]
+            L += ["  </PUnstructuredGrid>", "</VTKFile>"]
+            with open(os.path.join(self.dir, name), "w") as fh:
+                fh.write("\n".join(L) + "\n")
+        self.records.append((t, name))
         self._write_pvd()
 
     def _write(self, msh, fields, t):
@@ -158,7 +200,7 @@ class VTKFile:
             return self._write_binary(msh, fields, t)
         head = self._static_part(msh)
         step = int(t)
-        name = f"{self.stem}_p0_{step:06d}.vtu"
+        name = f"{self.stem}_p{self.rank}_{step:06d}.vtu"
         L = []
         for fname, vals in fields.items():
             v = np.asarray(vals, dtype=np.float64)
@@ -170,10 +212,11 @@ class VTKFile:
         with open(os.path.join(self.dir, name), "wb") as fh:
             fh.write(head)
             fh.write(b"\n".join(L) + b"\n")
-        self.records.append((t, name))
-        self._write_pvd()
+        self._record(t, step, name, fields)
 
     def _write_pvd(self):
+        if self.rank != 0:
+            return
         L = ['<?xml version="1.0"?>', '<VTKFile type="Collection" version="0.1">', "  <Collection>"]
         L += [f'    <DataSet timestep="{t}" part="0" file="{n}" />' for t, n in self.records]
         L += ["  </Collection>", "</VTKFile>"]
@@ -211,6 +254,10 @@ def read_vtu_points_cells(path):
             if nm in named:
                 a = block(named[nm]).astype(np.float64)
                 out[nm] = a.reshape(npts, -1) if a.size != npts else a
+        ghost = [block(t) for t in tags if 'Name="vtkGhostType"' in t]
+        out.update(cell_ghost=ghost[0].astype(np.int64), point_ghost=ghost[1].astype(np.int64),
+                   cell_gid=block(named["vtkOriginalCellIds"]).astype(np.int64),
+                   point_gid=block(named["vtkOriginalPointIds"]).astype(np.int64))
         return out
 
     def data(pattern):
@@ -224,4 +271,11 @@ def read_vtu_points_cells(path):
         if m:
             a = np.array(m.group(1).split(), dtype=np.float64)
             out[nm] = a.reshape(npts, -1) if a.size != npts else a
+    ghost = re.findall(r'Name="vtkGhostType"[^>]*>([^<]*)</DataArray>', txt)
+    if len(ghost) == 2:
+        out["cell_ghost"], out["point_ghost"] = (np.array(g.split(), dtype=np.int64) for g in ghost)
+    for key, nm in (("cell_gid", "vtkOriginalCellIds"), ("point_gid", "vtkOriginalPointIds")):
+        m = re.search(rf'Name="{nm}"[^>]*>([^<]*)</DataArray>', txt)
+        if m:
+            out[key] = np.array(m.group(1).split(), dtype=np.int64)
     return out

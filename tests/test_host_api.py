@@ -247,3 +247,37 @@ def test_binary_vtu_round_trips_bit_exactly(tmp_path):
         assert 'header_type="UInt64"' in head and 'format="appended"' in head
     with pytest.raises(ValueError):
         io_vtk.VTKFile(None, str(tmp_path / "x" / "p.pvd"), "w", fmt="hdf5")
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "binary"])
+def test_parallel_vtu_pieces_merge_to_the_global_fields(tmp_path, fmt):
+    """Multi-rank output (layout of reference examples/PhaseField/2003_example_mpi/
+    paraview-solutions_vtu/): one piece per rank with global ids and ghost marks + a .pvtu by rank 0.  Merging the
+    non-ghost nodes of all pieces gives back the global fields; every global cell is non-ghost in exactly one piece."""
+    from phasefieldx_b200 import io_vtk, mesh as M
+    from phasefieldx_b200.distributed import RankMesh
+    msh = M.create_box(None, [[0, 0, 0], [2, 1, 1]], [7, 4, 3])
+    x, cells = msh.geometry.x, msh.cells
+    rng = np.random.default_rng(2)
+    phi_g, u_g = rng.uniform(size=len(x)), rng.standard_normal((len(x), 3))
+    world = 3
+    for r in range(world):
+        rm = RankMesh(x, cells, "tetrahedron", world, r)
+        vt = io_vtk.VTKFile(None, str(tmp_path / "out" / "phasefieldx.pvd"), "w", fmt=fmt, rank=r, world=world)
+        vt.write_function(rm.piece("tetrahedron"), {"phi": phi_g[rm.l2g], "u": u_g[rm.l2g]}, 7, background=True)
+        vt.close()
+    pvtu = (tmp_path / "out" / "phasefieldx000007.pvtu").read_text()
+    assert all(f'Piece Source="phasefieldx_p{r}_000007.vtu"' in pvtu for r in range(world)) and 'Name="u" NumberOfComponents="3"' in pvtu
+    assert 'file="phasefieldx000007.pvtu"' in (tmp_path / "out" / "phasefieldx.pvd").read_text()
+    phi, u, seen_pt, seen_cell = np.zeros(len(x)), np.zeros((len(x), 3)), np.zeros(len(x), int), np.zeros(len(cells), int)
+    for r in range(world):
+        d = io_vtk.read_vtu_points_cells(str(tmp_path / "out" / f"phasefieldx_p{r}_000007.vtu"))
+        own = d["point_ghost"] == 0
+        gid = d["point_gid"][own]
+        phi[gid], u[gid] = d["phi"][own], d["u"][own]
+        seen_pt[gid] += 1
+        seen_cell[d["cell_gid"][d["cell_ghost"] == 0]] += 1
+        assert np.array_equal(d["points"], x[d["point_gid"]])                       # local points are the global ones
+        assert np.array_equal(np.sort(d["point_gid"][d["cells"]], 1), np.sort(cells[d["cell_gid"]], 1))
+    assert np.all(seen_pt == 1) and np.all(seen_cell == 1)
+    assert np.array_equal(phi, phi_g) and np.array_equal(u, u_g)

@@ -9,6 +9,7 @@ import sys
 import tempfile
 
 import numpy as np
+
 import torch
 import torch.distributed as dist
 
@@ -50,8 +51,11 @@ def update_boundary_conditions(bcs_, time):
     return 0, val, 0
 
 
+PIECES = os.environ.get("PFX_VTU_PIECES", "0") == "1"      # per-rank pieces + .pvtu instead of a gathered file
 solve(Data, msh, 5.0, V_u, V_phi, bcs, [], update_boundary_conditions, None, None, None, None, 1.0, path=tmp,
-      bcs_list_u_names=["top", "bottom"], min_stagger_iter=2, max_stagger_iter=500, stagger_error_tol=1e-8, vtu_every=4)
+      bcs_list_u_names=["top", "bottom"], min_stagger_iter=2, max_stagger_iter=500, stagger_error_tol=1e-8, vtu_every=4,
+      vtu_parallel=PIECES)
+dist.barrier()
 if rank == 0:
     S = AllResults(Data.results_folder_name)
     ref = np.load(os.path.join(ROOT, "tests", "golden", "ref_1711.npz"))
@@ -61,7 +65,17 @@ if rank == 0:
     np.testing.assert_allclose(en["PSI_a"].to_numpy()[1:5], ref["energy"][1:5, 9], rtol=1e-11)
     assert S.convergence_files["phasefieldx.conv"]["stagger"].tolist() == ref["conv"][:5, 1].astype(int).tolist()
     from phasefieldx_b200.io_vtk import read_vtu_points_cells
-    v = read_vtu_points_cells(os.path.join(Data.results_folder_name, "paraview-solutions_vtu", "phasefieldx_p0_000004.vtu"))
+    vdir = os.path.join(Data.results_folder_name, "paraview-solutions_vtu")
+    if PIECES:          # merge the owned nodes of the per-rank pieces back into the global numbering
+        assert os.path.exists(os.path.join(vdir, "phasefieldx000004.pvtu"))
+        v = {"phi": np.zeros(msh.num_nodes), "u": np.zeros((msh.num_nodes, 3))}
+        for r in range(world):
+            p = read_vtu_points_cells(os.path.join(vdir, f"phasefieldx_p{r}_000004.vtu"))
+            own = p["point_ghost"] == 0
+            v["phi"][p["point_gid"][own]] = p["phi"][own]
+            v["u"][p["point_gid"][own]] = p["u"][own]
+    else:
+        v = read_vtu_points_cells(os.path.join(vdir, "phasefieldx_p0_000004.vtu"))
     print("vtu:", v["phi"].shape, v["u"].shape, float(v["u"][:, 1].max()), float(v["u"][:, 1].min()), bool(np.isfinite(v["u"]).all()), flush=True)
     assert v["phi"].shape[0] == msh.num_nodes and np.isfinite(v["u"]).all()
     assert np.allclose(v["u"][d["top_nodes"], 1], 4e-4, rtol=0, atol=1e-15) and np.all(v["u"][d["bottom_nodes"], :2] == 0.0)
