@@ -21,9 +21,9 @@
 
 namespace pfx {
 
-constexpr int kCoarseMax = 3072;     // most coarse dofs of one region (one dense inverse)
-constexpr int kCoarseRegion = 1792;  // default region size (coarse u-dofs)
-constexpr int kCoarseTotal = 16384;  // default cap of the whole coarse space (coarse u-dofs)
+constexpr int kCoarseMax = 6144;     // most coarse dofs of one region (one dense inverse)
+constexpr int kCoarseRegion = 1792;  // 2D default region size (coarse u-dofs)
+constexpr int kCoarseTotal = 16384;  // 2D default cap of the whole coarse space (coarse u-dofs); 3D: one region of <= kCoarseMax
 constexpr int kCoarseRowsPerWarp = 4;                              // coarse solve: consecutive rows per warp
 constexpr int kCoarseRowsPerCta = kCoarseRowsPerWarp * (kThreads / 32);
 constexpr int kCoarseChunkNodes = 256;                             // update / direction kernels: one warp per chunk of <= this many nodes

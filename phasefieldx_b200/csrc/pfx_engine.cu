@@ -639,7 +639,13 @@ int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
     // region).  Defaults: at most kCoarseTotal coarse dofs in all, regions of <= kCoarseRegion.
     const char* eg = getenv("PFX_COARSE_AGG_BLOCKS");
     const char* er = getenv("PFX_COARSE_REGION");
-    const int total_cap = kCoarseTotal, reg_cap = std::min(kCoarseMax, std::max(m_u * 8, er ? atoi(er) : kCoarseRegion));
+    // 2D: many small aggregates (one per block up to kCoarseTotal dofs) in regions of kCoarseRegion — refining the
+    // aggregates pays (iterations ~ sqrt(H/h)) and compact regions lose little.  3D: block aggregates are only
+    // ~6 cells across, and cutting the coarse matrix into regions costs far more than coarser aggregates do
+    // (beam, 8 M tets: 1 499 iterations per step with 7 regions, 576 with one region of 5 730 dofs), so the
+    // whole coarse space is one region of at most kCoarseMax dofs.
+    const int total_cap = D == 3 ? kCoarseMax : kCoarseTotal;
+    const int reg_cap = std::min(kCoarseMax, std::max(m_u * 8, er ? atoi(er) : (D == 3 ? kCoarseMax : kCoarseRegion)));
     int g = (bm.nb * m_u + total_cap - 1) / total_cap;
     if (eg && atoi(eg) > 0) g = atoi(eg);
     g = std::max(g, 1);
@@ -700,6 +706,12 @@ int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
     }
     cs.lwork = std::max(l1, l2);
     if ((st = dev_alloc(c, &cs.work, (size_t)std::max(1, cs.lwork)))) return st;
+    {   // the coarse solve stages w of one region (up to kCoarseMax doubles) in dynamic shared memory
+        const int smem = kCoarseMax * (int)sizeof(double);
+        CK(cudaFuncSetAttribute(coarse_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(coarse_solve_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CK(cudaFuncSetAttribute(coarse_solve_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    }
     cs.enabled = true;
     return PFX_OK;
 }
