@@ -5,7 +5,7 @@
 // 10^6-node load step spends its time on.  Aggregates are runs of consecutive CTA blocks of the
 // RCB tree (spatially compact, contiguous node ranges); every aggregate carries its rigid-body
 // modes (u: translations + rotations, phi: the constant).  The coarse matrix is small enough
-// (<= kCoarseMax rows) that its inverse is kept explicitly, in fp32 (36 MB: L2 resident), and
+// (<= kCoarseMax rows per region) that its inverse is kept explicitly, in fp32 (~100-150 MB), and
 // the coarse solve is one dense mat-vec spread over the SMs.  Additive combination keeps M^-1
 // symmetric positive definite for ANY symmetric positive definite coarse matrix, so Z^T A Z may
 // lag behind the current tangent (it is refreshed once per load step / when iterations grow).
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kThreads) pcg_update_coarse_kernel(CoarseView 
     }
 }
 
-// 128-bit read of the coarse inverse with an L2 evict-last policy: the 36 MB matrix is re-read every
+// 128-bit read of the coarse inverse with an L2 evict-last policy: the matrix is re-read every
 // iteration while ~300 MB of vectors stream past it
 __device__ __forceinline__ float4 ld_keep(const float4* p, unsigned long long pol) {
     float4 v;
