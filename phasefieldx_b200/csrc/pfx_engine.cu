@@ -540,14 +540,12 @@ int fetch(pfx_ctx* c, double* dev, int n, double* out) {
 int rebuild_bc(pfx_ctx* c, bool is_u) {
     int64_t n = c->n_nodes * (is_u ? c->dim : 1);
     uint8_t* mask = is_u ? c->mask_u : c->mask_phi;
-    double* g = is_u ? c->g_u : c->g_phi;
     std::vector<BCSet>& sets = is_u ? c->bcs_u : c->bcs_phi;
     std::vector<uint8_t> hm(n, 0);
     for (auto& s : sets)
         for (int32_t d : s.dofs) hm[d] = 1;
     CK(cudaMemcpyAsync(mask, hm.data(), n, cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    (void)g;
     c->coarse.op[is_u ? 0 : 1].stale = true;      // the masked modes changed
     return PFX_OK;
 }

@@ -1489,7 +1489,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_coop_u_tri_kernel(BlockView b
     const int tid = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
     const int4 ma = bv.meta[2 * b], mb = bv.meta[2 * b + 1];
     const int n0 = ma.x, n_own = ma.y, h0 = ma.z, n_halo = ma.w, n_loc = n_own + n_halo, e0 = mb.x, ne = mb.y;
-    const int ML = bv.max_loc, chunk = 2 * kThreads, MO = (bv.max_own + 1) & ~1;
+    const int ML = bv.max_loc, chunk = 2 * kThreads;
     double2* sX = reinterpret_cast<double2*>(smem);
     double2* sU = sX + ML;
     double2* sV = sU + ML;                   // p on every local node
@@ -1660,7 +1660,7 @@ __global__ void __launch_bounds__(kThreads, 1) pcg_coop_phi_tri_kernel(BlockView
     const int tid = threadIdx.x, b = blockIdx.x, nb = gridDim.x;
     const int4 ma = bv.meta[2 * b], mb = bv.meta[2 * b + 1];
     const int n0 = ma.x, n_own = ma.y, h0 = ma.z, n_halo = ma.w, n_loc = n_own + n_halo, e0 = mb.x, ne = mb.y;
-    const int ML = bv.max_loc, chunk = 2 * kThreads, MO = (bv.max_own + 1) & ~1, MLe = (ML + 1) & ~1;
+    const int ML = bv.max_loc, chunk = 2 * kThreads, MLe = (ML + 1) & ~1;
     double2* sX = reinterpret_cast<double2*>(smem);
     double* sM = reinterpret_cast<double*>(sX + ML);     // cm
     double* sG = sM + MLe;                               // cg
