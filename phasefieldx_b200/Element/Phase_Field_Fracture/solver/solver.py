@@ -131,6 +131,8 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     if Data.save_solution_vtu and (rank == 0 or pieces):
         vtk_sol = VTKFile(None, os.path.join(result_folder_name, "paraview-solutions_vtu", "phasefieldx.pvd"), "w", fmt=vtu_format,
                           rank=rank if pieces else 0, world=world if pieces else 1)
+    if getattr(Data, "save_solution_xdmf", False):
+        logger.info(" save_solution_xdmf: XDMF/HDF5 output needs dolfinx and is not written (VTU output is unaffected)")
     logger.info(" S t a r t i n g    A n a l y s i s ")
     logger.info(" ---------------------------------- ")
     logger.info(" ---------------------------------- ")

@@ -29,6 +29,8 @@ class Run:
         self.vtk = None
         if Data.save_solution_vtu:
             self.vtk = VTKFile(None, os.path.join(self.folder, "paraview-solutions_vtu", "phasefieldx.pvd"), "w", fmt=vtu_format)
+        if getattr(Data, "save_solution_xdmf", False):
+            self.logger.info(" save_solution_xdmf: XDMF/HDF5 output needs dolfinx and is not written (VTU output is unaffected)")
         self.logger.info(" S t a r t i n g    A n a l y s i s ")
         self.logger.info(" ---------------------------------- ")
         self.logger.info(" ---------------------------------- ")
