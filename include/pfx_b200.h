@@ -42,6 +42,9 @@ enum { PFX_CELL_TRIANGLE = 0, PFX_CELL_QUADRILATERAL = 1, PFX_CELL_TETRAHEDRON =
 /* pfx/Element/Phase_Field_Fracture/split_energy_stress_tangent_functions.py:234-354 */
 enum { PFX_MODEL_ISOTROPIC = 0, PFX_MODEL_SPECTRAL = 1, PFX_MODEL_DEVIATORIC = 2,
        PFX_MODEL_HYBRID_SPECTRAL = 3, PFX_MODEL_HYBRID_DEVIATORIC = 4 };
+/* degradation function g(phi): quadratic (1-phi)^2; borden 3(1-phi)^2 - 2(1-phi)^3 as coded in the reference (s = 0).
+ * alessi / sargado are not built. */
+enum { PFX_DEGRADATION_QUADRATIC = 0, PFX_DEGRADATION_BORDEN = 1 };
 enum { PFX_FIELD_U = 0, PFX_FIELD_PHI = 1, PFX_FIELD_H = 2, PFX_FIELD_VC = 3, PFX_FIELD_VN = 4,
        PFX_FIELD_FATIGUE = 5, PFX_FIELD_ALPHA_BAR = 6, PFX_FIELD_ALPHA_C = 7, PFX_FIELD_U_OLD = 8,
        PFX_FIELD_PHI_OLD = 9, PFX_FIELD_ALPHA_N = 10, PFX_FIELD_ALPHA_BAR_N = 11 };
@@ -77,6 +80,7 @@ typedef struct {
     int32_t quad_points_1d;   /* Gauss points per direction for Q1 cells (default 3)       */
     int32_t block_nodes;      /* owned nodes per CTA tile, 0 = auto                         */
     int32_t cg_chunk;         /* CG iterations per CUDA-graph launch, 0 = auto             */
+    int32_t degradation_function; /* PFX_DEGRADATION_*: g of g_degradation_functions.py:12-64 (Input.degradation_function) */
 } pfx_params;
 
 typedef struct {

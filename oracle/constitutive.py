@@ -256,6 +256,32 @@ def dg_quadratic(phi):
     return -2.0 * (1.0 - phi)
 
 
+def g_borden(phi):
+    """reference g_degradation_functions.py:38-50 AS CODED (s = 0, although the docs say s = 1)"""
+    t = 1.0 - phi
+    return 3.0 * t * t - 2.0 * t * t * t
+
+
+def dg_borden(phi):
+    """reference g_degradation_functions.py:53-64"""
+    t = 1.0 - phi
+    return -6.0 * t + 6.0 * t * t
+
+
+def ddg_borden(phi):
+    """d/dphi of dg_borden (what ufl.derivative(F_phi, phi) differentiates, solver.py:224)"""
+    return 6.0 - 12.0 * (1.0 - phi)
+
+
+def degradation(name):
+    """(g, dg, ddg) of a degradation function; sargado / alessi are not restated."""
+    if name == "quadratic":
+        return g_quadratic, dg_quadratic, (lambda phi: 2.0 + 0.0 * phi)
+    if name == "borden":
+        return g_borden, dg_borden, ddg_borden
+    raise NotImplementedError(f"degradation_function {name!r}")
+
+
 def fatigue_asymptotic(alpha_bar, alpha_T):
     """reference fatigue_degradation_functions.py:19-38"""
     aux = (2.0 * alpha_T / (alpha_bar + alpha_T)) ** 2

@@ -45,8 +45,8 @@ class Params:
         self.fatigue = fatigue
         self.fatigue_degradation_function = fatigue_degradation_function
         self.fatigue_val = fatigue_val
-        if degradation_function != "quadratic":
-            raise NotImplementedError("oracle covers the quadratic degradation function (SURVEY §8f N2)")
+        if degradation_function not in ("quadratic", "borden"):
+            raise NotImplementedError("oracle covers the quadratic and borden degradation functions (SURVEY §8f N2)")
 
     @classmethod
     def from_input(cls, Data):
@@ -76,6 +76,9 @@ def _bc_vectors(n, bcs):
 class Oracle:
     def __init__(self, points, cells, cell_type, params, degree=None, projection="exact"):
         self.p = params
+        self.g, self.dg, self.ddg = cons.degradation(params.degradation_function)
+        if degree is None and params.degradation_function != "quadratic":
+            degree = 5          # cubic g: g(φ)·V_c·w and g''(φ)·H·N·N are of degree 5 / 4 on P1 simplices
         self.t = Tables(points, cells, cell_type, degree)
         t = self.t
         self.d, self.nv, self.nn, self.ne = t.d, t.nv, t.nn, t.ne
@@ -137,14 +140,14 @@ class Oracle:
     # ------------------------------------------------------------------ u-problem (solver.py:173-187)
     def F_int_u(self, u, phi, s=None):
         s = self.split(u, False) if s is None else s
-        gq = cons.g_quadratic(self.at_qp(phi)) + self.p.k
+        gq = self.g(self.at_qp(phi)) + self.p.k
         sig = gq[..., None, None] * s["sig_a"] + s["sig_b"]
         fe = np.einsum("eq,eqij,eqijm->em", self.t.W, sig, self.Bm)
         return self._vec(fe, self.edof_u, self.nn * self.d)
 
     def J_u(self, u, phi, s=None):
         s = self.split(u, True) if s is None else s
-        gq = cons.g_quadratic(self.at_qp(phi)) + self.p.k
+        gq = self.g(self.at_qp(phi)) + self.p.k
         C = gq[..., None, None, None, None] * s["C_a"] + s["C_b"]
         Ke = np.einsum("eq,eqijm,eqijkl,eqkln->emn", self.t.W, self.Bm, C, self.Bm, optimize=True)
         return self._csr(Ke, self.edof_u, self.nn * self.d)
@@ -264,11 +267,26 @@ class Oracle:
         self.u, its, reason, hist = self._snes(res, jac, self.u, mask, g)
         return its, reason, hist
 
+    def F_phi(self, phi, H, Fat=None):
+        """F_phi = dg(phi)·H·w + (F·)Gc(phi·w/l + l grad phi·grad w), general degradation (solver.py:214-222)"""
+        K0 = self.K_phi(np.zeros_like(H), Fat)                       # the crack-surface part alone
+        fe = np.einsum("eq,eq,qa->ea", self.t.W, self.dg(self.at_qp(phi)) * self.at_qp(H), self.t.N)
+        return K0 @ phi + self._vec(fe, self.edof_s, self.nn)
+
+    def J_phi(self, phi, H, Fat=None):
+        K0 = self.K_phi(np.zeros_like(H), Fat)
+        Ke = np.einsum("eq,eq,qa,qb->eab", self.t.W, self.ddg(self.at_qp(phi)) * self.at_qp(H), self.t.N, self.t.N)
+        return K0 + self._csr(Ke, self.edof_s, self.nn)
+
     def solve_phi(self, bcs_phi):
         mask, g = _bc_vectors(self.nn, bcs_phi)
-        K = self.K_phi(self.H, self.Fatigue)
-        b = self.b_phi(self.H)
-        self.phi, its, reason, hist = self._snes(lambda x: K @ x - b, lambda x: K, self.phi, mask, g)
+        if self.p.degradation_function == "quadratic":
+            K = self.K_phi(self.H, self.Fatigue)
+            b = self.b_phi(self.H)
+            self.phi, its, reason, hist = self._snes(lambda x: K @ x - b, lambda x: K, self.phi, mask, g)
+        else:
+            self.phi, its, reason, hist = self._snes(lambda x: self.F_phi(x, self.H, self.Fatigue),
+                                                     lambda x: self.J_phi(x, self.H, self.Fatigue), self.phi, mask, g)
         return its, reason, hist
 
     # ------------------------------------------------------------------ one load step (solver.py:319-411)
@@ -289,7 +307,7 @@ class Oracle:
             self.V_c = self.project(s["psi_a"])
             self.H = np.maximum(self.V_c, self.V_n) if p.irreversibility == "miehe" else self.V_c.copy()
             if p.fatigue:
-                gq = cons.g_quadratic(self.at_qp(self.phi_old))
+                gq = self.g(self.at_qp(self.phi_old))
                 self.alpha_c = self.project(gq * self.at_qp(self.V_c))
                 da = self.alpha_c - self.alpha_n
                 delta = np.abs(da) * np.heaviside(da / dt, 1)
@@ -327,7 +345,7 @@ class Oracle:
         """The 11 data columns of total.energy (solver.py:434-457)."""
         p, t = self.p, self.t
         s = self.split(self.u, False)
-        gq = cons.g_quadratic(self.at_qp(self.phi))
+        gq = self.g(self.at_qp(self.phi))
         PSI_a = np.einsum("eq,eq->", t.W, s["psi_a"])
         PSI_b = np.einsum("eq,eq->", t.W, s["psi_b"])
         E = np.einsum("eq,eq,eq->", t.W, gq, s["psi_a"]) + PSI_b      # note: k omitted (energy.py:81-82)

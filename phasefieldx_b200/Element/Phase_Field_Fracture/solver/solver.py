@@ -78,8 +78,9 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     logger.info(f"  stagger error tolerance: {stagger_error_tol}")
     if bcs_list_u_names is None:
         bcs_list_u_names = [f"bc_u_{i}" for i in range(len(bc_list_u))]
-    if Data.degradation_function != "quadratic":
-        raise NotImplementedError("only the quadratic degradation function is on the GPU path (SURVEY §8f N2)")
+    if Data.degradation_function not in _lib.DEGRADATION:
+        raise NotImplementedError("degradation_function must be 'quadratic' or 'borden' on the GPU path (SURVEY §8f N2; the "
+                                  "reference's sargado derivative overflows at form-build time, Appendix A Q10)")
     if Data.fatigue and Data.fatigue_degradation_function != "asymptotic":
         raise NotImplementedError("fatigue_degradation_function must be 'asymptotic' (reference returns an "
                                   "un-raised ValueError for 'logarithmic', fatigue_degradation_functions.py:64-65)")
@@ -91,7 +92,8 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     rmesh, keep_u, keep_phi = None, [], []
     engine_kw = dict(k=float(Data.k), model=_lib.model_code(Data.degradation, split),
                      irreversibility=(Data.irreversibility == "miehe"), fatigue=bool(Data.fatigue),
-                     fatigue_val=float(Data.fatigue_val), device=device, **(solver_options or {}))
+                     fatigue_val=float(Data.fatigue_val), device=device, degradation_function=Data.degradation_function,
+                     **(solver_options or {}))
     if dist is None:
         eng = _lib.Engine(points, cells, ctype, Data.lambda_, Data.mu, Data.Gc, Data.l, **engine_kw)
     else:

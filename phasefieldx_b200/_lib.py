@@ -33,7 +33,7 @@ class PfxParams(C.Structure):
                 ("fatigue_val", C.c_double), ("snes_rtol", C.c_double), ("snes_atol", C.c_double),
                 ("snes_stol", C.c_double), ("snes_max_it", C.c_int32), ("cg_rtol", C.c_double),
                 ("cg_max_it", C.c_int32), ("proj_rtol", C.c_double), ("quad_points_1d", C.c_int32),
-                ("block_nodes", C.c_int32), ("cg_chunk", C.c_int32)]
+                ("block_nodes", C.c_int32), ("cg_chunk", C.c_int32), ("degradation_function", C.c_int32)]
 
 
 class PfxStepOpts(C.Structure):
@@ -152,6 +152,9 @@ MODEL = {("isotropic", None): 0, ("anisotropic", "spectral"): 1, ("anisotropic",
          ("hybrid", "spectral"): 3, ("hybrid", "deviatoric"): 4}
 
 
+DEGRADATION = {"quadratic": 0, "borden": 1}
+
+
 def model_code(degradation, split_energy):
     """Dispatch of reference split_energy_stress_tangent_functions.py:234-354."""
     if degradation == "isotropic":
@@ -222,7 +225,8 @@ class Engine:
     """One pfx_ctx: device-resident state of a staggered phase-field fracture problem."""
 
     def __init__(self, coords, cells, cell_type, lambda_, mu, Gc, l, k=0.0, model=0, irreversibility=False,
-                 fatigue=False, fatigue_val=0.05625, device=0, n_owned=0, cell_primary=None, **solver_opts):
+                 fatigue=False, fatigue_val=0.05625, device=0, n_owned=0, cell_primary=None, degradation_function="quadratic",
+                 **solver_opts):
         self.lib = load()
         self.coords = np.ascontiguousarray(coords, dtype=np.float64)
         if self.coords.ndim != 2 or self.coords.shape[1] != 3:
@@ -235,6 +239,11 @@ class Engine:
         self.lib.pfx_default_params(C.byref(p))
         p.lambda_, p.mu, p.Gc, p.l, p.k = lambda_, mu, Gc, l, k
         p.model, p.irreversibility, p.fatigue, p.fatigue_val = model, int(irreversibility), int(fatigue), fatigue_val
+        try:
+            p.degradation_function = DEGRADATION[degradation_function]
+        except KeyError:
+            raise NotImplementedError(f"degradation_function {degradation_function!r}: only 'quadratic' and 'borden' are on "
+                                      "the GPU path (SURVEY §8f N2)")
         for key, val in solver_opts.items():
             if not hasattr(p, key):
                 raise TypeError(f"unknown solver option {key!r}")

@@ -168,11 +168,15 @@ template <class Cell> PFX_HD double m3(int a, int b, int c) {
     if (Cell::D == 2) return same == 3 ? 1.0 / 10.0 : (same == 1 ? 1.0 / 30.0 : 1.0 / 60.0);
     return same == 3 ? 1.0 / 20.0 : (same == 1 ? 1.0 / 60.0 : 1.0 / 120.0);
 }
-// mean over the simplex of (1-φ)² for P1 φ
-template <class Cell> PFX_HD double gbar_simplex(const double* phi) {
-    double s1 = 0.0, s2 = 0.0;
-    for (int a = 0; a < Cell::NV; ++a) { double t = 1.0 - phi[a]; s1 += t; s2 += t * t; }
-    return (s2 + s1 * s1) * ((Cell::D == 2) ? 1.0 / 12.0 : 1.0 / 20.0);
+// mean over the simplex of g(φ) for P1 φ: with t = 1-φ and power sums p_k = Σ t_a^k,
+// mean t² = (p1² + p2)·2 d!/(d+2)!/2,  mean t³ = (p1³ + 3 p1 p2 + 2 p3)·d!/(d+3)!  (complete homogeneous sums)
+template <class Cell> PFX_HD double gbar_simplex(const double* phi, int dfun = 0) {
+    double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    for (int a = 0; a < Cell::NV; ++a) { double t = 1.0 - phi[a]; s1 += t; s2 += t * t; s3 += t * t * t; }
+    const double m2 = (s2 + s1 * s1) * ((Cell::D == 2) ? 1.0 / 12.0 : 1.0 / 20.0);
+    if (dfun == 0) return m2;
+    const double m3 = (s1 * s1 * s1 + 3.0 * s1 * s2 + 2.0 * s3) * ((Cell::D == 2) ? 1.0 / 60.0 : 1.0 / 120.0);
+    return 3.0 * m2 - 2.0 * m3;
 }
 
 // ============================================================================= u-space
@@ -189,7 +193,7 @@ PFX_HD void elem_apply_u(const Material& m_, int n1d, const double* X, const dou
     Geo<Cell> geo; geo.init(X, n1d);
     double e[NS] = {}, de[NS], dsa[NS], dsb[NS], S[NS];
     if constexpr (Cell::simplex) {
-        double gb = gbar_simplex<Cell>(phi) + m.k;
+        double gb = gbar_simplex<Cell>(phi, m_.dfun) + m.k;
         if (m.smodel != M_ISO) sym_grad<Cell>(geo.G, U, e);
         sym_grad<Cell>(geo.G, V, de);
         dstress_split<D>(mm, m.smodel, e, de, dsa, dsb);
@@ -199,7 +203,7 @@ PFX_HD void elem_apply_u(const Material& m_, int n1d, const double* X, const dou
         double N[NV], G[NV][D];
         for (int q = 0; q < geo.nq; ++q) {
             double w = geo.eval(q, N, G);
-            double ph = interp<NV>(N, phi), gq = (1.0 - ph) * (1.0 - ph) + m.k;
+            double ph = interp<NV>(N, phi), gq = g_fun(m_.dfun, ph) + m.k;
             if (m.smodel != M_ISO) sym_grad<Cell>(G, U, e);
             sym_grad<Cell>(G, V, de);
             dstress_split<D>(mm, m.smodel, e, de, dsa, dsb);
@@ -218,7 +222,7 @@ template <class Cell>
 PFX_HD void elem_tangent_u(const Material& m, const double* X, const double* phi, const double* U, double* T) {
     constexpr int D = Cell::D, NS = SymN<D>::N;
     Geo<Cell> geo; geo.init(X, 1);
-    const double gb = gbar_simplex<Cell>(phi) + m.k;
+    const double gb = gbar_simplex<Cell>(phi, m.dfun) + m.k;
     double e[NS], de[NS], dsa[NS], dsb[NS];
     sym_grad<Cell>(geo.G, U, e);
     int t = 0;
@@ -261,7 +265,7 @@ PFX_HD void elem_residual_u(const Material& m, int n1d, const double* X, const d
     Geo<Cell> geo; geo.init(X, n1d);
     double e[NS], sa[NS], sb[NS], S[NS];
     if constexpr (Cell::simplex) {
-        double gb = gbar_simplex<Cell>(phi) + m.k;
+        double gb = gbar_simplex<Cell>(phi, m.dfun) + m.k;
         sym_grad<Cell>(geo.G, U, e);
         stress_split<D, double>(m, m.smodel, e, sa, sb);
         for (int i = 0; i < NS; ++i) S[i] = gb * sa[i] + sb[i];
@@ -270,7 +274,7 @@ PFX_HD void elem_residual_u(const Material& m, int n1d, const double* X, const d
         double N[NV], G[NV][D];
         for (int q = 0; q < geo.nq; ++q) {
             double w = geo.eval(q, N, G);
-            double ph = interp<NV>(N, phi), gq = (1.0 - ph) * (1.0 - ph) + m.k;
+            double ph = interp<NV>(N, phi), gq = g_fun(m.dfun, ph) + m.k;
             sym_grad<Cell>(G, U, e);
             stress_split<D, double>(m, m.smodel, e, sa, sb);
             for (int i = 0; i < NS; ++i) S[i] = gq * sa[i] + sb[i];
@@ -292,10 +296,10 @@ PFX_HD void elem_diag_u(const Material& m, int n1d, const double* X, const doubl
     for (int q = 0; q < nq; ++q) {
         double w, gq;
         if constexpr (Cell::simplex) {
-            geo.eval(0, N, G); w = geo.vol; gq = gbar_simplex<Cell>(phi) + m.k;
+            geo.eval(0, N, G); w = geo.vol; gq = gbar_simplex<Cell>(phi, m.dfun) + m.k;
         } else {
             w = geo.eval(q, N, G);
-            double ph = interp<NV>(N, phi); gq = (1.0 - ph) * (1.0 - ph) + m.k;
+            double ph = interp<NV>(N, phi); gq = g_fun(m.dfun, ph) + m.k;
         }
         if (m.smodel != M_ISO) sym_grad<Cell>(G, U, e);
         for (int a = 0; a < NV; ++a)
@@ -330,10 +334,10 @@ PFX_HD void elem_diagblk_u(const Material& m, int n1d, const double* X, const do
     for (int q = 0; q < nq; ++q) {
         double w, gq;
         if constexpr (Cell::simplex) {
-            geo.eval(0, N, G); w = geo.vol; gq = gbar_simplex<Cell>(phi) + m.k;
+            geo.eval(0, N, G); w = geo.vol; gq = gbar_simplex<Cell>(phi, m.dfun) + m.k;
         } else {
             w = geo.eval(q, N, G);
-            double ph = interp<NV>(N, phi); gq = (1.0 - ph) * (1.0 - ph) + m.k;
+            double ph = interp<NV>(N, phi); gq = g_fun(m.dfun, ph) + m.k;
         }
         if (m.smodel != M_ISO) sym_grad<Cell>(G, U, e);
         for (int a = 0; a < NV; ++a) {
@@ -472,6 +476,46 @@ PFX_HD void elem_diag_mass(int n1d, const double* X, double* out) {
     }
 }
 
+// Phase-field forms for a general degradation function g (solver.py:214-224), by quadrature (degree-5 rule on
+// simplices: exact for the cubic borden function with P1 fields; n1d x n1d Gauss on Q1):
+//   mode 0: out[a] = F_phi_a   = ∫ (dg(φ) H + F Gc/l φ) N_a + F Gc l ∇φ·∇N_a
+//   mode 1: out[a] = (J_phi p)_a = ∫ (ddg(φ) H + F Gc/l) p N_a + F Gc l ∇p·∇N_a
+//   mode 2: out[a] = diag(J_phi)_a
+// F = fatigue degradation field (P1, interpolated) or 1.
+template <class Cell>
+PFX_HD void elem_phi_general(int mode, const Material& m, int n1d, const double* X, const double* phi, const double* H,
+                             const double* Fat, const double* p, double* out) {
+    constexpr int NV = Cell::NV, D = Cell::D;
+    for (int a = 0; a < NV; ++a) out[a] = 0.0;
+    Geo<Cell> geo; geo.init(X, n1d);
+    double N[NV], G[NV][D];
+    const double* v = mode == 0 ? phi : p;
+    for (int q = 0; q < geo.nq; ++q) {
+        double w = geo.eval(q, N, G);
+        const double ph = interp<NV>(N, phi), hq = interp<NV>(N, H), fq = m.fatigue ? interp<NV>(N, Fat) : 1.0;
+        const double cg = fq * m.Gc * m.l;
+        if (mode == 2) {
+            const double cmq = ddg_fun(m.dfun, ph) * hq + fq * m.Gc / m.l;
+            for (int a = 0; a < NV; ++a) {
+                double gg = 0.0;
+                for (int i = 0; i < D; ++i) gg += G[a][i] * G[a][i];
+                out[a] += w * (cmq * N[a] * N[a] + cg * gg);
+            }
+            continue;
+        }
+        const double vq = interp<NV>(N, v);
+        const double src = mode == 0 ? dg_fun(m.dfun, ph) * hq + fq * m.Gc / m.l * ph
+                                     : (ddg_fun(m.dfun, ph) * hq + fq * m.Gc / m.l) * vq;
+        double gv[D];
+        for (int i = 0; i < D; ++i) { gv[i] = 0.0; for (int a = 0; a < NV; ++a) gv[i] += G[a][i] * v[a]; }
+        for (int a = 0; a < NV; ++a) {
+            double gg = 0.0;
+            for (int i = 0; i < D; ++i) gg += G[a][i] * gv[i];
+            out[a] += w * (src * N[a] + cg * gg);
+        }
+    }
+}
+
 // out[a] = ∫ ψ_a(u) N_a     (RHS of project(psi_a(u_new), V_c), solver.py:355); which = 1: ψ_b instead
 // (solver_anisotropic.py:236-237 projects both parts for output)
 template <class Cell>
@@ -497,7 +541,7 @@ PFX_HD void elem_rhs_psi(const Material& m, int n1d, const double* X, const doub
 
 // out[a] = ∫ g(φ_old) V_c N_a     (RHS of project(g(Φ_old)*V_c, alpha_c), solver.py:363)
 template <class Cell>
-PFX_HD void elem_rhs_fatigue(int n1d, const double* X, const double* phi, const double* Vc, double* out) {
+PFX_HD void elem_rhs_fatigue(int n1d, const double* X, const double* phi, const double* Vc, double* out, int dfun = 0) {
     constexpr int NV = Cell::NV, D = Cell::D;
     for (int a = 0; a < NV; ++a) out[a] = 0.0;
     Geo<Cell> geo; geo.init(X, n1d);
@@ -505,7 +549,7 @@ PFX_HD void elem_rhs_fatigue(int n1d, const double* X, const double* phi, const 
     for (int q = 0; q < geo.nq; ++q) {
         double w = geo.eval(q, N, G);
         double ph = interp<NV>(N, phi), vq = interp<NV>(N, Vc);
-        double gq = (1.0 - ph) * (1.0 - ph);
+        double gq = g_fun(dfun, ph);
         for (int a = 0; a < NV; ++a) out[a] += w * gq * vq * N[a];
     }
 }
@@ -545,7 +589,7 @@ PFX_HD void elem_energies(const Material& m, int n1d, const double* X, const dou
         if constexpr (!Cell::simplex) { sym_grad<Cell>(G, U, e); energy_split<D>(m, m.emodel, e, pa, pb); }
         double ph = interp<NV>(N, phi), g2 = 0.0;
         for (int i = 0; i < D; ++i) { double gi = 0.0; for (int a = 0; a < NV; ++a) gi += G[a][i] * phi[a]; g2 += gi * gi; }
-        double gq = (1.0 - ph) * (1.0 - ph);
+        double gq = g_fun(m.dfun, ph);
         s[0] += w * gq * pa; s[1] += w * pa; s[2] += w * pb;
         s[3] += w * ph * ph; s[4] += w * g2;
         if (m.fatigue) {

@@ -364,13 +364,25 @@ int coop_u(pfx_ctx* c, const KArgs& a, const CoopArgs& ca, bool configure) {
 
 template <class Cell>
 int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
+    if (a.m.dfun != 0 || c->configuring) {
+        // general degradation function: quadrature-based phase-field forms; the u-forms go through the generic
+        // kernels (the hand-tuned triangle kernels have (1-phi)^2 built in)
+        if (op == OP_APPLY_PHI) { int st = launch_scatter_op<OpPhiG<Cell, 1>>(c, a); if (st || !c->configuring) return st; }
+        if (op == OP_RESIDUAL_PHI) { int st = launch_scatter_op<OpPhiG<Cell, 0>>(c, a); if (st || !c->configuring) return st; }
+        if (op == OP_DIAG_PHI) { int st = launch_scatter_op<OpPhiG<Cell, 2>>(c, a); if (st || !c->configuring) return st; }
+        if (op == OP_APPLY_U && !c->configuring) {
+            if (a.m.smodel == M_ISO) return launch_scatter_op<OpApplyU<Cell, M_ISO>>(c, a);
+            if (a.m.smodel == M_SPECTRAL) return launch_scatter_op<OpApplyU<Cell, M_SPECTRAL>>(c, a);
+            return launch_scatter_op<OpApplyU<Cell, M_VOLDEV>>(c, a);
+        }
+    }
     if (op == OP_APPLY_MASS && std::is_same<Cell, Tri>::value && c->ones && !c->configuring && c->apply_variant >= 3 &&
         c->bm.max_elems <= 2 * kThreads && a.mask == nullptr) {
         KArgs m = a;                      // M = the phi operator with coefficients (1, 0)
         m.cm = c->ones; m.cg = c->zeros;
         return launch_apply_phi_tri_v3(c, m);
     }
-    if (op == OP_APPLY_PHI && std::is_same<Cell, Tri>::value && c->cm) {
+    if (op == OP_APPLY_PHI && std::is_same<Cell, Tri>::value && c->cm && (a.m.dfun == 0 || c->configuring)) {
         if (c->configuring) { int st = launch_apply_phi_tri_v3(c, a); if (st) return st; }
         else if (c->apply_variant >= 3 && c->bm.max_elems <= 2 * kThreads && a.input_masked && c->phi_coeff_fresh)
             return launch_apply_phi_tri_v3(c, a);
@@ -607,7 +619,7 @@ __global__ void pcg_setup_kernel(double* S, double rtol2, int bref_slot) {
 
 // does the apply of this operator run on a kernel that waits for the halo in its own prologue?
 bool apply_waits_for_halo(const pfx_ctx* c, int kind) {
-    if (c->cell_type != PFX_CELL_TRIANGLE || c->apply_variant < 3 || c->bm.max_elems > 2 * kThreads) return false;
+    if (c->cell_type != PFX_CELL_TRIANGLE || c->apply_variant < 3 || c->bm.max_elems > 2 * kThreads || c->mat.dfun != 0) return false;
     return kind == LIN_U || (kind == LIN_PHI && c->cm && c->phi_coeff_fresh);
 }
 
@@ -957,7 +969,7 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
     const double* dinv = kind == LIN_MASS ? c->dinv_mass : c->w_dinv;
     *converged = false;
     *iters = 0;
-    if ((kind == LIN_U || (kind == LIN_PHI && c->cm && c->phi_coeff_fresh)) && c->n_ranks == 1 &&
+    if (c->mat.dfun == 0 && (kind == LIN_U || (kind == LIN_PHI && c->cm && c->phi_coeff_fresh)) && c->n_ranks == 1 &&
         c->coop_capacity >= c->bm.nb && c->coop_bar) {
         // small mesh: the whole solve in one cooperative launch (re-launched only if max_iters runs out)
         KArgs a = base_args(c);
@@ -1063,7 +1075,7 @@ int newton(pfx_ctx* c, bool is_u, NewtonOut* out) {
     double ttol = 0, snorm = 0, xnorm = 0, vals[4];
     int st;
     c->phi_coeff_fresh = false;
-    if (!is_u && c->cm) {               // H and the fatigue field are fixed during the phi solve
+    if (!is_u && c->cm && c->mat.dfun == 0) {               // H and the fatigue field are fixed during the phi solve
         int64_t nall = c->n_nodes;
         phi_coeff_kernel<<<vgrid(c, nall), kThreads, 0, c->stream>>>(nall, c->mat, c->H, c->Fat, c->cm, c->cg);
         c->launches++;
@@ -1282,6 +1294,10 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     Material& m = c->mat;
     m.lam = prm->lambda_; m.mu = prm->mu; m.Gc = prm->Gc; m.l = prm->l; m.k = prm->k;
     m.fatigue = prm->fatigue; m.alpha_T = prm->fatigue_val;
+    if (prm->degradation_function != PFX_DEGRADATION_QUADRATIC && prm->degradation_function != PFX_DEGRADATION_BORDEN) {
+        c->err = "unknown degradation function"; return PFX_ERR_BAD_ARG;
+    }
+    m.dfun = prm->degradation_function;
     switch (prm->model) {
         case PFX_MODEL_ISOTROPIC: m.smodel = M_ISO; m.emodel = M_ISO; break;
         case PFX_MODEL_SPECTRAL: m.smodel = M_SPECTRAL; m.emodel = M_SPECTRAL; break;

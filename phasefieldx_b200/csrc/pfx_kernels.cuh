@@ -406,6 +406,43 @@ struct OpDiagPhi {
     }
 };
 
+// Phase-field forms for a general degradation function (elem_phi_general; MODE 0 residual, 1 apply, 2 diagonal).
+// Staged: X phi H F v — used instead of the three Ops above when the degradation function is not quadratic.
+template <class Cell, int MODE>
+struct OpPhiG {
+    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = 1, NRED = (MODE == 1) ? 1 : 0;
+    static constexpr int NF = odd<D + 4>::value;
+    __device__ static void load(const KArgs& a, int g, double* s) {
+        for (int i = 0; i < D; ++i) s[i] = a.X[(size_t)g * D + i];
+        s[D] = a.phi[g];
+        s[D + 1] = a.H[g];
+        s[D + 2] = a.m.fatigue ? a.Fat[g] : 1.0;
+        double vv = 0.0;
+        if (MODE == 1) { vv = a.v[g]; if (a.mask && a.mask[g]) vv = 0.0; }
+        s[D + 3] = vv;
+    }
+    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
+        double X[NV * D], ph[NV], H[NV], F[NV], p[NV];
+        for (int k = 0; k < NV; ++k) {
+            for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i];
+            ph[k] = nd[k][D]; H[k] = nd[k][D + 1]; F[k] = nd[k][D + 2]; p[k] = nd[k][D + 3];
+        }
+        elem_phi_general<Cell>(MODE, a.m, a.n1d, X, ph, H, F, p, out);
+    }
+    __device__ static void store(const KArgs& a, int g, const double* acc, double* red) {
+        if (MODE == 0) {
+            a.y[g] = acc[0];
+        } else if (MODE == 1) {
+            double vin = a.v[g];
+            double yv = (a.mask && a.mask[g]) ? vin : acc[0];
+            a.y[g] = yv;
+            red[0] += vin * yv;
+        } else {
+            a.y[g] = (a.mask && a.mask[g]) ? 1.0 : 1.0 / acc[0];
+        }
+    }
+};
+
 template <class Cell>
 struct OpApplyMass {       // staged: X p
     static constexpr int D = Cell::D, NV = Cell::NV, NOUT = 1, NRED = 1;
@@ -464,7 +501,7 @@ struct OpRhsFatigue {      // staged: X f1(=phi_old) f2(=V_c)
     __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t) {
         double X[NV * D], p[NV], v[NV];
         for (int k = 0; k < NV; ++k) { for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i]; p[k] = nd[k][D]; v[k] = nd[k][D + 1]; }
-        elem_rhs_fatigue<Cell>(a.n1d, X, p, v, out);
+        elem_rhs_fatigue<Cell>(a.n1d, X, p, v, out, a.m.dfun);
     }
     __device__ static void store(const KArgs& a, int g, const double* acc, double*) { a.y[g] = acc[0]; }
 };

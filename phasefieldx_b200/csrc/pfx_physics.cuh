@@ -32,7 +32,22 @@ struct Material {
     int emodel;   // split used by psi_a/psi_b
     int fatigue;
     double alpha_T;
+    int dfun;     // degradation function: 0 quadratic (1-phi)^2, 1 borden 3t^2 - 2t^3 with t = 1-phi
 };
+
+// degradation function g, dg/dphi, d2g/dphi2 (reference g_degradation_functions.py:12-64 as coded: borden with
+// s = 0)
+PFX_HD double g_fun(int dfun, double phi) {
+    const double t = 1.0 - phi;
+    return dfun == 1 ? t * t * (3.0 - 2.0 * t) : t * t;
+}
+PFX_HD double dg_fun(int dfun, double phi) {
+    const double t = 1.0 - phi;
+    return dfun == 1 ? 6.0 * t * (t - 1.0) : -2.0 * t;
+}
+PFX_HD double ddg_fun(int dfun, double phi) {
+    return dfun == 1 ? 6.0 - 12.0 * (1.0 - phi) : 2.0;
+}
 
 // ----------------------------------------------------------------------------- dual numbers
 struct Dual {

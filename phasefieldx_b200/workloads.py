@@ -106,7 +106,8 @@ def make_engine(w, device=0, **opts):
     model = _lib.model_code(p["degradation"], None if p["split_energy"] == "no" else p["split_energy"])
     e = _lib.Engine(w.msh.geometry.x, w.msh.cells, w.cell_type, lam, mu, p["Gc"], p["l"], k=p["k"], model=model,
                     irreversibility=(p["irreversibility"] == "miehe"), fatigue=p["fatigue"],
-                    fatigue_val=p.get("fatigue_val", 0.05625), device=device, **opts)
+                    fatigue_val=p.get("fatigue_val", 0.05625), device=device,
+                    degradation_function=p.get("degradation_function", "quadratic"), **opts)
     for i, (_, dofs) in enumerate(w.bc_sets):
         e.set_bc_u(i, dofs)
     for i, v in enumerate(w.bc_values(0.0)):

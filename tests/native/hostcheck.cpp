@@ -41,7 +41,7 @@ static void assemble(int op, const Material& m, int n1d, int64_t ne, const doubl
             case 6: gs(f0, a0); elem_apply_mass<Cell>(n1d, X, a0, o); break;
             case 7: elem_diag_mass<Cell>(n1d, X, o); break;
             case 8: gv(f0, a0); elem_rhs_psi<Cell>(m, n1d, X, a0, o); break;
-            case 9: gs(f0, a0); gs(f1, a1); elem_rhs_fatigue<Cell>(n1d, X, a0, a1, o); break;
+            case 9: gs(f0, a0); gs(f1, a1); elem_rhs_fatigue<Cell>(n1d, X, a0, a1, o, m.dfun); break;
             case 10: gs(f0, a0); gs(f1, a1); elem_l2<Cell, 1>(n1d, X, a0, a1, out); continue;
             case 11: gv(f0, a0); gv(f1, a1); elem_l2<Cell, D>(n1d, X, a0, a1, out); continue;
             case 12: gv(f0, a0); gs(f1, a1); gs(f2, a2); gs(f3, a3); elem_energies<Cell>(m, n1d, X, a0, a1, a2, a3, out); continue;
@@ -55,6 +55,10 @@ static void assemble(int op, const Material& m, int n1d, int64_t ne, const doubl
                     break;
                 } else return;
             case 14: gs(f0, a0); gv(f1, a1); elem_diagblk_u<Cell>(m, n1d, X, a0, a1, o); nout = D * (D + 1) / 2; break;  // nodal blocks
+            case 15: case 16: case 17:          // general-g phase-field forms: phi, H, Fat, p
+                gs(f0, a0); gs(f1, a1); gs(f2, a2); gs(f3, a3);
+                elem_phi_general<Cell>(op - 15, m, n1d, X, a0, a1, a2, a3, o);
+                break;
             default: return;
         }
         for (int a = 0; a < NV; ++a) for (int i = 0; i < nout; ++i) out[c[a] * nout + i] += o[a * nout + i];
@@ -78,7 +82,7 @@ void hc_split_dual(int d, const double* mat, int smodel, int emodel, int64_t n, 
 void hc_assemble(int op, int cell_type, const double* mat, int smodel, int emodel, int fatigue, int n1d, int64_t ne,
                  const double* coords, const int32_t* cells, const double* f0, const double* f1, const double* f2,
                  const double* f3, double* out) {
-    Material m{mat[0], mat[1], mat[2], mat[3], mat[4], smodel, emodel, fatigue, 0.0};
+    Material m{mat[0], mat[1], mat[2], mat[3], mat[4], smodel, emodel, fatigue & 1, 0.0, fatigue >> 8};   // bits 8..: degradation function
     if (cell_type == 0) assemble<Tri>(op, m, n1d, ne, coords, cells, f0, f1, f2, f3, out);
     else if (cell_type == 1) assemble<Quad>(op, m, n1d, ne, coords, cells, f0, f1, f2, f3, out);
     else assemble<Tet>(op, m, n1d, ne, coords, cells, f0, f1, f2, f3, out);

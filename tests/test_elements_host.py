@@ -234,3 +234,47 @@ def test_coarse_space_aggregates_colouring_and_regions(hostcheck):
         for k in range(d):
             means = np.bincount(node_agg, weights=r[:, k], minlength=n_agg) / sizes
             assert np.abs(means).max() < 1e-5
+
+
+@pytest.mark.parametrize("deg,sp", [("isotropic", "no"), ("anisotropic", "spectral"), ("hybrid", "spectral")])
+@pytest.mark.parametrize("dfun", ["quadratic", "borden"])
+def test_general_degradation_element_integrals_match_oracle(hostcheck, deg, sp, dfun):
+    """the borden degradation function (reference g_degradation_functions.py:38-64 as coded,
+    s = 0) in the element integrals — closed-form simplex mean of g(phi) in the u-forms, quadrature-based
+    F_phi / J_phi / diag(J_phi) with dg, ddg — against the oracle (exact on P1 simplices); the general phi
+    forms also reproduce the quadratic ones."""
+    rng = np.random.default_rng(21)
+    sm, em = CODES[(deg, sp)]
+    code = {"quadratic": 0, "borden": 1}[dfun]
+    for ctype, m in perturbed_meshes(rng):
+        if ctype == "quadrilateral":
+            continue                              # Q1: the reference's quadrature degree is not recoverable (SURVEY H5)
+        Pm = Params(E=210.0, nu=0.3, Gc=0.0027, l=0.1, degradation=deg, split_energy=sp, irreversibility="miehe", k=1e-3,
+                    degradation_function=dfun)
+        o = Oracle(m.geometry.x, m.cells, m.cell_type, Pm, degree=5)
+        nn, d = o.nn, o.d
+        o.u = rng.normal(size=nn * d) * 1e-3
+        o.phi, o.H = rng.uniform(0, 1, nn), rng.uniform(0, 2, nn)
+        o.Fatigue = np.ones(nn)
+        v, p = rng.normal(size=nn * d), rng.normal(size=nn)
+        mat = np.array([Pm.lambda_, Pm.mu, Pm.Gc, Pm.l, Pm.k])
+        cells = np.ascontiguousarray(m.cells, dtype=np.int32)
+        X = np.ascontiguousarray(m.geometry.x)
+
+        def asm(op, f0=None, f1=None, f2=None, f3=None, n=nn):
+            out = np.zeros(n)
+            hostcheck.hc_assemble(op, CT[ctype], dp(mat), sm, em, code << 8, 3, ctypes.c_int64(len(cells)), dp(X),
+                                  cells.ctypes.data_as(PI), dp(f0), dp(f1), dp(f2), dp(f3), dp(out))
+            return out
+        tol = 1e-11
+        J = o.J_u(o.u, o.phi)
+        assert rel(asm(0, o.phi, o.u, v, n=nn * d), J @ v) < tol
+        assert rel(asm(1, o.phi, o.u, n=nn * d), o.F_int_u(o.u, o.phi)) < tol
+        assert rel(asm(2, o.phi, o.u, n=nn * d), J.diagonal()) < tol
+        Jp = o.J_phi(o.phi, o.H, o.Fatigue)
+        assert rel(asm(15, o.phi, o.H, o.Fatigue, p), o.F_phi(o.phi, o.H, o.Fatigue)) < tol
+        assert rel(asm(16, o.phi, o.H, o.Fatigue, p), Jp @ p) < tol
+        assert rel(asm(17, o.phi, o.H, o.Fatigue, p), Jp.diagonal()) < tol
+        s = asm(12, o.u, o.phi, o.Fatigue, o.abar_c, n=8)
+        en = o.energies()
+        assert abs(s[0] + s[2] - en["E"]) < tol * abs(en["E"])
