@@ -92,3 +92,14 @@ def test_rank_mesh_local_views_cover_the_mesh():
             sent_global = rm.l2g[rm.plan["send_idx"][rm.plan["send_off"][j]: rm.plan["send_off"][j + 1]]]
             assert np.array_equal(Q["l2g"][gs[j]: gs[j] + n_send], sent_global)     # lands on the right ghosts
     assert np.all(owned_seen == 1)
+
+
+def test_unknown_degradation_function_is_rejected_before_any_device_work():
+    """Only the degradation functions built on the GPU path are accepted (SURVEY §8f N2 / Appendix A Q10);
+    the binding refuses the others without needing a device."""
+    from phasefieldx_b200 import _lib, mesh as M
+    msh = M.create_rectangle(None, [[0, 0], [1, 1]], [2, 2])
+    assert _lib.DEGRADATION == {"quadratic": 0, "borden": 1}
+    for name in ("alessi", "sargado", "cubic"):
+        with pytest.raises(NotImplementedError):
+            _lib.Engine(msh.geometry.x, msh.cells, "triangle", 1.0, 1.0, 1.0, 0.1, degradation_function=name)
