@@ -8,6 +8,8 @@ container only; the GPU box has no /root/reference).
   ref_1713.npz       same for example 1713 (structured 200x100 Q1 mesh, no mesh file needed)
   ref_1712.npz       same for example 1712 (shear, spectral)
   ref_1800.npz       first 40 rows of the fatigue example 1800 (total.energy incl. alpha_acum, conv, dof)
+  ref_degradation.npz   g and dg of the reference's own g_degradation_functions.py (quadratic, borden) on a grid of
+                     phi, executed unmodified (plain Python arithmetic; loaded by file path)
   ref_constitutive.npz  outputs of the reference's own constitutive layer
                      (Math/invariants.py, Math/tensor_decomposition.py, Materials/elastic_isotropic.py,
                      split_energy_stress_tangent_functions.py) executed UNMODIFIED under the torch-fp64
@@ -51,6 +53,17 @@ def main():
                         conv=table(os.path.join(fat, "phasefieldx.conv"), 40), dof=table(os.path.join(fat, "top.dof"), 40))
     from ufl_shim import reference_constitutive
     np.savez_compressed(os.path.join(HERE, "ref_constitutive.npz"), **reference_constitutive())
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_g", os.path.join(REF, "src", "phasefieldx", "Element", "Phase_Field_Fracture", "g_degradation_functions.py"))
+    ref_g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_g)
+    phi = np.linspace(-0.25, 1.25, 61)
+    out = {"phi": phi}
+    for name in ("quadratic", "borden"):
+        out["g_" + name] = np.array([ref_g.g(float(v), name) for v in phi])
+        out["dg_" + name] = np.array([ref_g.dg(float(v), name) for v in phi])
+    np.savez_compressed(os.path.join(HERE, "ref_degradation.npz"), **out)
     print("fixtures written to", HERE)
 
 
