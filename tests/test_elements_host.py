@@ -278,3 +278,7 @@ def test_general_degradation_element_integrals_match_oracle(hostcheck, deg, sp, 
         s = asm(12, o.u, o.phi, o.Fatigue, o.abar_c, n=8)
         en = o.energies()
         assert abs(s[0] + s[2] - en["E"]) < tol * abs(en["E"])
+        # fatigue projection RHS  ∫ g(phi_old) V_c N  (solver.py:363) with the general g
+        phi_old, Vc = rng.uniform(0, 1, nn), rng.uniform(0, 1, nn)
+        fe = np.einsum("eq,eq,qa->ea", o.t.W, o.g(o.at_qp(phi_old)) * o.at_qp(Vc), o.t.N)
+        assert rel(asm(9, phi_old, Vc), o._vec(fe, o.edof_s, nn)) < tol
