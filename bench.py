@@ -37,7 +37,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "staggered_load_steps_per_second"
 UNIT = "steps/s"
-SAMPLE_N = 160           # CPU sample: same workload on a SAMPLE_N x SAMPLE_N grid
+SAMPLE_N = int(os.environ.get("PFX_BENCH_SAMPLE_N", "160"))   # CPU sample: same workload on a SAMPLE_N x SAMPLE_N grid (env: tests shrink it)
 
 
 def measured_peak():
