@@ -73,8 +73,13 @@ typedef struct {
     double fatigue_val;       /* alpha_T of the asymptotic f (fatigue_degradation_functions.py:19-38) */
     /* solver controls (PETSc option dicts are hard-coded in solver.py:188-196, 227-235)   */
     double snes_rtol, snes_atol, snes_stol;  /* 1e-8, 1e-9, 1e-8                            */
-    int32_t snes_max_it;                     /* 50                                         */
-    double cg_rtol;           /* PCG ||r|| <= cg_rtol*||b|| standing in for MUMPS (default 1e-11) */
+    int32_t snes_max_it;                     /* 50000                                      */
+    /* PCG stop test standing in for the MUMPS solve: ||r|| <= cg_rtol * max(||b||, largest ||b|| this operator has
+     * seen in the current load step) — i.e. every solve of a step reaches the same ABSOLUTE accuracy as its first
+     * one (default 1e-11; PFX_CG_ADAPTIVE=0: purely relative test).  A solve whose right-hand side is already
+     * below that floor returns delta = 0 after 0 iterations and is counted in pfx_step_report.cg_floor_solves;
+     * Newton then ends through the SNES stol test (reason 4). */
+    double cg_rtol;
     int32_t cg_max_it;        /* default 200000                                            */
     double proj_rtol;         /* mass-PCG tolerance of project() (default 1e-13) */
     int32_t quad_points_1d;   /* Gauss points per direction for Q1 cells (default 3)       */
@@ -106,6 +111,12 @@ typedef struct {
     double* hist_err_phi;
     double* hist_fnorm_u;
     double* hist_fnorm_phi;
+    /* device time per phase of the step (CUDA events on the context stream), ms, summed over the stagger
+     * iterations: [0] u residual / tangent / diagonal set-up, [1] u coarse-space set-up, [2] u PCG,
+     * [3] projection + history (solver.py:355-360), [4] fatigue block, [5] phi set-up, [6] phi coarse-space
+     * set-up, [7] phi PCG, [8] L2 error norms, [9] everything else */
+    double phase_ms[10];
+    int64_t cg_floor_solves;  /* PCG solves that met the per-step absolute floor before the first iteration */
 } pfx_step_report;
 
 /* ---- library-level ---------------------------------------------------------------- */
@@ -173,7 +184,8 @@ int pfx_l2_error(pfx_ctx* ctx, int field_a, int field_b, double* err); /* errors
  * 1 apply_phi, 2 apply_mass, 3 residual_u, 4 one full u-PCG iteration); CUDA events on the
  * context stream, L2 flushed between launches when flush_l2 != 0.  ms_out[reps]. */
 int pfx_time_operator(pfx_ctx* ctx, int kind, int reps, int flush_l2, float* ms_out);
-/* algorithmic bytes of one launch of `kind` for this mesh (SURVEY §8d formulas) */
+/* algorithmic bytes of one launch of `kind` for this mesh (SURVEY §8d formulas); kind 5: the bytes the u-apply
+ * implementation actually streams (with cached element tangents: 168 B per tetrahedron + X, v, y per node) */
 int pfx_algorithmic_bytes(pfx_ctx* ctx, int kind, double* bytes);
 /* kernels launched by this context since creation (bench `gpu_launches`) */
 int pfx_launch_count(pfx_ctx* ctx, int64_t* n);

@@ -21,7 +21,7 @@ def solve(Data, msh, final_time, V_u, bc_list_u=[], update_boundary_conditions=N
           device=0, solver_options=None, vtu_format="ascii"):
     """Reference signature; `f_list_u`, `ds_bound` and `quadrature_degree` are accepted and unused (P1/Q1
     elements with a constant tangent are integrated exactly by the kernels' fixed rules)."""
-    options = {"ksp_type": "two-level pcg, matrix-free on GPU", "snes_linesearch_type": "none", "snes_max_it": 50,
+    options = {"ksp_type": "two-level pcg, matrix-free on GPU", "snes_linesearch_type": "none", "snes_max_it": 50000,
                "snes_rtol": 1e-8, "snes_atol": 1e-9}
     run = Run(Data, msh, path, options, vtu_format)
     logger, folder = run.logger, run.folder

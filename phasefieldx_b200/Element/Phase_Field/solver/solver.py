@@ -21,7 +21,7 @@ def solve(Data, msh, final_time, V_Φ, bc_list_phi=[], update_boundary_condition
         raise NotImplementedError("only the AT2 geometric crack function is on the GPU path (SURVEY §8f N2)")
     if V_gradient_Φ is not None:
         raise NotImplementedError("gradient output (V_gradient_Φ) is not available")
-    options = {"ksp_type": "two-level pcg, matrix-free on GPU", "snes_linesearch_type": "none", "snes_max_it": 50,
+    options = {"ksp_type": "two-level pcg, matrix-free on GPU", "snes_linesearch_type": "none", "snes_max_it": 50000,
                "snes_rtol": 1e-8, "snes_atol": 1e-9}
     run = Run(Data, msh, path, options, vtu_format)
     logger, folder = run.logger, run.folder

@@ -121,7 +121,7 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
         eng.set_traction(i, nodes, w)
     if rmesh is not None:
         attach(eng, rmesh, dist)
-    for key, val in (("ksp_type", "pcg (Jacobi), matrix-free on GPU"), ("snes_linesearch_type", "none"),
+    for key, val in (("ksp_type", "two-level pcg (block-Jacobi + aggregate coarse space), matrix-free on GPU"), ("snes_linesearch_type", "none"),
                      ("snes_max_it", eng.params.snes_max_it), ("snes_rtol", eng.params.snes_rtol),
                      ("snes_atol", eng.params.snes_atol), ("cg_rtol", eng.params.cg_rtol)):
         logger.info(f"   {key}: {val}")

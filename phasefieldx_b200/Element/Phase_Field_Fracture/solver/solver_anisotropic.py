@@ -27,7 +27,7 @@ def solve(Data, msh, final_time, V_u, bc_list_u=[], update_boundary_conditions=N
           update_loading=None, ds_bound=None, dt=1.0, path=None, quadrature_degree=2, bcs_list_u_names=None,
           device=0, solver_options=None, vtu_format="ascii"):
     """Reference signature; `f_list_u`, `ds_bound`, `quadrature_degree` are accepted and unused."""
-    options = {"ksp_type": "two-level pcg, matrix-free on GPU", "snes_linesearch_type": "none", "snes_max_it": 50,
+    options = {"ksp_type": "two-level pcg, matrix-free on GPU", "snes_linesearch_type": "none", "snes_max_it": 50000,
                "snes_rtol": 1e-8, "snes_atol": 1e-9}
     run = Run(Data, msh, path, options, vtu_format)
     logger, folder = run.logger, run.folder
@@ -35,10 +35,12 @@ def solve(Data, msh, final_time, V_u, bc_list_u=[], update_boundary_conditions=N
         bcs_list_u_names = [f"bc_u_{i}" for i in range(len(bc_list_u))]
     points, cells, ctype = fem.extract_mesh(msh)
     split = None if Data.split_energy == "no" else Data.split_energy
-    # "anisotropic" degradation = split stresses in F_u (the reference always uses sigma_a + sigma_b here)
+    # reference solver_anisotropic.py:130-133, 236-237: F_u = (sigma_a + sigma_b)(u, Data) : eps(du) and the output
+    # energies psi_a / psi_b(u, Data) dispatch on Data.degradation — "isotropic": psi_a = psi, psi_b = 0 whatever
+    # split_energy says; "hybrid": unsplit stress, split energies; "anisotropic": both split.  sigma_a + sigma_b is
+    # the full stress in every case.
     eng = _lib.Engine(points, cells, ctype, Data.lambda_, Data.mu, 1.0, 1.0, k=0.0,
-                      model=_lib.model_code("anisotropic" if split else "isotropic", split), device=device,
-                      **(solver_options or {}))
+                      model=_lib.model_code(Data.degradation, split), device=device, **(solver_options or {}))
     d = eng.dim
     try:
         for i, bc in enumerate(bc_list_u):

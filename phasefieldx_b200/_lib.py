@@ -48,7 +48,11 @@ class PfxStepReport(C.Structure):
                 ("cg_its_proj", C.c_int64), ("gpu_ms", C.c_double), ("history_len", C.c_int32), ("hist_u_its", C.POINTER(C.c_int32)),
                 ("hist_phi_its", C.POINTER(C.c_int32)), ("hist_err_u", C.POINTER(C.c_double)),
                 ("hist_err_phi", C.POINTER(C.c_double)), ("hist_fnorm_u", C.POINTER(C.c_double)),
-                ("hist_fnorm_phi", C.POINTER(C.c_double))]
+                ("hist_fnorm_phi", C.POINTER(C.c_double)), ("phase_ms", C.c_double * 10), ("cg_floor_solves", C.c_int64)]
+
+
+PHASES = ("u_setup", "u_coarse_setup", "u_pcg", "projection", "fatigue", "phi_setup", "phi_coarse_setup", "phi_pcg", "norms",
+          "other")
 
 
 # every symbol include/pfx_b200.h declares (tests check the library exports all of them)
@@ -325,6 +329,7 @@ class Engine:
         rep = dict(stagger=r.stagger_iters, u_its=r.u_newton_its, phi_its=r.phi_newton_its, u_reason=r.u_reason,
                    phi_reason=r.phi_reason, err_u=r.err_u, err_phi=r.err_phi, fnorm_u=r.fnorm_u, fnorm_phi=r.fnorm_phi,
                    cg_its_u=r.cg_its_u, cg_its_phi=r.cg_its_phi, cg_its_proj=r.cg_its_proj, gpu_ms=r.gpu_ms,
+                   phase_ms=dict(zip(PHASES, (float(v) for v in r.phase_ms))), cg_floor_solves=r.cg_floor_solves,
                    history={k: v[: r.history_len].copy() for k, v in hist.items()}, status=st)
         if st in (PFX_ERR_NOT_CONVERGED_U, PFX_ERR_NOT_CONVERGED_PHI):
             # reference solver.py:343-344 / :389-390
@@ -340,8 +345,10 @@ class Engine:
             raise RuntimeError(f"Solver did not converge, got {r.u_reason if is_u else r.phi_reason}.")
         self._ck(st)
         if is_u:
-            return dict(its=r.u_newton_its, reason=r.u_reason, fnorm=r.fnorm_u, cg_its=r.cg_its_u, gpu_ms=r.gpu_ms)
-        return dict(its=r.phi_newton_its, reason=r.phi_reason, fnorm=r.fnorm_phi, cg_its=r.cg_its_phi, gpu_ms=r.gpu_ms)
+            return dict(its=r.u_newton_its, reason=r.u_reason, fnorm=r.fnorm_u, cg_its=r.cg_its_u, gpu_ms=r.gpu_ms,
+                        cg_floor_solves=r.cg_floor_solves)
+        return dict(its=r.phi_newton_its, reason=r.phi_reason, fnorm=r.fnorm_phi, cg_its=r.cg_its_phi, gpu_ms=r.gpu_ms,
+                    cg_floor_solves=r.cg_floor_solves)
 
     def project_psi(self, which):
         """Nodal L2 projection of psi_a ("a") or psi_b ("b") of the current displacement field."""

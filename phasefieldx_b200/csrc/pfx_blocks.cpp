@@ -86,8 +86,9 @@ std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int6
     }
     auto block_of_new = [&](int32_t nw) -> int { return nw < n_owned ? part[bm.perm[nw]] : -1; };
 
-    // ---- 3. element lists per block (primary first) --------------------------------------
-    std::vector<int32_t> cnt_p(nb, 0), cnt_s(nb, 0);
+    // ---- 3. element lists per block: own cells first (the block holds the cell's lowest owned node; rank-primary
+    //         ones lead), then the other cells touching an owned node ---------------------------------------------
+    std::vector<int32_t> cnt_p(nb, 0), cnt_l(nb, 0), cnt_s(nb, 0);
     auto visit = [&](auto&& fn) {
         for (int64_t c = 0; c < n_cells; ++c) {
             int blk[4]; int nblk = 0; int32_t low = INT32_MAX; int lowb = -1;
@@ -101,19 +102,29 @@ std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int6
                 if (!seen) blk[nblk++] = b;
             }
             bool prim = cell_primary ? cell_primary[c] != 0 : true;
-            for (int k = 0; k < nblk; ++k) fn(c, blk[k], prim && blk[k] == lowb);
+            for (int k = 0; k < nblk; ++k) fn(c, blk[k], blk[k] == lowb ? (prim ? 0 : 1) : 2);
         }
     };
-    visit([&](int64_t, int b, bool p) { (p ? cnt_p : cnt_s)[b]++; });
+    visit([&](int64_t, int b, int grp) { (grp == 0 ? cnt_p : (grp == 1 ? cnt_l : cnt_s))[b]++; });
     bm.elem_off.assign(nb + 1, 0);
     bm.nprim.assign(nb, 0);
-    for (int b = 0; b < nb; ++b) { bm.elem_off[b + 1] = bm.elem_off[b] + cnt_p[b] + cnt_s[b]; bm.nprim[b] = cnt_p[b]; }
+    bm.nlow.assign(nb, 0);
+    bm.own_c0.assign(nb + 1, 0);
+    for (int b = 0; b < nb; ++b) {
+        bm.elem_off[b + 1] = bm.elem_off[b] + cnt_p[b] + cnt_l[b] + cnt_s[b];
+        bm.nprim[b] = cnt_p[b];
+        bm.nlow[b] = cnt_p[b] + cnt_l[b];
+        bm.own_c0[b + 1] = bm.own_c0[b] + bm.nlow[b];
+    }
+    bm.n_own_cells = bm.own_c0[nb];
     bm.total_elems = bm.elem_off[nb];
     bm.elem_gid.resize(bm.total_elems);
     {
-        std::vector<int32_t> cp(nb), cs(nb);
-        for (int b = 0; b < nb; ++b) { cp[b] = bm.elem_off[b]; cs[b] = bm.elem_off[b] + cnt_p[b]; }
-        visit([&](int64_t c, int b, bool p) { bm.elem_gid[(p ? cp : cs)[b]++] = (int32_t)c; });
+        std::vector<int32_t> cur[3] = {std::vector<int32_t>(nb), std::vector<int32_t>(nb), std::vector<int32_t>(nb)};
+        for (int b = 0; b < nb; ++b) {
+            cur[0][b] = bm.elem_off[b]; cur[1][b] = cur[0][b] + cnt_p[b]; cur[2][b] = cur[1][b] + cnt_l[b];
+        }
+        visit([&](int64_t c, int b, int grp) { bm.elem_gid[cur[grp][b]++] = (int32_t)c; });
     }
 
     // ---- 4. halo lists + local connectivity ------------------------------------------------
@@ -292,6 +303,94 @@ std::string build_partition(int nv, int64_t n_nodes, int64_t n_cells, const doub
         for (int q : nb) {
             for (int64_t g : want[r][q]) R.send_idx.push_back((int32_t)g2l[g]);
             R.send_off.push_back((int64_t)R.send_idx.size());
+        }
+    }
+    return "";
+}
+
+// =============================================================================== node graph (sliced ELL)
+std::string build_node_graph(const BlockMesh& bm, int64_t n_cells, const int32_t* cells, NodeGraph& g) {
+    const int nv = bm.nv;
+    if (nv != 4 || bm.dim != 3) return "node graph: tetrahedra only";
+    g = NodeGraph();
+    const int64_t n_rows = bm.n_owned;
+    g.n_rows = n_rows;
+    // nodes of every local cell in the compact own-cell order
+    g.cell_nodes.assign((size_t)bm.n_own_cells * 4, 0);
+    for (int b = 0; b < bm.nb; ++b)
+        for (int j = 0; j < bm.nlow[b]; ++j) {
+            const int64_t c = bm.elem_gid[bm.elem_off[b] + j];
+            for (int a = 0; a < 4; ++a) g.cell_nodes[4 * ((size_t)bm.own_c0[b] + j) + a] = bm.iperm[cells[c * 4 + a]];
+        }
+    (void)n_cells;
+    // node -> incident cells
+    g.nc_ptr.assign(n_rows + 1, 0);
+    for (int64_t c = 0; c < bm.n_own_cells; ++c)
+        for (int a = 0; a < 4; ++a) {
+            const int32_t n = g.cell_nodes[4 * c + a];
+            if (n < n_rows) g.nc_ptr[n + 1]++;
+        }
+    for (int64_t i = 0; i < n_rows; ++i) g.nc_ptr[i + 1] += g.nc_ptr[i];
+    if ((int64_t)bm.n_own_cells >= ((int64_t)1 << 29)) return "node graph: too many cells";
+    g.nc_code.resize(g.nc_ptr[n_rows]);
+    g.nc_kpos.resize(g.nc_ptr[n_rows]);
+    {
+        std::vector<int32_t> cur(g.nc_ptr.begin(), g.nc_ptr.end() - 1);
+        for (int64_t c = 0; c < bm.n_own_cells; ++c)
+            for (int a = 0; a < 4; ++a) {
+                const int32_t n = g.cell_nodes[4 * c + a];
+                if (n < n_rows) g.nc_code[cur[n]++] = (int32_t)((c << 2) | a);
+            }
+    }
+    // rows: sorted distinct nodes of the incident cells (the node itself included)
+    g.n_slices = (n_rows + kSlice - 1) / kSlice;
+    g.slice_k0.assign(g.n_slices + 1, 0);
+    std::vector<int32_t> row_ptr(n_rows + 1, 0), row_col, tmp;
+    row_col.reserve((size_t)n_rows * 16);
+    for (int64_t i = 0; i < n_rows; ++i) {
+        tmp.clear();
+        tmp.push_back((int32_t)i);
+        for (int32_t q = g.nc_ptr[i]; q < g.nc_ptr[i + 1]; ++q) {
+            const int64_t c = g.nc_code[q] >> 2;
+            for (int a = 0; a < 4; ++a) tmp.push_back(g.cell_nodes[4 * c + a]);
+        }
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        if (tmp.size() > 255) return "node graph: a node has more than 255 neighbours";
+        row_col.insert(row_col.end(), tmp.begin(), tmp.end());
+        row_ptr[i + 1] = (int32_t)row_col.size();
+        g.max_k = std::max(g.max_k, (int)tmp.size());
+    }
+    for (int64_t s = 0; s < g.n_slices; ++s) {
+        int mk = 0;
+        for (int64_t i = s * kSlice; i < std::min<int64_t>(n_rows, (s + 1) * kSlice); ++i) mk = std::max(mk, row_ptr[i + 1] - row_ptr[i]);
+        g.slice_k0[s + 1] = g.slice_k0[s] + mk;
+    }
+    g.total_k = g.slice_k0[g.n_slices];
+    if (g.total_k * kSlice >= ((int64_t)1 << 31)) return "node graph: too many entries";
+    g.col.resize((size_t)g.total_k * kSlice);
+    for (int64_t s = 0; s < g.n_slices; ++s)
+        for (int lane = 0; lane < kSlice; ++lane) {
+            const int64_t i = s * kSlice + lane;
+            const int len = g.slice_k0[s + 1] - g.slice_k0[s];
+            for (int k = 0; k < len; ++k) {
+                int32_t cj = (int32_t)std::min<int64_t>(i, n_rows - 1);          // padding: the row itself (value 0)
+                if (i < n_rows && k < row_ptr[i + 1] - row_ptr[i]) cj = row_col[row_ptr[i] + k];
+                g.col[((size_t)g.slice_k0[s] + k) * kSlice + lane] = cj;
+            }
+        }
+    // entry positions of the four nodes of every incident cell inside the row
+    for (int64_t i = 0; i < n_rows; ++i) {
+        const int32_t* rc = &row_col[row_ptr[i]];
+        const int len = row_ptr[i + 1] - row_ptr[i];
+        for (int32_t q = g.nc_ptr[i]; q < g.nc_ptr[i + 1]; ++q) {
+            const int64_t c = g.nc_code[q] >> 2;
+            uint32_t kp = 0;
+            for (int a = 0; a < 4; ++a) {
+                const int32_t* f = std::lower_bound(rc, rc + len, g.cell_nodes[4 * c + a]);
+                kp |= (uint32_t)(f - rc) << (8 * a);
+            }
+            g.nc_kpos[q] = kp;
         }
     }
     return "";

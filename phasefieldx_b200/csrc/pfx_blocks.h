@@ -37,6 +37,12 @@ struct BlockMesh {
                                      // slot 7 = 0xFFFE when the node has more than 8: rest in inc[])
     int max_own = 0, max_loc = 0, max_elems = 0;
     int64_t total_elems = 0;         // with overlap duplicates
+    // ---- own cells: every local cell is "own" for exactly ONE block, the one holding its lowest-numbered owned node.
+    // A block's list starts with its own cells (rank-primary ones first); own_c0[b] + j is a compact index over all
+    // local cells (per-cell data such as the cached element tangents is stored once, in this order).
+    std::vector<int32_t> nlow;       // [nb] own cells of the block (>= nprim)
+    std::vector<int32_t> own_c0;     // [nb+1] compact own-cell index of the block's first own cell
+    int64_t n_own_cells = 0;
 };
 
 // Build blocks of at most `max_own` owned nodes by recursive coordinate bisection of the owned
@@ -64,6 +70,25 @@ struct AggregateSet {
 // reg_aggs aggregates.  Returns "" or an error text.
 std::string build_aggregates(const BlockMesh& bm, int64_t n_cells, const double* coords, const int32_t* cells, int g,
                              int reg_aggs, int chunk_nodes, AggregateSet& out);
+
+// Node graph of a simplex mesh in sliced-ELL layout (3D assembled operators, pfx_sparse.cuh).  Rows = owned nodes
+// in block order; a slice = kSlice consecutive rows; entry k of every row of a slice is stored side by side
+// (position (slice_k0[s] + k) * kSlice + lane), so a warp that handles one slice reads its column indices and
+// matrix values fully coalesced.  Rows are padded to the longest row of their slice with the row's own index.
+constexpr int kSlice = 32;
+struct NodeGraph {
+    int64_t n_rows = 0, n_slices = 0, total_k = 0;     // total_k = sum of slice lengths
+    int max_k = 0;
+    std::vector<int32_t> slice_k0;     // [n_slices+1]
+    std::vector<int32_t> col;          // [total_k * kSlice] column node (new numbering; ghosts allowed)
+    std::vector<int32_t> cell_nodes;   // [n_own_cells * 4] nodes of every local cell (new numbering), compact own-cell index
+    std::vector<int32_t> nc_ptr;       // [n_rows+1] cells incident to every owned node ...
+    std::vector<int32_t> nc_code;      // ... as (compact own-cell index << 2 | vertex of the node in the cell), ascending
+    std::vector<uint32_t> nc_kpos;     // ... and the row entries k of the cell's four nodes, one byte per vertex
+};
+
+// cells / coords in caller ids as given to build_blocks.  Returns "" or an error text.
+std::string build_node_graph(const BlockMesh& bm, int64_t n_cells, const int32_t* cells, NodeGraph& out);
 
 struct RankPart {
     std::vector<int64_t> l2g;            // local -> global node (owned first, then ghosts by owner, by gid)

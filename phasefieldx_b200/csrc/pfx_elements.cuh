@@ -256,6 +256,50 @@ PFX_HD void elem_apply_u_tan(const double* X, const double* V, const double* T, 
     add_div<Cell>(geo.G, S, 1.0, out);
 }
 
+// strain (sym storage) of the unit displacement N_a e_i on a simplex with shape gradients G
+template <int D>
+PFX_HD void unit_strain(const double* Ga, int i, double* de) {
+    for (int s = 0; s < SymN<D>::N; ++s) de[s] = 0.0;
+    de[i] = Ga[i];
+    if (D == 2) { de[2] = 0.5 * Ga[1 - i]; }
+    else {
+        if (i == 0) { de[3] = 0.5 * Ga[1]; de[4] = 0.5 * Ga[2]; }
+        if (i == 1) { de[3] = 0.5 * Ga[0]; de[5] = 0.5 * Ga[2]; }
+        if (i == 2) { de[4] = 0.5 * Ga[0]; de[5] = 0.5 * Ga[1]; }
+    }
+}
+
+// y = A x for the cached tangent (packed upper triangle T of the symmetric NS x NS matrix A of the bilinear form)
+template <int NS>
+PFX_HD void tan_mv(const double* T, const double* x, double* y) {
+    for (int i = 0; i < NS; ++i) y[i] = 0.0;
+    int t = 0;
+    for (int i = 0; i < NS; ++i)
+        for (int j = i; j < NS; ++j) {
+            const double a = T[t++];
+            y[i] += a * x[j];
+            if (j != i) y[j] += a * x[i];
+        }
+}
+
+// row a of the element matrix from the cached tangent: K[b][i][j] = de_(a,i)' A de_(b,j)  (NV blocks of D x D)
+template <class Cell>
+PFX_HD void elem_matrix_row_tan(const double (*G)[Cell::D], const double* T, int a, double* K) {
+    constexpr int NV = Cell::NV, D = Cell::D, NS = SymN<D>::N;
+    double dea[D][NS], de[NS], Ad[NS];
+    for (int i = 0; i < D; ++i) unit_strain<D>(G[a], i, dea[i]);
+    for (int b = 0; b < NV; ++b)
+        for (int j = 0; j < D; ++j) {
+            unit_strain<D>(G[b], j, de);
+            tan_mv<NS>(T, de, Ad);
+            for (int i = 0; i < D; ++i) {
+                double q = 0.0;
+                for (int s = 0; s < NS; ++s) q += dea[i][s] * Ad[s];
+                K[(b * D + i) * D + j] = q;
+            }
+        }
+}
+
 // out[NV*D] = ∫ ((g(φ)+k) σ_a(u) + σ_b(u)) : ε(N_a e_i)     (F_u, solver.py:173-177)
 template <class Cell>
 PFX_HD void elem_residual_u(const Material& m, int n1d, const double* X, const double* phi,

@@ -22,6 +22,7 @@
 #include "pfx_comm.h"
 #include "pfx_kernels.cuh"
 #include "pfx_coarse.cuh"
+#include "pfx_sparse.cuh"
 
 using namespace pfx;
 
@@ -70,6 +71,15 @@ struct CoarseOp {
     bool ref_open = false;
     int open_steps = 0;
     cudaGraphExec_t graph = nullptr;
+};
+
+// assembled operators of tetrahedral meshes (pfx_sparse.cuh)
+struct Sparse {
+    bool enabled = false;
+    SparseView sv;
+    double *Ku = nullptr, *Kphi = nullptr, *Km = nullptr;
+    int64_t total_k = 0;
+    bool phi_fresh = false;          // Kphi belongs to the current H / fatigue field
 };
 
 struct Coarse {
@@ -143,23 +153,30 @@ struct pfx_ctx {
     std::vector<void*> allocs;
     std::string err;
     int64_t launches = 0;
+    int64_t floor_solves = 0;     // PCG solves of the current load step that met the per-step absolute floor before iterating
+    // per-phase device timers of pfx_load_step: events recorded at phase boundaries, read after the final sync
+    std::vector<cudaEvent_t> ph_events;
+    std::vector<int> ph_ids;
+    size_t ph_used = 0;
+    bool ph_on = false;
     double* flush_buf = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t flush_n = 0;
     bool configuring = false;
     bool verbose = false;         // PFX_VERBOSE=1: per-Newton-iteration trace on stderr
     bool cg_adaptive = true;      // PFX_CG_ADAPTIVE=0: every PCG solve to cg_rtol of its own right-hand side
-    double* tan = nullptr;        // cached element tangents (tets + nonlinear split)
+    double* tan = nullptr;        // cached element tangents [n_own_cells][21] (tets)
+    bool tan_fresh = false;       // the cached tangents (and the matrices assembled from them) belong to the current u, phi
     double *cm = nullptr, *cg = nullptr;   // phi-operator nodal coefficients (triangles, v3 path)
     double *ones = nullptr, *zeros = nullptr;   // coefficients that turn the phi operator into the mass matrix
     int phi_v3_ctas = 0;
-    bool use_tan = false;
+    Sparse sp;
     int coop_capacity = 0;        // co-resident CTAs of the whole-PCG cooperative kernel (0: unavailable)
     unsigned long long* coop_bar = nullptr;
     bool phi_coeff_fresh = false;
     bool generic_apply = false;   // PFX_GENERIC_APPLY=1: use the generic scatter kernel for J_u·v on triangles
-    int apply_variant = 3;        // PFX_APPLY_VARIANT: 3 persistent + prefetched indices (default), 4 three-stage ring (slower: 2 CTAs/SM), 2 persistent, 1 one CTA per block
-    int persist_ctas = 0, v3_ctas = 0, v3_tan_ctas = 0, v4_ctas = 0, num_sms = 148;
+    int apply_variant = 3;        // PFX_APPLY_VARIANT: 3 persistent TMA-staged kernel (default), 1 one CTA per block
+    int v3_ctas = 0, num_sms = 148;
     Coarse coarse;
 };
 
@@ -180,6 +197,23 @@ int dev_upload(pfx_ctx* c, T** p, const std::vector<T>& h) {
     if (!h.empty()) CK(cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return PFX_OK;
+}
+
+// phase ids of pfx_step_report.phase_ms
+enum { PH_U_SETUP = 0, PH_U_COARSE = 1, PH_U_PCG = 2, PH_PROJECTION = 3, PH_FATIGUE = 4, PH_PHI_SETUP = 5, PH_PHI_COARSE = 6,
+       PH_PHI_PCG = 7, PH_NORMS = 8, PH_OTHER = 9, PH_COUNT = 10 };
+
+// the phase `id` starts now on the context stream (no-op outside pfx_load_step)
+inline void mark(pfx_ctx* c, int id) {
+    if (!c->ph_on) return;
+    if (c->ph_used == c->ph_events.size()) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) { c->ph_on = false; return; }
+        c->ph_events.push_back(e);
+        c->ph_ids.push_back(0);
+    }
+    cudaEventRecord(c->ph_events[c->ph_used], c->stream);
+    c->ph_ids[c->ph_used++] = id;
 }
 
 inline int vgrid(const pfx_ctx* c, int64_t n) {
@@ -229,68 +263,22 @@ int launch_apply_u_tri(pfx_ctx* c, const KArgs& a) {
     return PFX_OK;
 }
 
-// persistent, double-buffered variant (requires the input to be zero on Dirichlet dofs when masked)
 template <int SM>
-int launch_apply_u_tri_persist(pfx_ctx* c, const KArgs& a) {
-    BlockView bv = c->bv;
-    bv.chunk = std::min((c->bm.max_elems + 31) / 32 * 32, 2 * kThreads);
-    size_t ML = (size_t)c->bm.max_loc, MI = ((size_t)c->bv.max_inc + 7) & ~(size_t)7;
-    size_t stage = ML * 16 * (SM != M_ISO ? 3 : 2) + ((ML + 1) & ~(size_t)1) * 8 + MI * 2;
-    size_t smem = 2 * stage + 3 * (size_t)bv.chunk * sizeof(double2);
-    if (c->configuring) {
-        CK(cudaFuncSetAttribute(apply_u_tri_persist_kernel<SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apply_u_tri_persist_kernel<SM>, kThreads, smem));
-        c->persist_ctas = std::max(1, nb) * c->num_sms;
-        return PFX_OK;
-    }
-    int grid = std::min(c->bm.nb, c->persist_ctas);
-    apply_u_tri_persist_kernel<SM><<<grid, kThreads, smem, c->stream>>>(bv, a);
-    c->launches++;
-    CK(cudaGetLastError());
-    return PFX_OK;
-}
-
-template <int SM, bool TAN = false>
 int launch_apply_u_tri_v3(pfx_ctx* c, const KArgs& a) {
     BlockView bv = c->bv;
     bv.chunk = 2 * kThreads;
     size_t ML = (size_t)c->bm.max_loc, MO = ((size_t)c->bm.max_own + 1) & ~(size_t)1;
-    size_t stage = ML * 16 * ((SM != M_ISO && !TAN) ? 3 : 2) + ((ML + 3) & ~(size_t)1) * 8 + MO * 16;
-    size_t smem = 2 * stage + (3 * (size_t)bv.chunk + 1) * sizeof(double2);
-    int& ctas = TAN ? c->v3_tan_ctas : c->v3_ctas;
-    if (c->configuring) {
-        CK(cudaFuncSetAttribute(apply_u_tri_v3_kernel<SM, TAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apply_u_tri_v3_kernel<SM, TAN>, kThreads, smem));
-        ctas = std::max(1, nb) * c->num_sms;
-        return PFX_OK;
-    }
-    int grid = std::min(c->bm.nb, ctas);
-    apply_u_tri_v3_kernel<SM, TAN><<<grid, kThreads, smem, c->stream>>>(bv, a);
-    c->launches++;
-    CK(cudaGetLastError());
-    return PFX_OK;
-}
-
-template <int SM>
-int launch_apply_u_tri_v4(pfx_ctx* c, const KArgs& a) {
-    BlockView bv = c->bv;
-    bv.chunk = 2 * kThreads;
-    size_t ML = (size_t)c->bm.max_loc, MO = ((size_t)c->bm.max_own + 1) & ~(size_t)1;
     size_t stage = ML * 16 * (SM != M_ISO ? 3 : 2) + ((ML + 3) & ~(size_t)1) * 8 + MO * 16;
-    size_t smem = 3 * stage + (3 * (size_t)bv.chunk + 1) * sizeof(double2);
+    size_t smem = 2 * stage + (3 * (size_t)bv.chunk + 1) * sizeof(double2);
     if (c->configuring) {
-        c->v4_ctas = 0;
-        if (smem > 110 * 1024) return PFX_OK;          // two CTAs per SM must fit: otherwise stay on v3
-        CK(cudaFuncSetAttribute(apply_u_tri_v4_kernel<SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(apply_u_tri_v3_kernel<SM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apply_u_tri_v4_kernel<SM>, kThreads, smem));
-        c->v4_ctas = std::max(1, nb) * c->num_sms;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, apply_u_tri_v3_kernel<SM>, kThreads, smem));
+        c->v3_ctas = std::max(1, nb) * c->num_sms;
         return PFX_OK;
     }
-    int grid = std::min(c->bm.nb, c->v4_ctas);
-    apply_u_tri_v4_kernel<SM><<<grid, kThreads, smem, c->stream>>>(bv, a);
+    int grid = std::min(c->bm.nb, c->v3_ctas);
+    apply_u_tri_v3_kernel<SM><<<grid, kThreads, smem, c->stream>>>(bv, a);
     c->launches++;
     CK(cudaGetLastError());
     return PFX_OK;
@@ -389,33 +377,16 @@ int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
     }
     switch (op) {
         case OP_APPLY_U:
-            if (std::is_same<Cell, Tri>::value && c->configuring) {      // opt every triangle variant in
-                int st = (a.m.smodel == M_ISO) ? launch_apply_u_tri_persist<M_ISO>(c, a)
-                         : (a.m.smodel == M_SPECTRAL ? launch_apply_u_tri_persist<M_SPECTRAL>(c, a)
-                                                     : launch_apply_u_tri_persist<M_VOLDEV>(c, a));
+            if (std::is_same<Cell, Tri>::value && c->configuring) {      // opt the persistent variant in
+                int st = (a.m.smodel == M_ISO) ? launch_apply_u_tri_v3<M_ISO>(c, a)
+                         : (a.m.smodel == M_SPECTRAL ? launch_apply_u_tri_v3<M_SPECTRAL>(c, a)
+                                                     : launch_apply_u_tri_v3<M_VOLDEV>(c, a));
                 if (st) return st;
-                st = (a.m.smodel == M_ISO) ? launch_apply_u_tri_v3<M_ISO>(c, a)
-                     : (a.m.smodel == M_SPECTRAL ? launch_apply_u_tri_v3<M_SPECTRAL>(c, a)
-                                                 : launch_apply_u_tri_v3<M_VOLDEV>(c, a));
-                if (st) return st;
-                st = (a.m.smodel == M_ISO) ? launch_apply_u_tri_v4<M_ISO>(c, a)
-                     : (a.m.smodel == M_SPECTRAL ? launch_apply_u_tri_v4<M_SPECTRAL>(c, a)
-                                                 : launch_apply_u_tri_v4<M_VOLDEV>(c, a));
-                if (st) return st;
-            } else if (std::is_same<Cell, Tri>::value && c->apply_variant == 4 && c->v4_ctas > 0 && c->bm.max_elems <= 2 * kThreads &&
-                       (a.mask == nullptr || a.input_masked)) {
-                if (a.m.smodel == M_ISO) return launch_apply_u_tri_v4<M_ISO>(c, a);
-                if (a.m.smodel == M_SPECTRAL) return launch_apply_u_tri_v4<M_SPECTRAL>(c, a);
-                return launch_apply_u_tri_v4<M_VOLDEV>(c, a);
             } else if (std::is_same<Cell, Tri>::value && c->apply_variant >= 3 && c->bm.max_elems <= 2 * kThreads &&
                        (a.mask == nullptr || a.input_masked)) {
                 if (a.m.smodel == M_ISO) return launch_apply_u_tri_v3<M_ISO>(c, a);
                 if (a.m.smodel == M_SPECTRAL) return launch_apply_u_tri_v3<M_SPECTRAL>(c, a);
                 return launch_apply_u_tri_v3<M_VOLDEV>(c, a);
-            } else if (std::is_same<Cell, Tri>::value && c->apply_variant >= 2 && (a.mask == nullptr || a.input_masked)) {
-                if (a.m.smodel == M_ISO) return launch_apply_u_tri_persist<M_ISO>(c, a);
-                if (a.m.smodel == M_SPECTRAL) return launch_apply_u_tri_persist<M_SPECTRAL>(c, a);
-                return launch_apply_u_tri_persist<M_VOLDEV>(c, a);
             }
             if (std::is_same<Cell, Tri>::value && !c->generic_apply) {
                 if (a.m.smodel == M_ISO) return launch_apply_u_tri<M_ISO>(c, a);
@@ -436,15 +407,6 @@ int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
         case OP_RHS_FATIGUE: return launch_scatter_op<OpRhsFatigue<Cell>>(c, a);
         case OP_TANGENT_U:
             if constexpr (Cell::simplex) return launch_scatter_op<OpTangentU<Cell>>(c, a);
-            break;
-        case OP_APPLY_U_TAN:
-            if constexpr (std::is_same<Cell, Tri>::value) {
-                // persistent TMA-staged kernel fed by the cached element tangents (the split model no longer matters)
-                if (c->configuring) { int st = launch_apply_u_tri_v3<M_SPECTRAL, true>(c, a); if (st) return st; }
-                else if (c->apply_variant >= 3 && c->bm.max_elems <= 2 * kThreads && (a.mask == nullptr || a.input_masked))
-                    return launch_apply_u_tri_v3<M_SPECTRAL, true>(c, a);
-            }
-            if constexpr (Cell::simplex) return launch_scatter_op<OpApplyUTan<Cell>>(c, a);
             break;
         case OP_DIAGBLK_U: return launch_scatter_op<OpDiagBlkU<Cell>>(c, a);
     }
@@ -490,7 +452,7 @@ KArgs base_args(pfx_ctx* c) {
     a.n1d = c->prm.quad_points_1d;
     a.X = c->X; a.u = c->u; a.phi = c->phi; a.H = c->H; a.Fat = c->Fat;
     a.partial = c->partial; a.result = c->red; a.counter = c->counter;
-    a.tan = c->tan; a.tan_stride = c->bm.total_elems;
+    a.tan = c->tan;
     a.cm = c->cm; a.cg = c->cg;
     return a;
 }
@@ -625,11 +587,62 @@ bool apply_waits_for_halo(const pfx_ctx* c, int kind) {
 
 int apply_lin(pfx_ctx* c, int kind, const double* v, double* y, const uint8_t* mask, double* result, const double* stop,
               int input_masked = 0, const PeerView* pv = nullptr, int wait_halo = 0) {
+    if (c->sp.enabled && (mask == nullptr || input_masked)) {
+        // tetrahedra: one SpMV with the assembled operator
+        const Sparse& sp = c->sp;
+        const int grid = (int)((sp.sv.n_slices * 32 + kThreads - 1) / kThreads);
+        const double* K = nullptr;
+        if (kind == LIN_U && c->tan_fresh) K = sp.Ku;
+        else if (kind == LIN_PHI && sp.phi_fresh) K = sp.Kphi;
+        else if (kind == LIN_MASS) K = sp.Km;
+        if (K) {
+            if (kind == LIN_U) spmv_u_tet_kernel<<<grid, kThreads, 0, c->stream>>>(sp.sv, K, v, y, mask, c->partial, result, c->counter, stop, pv);
+            else spmv_s_tet_kernel<<<grid, kThreads, 0, c->stream>>>(sp.sv, K, v, y, mask, c->partial, result, c->counter, stop, pv);
+            c->launches++;
+            CK(cudaGetLastError());
+            return PFX_OK;
+        }
+    }
     KArgs a = base_args(c);
     a.v = v; a.y = y; a.mask = mask; a.result = result; a.stop = stop; a.input_masked = input_masked;
     a.pv = pv; a.wait_halo = wait_halo;
-    int op = kind == LIN_U ? (c->use_tan ? OP_APPLY_U_TAN : OP_APPLY_U) : (kind == LIN_PHI ? OP_APPLY_PHI : OP_APPLY_MASS);
+    int op = kind == LIN_U ? OP_APPLY_U : (kind == LIN_PHI ? OP_APPLY_PHI : OP_APPLY_MASS);
     return launch_scatter(c, op, a);
+}
+
+// tetrahedra: element tangents of the current (u, phi) and the matrix assembled from them, together with the
+// Jacobi / block-Jacobi data of the PCG (the diagonal blocks fall out of the assembly)
+int refresh_tangent(pfx_ctx* c) {
+    if (!c->sp.enabled) return PFX_OK;
+    KArgs t = base_args(c);
+    int st = launch_scatter(c, OP_TANGENT_U, t);
+    if (st) return st;
+    const bool blk = c->coarse.enabled && c->coarse.block_jacobi;
+    const int grid = (int)((c->sp.sv.n_rows + 127) / 128);
+    assemble_u_tet_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->X, c->tan, c->mask_u, c->sp.Ku, c->w_dinv, blk ? c->coarse.dblk : nullptr);
+    c->launches++;
+    CK(cudaGetLastError());
+    c->tan_fresh = true;
+    return PFX_OK;
+}
+
+// phase-field coefficient fields of the current H / fatigue field; tetrahedra: J_phi assembled from them (and 1/diag)
+int refresh_phi_operator(pfx_ctx* c) {
+    c->phi_coeff_fresh = false;
+    c->sp.phi_fresh = false;
+    if (!c->cm || c->mat.dfun != 0) return PFX_OK;
+    const int64_t nall = c->n_nodes;
+    phi_coeff_kernel<<<vgrid(c, nall), kThreads, 0, c->stream>>>(nall, c->mat, c->H, c->Fat, c->cm, c->cg);
+    c->launches++;
+    c->phi_coeff_fresh = true;
+    if (c->sp.enabled) {
+        const int grid = (int)((c->sp.sv.n_rows + 127) / 128);
+        assemble_s_tet_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->X, c->cm, c->cg, c->mask_phi, c->sp.Kphi, c->w_dinv);
+        c->launches++;
+        c->sp.phi_fresh = true;
+    }
+    CK(cudaGetLastError());
+    return PFX_OK;
 }
 
 // --------------------------------------------------------------------------- coarse space
@@ -971,6 +984,7 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
     *iters = 0;
     if (c->mat.dfun == 0 && (kind == LIN_U || (kind == LIN_PHI && c->cm && c->phi_coeff_fresh)) && c->n_ranks == 1 &&
         c->coop_capacity >= c->bm.nb && c->coop_bar) {
+        mark(c, kind == LIN_U ? PH_U_PCG : PH_PHI_PCG);
         // small mesh: the whole solve in one cooperative launch (re-launched only if max_iters runs out)
         KArgs a = base_args(c);
         a.mask = mask;
@@ -993,15 +1007,20 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
             if (*iters >= c->prm.cg_max_it) break;
             ca.resume = 1;
         }
+        if (*converged && *iters == 0 && ca.bref_slot >= 0 && c->h_pinned[S_RR] > 0.0) c->floor_solves++;
         return PFX_OK;
     }
     int g = vgrid(c, n);
     int st;
     bool coarse_on = false;
     if (coarse_active(c, kind)) {
-        if (c->coarse.op[kind].stale && (st = coarse_setup(c, kind, mask))) return st;
+        if (c->coarse.op[kind].stale) {
+            mark(c, kind == LIN_U ? PH_U_COARSE : PH_PHI_COARSE);
+            if ((st = coarse_setup(c, kind, mask))) return st;
+        }
         coarse_on = c->coarse.op[kind].valid;
     }
+    if (kind != LIN_MASS) mark(c, kind == LIN_U ? PH_U_PCG : PH_PHI_PCG);
     const int bref_slot = (c->cg_adaptive && kind != LIN_MASS) ? S_BREF + kind : -1;
     pcg_init_kernel<<<g, kThreads, 0, c->stream>>>(n, c->w_F, mask, dinv, nullptr, nullptr, c->w_x, c->w_r, c->w_p,
                                                   c->partial, c->S + S_STAGE, c->counter);
@@ -1040,6 +1059,7 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
         if (c->h_pinned[S_DONE] != 0.0) { *converged = true; break; }
         if (*iters >= max_it) break;
     }
+    if (*converged && *iters == 0 && bref_slot >= 0 && c->h_pinned[S_RR] > 0.0) c->floor_solves++;
     if (coarse_on) {                 // lagged coarse matrix: refresh when it stops paying
         CoarseOp& op = c->coarse.op[kind];
         if (op.ref_open) op.ref_its = std::max(op.ref_its, *iters);
@@ -1050,7 +1070,7 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
 
 // inverse nodal diagonal blocks of the current J_u (smoother of the two-level PCG)
 int block_diag(pfx_ctx* c) {
-    if (!coarse_active(c, LIN_U) || !c->coarse.block_jacobi) return PFX_OK;
+    if (!coarse_active(c, LIN_U) || !c->coarse.block_jacobi || c->sp.enabled) return PFX_OK;
     KArgs d = base_args(c);
     d.y = c->coarse.dblk; d.mask = c->mask_u;
     return launch_scatter(c, OP_DIAGBLK_U, d);
@@ -1075,33 +1095,31 @@ int newton(pfx_ctx* c, bool is_u, NewtonOut* out) {
     double ttol = 0, snorm = 0, xnorm = 0, vals[4];
     int st;
     c->phi_coeff_fresh = false;
-    if (!is_u && c->cm && c->mat.dfun == 0) {               // H and the fatigue field are fixed during the phi solve
-        int64_t nall = c->n_nodes;
-        phi_coeff_kernel<<<vgrid(c, nall), kThreads, 0, c->stream>>>(nall, c->mat, c->H, c->Fat, c->cm, c->cg);
-        c->launches++;
-        c->phi_coeff_fresh = true;
-    }
+    c->sp.phi_fresh = false;
+    if (!is_u && (st = refresh_phi_operator(c))) return st;    // H and the fatigue field are fixed during the phi solve
+    const bool sparse_op = c->sp.enabled && (is_u || c->sp.phi_fresh);   // operator + Jacobi data come from the assembly
     for (int it = 0;; ++it) {
+        mark(c, is_u ? PH_U_SETUP : PH_PHI_SETUP);
         // residual with lifting (dolfinx assemble_residual idiom)
         KArgs a = base_args(c);
         a.y = c->w_t0;
         st = launch_scatter(c, is_u ? OP_RESIDUAL_U : OP_RESIDUAL_PHI, a);
         if (st) return st;
-        auto refresh_tangent = [&]() -> int {
-            if (!is_u || !c->use_tan) return PFX_OK;
-            KArgs t = base_args(c);
-            return launch_scatter(c, OP_TANGENT_U, t);
-        };
         const double* lift = nullptr;
         if (it == 0) {
-            if ((st = refresh_tangent())) return st;
-            // gap on every local dof (ghost entries feed the halo elements of the apply)
+            // gap on every local dof (ghost entries feed the halo elements of the apply); no gap (every stagger
+            // iteration after the first of a load step) => no lifting term and no linearisation needed yet
             int64_t nall = c->n_nodes * nc;
             bc_gap_kernel<<<vgrid(c, nall), kThreads, 0, c->stream>>>(nall, x, g, mask, c->w_p, c->partial, c->red, c->counter);
             c->launches++;
-            st = apply_lin(c, kind, c->w_p, c->w_t1, nullptr, c->red, nullptr);
-            if (st) return st;
-            lift = c->w_t1;
+            double gap2 = 0.0;
+            if ((st = fetch(c, c->red, 1, &gap2))) return st;
+            if (gap2 != 0.0) {
+                if (is_u && (st = refresh_tangent(c))) return st;
+                st = apply_lin(c, kind, c->w_p, c->w_t1, nullptr, c->red, nullptr);
+                if (st) return st;
+                lift = c->w_t1;
+            }
         }
         snes_residual_kernel<<<gr, kThreads, 0, c->stream>>>(n, c->w_t0, lift, (is_u && c->has_fext) ? c->fext : nullptr, x, g,
                                                             mask, c->w_F, c->partial, c->red, c->counter);
@@ -1121,13 +1139,16 @@ int newton(pfx_ctx* c, bool is_u, NewtonOut* out) {
             if (snorm < c->prm.snes_stol * xnorm) { out->reason = 4; return PFX_OK; }
         }
         if (it >= c->prm.snes_max_it) { out->reason = -5; return PFX_OK; }
-        if (it > 0 && (st = refresh_tangent())) return st;
-        // Jacobi data of the current tangent
-        KArgs d = base_args(c);
-        d.y = c->w_dinv; d.mask = mask;
-        st = launch_scatter(c, is_u ? OP_DIAG_U : OP_DIAG_PHI, d);
-        if (st) return st;
-        if (is_u && (st = block_diag(c))) return st;
+        if (sparse_op) {
+            if (is_u && !c->tan_fresh && (st = refresh_tangent(c))) return st;
+        } else {
+            // Jacobi data of the current tangent
+            KArgs d = base_args(c);
+            d.y = c->w_dinv; d.mask = mask;
+            st = launch_scatter(c, is_u ? OP_DIAG_U : OP_DIAG_PHI, d);
+            if (st) return st;
+            if (is_u && (st = block_diag(c))) return st;
+        }
         int64_t cg = 0; bool conv = false;
         std::chrono::steady_clock::time_point tp0;
         if (c->verbose) { cudaStreamSynchronize(c->stream); tp0 = std::chrono::steady_clock::now(); }
@@ -1139,9 +1160,11 @@ int newton(pfx_ctx* c, bool is_u, NewtonOut* out) {
             fprintf(stderr, "[pfx] %s newton it %d: |F| %.3e  pcg its %lld  |r|/|b| %.2e  %.2f ms (%.1f us/it)\n", is_u ? "u  " : "phi",
                     it, fnorm, (long long)cg, std::sqrt(c->h_pinned[S_RR]) / std::max(fnorm, 1e-300), ms, 1e3 * ms / std::max<int64_t>(cg, 1));
         }
+        mark(c, is_u ? PH_U_SETUP : PH_PHI_SETUP);
         if (!conv) { out->reason = -3; return PFX_OK; }      // linear solve failed (KSP analogue)
         newton_update_kernel<<<gr, kThreads, 0, c->stream>>>(n, x, c->w_x, c->w_F, mask, c->partial, c->red, c->counter);
         c->launches++;
+        c->tan_fresh = false;
         CK(cudaGetLastError());
         st = fetch(c, c->red, 1, vals);
         if (st) return st;
@@ -1194,8 +1217,19 @@ const double* field_ptr(pfx_ctx* c, int f, int* nc) {
     return nullptr;
 }
 
+// device buffers of a redefined BC / traction set are released before the new ones are made
+template <class T>
+void dev_release(pfx_ctx* c, T** p) {
+    if (!*p) return;
+    auto it = std::find(c->allocs.begin(), c->allocs.end(), (void*)*p);
+    if (it != c->allocs.end()) c->allocs.erase(it);
+    cudaFree(*p);
+    *p = nullptr;
+}
+
 int set_bc_common(pfx_ctx* c, bool is_u, int bc_id, const int32_t* dofs, int64_t n) {
     if (!c || bc_id < 0 || n < 0 || (n > 0 && !dofs)) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
     std::vector<BCSet>& sets = is_u ? c->bcs_u : c->bcs_phi;
     if ((size_t)bc_id >= sets.size()) sets.resize(bc_id + 1);
     BCSet& s = sets[bc_id];
@@ -1210,6 +1244,8 @@ int set_bc_common(pfx_ctx* c, bool is_u, int bc_id, const int32_t* dofs, int64_t
         if (c->bm.iperm[node] < c->n_owned) owned.push_back(s.dofs[k]);
     }
     s.n = n; s.n_owned = (int64_t)owned.size();
+    CK(cudaStreamSynchronize(c->stream));
+    dev_release(c, &s.d_dofs); dev_release(c, &s.d_owned); dev_release(c, &s.d_vals);
     int st = dev_upload(c, &s.d_dofs, s.dofs);
     if (st) return st;
     st = dev_upload(c, &s.d_owned, owned);
@@ -1221,6 +1257,7 @@ int set_bc_common(pfx_ctx* c, bool is_u, int bc_id, const int32_t* dofs, int64_t
 
 int set_bc_values_common(pfx_ctx* c, bool is_u, int bc_id, const double* values, int64_t n) {
     if (!c) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
     std::vector<BCSet>& sets = is_u ? c->bcs_u : c->bcs_phi;
     if (bc_id < 0 || (size_t)bc_id >= sets.size() || sets[bc_id].n != n || (n > 0 && !values)) {
         c->err = "bc values: unknown id or length mismatch";
@@ -1266,7 +1303,7 @@ void pfx_default_params(pfx_params* p) {
     memset(p, 0, sizeof(*p));
     p->lambda_ = 121.15384615384615; p->mu = 80.76923076923077; p->Gc = 0.0027; p->l = 0.015; p->k = 0.0;
     p->model = PFX_MODEL_ISOTROPIC; p->irreversibility = 0; p->fatigue = 0; p->fatigue_val = 0.05625;
-    p->snes_rtol = 1e-8; p->snes_atol = 1e-9; p->snes_stol = 1e-8; p->snes_max_it = 50;
+    p->snes_rtol = 1e-8; p->snes_atol = 1e-9; p->snes_stol = 1e-8; p->snes_max_it = 50000;
     p->cg_rtol = 1e-11; p->cg_max_it = 200000; p->proj_rtol = 1e-13;
     p->quad_points_1d = 3; p->block_nodes = 0; p->cg_chunk = 0;
 }
@@ -1336,11 +1373,14 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
         er = build_blocks(c->nv, c->dim, c->n_nodes, c->n_owned, mesh->n_cells, mesh->coords, mesh->cells,
                           mesh->cell_primary, target, c->bm);
         if (!er.empty()) { c->err = er; return PFX_ERR_BAD_ARG; }
-        // triangles: keep every block within two element passes of the CTA (2 x kThreads)
-        if (c->cell_type != PFX_CELL_TRIANGLE || prm->block_nodes > 0 || c->bm.max_elems <= 2 * kThreads ||
-            target <= 64 || attempt >= 8)
+        if (prm->block_nodes > 0 || target <= 64 || attempt >= 8) break;
+        if (c->cell_type == PFX_CELL_TRIANGLE) {
+            // triangles: keep every block within two element passes of the CTA (2 x kThreads)
+            if (c->bm.max_elems <= 2 * kThreads) break;
+            target = std::max(64, target - std::max(4, (c->bm.max_elems - 2 * kThreads) / 4));
+        } else {
             break;
-        target = std::max(64, target - std::max(4, (c->bm.max_elems - 2 * kThreads) / 4));
+        }
     }
     BlockMesh& bm = c->bm;
     int32_t *d_node0, *d_hoff, *d_halo, *d_eoff, *d_nprim, *d_incp;
@@ -1367,6 +1407,12 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
         int mi = 0;
         for (int b = 0; b < bm.nb; ++b) mi = std::max(mi, bm.inc_ptr[bm.node0[b + 1]] - bm.inc_ptr[bm.node0[b]]);
         c->bv.max_inc = mi;
+    }
+    {   // own cells (compact per-cell index)
+        int32_t *d_nlow, *d_c0;
+        if ((st = dev_upload(c, &d_nlow, bm.nlow))) return st;
+        if ((st = dev_upload(c, &d_c0, bm.own_c0))) return st;
+        c->bv.nlow = d_nlow; c->bv.own_c0 = d_c0;
     }
 
     // ---- fields
@@ -1396,16 +1442,34 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     CK(cudaEventCreate(&c->ev1));
     c->graph_iters = prm->cg_chunk > 0 ? (prm->cg_chunk + 1) / 2 * 2 : 32;
 
-    // triangles: the cached-tangent variant of the persistent kernel (PFX_TRI_TANGENT_CACHE=1) measures 50 us
-    // against 54 us for the re-derived spectral tangent at 1.7x the bytes: the kernel is bound by its per-block
-    // pipeline latency, not by fp64 work, so it stays opt-in
-    const char* ttc = getenv("PFX_TRI_TANGENT_CACHE");
-    const bool tan_cells = c->cell_type == PFX_CELL_TETRAHEDRON || (c->cell_type == PFX_CELL_TRIANGLE && ttc && ttc[0] == '1');
-    if (tan_cells && c->mat.smodel != M_ISO && !getenv("PFX_NO_TANGENT_CACHE")) {
-        if ((st = dev_alloc(c, &c->tan, (size_t)21 * (size_t)bm.total_elems))) return st;
-        c->use_tan = true;
+    // tetrahedra: assembled operators (pfx_sparse.cuh) from cached element tangents; PFX_NO_SPARSE=1 keeps the
+    // matrix-free scatter kernels (slow in 3D; an independent cross-check of the assembly)
+    {
+        const char* ns = getenv("PFX_NO_SPARSE");
+        if (c->cell_type == PFX_CELL_TETRAHEDRON && !(ns && ns[0] == '1')) {
+            NodeGraph ng;
+            std::string eg = build_node_graph(bm, mesh->n_cells, mesh->cells, ng);
+            if (!eg.empty()) { c->err = eg; return PFX_ERR_BAD_ARG; }
+            Sparse& sp = c->sp;
+            int32_t *d_k0, *d_col, *d_cn, *d_ncp, *d_ncc;
+            uint32_t* d_nck;
+            if ((st = dev_upload(c, &d_k0, ng.slice_k0))) return st;
+            if ((st = dev_upload(c, &d_col, ng.col))) return st;
+            if ((st = dev_upload(c, &d_cn, ng.cell_nodes))) return st;
+            if ((st = dev_upload(c, &d_ncp, ng.nc_ptr))) return st;
+            if ((st = dev_upload(c, &d_ncc, ng.nc_code))) return st;
+            if ((st = dev_upload(c, &d_nck, ng.nc_kpos))) return st;
+            sp.sv.n_rows = ng.n_rows; sp.sv.n_slices = ng.n_slices; sp.sv.slice_k0 = d_k0; sp.sv.col = d_col;
+            sp.sv.cell_nodes = (const int4*)d_cn; sp.sv.nc_ptr = d_ncp; sp.sv.nc_code = d_ncc; sp.sv.nc_kpos = d_nck;
+            sp.total_k = ng.total_k;
+            if ((st = dev_alloc(c, &sp.Ku, (size_t)ng.total_k * 9 * 32))) return st;
+            if ((st = dev_alloc(c, &sp.Kphi, (size_t)ng.total_k * 32))) return st;
+            if ((st = dev_alloc(c, &sp.Km, (size_t)ng.total_k * 32))) return st;
+            if ((st = dev_alloc(c, &c->tan, (size_t)21 * (size_t)std::max<int64_t>(bm.n_own_cells, 1)))) return st;
+            sp.enabled = true;
+        }
     }
-    if (c->cell_type == PFX_CELL_TRIANGLE) {
+    if (c->cell_type == PFX_CELL_TRIANGLE || c->sp.enabled) {
         if ((st = dev_alloc(c, &c->cm, (size_t)N + 2))) return st;
         if ((st = dev_alloc(c, &c->cg, (size_t)N + 2))) return st;
         if ((st = dev_alloc(c, &c->zeros, (size_t)N + 2))) return st;
@@ -1428,10 +1492,17 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
         }
         c->configuring = false;
     }
-    // ---- constant data: 1/diag(M)
-    KArgs a = base_args(c);
-    a.y = c->dinv_mass;
-    if ((st = launch_scatter(c, OP_DIAG_MASS, a))) return st;
+    // ---- constant data: 1/diag(M) (tetrahedra: the assembled mass matrix as well)
+    if (c->sp.enabled) {
+        const int grid = (int)((c->sp.sv.n_rows + 127) / 128);
+        assemble_s_tet_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->X, c->ones, c->zeros, nullptr, c->sp.Km, c->dinv_mass);
+        c->launches++;
+        CK(cudaGetLastError());
+    } else {
+        KArgs a = base_args(c);
+        a.y = c->dinv_mass;
+        if ((st = launch_scatter(c, OP_DIAG_MASS, a))) return st;
+    }
     CK(cudaStreamSynchronize(c->stream));
     return build_coarse(c, mesh);
 }
@@ -1439,6 +1510,7 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
 int pfx_destroy(pfx_ctx* c) {
     if (!c) return PFX_OK;
     cudaSetDevice(c->device);
+    for (cudaEvent_t e : c->ph_events) cudaEventDestroy(e);
     if (c->stream) cudaStreamSynchronize(c->stream);
     for (int k = 0; k < 3; ++k)
         if (c->graph[k]) cudaGraphExecDestroy(c->graph[k]);
@@ -1463,8 +1535,11 @@ int pfx_set_bc_values_phi(pfx_ctx* c, int id, const double* v, int64_t n) { retu
 
 int pfx_set_traction(pfx_ctx* c, int t_id, const int32_t* nodes, const double* w, int64_t n) {
     if (!c || t_id < 0 || n < 0 || (n > 0 && (!nodes || !w))) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
     if ((size_t)t_id >= c->tractions.size()) c->tractions.resize(t_id + 1);
     Traction& t = c->tractions[t_id];
+    CK(cudaStreamSynchronize(c->stream));
+    dev_release(c, &t.d_nodes); dev_release(c, &t.d_w);
     std::vector<int32_t> nn(n);
     std::vector<double> ww(w, w + n);
     for (int64_t k = 0; k < n; ++k) {
@@ -1482,6 +1557,7 @@ int pfx_set_traction(pfx_ctx* c, int t_id, const int32_t* nodes, const double* w
 
 int pfx_set_traction_value(pfx_ctx* c, int t_id, const double* T) {
     if (!c || !T || t_id < 0 || (size_t)t_id >= c->tractions.size()) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
     for (int k = 0; k < c->dim; ++k) c->tractions[t_id].T[k] = T[k];
     return rebuild_fext(c);
 }
@@ -1491,6 +1567,7 @@ int pfx_get_field(pfx_ctx* c, int field, double* host, int64_t n) {
     int nc;
     const double* d = field_ptr(c, field, &nc);
     if (!d || n != c->n_nodes * nc) { c->err = "get_field: unknown field or wrong length"; return PFX_ERR_BAD_ARG; }
+    CK(cudaSetDevice(c->device));
     std::vector<double> tmp(n);
     CK(cudaMemcpyAsync(tmp.data(), d, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -1504,11 +1581,13 @@ int pfx_set_field(pfx_ctx* c, int field, const double* host, int64_t n) {
     int nc;
     double* d = const_cast<double*>(field_ptr(c, field, &nc));
     if (!d || n != c->n_nodes * nc) { c->err = "set_field: unknown field or wrong length"; return PFX_ERR_BAD_ARG; }
+    CK(cudaSetDevice(c->device));
     std::vector<double> tmp(n);
     for (int64_t i = 0; i < c->n_nodes; ++i)
         for (int k = 0; k < nc; ++k) tmp[i * nc + k] = host[(int64_t)c->bm.perm[i] * nc + k];
     CK(cudaMemcpyAsync(d, tmp.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    c->tan_fresh = false;
     c->coarse.op[0].stale = c->coarse.op[1].stale = true;
     return PFX_OK;
 }
@@ -1527,6 +1606,8 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
     double err_phi = 1.0, err_u = 1.0;
     int it = 0, st;
     CK(cudaEventRecord(c->ev0, c->stream));
+    c->ph_on = true; c->ph_used = 0; c->floor_solves = 0;
+    mark(c, PH_OTHER);
     CK(cudaMemsetAsync(c->S + S_BREF, 0, 3 * sizeof(double), c->stream));      // per-step PCG reference norms
     for (int k = 0; k < 2 && c->coarse.enabled; ++k) {
         CoarseOp& op = c->coarse.op[k];
@@ -1541,6 +1622,7 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
         NewtonOut nu;
         if ((st = newton(c, true, &nu))) return st;
         rep->u_newton_its = nu.its; rep->u_reason = nu.reason; rep->fnorm_u = nu.fnorm; rep->cg_its_u += nu.cg_its;
+        mark(c, PH_NORMS);
         if ((st = l2_error(c, true, c->u, c->u_old, &err_u))) return st;
         if (nu.reason <= 0) {
             rep->stagger_iters = it;
@@ -1549,6 +1631,7 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
         }
         CK(cudaMemcpyAsync(c->u_old, c->u, N * D * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         // ---- history (solver.py:355-360)
+        mark(c, PH_PROJECTION);
         KArgs a = base_args(c);
         a.y = c->w_F;
         if ((st = launch_scatter(c, OP_RHS_PSI, a))) return st;
@@ -1561,6 +1644,7 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
         }
         // ---- fatigue (solver.py:362-375)
         if (c->prm.fatigue) {
+            mark(c, PH_FATIGUE);
             KArgs f = base_args(c);
             f.f1 = c->phi_old; f.f2 = c->Vc; f.y = c->w_F;
             if ((st = launch_scatter(c, OP_RHS_FATIGUE, f))) return st;
@@ -1573,6 +1657,7 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
         NewtonOut np;
         if ((st = newton(c, false, &np))) return st;
         rep->phi_newton_its = np.its; rep->phi_reason = np.reason; rep->fnorm_phi = np.fnorm; rep->cg_its_phi += np.cg_its;
+        mark(c, PH_NORMS);
         if ((st = l2_error(c, false, c->phi, c->phi_old, &err_phi))) return st;
         if (np.reason <= 0) {
             rep->stagger_iters = it;
@@ -1592,6 +1677,7 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
         }
     }
     // ---- end of step (solver.py:401-411)
+    mark(c, PH_OTHER);
     if (c->prm.irreversibility) {
         nodal_max_kernel<<<gN, kThreads, 0, c->stream>>>(N, c->Vn, c->Vc, c->Vn);
         c->launches++;
@@ -1605,6 +1691,14 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     rep->gpu_ms = ms;
+    // per-phase split: time from each phase mark to the next one (the last phase runs to ev1)
+    for (size_t k = 0; k < c->ph_used; ++k) {
+        float d = 0.f;
+        cudaEvent_t next = (k + 1 < c->ph_used) ? c->ph_events[k + 1] : c->ev1;
+        if (cudaEventElapsedTime(&d, c->ph_events[k], next) == cudaSuccess) rep->phase_ms[c->ph_ids[k]] += d;
+    }
+    c->ph_on = false;
+    rep->cg_floor_solves = c->floor_solves;
     rep->stagger_iters = it;
     rep->err_u = err_u; rep->err_phi = err_phi;
     return PFX_OK;
@@ -1615,6 +1709,7 @@ static int solve_single(pfx_ctx* c, bool is_u, pfx_step_report* rep) {
     if (!c || !rep) return PFX_ERR_BAD_ARG;
     CK(cudaSetDevice(c->device));
     memset(rep, 0, sizeof(*rep));
+    c->ph_on = false; c->floor_solves = 0;
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(c->S + S_BREF, 0, 3 * sizeof(double), c->stream));
     NewtonOut no;
@@ -1625,6 +1720,7 @@ static int solve_single(pfx_ctx* c, bool is_u, pfx_step_report* rep) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     rep->gpu_ms = ms;
+    rep->cg_floor_solves = c->floor_solves;
     if (is_u) { rep->u_newton_its = no.its; rep->u_reason = no.reason; rep->fnorm_u = no.fnorm; rep->cg_its_u = no.cg_its; }
     else { rep->phi_newton_its = no.its; rep->phi_reason = no.reason; rep->fnorm_phi = no.fnorm; rep->cg_its_phi = no.cg_its; }
     if (no.reason <= 0) {
@@ -1681,17 +1777,35 @@ int pfx_energies(pfx_ctx* c, double out[11]) {
 static int host_apply(pfx_ctx* c, int op, int nc, const double* v, double* y, const uint8_t* mask) {
     int64_t n = c->n_nodes * nc;
     std::vector<double> tmp(n);
+    const bool is_apply = (op == OP_APPLY_U || op == OP_APPLY_PHI || op == OP_APPLY_MASS);
     if (v) {
         for (int64_t i = 0; i < c->n_nodes; ++i)
             for (int k = 0; k < nc; ++k) tmp[i * nc + k] = v[(int64_t)c->bm.perm[i] * nc + k];
         CK(cudaMemcpyAsync(c->w_p, tmp.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     }
-    KArgs a = base_args(c);
-    a.v = c->w_p; a.y = c->w_Ap; a.mask = mask;
-    int st = launch_scatter(c, op, a);
-    if (st) return st;
+    int st;
+    if (is_apply) {
+        // the operators of the PCG path: they take an input that is zero on Dirichlet dofs and write zero rows there;
+        // the identity rows of the assembled operator (y = v on those dofs) are restored afterwards
+        if (mask) {
+            CK(cudaMemcpyAsync(c->w_t0, c->w_p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            mask_zero_kernel<<<vgrid(c, n), kThreads, 0, c->stream>>>(n, mask, c->w_p);
+        }
+        if (op == OP_APPLY_U && (st = refresh_tangent(c))) return st;            // linearise at the current state
+        if (op == OP_APPLY_PHI && (st = refresh_phi_operator(c))) return st;
+        st = apply_lin(c, op == OP_APPLY_U ? LIN_U : (op == OP_APPLY_PHI ? LIN_PHI : LIN_MASS), c->w_p, c->w_Ap, mask, c->red, nullptr,
+                       mask ? 1 : 0);
+        if (op == OP_APPLY_PHI) c->phi_coeff_fresh = c->sp.phi_fresh = false;
+        if (st) return st;
+        if (mask) mask_restore_kernel<<<vgrid(c, n), kThreads, 0, c->stream>>>(n, mask, c->w_t0, c->w_Ap);
+    } else {
+        KArgs a = base_args(c);
+        a.v = c->w_p; a.y = c->w_Ap; a.mask = mask;
+        if ((st = launch_scatter(c, op, a))) return st;
+    }
     CK(cudaMemcpyAsync(tmp.data(), c->w_Ap, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
     for (int64_t i = 0; i < c->n_owned; ++i)
         for (int k = 0; k < nc; ++k) y[(int64_t)c->bm.perm[i] * nc + k] = tmp[i * nc + k];
     return PFX_OK;
@@ -1720,6 +1834,17 @@ int pfx_residual_u(pfx_ctx* c, double* f) {
 int pfx_diag_u(pfx_ctx* c, double* d) {
     if (!c || !d) return PFX_ERR_BAD_ARG;
     CK(cudaSetDevice(c->device));
+    if (c->sp.enabled) {                               // the diagonal falls out of the assembly
+        int st0 = refresh_tangent(c);
+        if (st0) return st0;
+        int64_t n = c->n_owned * c->dim;
+        std::vector<double> tmp(n);
+        CK(cudaMemcpyAsync(tmp.data(), c->w_dinv, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int64_t i = 0; i < c->n_owned; ++i)
+            for (int k = 0; k < c->dim; ++k) d[(int64_t)c->bm.perm[i] * c->dim + k] = 1.0 / tmp[i * c->dim + k];
+        return PFX_OK;
+    }
     int st = host_apply(c, OP_DIAG_U, c->dim, nullptr, d, c->mask_u);
     if (st) return st;
     for (int64_t i = 0; i < c->n_owned; ++i)                                 // kernel stores 1/diag
@@ -1769,15 +1894,16 @@ int pfx_algorithmic_bytes(pfx_ctx* c, int kind, double* bytes) {
     switch (kind) {
         case 0:                                                                                  // u-apply
             *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d + (nl ? 8 * d : 0));
-            if (c->use_tan)      // cached element tangent instead of u and phi: X, v, y per node + NT doubles per cell
-                *bytes = conn + Nn * (3 * 8 * d) + Ne * 8.0 * (d == 2 ? 6 : 21);
+            break;
+        case 5:      // bytes the u-apply implementation streams: with cached element tangents X, v, y per node + 21 doubles per cell
+            *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d + (nl ? 8 * d : 0));
+            if (c->sp.enabled) *bytes = (double)c->sp.total_k * 32.0 * (72.0 + 4.0) + Nn * (8 * d + 8 * d);
             break;
         case 1: *bytes = conn + Nn * (8 * d + 24 + (c->mat.fatigue ? 8 : 0)); break;             // phi-apply
         case 2: *bytes = conn + Nn * (8 * d + 16); break;                                        // mass-apply
         case 3: *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d); break;                         // residual_u
         case 4:                                                                                  // u-PCG iteration
             *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d + (nl ? 8 * d : 0)) + 11.0 * 8.0 * d * Nn;
-            if (c->use_tan) *bytes = conn + Nn * (3 * 8 * d) + Ne * 8.0 * (d == 2 ? 6 : 21) + 11.0 * 8.0 * d * Nn;
             if (coarse_active(c, LIN_U)) {
                 // two-level iteration: inverse diagonal blocks instead of the diagonal (read twice), the mode
                 // geometry (fp32, read twice), the Dirichlet flags, and the fp32 coarse inverse
@@ -1803,9 +1929,8 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
     bool timed_coarse = false;
-    if ((kind == 0 || kind == 4) && c->use_tan) {          // linearise at the current state first
-        KArgs t = base_args(c);
-        int st = launch_scatter(c, OP_TANGENT_U, t);
+    if (kind == 0 || kind == 4) {                          // tetrahedra: linearise + assemble at the current state first
+        int st = refresh_tangent(c);
         if (st) return st;
     }
     if (kind == 0) {
@@ -1813,14 +1938,21 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
         mask_zero_kernel<<<vgrid(c, nall), kThreads, 0, c->stream>>>(nall, c->mask_u, c->w_p);
         CK(cudaGetLastError());
     }
+    if (kind == 1) {
+        mask_zero_kernel<<<vgrid(c, c->n_nodes), kThreads, 0, c->stream>>>(c->n_nodes, c->mask_phi, c->w_p);
+        int st = refresh_phi_operator(c);
+        if (st) return st;
+    }
     // kind 4: a genuine PCG on J_u with right-hand side = current contents of w_p and a
     // tolerance of zero, so every timed iteration does full work
     if (kind == 4) {
-        KArgs d = base_args(c);
-        d.y = c->w_dinv; d.mask = c->mask_u;
-        int st = launch_scatter(c, OP_DIAG_U, d);
-        if (st) return st;
-        if ((st = block_diag(c))) return st;
+        int st = PFX_OK;
+        if (!c->sp.enabled) {
+            KArgs d = base_args(c);
+            d.y = c->w_dinv; d.mask = c->mask_u;
+            if ((st = launch_scatter(c, OP_DIAG_U, d))) return st;
+            if ((st = block_diag(c))) return st;
+        }
         int64_t n = c->n_owned * c->dim;
         CK(cudaMemcpyAsync(c->w_F, c->w_p, n * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         pcg_init_kernel<<<vgrid(c, n), kThreads, 0, c->stream>>>(n, c->w_F, c->mask_u, c->w_dinv, nullptr, nullptr, c->w_x, c->w_r,
@@ -1844,7 +1976,7 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
         CK(cudaEventRecord(e0, c->stream));
         int st = PFX_OK;
         if (kind == 0) st = apply_lin(c, LIN_U, c->w_p, c->w_Ap, c->mask_u, c->red, nullptr, 1);   // the launch PCG makes
-        else if (kind == 1) st = apply_lin(c, LIN_PHI, c->w_p, c->w_Ap, c->mask_phi, c->red, nullptr);
+        else if (kind == 1) st = apply_lin(c, LIN_PHI, c->w_p, c->w_Ap, c->mask_phi, c->red, nullptr, 1);
         else if (kind == 2) st = apply_lin(c, LIN_MASS, c->w_p, c->w_Ap, nullptr, c->red, nullptr);
         else if (kind == 3) { KArgs a = base_args(c); a.y = c->w_t0; st = launch_scatter(c, OP_RESIDUAL_U, a); }
         else if (kind == 4) {
@@ -1858,6 +1990,7 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
     }
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
+    if (kind == 1) c->phi_coeff_fresh = c->sp.phi_fresh = false;
     return PFX_OK;
 }
 

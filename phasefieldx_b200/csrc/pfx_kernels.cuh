@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "pfx_elements.cuh"
+#include "pfx_blocks.h"
 
 namespace pfx {
 
@@ -37,6 +38,9 @@ struct BlockView {
     const int4* meta; // [2*nb] packed {n0, n_own, h0, n_halo | e0, n_elems, inc0, n_inc}
     const uint4* inc8; // triangles: 8 incidence codes per owned node
     int chunk;        // elements per phase-B pass
+    // own cells (pfx_blocks.h): every local cell leads the list of exactly one block; compact index own_c0[b] + j
+    const int32_t* nlow;       // [nb] own cells
+    const int32_t* own_c0;     // [nb+1] compact own-cell index
 };
 
 struct PeerView;
@@ -65,8 +69,7 @@ struct KArgs {
                             // dot product to the peers' mailboxes in the epilogue (null otherwise)
     const double* cm;       // precomputed phi-operator coefficients 2H + F·Gc/l and F·Gc·l (per node)
     const double* cg;
-    double* tan;            // cached element tangents, SoA [21][tan_stride] (tets, nonlinear split)
-    int64_t tan_stride;
+    double* tan;            // cached element tangents [n_own_cells][21] (tets), compact own-cell index
 };
 
 constexpr int kMaxRanks = 8;
@@ -207,11 +210,13 @@ __device__ __forceinline__ void grid_reduce(double* vals, double* partial, doubl
 // Each Op: NF staged doubles per local node (odd => conflict-free AoS), NOUT rows per node,
 // NRED partial sums; load(), elem(), store().
 enum { OP_APPLY_U, OP_RESIDUAL_U, OP_DIAG_U, OP_APPLY_PHI, OP_RESIDUAL_PHI, OP_DIAG_PHI, OP_APPLY_MASS,
-       OP_DIAG_MASS, OP_RHS_PSI, OP_RHS_FATIGUE, OP_TANGENT_U, OP_APPLY_U_TAN, OP_DIAGBLK_U };
+       OP_DIAG_MASS, OP_RHS_PSI, OP_RHS_FATIGUE, OP_TANGENT_U, OP_DIAGBLK_U };
 
 template <int V> struct odd { static constexpr int value = (V & 1) ? V : V + 1; };
 template <class Op, class = void> struct min_blocks { static constexpr int value = (Op::NV == 3) ? 4 : (Op::D == 2 ? 3 : (Op::NOUT == 1 ? 2 : 1)); };
 template <class Op> struct min_blocks<Op, decltype((void)Op::MINB)> { static constexpr int value = Op::MINB; };
+template <class Op, class = void> struct own_only { static constexpr bool value = false; };
+template <class Op> struct own_only<Op, decltype((void)Op::OWN)> { static constexpr bool value = Op::OWN; };
 
 template <class Cell, int SM>
 struct OpApplyU {          // staged: X[D] phi v[D] (u[D]); SM = compile-time stress split
@@ -507,10 +512,11 @@ struct OpRhsFatigue {      // staged: X f1(=phi_old) f2(=V_c)
 };
 
 template <class Cell>
-struct OpTangentU {        // staged: X phi u ; writes the cached tangent of every listed cell, no nodal output
+struct OpTangentU {        // staged: X phi u ; writes the cached tangent of the block's OWN cells, no nodal output
     static constexpr int D = Cell::D, NV = Cell::NV, NOUT = 1, NRED = 0;
     static constexpr int NF = odd<D + 1 + D>::value;
     static constexpr int MINB = 1;
+    static constexpr bool OWN = true;       // scatter_kernel: only the own cells, `gid` = compact own-cell index
     __device__ static void load(const KArgs& a, int g, double* s) { OpResidualU<Cell>::load(a, g, s); }
     __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t gid) {
         double X[NV * D], ph[NV], U[NV * D], T[21];
@@ -520,33 +526,10 @@ struct OpTangentU {        // staged: X phi u ; writes the cached tangent of eve
         }
         elem_tangent_u<Cell>(a.m, X, ph, U, T);
         constexpr int NT = SymN<D>::N * (SymN<D>::N + 1) / 2;
-        for (int t = 0; t < NT; ++t) a.tan[(size_t)t * a.tan_stride + gid] = T[t];
+        for (int t = 0; t < NT; ++t) a.tan[(size_t)gid * NT + t] = T[t];
         for (int k = 0; k < NV; ++k) out[k] = 0.0;
     }
     __device__ static void store(const KArgs&, int, const double*, double*) {}
-};
-
-template <class Cell>
-struct OpApplyUTan {       // staged: X v ; contracts the cached tangent
-    static constexpr int D = Cell::D, NV = Cell::NV, NOUT = D, NRED = 1;
-    static constexpr int NF = odd<2 * D>::value;
-    static constexpr int MINB = 2;
-    __device__ static void load(const KArgs& a, int g, double* s) {
-        for (int i = 0; i < D; ++i) {
-            s[i] = a.X[(size_t)g * D + i];
-            double vv = a.v[(size_t)g * D + i];
-            if (a.mask && a.mask[(size_t)g * D + i]) vv = 0.0;
-            s[D + i] = vv;
-        }
-    }
-    __device__ static void elem(const KArgs& a, const double* const* nd, double* out, int64_t gid) {
-        constexpr int NT = SymN<D>::N * (SymN<D>::N + 1) / 2;
-        double X[NV * D], V[NV * D], T[NT];
-        for (int t = 0; t < NT; ++t) T[t] = __ldg(&a.tan[(size_t)t * a.tan_stride + gid]);
-        for (int k = 0; k < NV; ++k) for (int i = 0; i < D; ++i) { X[k * D + i] = nd[k][i]; V[k * D + i] = nd[k][D + i]; }
-        elem_apply_u_tan<Cell>(X, V, T, out);
-    }
-    __device__ static void store(const KArgs& a, int g, const double* acc, double* red) { OpApplyU<Cell, M_ISO>::store(a, g, acc, red); }
 };
 
 template <class Op>
@@ -558,7 +541,8 @@ __global__ void __launch_bounds__(kThreads, min_blocks<Op>::value) scatter_kerne
     const int b = blockIdx.x, tid = threadIdx.x;
     const int n0 = bv.node0[b], n_own = bv.node0[b + 1] - n0;
     const int h0 = bv.halo_off[b], n_loc = n_own + bv.halo_off[b + 1] - h0;
-    const int e0 = bv.elem_off[b], ne = bv.elem_off[b + 1] - e0;
+    const int e0 = bv.elem_off[b], ne = own_only<Op>::value ? bv.nlow[b] : bv.elem_off[b + 1] - e0;
+    const int64_t gid0 = own_only<Op>::value ? (int64_t)bv.own_c0[b] : (int64_t)e0;
     const int chunk = bv.chunk;
     double* s_nodes = smem;
     double* s_ebuf = smem + (size_t)bv.max_loc * NF;
@@ -589,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, min_blocks<Op>::value) scatter_kerne
             const double* nd[4] = {s_nodes + (size_t)lc.x * NF, s_nodes + (size_t)lc.y * NF,
                                    s_nodes + (size_t)lc.z * NF, s_nodes + (size_t)lc.w * NF};
             double out[NV * NOUT];
-            Op::elem(a, nd, out, (int64_t)e0 + c0 + j);
+            Op::elem(a, nd, out, gid0 + c0 + j);
 #pragma unroll
             for (int k = 0; k < NV * NOUT; ++k) s_ebuf[k * chunk + j] = out[k];
         }
@@ -614,6 +598,51 @@ __global__ void __launch_bounds__(kThreads, min_blocks<Op>::value) scatter_kerne
     if (tid < n_own) Op::store(a, n0 + tid, acc, red);
     if (Op::NRED > 0) grid_reduce<(Op::NRED > 0 ? Op::NRED : 1)>(red, a.partial, a.result, a.counter, s_red, a.pv);
 }
+
+// ----------------------------------------------------------------------------- async staging helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a transaction count that never completes (a bug) must not hang the GPU — after ~2 s the wait
+// gives up (the result is then garbage and the parity checks fail loudly)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    unsigned long long t0 = 0;
+    for (uint32_t spins = 0;; ++spins) {
+        asm volatile(
+            "{\n.reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        if ((spins & 0x3FFu) == 0x3FFu) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) return;
+        }
+    }
+}
+// 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ============================================================================= hot kernel
 // J_u·v on P1 triangles (config 1-3 meshes): same three phases as scatter_kernel, specialised:
@@ -671,24 +700,6 @@ __device__ __forceinline__ void tri_apply_elem(const Material& m, double2 x0, do
     S[0] *= vol; S[1] *= vol; S[2] *= vol;
     f1 = make_double2(S[0] * g1x + S[2] * g1y, S[2] * g1x + S[1] * g1y);
     f2 = make_double2(S[0] * g2x + S[2] * g2y, S[2] * g2x + S[1] * g2y);
-    f0 = make_double2(-(f1.x + f2.x), -(f1.y + f2.y));
-}
-
-// Same element action from the cached element tangent T (elem_tangent_u: symmetric 3x3 of the bilinear
-// form de':C:de in sym storage, shear rows weighted by 2, area and g(phi)+k folded in): 33 multiply-adds
-// instead of the eigen-decomposition of the strain.
-__device__ __forceinline__ void tri_apply_elem_tan(double2 x0, double2 x1, double2 x2, double2 v0, double2 v1, double2 v2,
-                                                   const double* T, double2& f0, double2& f1, double2& f2) {
-    const double ax = x1.x - x0.x, ay = x1.y - x0.y, bx = x2.x - x0.x, by = x2.y - x0.y;
-    const double det = ax * by - ay * bx, inv = __drcp_rn(det);
-    const double g1x = by * inv, g1y = -bx * inv, g2x = -ay * inv, g2y = ax * inv;
-    const double g0x = -(g1x + g2x), g0y = -(g1y + g2y);
-    const double de0 = g0x * v0.x + g1x * v1.x + g2x * v2.x, de1 = g0y * v0.y + g1y * v1.y + g2y * v2.y,
-                 de2 = 0.5 * (g0y * v0.x + g1y * v1.x + g2y * v2.x + g0x * v0.y + g1x * v1.y + g2x * v2.y);
-    const double S0 = T[0] * de0 + T[1] * de1 + T[2] * de2, S1 = T[1] * de0 + T[3] * de1 + T[4] * de2,
-                 S2 = 0.5 * (T[2] * de0 + T[4] * de1 + T[5] * de2);
-    f1 = make_double2(S0 * g1x + S2 * g1y, S2 * g1x + S1 * g1y);
-    f2 = make_double2(S0 * g2x + S2 * g2y, S2 * g2x + S1 * g2y);
     f0 = make_double2(-(f1.x + f2.x), -(f1.y + f2.y));
 }
 
@@ -768,205 +779,22 @@ __global__ void __launch_bounds__(kThreads, 4) apply_u_tri_kernel(BlockView bv, 
     grid_reduce<1>(red, a.partial, a.result, a.counter, s_red, a.pv);
 }
 
-// ----------------------------------------------------------------------------- async staging helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n.reg .pred p;\nWAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-D bulk copy global -> shared (TMA engine), completion counted in bytes on the mbarrier
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// ============================================================================= hot kernel, persistent
-// Same arithmetic as apply_u_tri_kernel, restructured for Blackwell: a persistent grid (a few CTAs
-// per SM, each walking blocks b, b+grid, ...) with DOUBLE-BUFFERED asynchronous staging — the
-// contiguous owned ranges of X, v, u and the incidence list arrive by 1-D bulk copies (TMA engine,
-// mbarrier complete_tx), phi and the halo nodes by per-thread cp.async — so the loads of block
-// i+1 are in flight while block i is computed.  Contract: when a.mask != null the INPUT is already
-// zero on Dirichlet dofs (true for every PCG direction) and the output rows of those dofs are
-// written as zero; the public pfx_apply_u wrapper restores y = v there.
-struct TriStage {
-    double2 *X, *V, *U;
-    double* P;
-    uint16_t* inc;
-};
-
-template <int SM>
-__global__ void __launch_bounds__(kThreads, 3) apply_u_tri_persist_kernel(BlockView bv, KArgs a) {
-    constexpr bool NL = (SM != M_ISO);
-    extern __shared__ double smem[];
-    __shared__ double s_red[kMaxRed * 32];
-    __shared__ uint64_t s_bar[2];
-    if (a.stop && a.stop[0] != 0.0) return;
-    const int tid = threadIdx.x;
-    const int ML = bv.max_loc, chunk = bv.chunk, MI = (bv.max_inc + 7) & ~7;
-    // ---- shared-memory carve-up (every sub-array 16-byte aligned): [stage 0][stage 1][element buffer]
-    const size_t oV = (size_t)ML * 16, oU = 2 * oV, oP = oV * (NL ? 3 : 2), oI = oP + (size_t)((ML + 1) & ~1) * 8;
-    const size_t stage_bytes = oI + (size_t)MI * 2;
-    char* const sbase = reinterpret_cast<char*>(smem);
-    auto stage = [&](int s_) -> TriStage {
-        char* p = sbase + (size_t)s_ * stage_bytes;
-        TriStage t;
-        t.X = reinterpret_cast<double2*>(p); t.V = reinterpret_cast<double2*>(p + oV);
-        t.U = reinterpret_cast<double2*>(p + oU); t.P = reinterpret_cast<double*>(p + oP);
-        t.inc = reinterpret_cast<uint16_t*>(p + oI);
-        return t;
-    };
-    double2* sE = reinterpret_cast<double2*>(sbase + 2 * stage_bytes);
-    const double2* X2 = reinterpret_cast<const double2*>(a.X);
-    const double2* V2 = reinterpret_cast<const double2*>(a.v);
-    const double2* U2 = reinterpret_cast<const double2*>(a.u);
-    const uchar2* M2 = reinterpret_cast<const uchar2*>(a.mask);
-    if (tid == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    // issue the asynchronous staging of block `blk` into stage `s`; hidx = this thread's halo node id
-    auto issue = [&](int blk, int s, int hidx) {
-        const TriStage T = stage(s);
-        const int n0 = bv.node0[blk], n_own = bv.node0[blk + 1] - n0;
-        const int n_halo = bv.halo_off[blk + 1] - bv.halo_off[blk];
-        const int i0 = bv.inc_ptr[n0], ninc = bv.inc_ptr[n0 + n_own] - i0;
-        if (tid == 0) {
-            fence_proxy_async();
-            uint32_t bytes = (uint32_t)n_own * 16u * (NL ? 3u : 2u) + (uint32_t)ninc * 2u;
-            mbar_expect_tx(&s_bar[s], bytes);
-            bulk_g2s(T.X, X2 + n0, (uint32_t)n_own * 16u, &s_bar[s]);
-            bulk_g2s(T.V, V2 + n0, (uint32_t)n_own * 16u, &s_bar[s]);
-            if (NL) bulk_g2s(T.U, U2 + n0, (uint32_t)n_own * 16u, &s_bar[s]);
-            bulk_g2s(T.inc, bv.inc + i0, (uint32_t)ninc * 2u, &s_bar[s]);
-        }
-        if (tid < n_own) cp_async8(T.P + tid, a.phi + n0 + tid);
-        for (int i = tid; i < n_halo; i += kThreads) {
-            int g = (i == tid) ? hidx : bv.halo[bv.halo_off[blk] + i];
-            cp_async16(T.X + n_own + i, X2 + g);
-            cp_async16(T.V + n_own + i, V2 + g);
-            if (NL) cp_async16(T.U + n_own + i, U2 + g);
-            cp_async8(T.P + n_own + i, a.phi + g);
-        }
-        cp_async_commit();
-    };
-    auto halo_index = [&](int blk) -> int {
-        if (blk >= bv.nb) return 0;
-        int h0 = bv.halo_off[blk], nh = bv.halo_off[blk + 1] - h0;
-        return tid < nh ? bv.halo[h0 + tid] : 0;
-    };
-
-    const int stride = gridDim.x;
-    int blk = blockIdx.x;
-    double red = 0.0;
-    if (blk < bv.nb) {
-        issue(blk, 0, halo_index(blk));
-    }
-    int hnext = halo_index(blk + stride);
-    uint32_t phases = 0u;              // bit s = parity of stage s' mbarrier
-    for (int it = 0; blk < bv.nb; blk += stride, ++it) {
-        const int s = it & 1;
-        const int n0 = bv.node0[blk], n_own = bv.node0[blk + 1] - n0;
-        const int e0 = bv.elem_off[blk], ne = bv.elem_off[blk + 1] - e0;
-        const int i0 = bv.inc_ptr[n0];
-        // connectivity of this thread's first two cells, mask and incidence range: issued before the wait
-        ushort4 lc0 = make_ushort4(0, 0, 0, 0), lc1 = lc0;
-        if (tid < ne) lc0 = bv.lconn[e0 + tid];
-        if (tid + kThreads < ne) lc1 = bv.lconn[e0 + tid + kThreads];
-        int cur = 0, end = 0;
-        uchar2 mk = make_uchar2(0, 0);
-        if (tid < n_own) {
-            cur = bv.inc_ptr[n0 + tid] - i0; end = bv.inc_ptr[n0 + tid + 1] - i0;
-            if (M2) mk = M2[n0 + tid];
-        }
-        // prefetch the next block of this CTA into the other stage (it was fully consumed one
-        // iteration ago; the __syncthreads at the end of that iteration ordered the reads)
-        const int nblk = blk + stride;
-        if (nblk < bv.nb) {
-            issue(nblk, s ^ 1, hnext);
-            hnext = halo_index(nblk + stride);
-            cp_async_wait<1>();            // everything but the group just committed has landed
-        } else {
-            cp_async_wait<0>();
-        }
-        mbar_wait(&s_bar[s], (phases >> s) & 1u);
-        phases ^= (1u << s);
-        __syncthreads();
-        const TriStage T = stage(s);
-        const double2 *sX = T.X, *sV = T.V, *sU = T.U;
-        const double* sP = T.P;
-        const uint16_t* s_inc = T.inc;
-        double2 acc = make_double2(0.0, 0.0);
-        for (int c0 = 0; c0 < ne; c0 += chunk) {
-            const int nc = min(chunk, ne - c0);
-            for (int j = tid; j < nc; j += kThreads) {
-                const int eid = c0 + j;
-                ushort4 lc = (eid == tid) ? lc0 : ((eid == tid + kThreads) ? lc1 : bv.lconn[e0 + eid]);
-                double2 f0, f1, f2;
-                const double2 z = make_double2(0.0, 0.0);
-                tri_apply_elem<SM>(a.m, sX[lc.x], sX[lc.y], sX[lc.z], sP[lc.x], sP[lc.y], sP[lc.z], sV[lc.x], sV[lc.y],
-                                   sV[lc.z], NL ? sU[lc.x] : z, NL ? sU[lc.y] : z, NL ? sU[lc.z] : z, f0, f1, f2);
-                sE[j] = f0; sE[chunk + j] = f1; sE[2 * chunk + j] = f2;
-            }
-            __syncthreads();
-            if (tid < n_own) {
-                while (cur < end) {
-                    int code = s_inc[cur];
-                    int j = (code >> 2) - c0;
-                    if (j >= nc) break;
-                    double2 f = sE[(code & 3) * chunk + j];
-                    acc.x += f.x; acc.y += f.y;
-                    ++cur;
-                }
-            }
-            if (c0 + chunk < ne) __syncthreads();
-        }
-        if (tid < n_own) {
-            if (mk.x) acc.x = 0.0;
-            if (mk.y) acc.y = 0.0;
-            const double2 vin = sV[tid];
-            reinterpret_cast<double2*>(a.y)[n0 + tid] = acc;
-            red += vin.x * acc.x + vin.y * acc.y;
-        }
-        __syncthreads();                   // stage s and sE are free again
-    }
-    double r1[1] = {red};
-    grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red, a.pv);
-}
-
 // ============================================================================= hot kernel, v3
-// apply_u_tri_persist_kernel plus: packed block metadata and every per-thread index of the NEXT
-// block prefetched in registers one iteration ahead (no dependent global loads on the critical
-// path), phi by bulk copy, two unrolled cells per thread, and phase C on a fixed-width (8)
-// incidence table staged by bulk copy — eight independent 128-bit shared loads per node instead
-// of a pointer-chasing loop.  Requires every block to list <= 2*kThreads cells (the block
-// builder sizes triangle blocks that way; otherwise the engine falls back to the v2 kernel).
-// TAN = true: the element action comes from the cached element tangents a.tan (refreshed once per Newton
-// linearisation by OpTangentU) instead of being re-derived from u and phi in every PCG iteration; u and
-// phi are then not staged at all.
-template <int SM, bool TAN = false>
+// Same arithmetic as apply_u_tri_kernel, restructured for Blackwell: a persistent grid (a few CTAs per SM,
+// each walking blocks b, b+grid, ...) with DOUBLE-BUFFERED asynchronous staging — the contiguous owned
+// ranges of X, v, u, phi and the fixed-width incidence table arrive by 1-D bulk copies (TMA engine,
+// mbarrier complete_tx), the halo nodes by per-thread cp.async — so the loads of block i+1 are in flight
+// while block i is computed.  Packed block metadata and every per-thread index of the NEXT block are
+// prefetched in registers one iteration ahead (no dependent global loads on the critical path), two
+// unrolled cells per thread, and phase C reads a fixed-width (8) incidence table — eight independent
+// 128-bit shared loads per node instead of a pointer-chasing loop.  Contract: when a.mask != null the
+// INPUT is already zero on Dirichlet dofs (true for every PCG direction) and the output rows of those
+// dofs are written as zero; the public pfx_apply_u wrapper restores y = v there.  Requires every block
+// to list <= 2*kThreads cells (the block builder sizes triangle blocks that way; otherwise the engine
+// falls back to apply_u_tri_kernel).
+template <int SM>
 __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView bv, KArgs a) {
-    constexpr bool NL = (SM != M_ISO) && !TAN;
+    constexpr bool NL = (SM != M_ISO);
     extern __shared__ double smem[];
     __shared__ double s_red[kMaxRed * 32];
     __shared__ uint64_t s_bar[2];
@@ -1000,21 +828,21 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
         if (tid == 0) {
             fence_proxy_async();
             const uint32_t nev = (uint32_t)(n_own & ~1);
-            uint32_t bytes = (uint32_t)n_own * 16u * (NL ? 3u : 2u) + (TAN ? 0u : nev * 8u) + (uint32_t)n_own * 16u;
+            uint32_t bytes = (uint32_t)n_own * 16u * (NL ? 3u : 2u) + nev * 8u + (uint32_t)n_own * 16u;
             mbar_expect_tx(&s_bar[s_], bytes);
             bulk_g2s(tX, X2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
             bulk_g2s(tV, V2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
             if (NL) bulk_g2s(tU, U2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
-            if (!TAN && nev) bulk_g2s(tP, a.phi + n0, nev * 8u, &s_bar[s_]);
+            if (nev) bulk_g2s(tP, a.phi + n0, nev * 8u, &s_bar[s_]);
             bulk_g2s(p + oI, bv.inc8 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
-            if (!TAN && (n_own & 1)) cp_async8(tP + n_own - 1, a.phi + n0 + n_own - 1);
+            if (n_own & 1) cp_async8(tP + n_own - 1, a.phi + n0 + n_own - 1);
         }
         for (int i = tid; i < n_halo; i += kThreads) {
             int g = (i == tid) ? hidx : bv.halo[h0 + i];
             cp_async16(tX + n_own + i, X2 + g);
             cp_async16(tV + n_own + i, V2 + g);
             if (NL) cp_async16(tU + n_own + i, U2 + g);
-            if (!TAN) cp_async8(tP + n_own + i, a.phi + g);
+            cp_async8(tP + n_own + i, a.phi + g);
         }
         cp_async_commit();
         (void)mb;
@@ -1048,16 +876,6 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
         } else {
             cp_async_wait<0>();
         }
-        // cached tangents of this thread's two cells: requested before the wait on the staged nodes
-        double T0[6], T1[6];
-        if (TAN) {
-            const double* tp = a.tan + mb.x + tid;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) {
-                T0[k] = (tid < ne) ? __ldg(tp + (size_t)k * a.tan_stride) : 0.0;
-                T1[k] = (tid + kThreads < ne) ? __ldg(tp + (size_t)k * a.tan_stride + kThreads) : 0.0;
-            }
-        }
         mbar_wait(&s_bar[s], (phases >> s) & 1u);
         phases ^= (1u << s);
         __syncthreads();
@@ -1071,20 +889,14 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
         if (tid < ne) {
             double2 f0, f1, f2;
             const int vx = lc0.x & 0xFFFF, vy = lc0.x >> 16, vz = lc0.y & 0xFFFF;
-            if (TAN)
-                tri_apply_elem_tan(sX[vx], sX[vy], sX[vz], sV[vx], sV[vy], sV[vz], T0, f0, f1, f2);
-            else
-                tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
+            tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
                                    sV[vz], NL ? sU[vx] : z, NL ? sU[vy] : z, NL ? sU[vz] : z, f0, f1, f2);
             sE[tid] = f0; sE[chunk + tid] = f1; sE[2 * chunk + tid] = f2;
         }
         if (tid + kThreads < ne) {
             double2 f0, f1, f2;
             const int vx = lc1.x & 0xFFFF, vy = lc1.x >> 16, vz = lc1.y & 0xFFFF;
-            if (TAN)
-                tri_apply_elem_tan(sX[vx], sX[vy], sX[vz], sV[vx], sV[vy], sV[vz], T1, f0, f1, f2);
-            else
-                tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
+            tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
                                    sV[vz], NL ? sU[vx] : z, NL ? sU[vy] : z, NL ? sU[vz] : z, f0, f1, f2);
             sE[tid + kThreads] = f0; sE[chunk + tid + kThreads] = f1; sE[2 * chunk + tid + kThreads] = f2;
         }
@@ -1133,171 +945,6 @@ __global__ void __launch_bounds__(kThreads, 3) apply_u_tri_v3_kernel(BlockView b
         lc0 = lc0n; lc1 = lc1n; mk = mkn; hnext = hnn;
         has_next = has_nn;
     }
-    double r1[1] = {red};
-    grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red, a.pv);
-}
-
-// ============================================================================= hot kernel, v4 (experiment, opt-in)
-// Same phases as v3 with a THREE-stage ring and a prefetch distance of two blocks (PFX_APPLY_VARIANT=4).
-// Knock-out timings of v3 on the bench mesh (57.6 us): without phase B 40.3, without phase C 53.3,
-// staging only 34.9 — the phases add up instead of overlapping.  Two blocks in flight per CTA do not
-// help: at 84 KB of shared memory only 2 CTAs fit per SM and the kernel slows to 65 us, i.e. the
-// phases themselves are latency-bound and what they need is more resident warps, not deeper
-// prefetching.  Kept as a parity-tested variant for the next round of work on this kernel.
-template <int SM>
-__global__ void __launch_bounds__(kThreads, 2) apply_u_tri_v4_kernel(BlockView bv, KArgs a) {
-    constexpr bool NL = (SM != M_ISO);
-    constexpr int NST = 3, PD = NST - 1;
-    extern __shared__ double smem[];
-    __shared__ double s_red[kMaxRed * 32];
-    __shared__ uint64_t s_bar[NST];
-    if (a.stop && a.stop[0] != 0.0) return;
-    const int tid = threadIdx.x;
-    const int ML = bv.max_loc, chunk = bv.chunk, MO = (bv.max_own + 1) & ~1;
-    const size_t oV = (size_t)ML * 16, oU = 2 * oV, oP = oV * (NL ? 3 : 2), oI = oP + (size_t)((ML + 3) & ~1) * 8;
-    const size_t stage_bytes = oI + (size_t)MO * 16;
-    char* const sbase = reinterpret_cast<char*>(smem);
-    double2* sE = reinterpret_cast<double2*>(sbase + NST * stage_bytes);    // [3*chunk + 1], last = zero slot
-    const int zslot = 3 * chunk;
-    const double2* X2 = reinterpret_cast<const double2*>(a.X);
-    const double2* V2 = reinterpret_cast<const double2*>(a.v);
-    const double2* U2 = reinterpret_cast<const double2*>(a.u);
-    const unsigned short* M2 = reinterpret_cast<const unsigned short*>(a.mask);
-    const uint2* LC = reinterpret_cast<const uint2*>(bv.lconn);
-    if (tid == 0) {
-        for (int k = 0; k < NST; ++k) mbar_init(&s_bar[k], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        sE[zslot] = make_double2(0.0, 0.0);
-    }
-    __syncthreads();
-    if (a.pv && a.wait_halo) halo_wait_cta(a.pv);
-
-    // stage the block described by ma into ring slot s_ (hidx: this thread's first halo node id)
-    auto issue = [&](int4 ma, int s_, int hidx) {
-        char* p = sbase + (size_t)s_ * stage_bytes;
-        double2 *tX = reinterpret_cast<double2*>(p), *tV = reinterpret_cast<double2*>(p + oV), *tU = reinterpret_cast<double2*>(p + oU);
-        double* tP = reinterpret_cast<double*>(p + oP);
-        const int n0 = ma.x, n_own = ma.y, h0 = ma.z, n_halo = ma.w;
-        if (tid == 0) {
-            fence_proxy_async();
-            const uint32_t nev = (uint32_t)(n_own & ~1);
-            uint32_t bytes = (uint32_t)n_own * 16u * (NL ? 3u : 2u) + nev * 8u + (uint32_t)n_own * 16u;
-            mbar_expect_tx(&s_bar[s_], bytes);
-            bulk_g2s(tX, X2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
-            bulk_g2s(tV, V2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
-            if (NL) bulk_g2s(tU, U2 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
-            if (nev) bulk_g2s(tP, a.phi + n0, nev * 8u, &s_bar[s_]);
-            bulk_g2s(p + oI, bv.inc8 + n0, (uint32_t)n_own * 16u, &s_bar[s_]);
-            if (n_own & 1) cp_async8(tP + n_own - 1, a.phi + n0 + n_own - 1);
-        }
-        for (int i = tid; i < n_halo; i += kThreads) {
-            int g = (i == tid) ? hidx : bv.halo[h0 + i];
-            cp_async16(tX + n_own + i, X2 + g);
-            cp_async16(tV + n_own + i, V2 + g);
-            if (NL) cp_async16(tU + n_own + i, U2 + g);
-            cp_async8(tP + n_own + i, a.phi + g);
-        }
-    };
-
-    const int stride = gridDim.x, nb = bv.nb;
-    int blk = blockIdx.x;                       // grid <= nb: every CTA owns at least one block
-    // metadata ring: A[j] / B[j] describe block blk + j*stride (A: n0, n_own, h0, n_halo; B: e0, n_elems, ..)
-    int4 A0 = bv.meta[2 * blk], B0 = bv.meta[2 * blk + 1];
-    int4 A1 = A0, B1 = B0, A2 = A0, A3 = A0;
-    if (blk + stride < nb) { A1 = bv.meta[2 * (blk + stride)]; B1 = bv.meta[2 * (blk + stride) + 1]; }
-    if (blk + 2 * stride < nb) A2 = bv.meta[2 * (blk + 2 * stride)];
-    if (blk + 3 * stride < nb) A3 = bv.meta[2 * (blk + 3 * stride)];
-    // prologue: blocks 0 and 1 into slots 0 and 1 (one cp.async group each, empty if the block does not exist)
-    issue(A0, 0, tid < A0.w ? bv.halo[A0.z + tid] : 0);
-    cp_async_commit();
-    if (blk + stride < nb) issue(A1, 1, tid < A1.w ? bv.halo[A1.z + tid] : 0);
-    cp_async_commit();
-    uint2 lc0 = make_uint2(0u, 0u), lc1 = lc0;
-    if (tid < B0.y) lc0 = LC[B0.x + tid];
-    if (tid + kThreads < B0.y) lc1 = LC[B0.x + tid + kThreads];
-    unsigned int mk = 0u;
-    if (M2 && tid < A0.y) mk = M2[A0.x + tid];
-    int h2 = (blk + 2 * stride < nb && tid < A2.w) ? bv.halo[A2.z + tid] : 0;     // halo ids of block +2
-    double red = 0.0;
-    for (int it = 0;; ++it) {
-        const int s = it % NST;
-        const int n0 = A0.x, n_own = A0.y, ne = B0.y;
-        const bool v1 = blk + stride < nb, v2 = blk + 2 * stride < nb, v3 = blk + 3 * stride < nb;
-        // block +2 into the slot block -1 has just released; metadata of block +4
-        if (v2) issue(A2, (it + PD) % NST, h2);
-        cp_async_commit();
-        int4 A4 = A3, B2 = B1;
-        if (blk + 4 * stride < nb) A4 = bv.meta[2 * (blk + 4 * stride)];
-        if (v2) B2 = bv.meta[2 * (blk + 2 * stride) + 1];
-        cp_async_wait<PD>();
-        mbar_wait(&s_bar[s], (uint32_t)(it / NST) & 1u);
-        __syncthreads();
-        const char* p = sbase + (size_t)s * stage_bytes;
-        const double2 *sX = reinterpret_cast<const double2*>(p), *sV = reinterpret_cast<const double2*>(p + oV),
-                      *sU = reinterpret_cast<const double2*>(p + oU);
-        const double* sP = reinterpret_cast<const double*>(p + oP);
-        const uint4* s_inc8 = reinterpret_cast<const uint4*>(p + oI);
-        // ---- phase B: two cells per thread
-        const double2 z = make_double2(0.0, 0.0);
-        if (tid < ne) {
-            double2 f0, f1, f2;
-            const int vx = lc0.x & 0xFFFF, vy = lc0.x >> 16, vz = lc0.y & 0xFFFF;
-            tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
-                               sV[vz], NL ? sU[vx] : z, NL ? sU[vy] : z, NL ? sU[vz] : z, f0, f1, f2);
-            sE[tid] = f0; sE[chunk + tid] = f1; sE[2 * chunk + tid] = f2;
-        }
-        if (tid + kThreads < ne) {
-            double2 f0, f1, f2;
-            const int vx = lc1.x & 0xFFFF, vy = lc1.x >> 16, vz = lc1.y & 0xFFFF;
-            tri_apply_elem<SM>(a.m, sX[vx], sX[vy], sX[vz], sP[vx], sP[vy], sP[vz], sV[vx], sV[vy],
-                               sV[vz], NL ? sU[vx] : z, NL ? sU[vy] : z, NL ? sU[vz] : z, f0, f1, f2);
-            sE[tid + kThreads] = f0; sE[chunk + tid + kThreads] = f1; sE[2 * chunk + tid + kThreads] = f2;
-        }
-        __syncthreads();
-        // ---- per-thread indices of later blocks (consumed one iteration later)
-        uint2 lc0n = make_uint2(0u, 0u), lc1n = lc0n;
-        unsigned int mkn = 0u;
-        int h3 = 0;
-        if (v1) {
-            if (tid < B1.y) lc0n = LC[B1.x + tid];
-            if (tid + kThreads < B1.y) lc1n = LC[B1.x + tid + kThreads];
-            if (M2 && tid < A1.y) mkn = M2[A1.x + tid];
-            if (v3 && tid < A3.w) h3 = bv.halo[A3.z + tid];
-        }
-        // ---- phase C: eight independent incident rows per owned node, fixed order
-        if (tid < n_own) {
-            const uint4 c8 = s_inc8[tid];
-            const unsigned cw[4] = {c8.x, c8.y, c8.z, c8.w};
-            double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int code = (int)((cw[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
-                const int idx = min((code & 3) * chunk + (code >> 2), zslot);
-                const double2 f = sE[idx];
-                acc.x += f.x; acc.y += f.y;
-            }
-            if ((c8.w >> 16) == 0xFFFEu) {                    // rare: valence > 8, rest from the CSR list
-                int k0 = bv.inc_ptr[n0 + tid] + 7, k1 = bv.inc_ptr[n0 + tid + 1];
-                for (int k = k0; k < k1; ++k) {
-                    const int code = bv.inc[k];
-                    if (code >= 0xFFFE) break;
-                    const double2 f = sE[(code & 3) * chunk + (code >> 2)];
-                    acc.x += f.x; acc.y += f.y;
-                }
-            }
-            if (mk & 0xFFu) acc.x = 0.0;
-            if (mk & 0xFF00u) acc.y = 0.0;
-            const double2 vin = sV[tid];
-            reinterpret_cast<double2*>(a.y)[n0 + tid] = acc;
-            red += vin.x * acc.x + vin.y * acc.y;
-        }
-        if (!v1) break;
-        __syncthreads();                         // slot s and sE are free again
-        blk += stride;
-        A0 = A1; B0 = B1; A1 = A2; B1 = B2; A2 = A3; A3 = A4;
-        lc0 = lc0n; lc1 = lc1n; mk = mkn; h2 = h3;
-    }
-    cp_async_wait<0>();
     double r1[1] = {red};
     grid_reduce<1>(r1, a.partial, a.result, a.counter, s_red, a.pv);
 }
@@ -2014,6 +1661,12 @@ __global__ void __launch_bounds__(kThreads) pcg_direction_kernel(int64_t n, doub
 __global__ void axpby_kernel(int64_t n, double* out, const double* a, double sa, const double* b, double sb) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = (a ? sa * a[i] : 0.0) + (b ? sb * b[i] : 0.0);
+}
+
+// identity rows of the Dirichlet dofs: y = v there (dolfinx assemble_matrix(bcs) puts 1 on the diagonal)
+__global__ void mask_restore_kernel(int64_t n, const uint8_t* mask, const double* v, double* y) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if (mask[i]) y[i] = v[i];
 }
 
 __global__ void mask_zero_kernel(int64_t n, const uint8_t* mask, double* v) {
