@@ -16,7 +16,12 @@ from phasefieldx_b200.files import append_results_to_file
 def solve(Data, msh, final_time, V_Φ, bc_list_phi=[], update_boundary_conditions=None, update_loading=None,
           ds_bound=None, dt=1.0, path=None, quadrature_degree=2, case="AT2", V_gradient_Φ=None, device=0,
           solver_options=None, vtu_format="ascii"):
-    """Reference signature; `update_loading`, `ds_bound`, `quadrature_degree` are accepted and unused."""
+    """Reference signature; `ds_bound`, `quadrature_degree` are accepted and unused.  `update_loading` (a UFL source
+    term -(f v / l + l grad_f . grad v) dx built from `ufl.SpatialCoordinate`, reference solver.py:124-130) changes the
+    solution and has no counterpart here: passing it raises instead of silently dropping the term."""
+    if update_loading is not None:
+        raise NotImplementedError("update_loading (UFL source term of reference Phase_Field/solver/solver.py:124-130) is not "
+                                  "available on the GPU path")
     if case != "AT2":
         raise NotImplementedError("only the AT2 geometric crack function is on the GPU path (SURVEY §8f N2)")
     if V_gradient_Φ is not None:

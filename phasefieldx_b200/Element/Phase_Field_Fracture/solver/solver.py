@@ -41,14 +41,16 @@ def _traction_sets(T_list_u):
 def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update_boundary_conditions=None,
           f_list_u=None, T_list_u=None, update_loading=None, ds_bound=None, dt=1.0, path=None,
           bcs_list_u_names=None, min_stagger_iter=2, max_stagger_iter=10000, stagger_error_tol=1e-8,
-          device=0, solver_options=None, vtu_every=1, vtu_format="ascii", vtu_parallel=False):
+          device=0, solver_options=None, vtu_every=1, vtu_format="ascii", vtu_parallel=False, vtu_keep=None,
+          step_callback=None):
     """Solve the phase-field fracture and fatigue problem (reference signature; `f_list_u` and
     `ds_bound` are accepted and unused exactly as in the reference).
     Extra keyword-only knobs (not in the reference): `device`, `solver_options` (pfx_params
     overrides such as cg_rtol), `vtu_every` (VTU cadence; default every step as the reference),
     `vtu_format` ("ascii" = the reference's layout, "binary" = raw appended data), `vtu_parallel` (multi-rank
     runs: every rank writes its own piece + a .pvtu index, dolfinx's parallel layout, instead of gathering the
-    fields on rank 0)."""
+    fields on rank 0), `vtu_keep` (keep only the k most recent step files on disk; default: all, as the reference),
+    `step_callback(step, report, reactions, energies)` called on every rank after the outputs of a load step."""
     if path is None:
         path = os.getcwd()
     result_folder_name = Data.results_folder_name
@@ -132,7 +134,7 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     pieces = bool(vtu_parallel) and dist is not None
     if Data.save_solution_vtu and (rank == 0 or pieces):
         vtk_sol = VTKFile(None, os.path.join(result_folder_name, "paraview-solutions_vtu", "phasefieldx.pvd"), "w", fmt=vtu_format,
-                          rank=rank if pieces else 0, world=world if pieces else 1)
+                          rank=rank if pieces else 0, world=world if pieces else 1, keep_last=vtu_keep)
     if getattr(Data, "save_solution_xdmf", False):
         logger.info(" save_solution_xdmf: XDMF/HDF5 output needs dolfinx and is not written (VTU output is unaffected)")
     logger.info(" S t a r t i n g    A n a l y s i s ")
@@ -189,8 +191,10 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
                                        '#step\tUx\tUy\tUz\tphi', step, bc_ux, bc_uy, bc_uz, 0.0)
             # reactions and energies are collective (global values on every rank); unlike the reference
             # (solver.py:427) the reaction files are also written in multi-rank runs
+            reactions = []
             for i in range(len(bc_list_u)):
                 R = eng.reaction(i)
+                reactions.append(R)
                 if rank == 0:
                     append_results_to_file(os.path.join(result_folder_name, bcs_list_u_names[i] + ".reaction"),
                                            '#step\tRx\tRy\tRz', step, float(R[0]), float(R[1]), float(R[2]))
@@ -207,6 +211,8 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
                     phi_out, u_out = gather_field(eng, rmesh, "phi", dist, dev), gather_field(eng, rmesh, "u", dist, dev)
                 if vtk_sol is not None:
                     vtk_sol.write_function(rmesh.piece(ctype) if pieces else msh, {"phi": phi_out, "u": u_out}, step, background=True)
+            if step_callback is not None:
+                step_callback(step, rep, reactions, en)
             t += dt
             step += 1
     finally:

@@ -38,13 +38,17 @@ class VTKFile:
     that reads back bit-exactly); everything that does not change between load steps —
     points, cells, id arrays — is formatted once and reused."""
 
-    def __init__(self, comm, filename, mode="w", fmt="ascii", rank=0, world=1):
+    def __init__(self, comm, filename, mode="w", fmt="ascii", rank=0, world=1, keep_last=None):
         """fmt "ascii": the reference's layout; "binary": same arrays as raw appended data (VTK
         `format="appended"`, UInt64 block headers) — a third of the bytes and no number formatting,
         for meshes where the ASCII file is what a load step waits for."""
         if fmt not in ("ascii", "binary"):
             raise ValueError("fmt must be 'ascii' or 'binary'")
         self.fmt = fmt
+        # keep_last = k: only the k most recent step files of this rank stay on disk (bounded disk use for long
+        # runs on large meshes); None (default, the reference's behaviour): every step file is kept
+        self.keep_last = None if keep_last is None else max(1, int(keep_last))
+        self._written = []
         self.rank, self.world = int(rank), int(world)
         self.pvd = filename
         self.dir = os.path.dirname(filename)
@@ -174,6 +178,11 @@ class VTKFile:
 
     def _record(self, t, step, piece_name, fields):
         """Book-keeping after a piece: rank 0 writes the .pvtu of a multi-rank step and the .pvd index."""
+        self._written.append(os.path.join(self.dir, piece_name))
+        while self.keep_last is not None and len(self._written) > self.keep_last:
+            old = self._written.pop(0)
+            if os.path.exists(old):
+                os.remove(old)
         if self.rank != 0:
             return
         name = piece_name
@@ -193,6 +202,8 @@ class VTKFile:
             with open(os.path.join(self.dir, name), "w") as fh:
                 fh.write("\n".join(L) + "\n")
         self.records.append((t, name))
+        if self.keep_last is not None:
+            self.records = self.records[-self.keep_last:]
         self._write_pvd()
 
     def _write(self, msh, fields, t):

@@ -8,6 +8,8 @@ container only; the GPU box has no /root/reference).
   ref_1713.npz       same for example 1713 (structured 200x100 Q1 mesh, no mesh file needed)
   ref_1712.npz       same for example 1712 (shear, spectral)
   ref_1800.npz       first 40 rows of the fatigue example 1800 (total.energy incl. alpha_acum, conv, dof)
+  ref_1711_final.vtu.gz  the reference's stored final VTU of example 1711 (5 089 points / 9 990 triangles in dolfinx ordering,
+                     phi, u), gzip-compressed as is: pins the VTU writer / reader to the reference's own file layout
   ref_degradation.npz   g and dg of the reference's own g_degradation_functions.py (quadratic, borden) on a grid of
                      phi, executed unmodified (plain Python arithmetic; loaded by file path)
   ref_constitutive.npz  outputs of the reference's own constitutive layer
@@ -51,6 +53,10 @@ def main():
     fat = os.path.join(REF, "examples", "Fatigue", "1800_Fatigue_Single_Edge_Notched_Tension_Test")
     np.savez_compressed(os.path.join(HERE, "ref_1800.npz"), energy=table(os.path.join(fat, "total.energy"), 40),
                         conv=table(os.path.join(fat, "phasefieldx.conv"), 40), dof=table(os.path.join(fat, "top.dof"), 40))
+    import gzip
+    vtu = os.path.join(EX, "1711_Single_Edge_Notched_Tension_Test", "paraview-solutions_vtu", "phasefieldx_p0_000149.vtu")
+    with open(vtu, "rb") as src, gzip.GzipFile(os.path.join(HERE, "ref_1711_final.vtu.gz"), "wb", mtime=0) as dst:
+        dst.write(src.read())
     from ufl_shim import reference_constitutive
     np.savez_compressed(os.path.join(HERE, "ref_constitutive.npz"), **reference_constitutive())
     import importlib.util

@@ -326,3 +326,63 @@ def test_borden_degradation_vs_oracle(ctype, monkeypatch):
     free = np.setdiff1d(np.arange(len(x)), seed)
     assert o.phi[free].max() > 0.05 and grew          # the seed did drive the field, through a nonlinear phi problem
     e.close()
+
+
+def _run_workload_pair(w, steps, times, monkeypatch=None, max_stagger=500, **opts):
+    """Oracle and engine side by side on a `workloads` instance; returns the per-step reports of both."""
+    from oracle.solver import BC, Oracle, Params
+    from phasefieldx_b200 import workloads as W
+    o = Oracle(w.msh.geometry.x, w.msh.cells, w.cell_type, Params(**w.params))
+    e = W.make_engine(w, **opts)
+    bcs = [BC(d) for _, d in w.bc_sets]
+    out = []
+    for step, t in zip(steps, times):
+        for i, v in enumerate(w.bc_values(t)):
+            bcs[i].values = v
+            e.set_bc_values_u(i, v)
+        ro = o.load_step(bcs, [], min_stagger_iter=w.min_stagger_iter, max_stagger_iter=max_stagger, tol=w.stagger_tol)
+        rg = e.load_step(min_stagger_iter=w.min_stagger_iter, max_stagger_iter=max_stagger, stagger_tol=w.stagger_tol)
+        out.append((step, ro, rg, float(o.phi.max())))
+        assert rg["stagger"] == ro["stagger"], (step, rg["stagger"], ro["stagger"])
+        _compare_step(o, e, bcs, step)
+        eg, eo = e.energies(), o.energies()
+        for key in eo:
+            assert abs(eg[key] - eo[key]) <= 1e-7 * abs(eo[key]) + 1e-18, (step, key, eg[key], eo[key])
+    stats = (e.block_stats(), e.coarse_stats())
+    e.close()
+    return out, stats
+
+
+def test_shear_n160_two_level_graph_path_vs_oracle(monkeypatch):
+    """The bench workload (config 2, reference plot_1712.py) at the size the CPU baseline of bench.py samples:
+    160 x 160 x 2 triangles, 25.9 k nodes — large enough for the production solver path (persistent TMA-staged
+    apply kernels, two-level PCG with the aggregate coarse space, CUDA-graph iterations, adaptive absolute PCG
+    floor) instead of the single-launch cooperative kernels of the small parity meshes."""
+    from phasefieldx_b200 import workloads as W
+    monkeypatch.setenv("PFX_NO_COOP", "1")
+    w = W.sen_shear(160)
+    out, (blocks, coarse) = _run_workload_pair(w, range(4), [0.0, 1.0, 2.0, 3.0])
+    assert coarse["active"] == 1 and coarse["setups"] >= 1 and blocks["n_blocks"] >= 32
+    assert all(rg["cg_its_u"] > 0 for step, ro, rg, _ in out[1:])
+
+
+@pytest.mark.parametrize("path", ["cooperative", "two_level"])
+def test_shear_through_peak_load_vs_oracle(path, monkeypatch):
+    """Notched shear specimen (spectral split, k = 0) driven THROUGH the peak load until the crack has formed
+    (phi_max > 0.95): dozens to a hundred stagger iterations per step, softening tangent, (1 - phi)^2 -> 0 in the
+    crack.  Same stagger counts as the oracle, fields within 1e-8, reactions within 1e-6, on both solver paths."""
+    from phasefieldx_b200 import workloads as W
+    opts = {}
+    if path == "cooperative":
+        n, last = 16, 13
+    else:
+        monkeypatch.setenv("PFX_NO_COOP", "1")
+        n, last, opts = 32, 11, dict(block_nodes=32)
+    w = W.sen_shear(n, l=0.06)
+    steps = list(range(last + 1))
+    out, (blocks, coarse) = _run_workload_pair(w, steps, [10.0 * s for s in steps], **opts)
+    phimax = [p for *_, p in out]
+    rx = [abs(ro["stagger"]) for _, ro, _, _ in out]
+    assert phimax[-1] > 0.95 and max(rx) >= 30            # crack formed; the peak took many stagger iterations
+    if path == "two_level":
+        assert coarse["active"] == 1 and coarse["setups"] >= 1

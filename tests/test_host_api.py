@@ -281,3 +281,47 @@ def test_parallel_vtu_pieces_merge_to_the_global_fields(tmp_path, fmt):
         assert np.array_equal(np.sort(d["point_gid"][d["cells"]], 1), np.sort(cells[d["cell_gid"]], 1))
     assert np.all(seen_pt == 1) and np.all(seen_cell == 1)
     assert np.array_equal(phi, phi_g) and np.array_equal(u, u_g)
+
+
+def test_reference_stored_vtu_parses_and_writer_reproduces_its_layout(tmp_path):
+    """O2 pinned on the reference's own file: tests/golden/ref_1711_final.vtu.gz is the stored final VTU of reference
+    example 1711 (examples/PhaseFieldFracture/1711_*/paraview-solutions_vtu/phasefieldx_p0_000149.vtu).  The reader
+    parses it; writing the same mesh and fields with VTKFile gives the same sequence of XML elements and DataArrays
+    (type, Name, NumberOfComponents) and the same numbers."""
+    import gzip
+    import re
+    from conftest import GOLDEN
+    from phasefieldx_b200 import io_vtk, mesh as M
+    ref_txt = gzip.open(os.path.join(GOLDEN, "ref_1711_final.vtu.gz")).read().decode()
+    src = tmp_path / "ref.vtu"
+    src.write_text(ref_txt)
+    ref = io_vtk.read_vtu_points_cells(str(src))
+    assert ref["points"].shape == (5089, 3) and ref["cells"].shape == (9990, 3)
+    assert ref["phi"].shape == (5089,) and ref["u"].shape == (5089, 3) and np.all(ref["u"][:, 2] == 0.0)
+    assert 0.99 < ref["phi"].max() < 1.05 and ref["cells"].min() == 0 and ref["cells"].max() == 5088
+    assert np.array_equal(ref["point_gid"], np.arange(5089)) and np.array_equal(ref["cell_gid"], np.arange(9990))
+    msh = M.Mesh(ref["points"], ref["cells"].astype(np.int32), "triangle")
+    vt = io_vtk.VTKFile(None, str(tmp_path / "out" / "phasefieldx.pvd"), "w")
+    vt.write_function(msh, {"phi": ref["phi"], "u": ref["u"][:, :2]}, 149)
+    vt.close()
+    mine_txt = (tmp_path / "out" / "phasefieldx_p0_000149.vtu").read_text()
+
+    def skeleton(txt):
+        out = []
+        for tag in re.findall(r"<(/?\w+)([^>]*)>", txt):
+            name, attrs = tag
+            if name == "DataArray":
+                a = dict(re.findall(r'(\w+)="([^"]*)"', attrs))
+                out.append(("DataArray", a.get("type"), a.get("Name"), a.get("NumberOfComponents"), a.get("format")))
+            elif name == "Piece":
+                out.append((name, attrs.strip()))
+            elif not name.startswith("?"):
+                out.append((name,))
+        return out
+    assert skeleton(mine_txt) == skeleton(ref_txt)
+    back = io_vtk.read_vtu_points_cells(str(tmp_path / "out" / "phasefieldx_p0_000149.vtu"))
+    for key in ("points", "cells", "phi", "u"):
+        assert np.array_equal(back[key], ref[key]), key
+    # the reference stores VTK_LAGRANGE_TRIANGLE (69) cells, offsets 3, 6, ...
+    types = re.search(r'Name="types"[^>]*>([^<]*)<', mine_txt).group(1).split()
+    assert set(types) == {"69"} == set(re.search(r'Name="types"[^>]*>([^<]*)<', ref_txt).group(1).split())
