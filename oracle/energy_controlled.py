@@ -174,7 +174,7 @@ class EnergyControlled(Oracle):
             en = self.energies()
             gamma = en["gamma"]
             rec = dict(step=step, iterations=its, lam=self.lam, tau=tau, dtau=dtau, gamma=gamma, energies=en,
-                       external=self.external_energy(), residual=hist[-1])
+                       external=self.external_energy(), residual=hist[-1], hist=hist)
             out.append(rec)
             if callback is not None:
                 callback(rec)

@@ -70,6 +70,10 @@ struct KArgs {
     const double* cm;       // precomputed phi-operator coefficients 2H + F·Gc/l and F·Gc·l (per node)
     const double* cg;
     double* tan;            // cached element tangents [n_own_cells][21] (tets), compact own-cell index
+    // monolithic (u, phi) operators of the energy-controlled solvers (pfx_monolithic.cuh)
+    const double* v2;       // phi-part of the input vector
+    double* y2;             // phi-part of the output
+    double coef;            // Gc + lambda c1 (variational scheme) or Gc
 };
 
 constexpr int kMaxRanks = 8;

@@ -130,3 +130,23 @@ def operator_state(w):
     phi = np.clip(np.exp(-dist / l), 0.0, 1.0)
     v = np.random.default_rng(0).uniform(-1, 1, size=u.size)
     return u.ravel(), phi, v
+
+
+def three_point_bending(divx=400, divy=100, variational=True):
+    """Config 4: energy-controlled three-point bending, symmetric half model [-4,0]x[0,1] of Q1 cells
+    (reference examples/PhaseFieldFractureEnergyControlled/plot_three_point_var.py:96-131, 229-271 and
+    plot_three_point_non_var.py): bc_y on the bottom-left support, bc_x on the symmetry line above the notch,
+    traction (0, -1/0.075) on the loaded patch of the top edge.  Returns (mesh, Input keywords, Dirichlet sets,
+    (traction nodes, nodal weights, T), solver keywords)."""
+    from . import fem
+    lx, ly, a0, surface = 4.0, 1.0, 0.2, 0.075
+    msh = M.create_rectangle(None, [np.array([-lx, 0.0]), np.array([0.0, ly])], [divx, divy], M.CellType.quadrilateral)
+    fb = M.locate_entities_boundary(msh, 1, lambda x: np.logical_and(np.isclose(x[1], 0), np.less(x[0], -lx + surface)))
+    fc = M.locate_entities_boundary(msh, 1, lambda x: np.logical_and(np.isclose(x[0], 0), np.greater_equal(x[1], a0)))
+    ft = M.locate_entities_boundary(msh, 1, lambda x: np.logical_and(np.isclose(x[1], ly), np.greater_equal(x[0], -surface)))
+    sets = [("bottom_left", _dofs(M.facet_nodes(msh, fb), 2, [1])), ("center", _dofs(M.facet_nodes(msh, fc), 2, [0]))]
+    nodes, w = fem.Measure(msh, ft).nodal_weights()
+    params = dict(E=20.8, nu=0.3, Gc=0.0005, l=0.03, degradation="isotropic", split_energy="no",
+                  degradation_function="quadratic", irreversibility="no", fatigue=False, k=0.0)
+    kw = dict(final_gamma=0.5, dtau=0.001, dtau_min=1e-12, dtau_max=1.0, c1=35.0 if variational else 1.0, c2=1.0)
+    return msh, params, sets, (nodes, w, np.array([0.0, -1.0 / surface])), kw

@@ -10,6 +10,9 @@ container only; the GPU box has no /root/reference).
   ref_1800.npz       first 40 rows of the fatigue example 1800 (total.energy incl. alpha_acum, conv, dof)
   ref_1711_final.vtu.gz  the reference's stored final VTU of example 1711 (5 089 points / 9 990 triangles in dolfinx ordering,
                      phi, u), gzip-compressed as is: pins the VTU writer / reader to the reference's own file layout
+  ref_energy_controlled.npz  first 12 rows of the stored outputs of the energy-controlled examples
+                     (examples/PhaseFieldFractureEnergyControlled/results_three_point_[non_]var: total.energy,
+                     bottom_left.reaction, lambda.dof)
   ref_degradation.npz   g and dg of the reference's own g_degradation_functions.py (quadratic, borden) on a grid of
                      phi, executed unmodified (plain Python arithmetic; loaded by file path)
   ref_constitutive.npz  outputs of the reference's own constitutive layer
@@ -53,6 +56,13 @@ def main():
     fat = os.path.join(REF, "examples", "Fatigue", "1800_Fatigue_Single_Edge_Notched_Tension_Test")
     np.savez_compressed(os.path.join(HERE, "ref_1800.npz"), energy=table(os.path.join(fat, "total.energy"), 40),
                         conv=table(os.path.join(fat, "phasefieldx.conv"), 40), dof=table(os.path.join(fat, "top.dof"), 40))
+    ec = os.path.join(REF, "examples", "PhaseFieldFractureEnergyControlled")
+    np.savez_compressed(os.path.join(HERE, "ref_energy_controlled.npz"),
+                        var_energy=table(os.path.join(ec, "results_three_point_var", "total.energy"), 12),
+                        var_reaction=table(os.path.join(ec, "results_three_point_var", "bottom_left.reaction"), 12),
+                        var_lambda=table(os.path.join(ec, "results_three_point_var", "lambda.dof"), 12),
+                        nonvar_energy=table(os.path.join(ec, "results_three_point_non_var", "total.energy"), 12),
+                        nonvar_reaction=table(os.path.join(ec, "results_three_point_non_var", "bottom_left.reaction"), 12))
     import gzip
     vtu = os.path.join(EX, "1711_Single_Edge_Notched_Tension_Test", "paraview-solutions_vtu", "phasefieldx_p0_000149.vtu")
     with open(vtu, "rb") as src, gzip.GzipFile(os.path.join(HERE, "ref_1711_final.vtu.gz"), "wb", mtime=0) as dst:
