@@ -158,6 +158,46 @@ int pfx_load_step(pfx_ctx* ctx, const pfx_step_opts* opts, pfx_step_report* out)
 int pfx_solve_u(pfx_ctx* ctx, pfx_step_report* out);
 int pfx_solve_phi(pfx_ctx* ctx, pfx_step_report* out);
 
+/* ---- energy-controlled monolithic solvers: one call = one Newton solve of the blocked system
+ * (u, phi, lambda) at the control value tau —
+ *   pfx/Element/Phase_Field_Fracture/solver/solver_ener_variational.py:167-259, 360 (`solver_snap.solve()`) and
+ *   solver_ener_non_variational.py:166-270 (variational = 0: no lambda term in F_phi, J_phi,lambda = None).
+ *   F_u = F_int(u, phi) - (1 - lambda c2) int T.w ds,  F_phi = int g'(phi) psi_a(u) v + (Gc + lambda c1) K_gamma phi,
+ *   F_lambda = c1 gamma(phi) + c2 int T.u ds - tau.
+ * The traction is the one registered with pfx_set_traction(ctx, 0, ...) / pfx_set_traction_value (T_list_u[0] of the
+ * reference signature); Dirichlet data: the u-sets only, already satisfied by u (homogeneous in every reference
+ * set-up).  Newton: dolfinx NewtonSolver semantics (residual criterion; defaults rtol 1e-9, atol 1e-10, max_it 50, the
+ * defaults scifem's BlockedNewtonSolver inherits).  The MUMPS solve of the bordered Jacobian is a flexible GMRES,
+ * block-preconditioned by the engine's PCG solvers (lin_rtol: relative residual of the linear solve; inner_rtol: of the
+ * block solves inside the preconditioner).  A solve that does not converge returns PFX_OK with converged = 0 (the
+ * reference catches the solver's exception and shrinks dtau, :486-514); the caller restores the last converged state
+ * with pfx_ec_checkpoint(ctx, 1).  Single-GPU contexts, non-hybrid models, no fatigue. */
+typedef struct {
+    double c1, c2;            /* solver_ener_variational.py:57-58                                */
+    int32_t variational;      /* 1: solver_ener_variational, 0: solver_ener_non_variational        */
+    double newton_rtol, newton_atol;
+    int32_t newton_max_it;
+    double lin_rtol;          /* default 1e-10                                                     */
+    int32_t gmres_restart;    /* default 40 (<= 62)                                                */
+    int32_t lin_max_it;       /* default 2000                                                      */
+    double inner_rtol;        /* default 1e-2                                                      */
+} pfx_ec_opts;
+
+typedef struct {
+    int32_t newton_its, converged;
+    int32_t reason;           /* 1 converged; -5 max_it; -3 linear solve failed; -4 NaN */
+    double residual, residual0;
+    int64_t gmres_its, cg_its_u, cg_its_phi;
+    double lambda_, gamma, external;   /* lambda, gamma(phi) and int T.u ds after the solve          */
+    double gpu_ms;
+} pfx_ec_report;
+
+void pfx_ec_default_opts(pfx_ec_opts* o);
+int pfx_ec_solve(pfx_ctx* ctx, const pfx_ec_opts* opts, double tau, double* lambda_inout, pfx_ec_report* out);
+/* restore = 0: remember (u, phi) as the last converged state (u_c, phi_c of the reference, :367-369);
+ * restore = 1: roll back to it (:489-491). */
+int pfx_ec_checkpoint(pfx_ctx* ctx, int restore);
+
 /* ---- per-step outputs --------------------------------------------------------------- */
 /* pfx/Reactions/reactions_forces.py:12-65, called per BC at solver.py:428-431 */
 int pfx_reaction(pfx_ctx* ctx, int bc_id, double R[3]);

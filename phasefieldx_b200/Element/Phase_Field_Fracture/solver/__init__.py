@@ -1,3 +1,3 @@
-from . import solver, solver_anisotropic  # noqa: F401
+from . import solver, solver_anisotropic, solver_ener_non_variational, solver_ener_variational  # noqa: F401
 
-__all__ = ["solver", "solver_anisotropic"]
+__all__ = ["solver", "solver_anisotropic", "solver_ener_variational", "solver_ener_non_variational"]

@@ -51,6 +51,18 @@ class PfxStepReport(C.Structure):
                 ("hist_fnorm_phi", C.POINTER(C.c_double)), ("phase_ms", C.c_double * 10), ("cg_floor_solves", C.c_int64)]
 
 
+class PfxEcOpts(C.Structure):
+    _fields_ = [("c1", C.c_double), ("c2", C.c_double), ("variational", C.c_int32), ("newton_rtol", C.c_double),
+                ("newton_atol", C.c_double), ("newton_max_it", C.c_int32), ("lin_rtol", C.c_double), ("gmres_restart", C.c_int32),
+                ("lin_max_it", C.c_int32), ("inner_rtol", C.c_double)]
+
+
+class PfxEcReport(C.Structure):
+    _fields_ = [("newton_its", C.c_int32), ("converged", C.c_int32), ("reason", C.c_int32), ("residual", C.c_double),
+                ("residual0", C.c_double), ("gmres_its", C.c_int64), ("cg_its_u", C.c_int64), ("cg_its_phi", C.c_int64),
+                ("lambda_", C.c_double), ("gamma", C.c_double), ("external", C.c_double), ("gpu_ms", C.c_double)]
+
+
 PHASES = ("u_setup", "u_coarse_setup", "u_pcg", "projection", "fatigue", "phi_setup", "phi_coarse_setup", "phi_pcg", "norms",
           "other")
 
@@ -59,7 +71,8 @@ PHASES = ("u_setup", "u_coarse_setup", "u_pcg", "projection", "fatigue", "phi_se
 SYMBOLS = [
     "pfx_version", "pfx_device_count", "pfx_status_string", "pfx_create", "pfx_destroy", "pfx_last_error",
     "pfx_default_params", "pfx_set_bc_u", "pfx_set_bc_values_u", "pfx_set_bc_phi", "pfx_set_bc_values_phi",
-    "pfx_set_traction", "pfx_set_traction_value", "pfx_load_step", "pfx_solve_u", "pfx_solve_phi", "pfx_reaction", "pfx_energies", "pfx_get_field",
+    "pfx_set_traction", "pfx_set_traction_value", "pfx_load_step", "pfx_solve_u", "pfx_solve_phi", "pfx_ec_default_opts", "pfx_ec_solve",
+    "pfx_ec_checkpoint", "pfx_reaction", "pfx_energies", "pfx_get_field",
     "pfx_set_field", "pfx_apply_u", "pfx_apply_phi", "pfx_apply_mass", "pfx_residual_u", "pfx_diag_u", "pfx_rhs_psi", "pfx_project_psi",
     "pfx_l2_error", "pfx_time_operator", "pfx_algorithmic_bytes", "pfx_launch_count", "pfx_block_stats", "pfx_coarse_stats",
     "pfx_partition_create", "pfx_partition_destroy", "pfx_partition_cell_rank", "pfx_partition_node_owner",
@@ -100,6 +113,10 @@ def load():
     lib.pfx_project_psi.argtypes = [C.c_void_p, C.c_int, pd]
     lib.pfx_solve_u.argtypes = [C.c_void_p, C.POINTER(PfxStepReport)]
     lib.pfx_solve_phi.argtypes = [C.c_void_p, C.POINTER(PfxStepReport)]
+    lib.pfx_ec_default_opts.argtypes = [C.POINTER(PfxEcOpts)]
+    lib.pfx_ec_default_opts.restype = None
+    lib.pfx_ec_solve.argtypes = [C.c_void_p, C.POINTER(PfxEcOpts), C.c_double, pd, C.POINTER(PfxEcReport)]
+    lib.pfx_ec_checkpoint.argtypes = [C.c_void_p, C.c_int]
     lib.pfx_reaction.argtypes = [C.c_void_p, C.c_int, pd]
     lib.pfx_energies.argtypes = [C.c_void_p, pd]
     lib.pfx_get_field.argtypes = [C.c_void_p, C.c_int, pd, C.c_int64]
@@ -363,6 +380,28 @@ class Engine:
     def solve_phi(self):
         """One Newton (SNES) solve of the phase-field problem at the current H / fatigue field."""
         return self._solve_single(self.lib.pfx_solve_phi, False)
+
+    def ec_solve(self, tau, lam, c1=1.0, c2=1.0, variational=True, **opts):
+        """One Newton solve of the energy-controlled blocked system (u, phi, lambda) at `tau`
+        (reference solver_ener_[non_]variational.py, `solver_snap.solve()`); returns the report with the new lambda.
+        opts: newton_rtol, newton_atol, newton_max_it, lin_rtol, gmres_restart, lin_max_it, inner_rtol."""
+        o = PfxEcOpts()
+        self.lib.pfx_ec_default_opts(C.byref(o))
+        o.c1, o.c2, o.variational = float(c1), float(c2), int(bool(variational))
+        for k, v in opts.items():
+            if not hasattr(o, k):
+                raise TypeError(f"unknown energy-controlled solver option {k!r}")
+            setattr(o, k, v)
+        lam_io = np.array([float(lam)])
+        r = PfxEcReport()
+        self._ck(self.lib.pfx_ec_solve(self.h, C.byref(o), float(tau), _pd(lam_io), C.byref(r)))
+        return dict(its=r.newton_its, converged=bool(r.converged), reason=r.reason, residual=r.residual, residual0=r.residual0,
+                    gmres_its=r.gmres_its, cg_its_u=r.cg_its_u, cg_its_phi=r.cg_its_phi, lam=r.lambda_, gamma=r.gamma,
+                    external=r.external, gpu_ms=r.gpu_ms)
+
+    def ec_checkpoint(self, restore=False):
+        """Remember (restore=False) or roll back to (restore=True) the last converged (u, phi)."""
+        self._ck(self.lib.pfx_ec_checkpoint(self.h, 1 if restore else 0))
 
     # ---------------------------------------------------------------- outputs
     def reaction(self, bc_id):

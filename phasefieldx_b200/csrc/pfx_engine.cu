@@ -23,6 +23,7 @@
 #include "pfx_kernels.cuh"
 #include "pfx_coarse.cuh"
 #include "pfx_sparse.cuh"
+#include "pfx_monolithic.cuh"
 
 using namespace pfx;
 
@@ -178,6 +179,7 @@ struct pfx_ctx {
     int apply_variant = 3;        // PFX_APPLY_VARIANT: 3 persistent TMA-staged kernel (default), 1 one CTA per block
     int v3_ctas = 0, num_sms = 148;
     Coarse coarse;
+    void* ec = nullptr;           // EnergyCtl of the energy-controlled solvers (pfx_ec.inc), created on first use
 };
 
 namespace {
@@ -1268,6 +1270,13 @@ int set_bc_values_common(pfx_ctx* c, bool is_u, int bc_id, const double* values,
     return push_bc_values(c, is_u);
 }
 
+#include "pfx_ec.inc"
+
+EnergyCtl& ec_of(pfx_ctx* c) {
+    if (!c->ec) c->ec = new EnergyCtl();
+    return *static_cast<EnergyCtl*>(c->ec);
+}
+
 }  // namespace
 
 // ================================================================================= C-ABI
@@ -1524,6 +1533,7 @@ int pfx_destroy(pfx_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
+    delete static_cast<EnergyCtl*>(c->ec);
     delete c;
     return PFX_OK;
 }
@@ -1701,6 +1711,37 @@ int pfx_load_step(pfx_ctx* c, const pfx_step_opts* o, pfx_step_report* rep) {
     rep->cg_floor_solves = c->floor_solves;
     rep->stagger_iters = it;
     rep->err_u = err_u; rep->err_phi = err_phi;
+    return PFX_OK;
+}
+
+// ------------------------------------------------------------------------------- energy-controlled solvers
+void pfx_ec_default_opts(pfx_ec_opts* o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->c1 = 1.0; o->c2 = 1.0; o->variational = 1;
+    o->newton_rtol = 1e-9; o->newton_atol = 1e-10; o->newton_max_it = 50;       // dolfinx NewtonSolver defaults
+    o->lin_rtol = 1e-10; o->gmres_restart = 40; o->lin_max_it = 2000; o->inner_rtol = 1e-2;
+}
+
+int pfx_ec_solve(pfx_ctx* c, const pfx_ec_opts* o, double tau, double* lambda_inout, pfx_ec_report* rep) {
+    if (!c || !o || !lambda_inout || !rep) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    return ec_solve(c, o, tau, lambda_inout, rep);
+}
+
+int pfx_ec_checkpoint(pfx_ctx* c, int restore) {
+    if (!c) return PFX_ERR_BAD_ARG;
+    CK(cudaSetDevice(c->device));
+    const size_t nu = (size_t)c->n_nodes * c->dim * sizeof(double), np = (size_t)c->n_nodes * sizeof(double);
+    if (restore) {
+        CK(cudaMemcpyAsync(c->u, c->u_old, nu, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->phi, c->phi_old, np, cudaMemcpyDeviceToDevice, c->stream));
+        c->tan_fresh = false;
+    } else {
+        CK(cudaMemcpyAsync(c->u_old, c->u, nu, cudaMemcpyDeviceToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->phi_old, c->phi, np, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    CK(cudaStreamSynchronize(c->stream));
     return PFX_OK;
 }
 

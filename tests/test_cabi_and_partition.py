@@ -35,16 +35,17 @@ def test_struct_layout_matches_header():
     """ctypes mirrors of pfx_params / pfx_step_report have the C field order of the header."""
     from phasefieldx_b200 import _lib
     header = open(os.path.join(ROOT, "include", "pfx_b200.h")).read()
-    body = re.search(r"typedef struct \{([^}]*)\} pfx_params;", header).group(1)
-    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
-    names = []
-    for decl in body.split(";"):
-        decl = decl.strip()
-        if not decl:
-            continue
-        typ, rest = decl.split(None, 1)
-        names += [n.strip() for n in rest.split(",")]
-    assert names == [f[0] for f in _lib.PfxParams._fields_]
+    for cname, mirror in (("pfx_params", _lib.PfxParams), ("pfx_ec_opts", _lib.PfxEcOpts), ("pfx_ec_report", _lib.PfxEcReport)):
+        body = re.search(r"typedef struct \{([^}]*)\} %s;" % cname, header).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            typ, rest = decl.split(None, 1)
+            names += [n.strip() for n in rest.split(",")]
+        assert names == [f[0] for f in mirror._fields_], cname
 
 
 @pytest.mark.parametrize("n_ranks", [2, 3, 8])
