@@ -86,6 +86,11 @@ typedef struct {
     int32_t block_nodes;      /* owned nodes per CTA tile, 0 = auto                         */
     int32_t cg_chunk;         /* CG iterations per CUDA-graph launch, 0 = auto             */
     int32_t degradation_function; /* PFX_DEGRADATION_*: g of g_degradation_functions.py:12-64 (Input.degradation_function) */
+    /* aggregate coarse space of the two-level PCG, 0 = automatic: coarse u-dofs per dense region (2D default 1792: many
+     * small aggregates in compact regions; one region of <= 6144 suits slender, weakly supported bodies such as the
+     * three-point bending beam, whose global bending mode a region-wise coarse matrix cannot represent) and CTA blocks
+     * per aggregate.  The environment variables PFX_COARSE_REGION / PFX_COARSE_AGG_BLOCKS override both. */
+    int32_t coarse_region, coarse_agg_blocks;
 } pfx_params;
 
 typedef struct {
@@ -180,7 +185,7 @@ typedef struct {
     double lin_rtol;          /* default 1e-10                                                     */
     int32_t gmres_restart;    /* default 40 (<= 62)                                                */
     int32_t lin_max_it;       /* default 2000                                                      */
-    double inner_rtol;        /* default 1e-2                                                      */
+    double inner_rtol;        /* default 0.1                                                       */
 } pfx_ec_opts;
 
 typedef struct {

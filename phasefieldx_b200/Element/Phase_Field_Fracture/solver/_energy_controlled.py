@@ -32,8 +32,10 @@ def solve(variational, Data, msh, final_gamma, V_u, V_Φ, bc_list_u=[], bc_list_
     if bcs_list_u_names is None:
         bcs_list_u_names = [f"bc_u_{i}" for i in range(n_react)]
     ec_opts = dict(solver_options or {})
-    engine_keys = ("cg_rtol", "cg_max_it", "block_nodes", "cg_chunk", "quad_points_1d", "proj_rtol")
+    engine_keys = ("cg_rtol", "cg_max_it", "block_nodes", "cg_chunk", "quad_points_1d", "proj_rtol", "coarse_region", "coarse_agg_blocks")
     engine_kw = {k: ec_opts.pop(k) for k in engine_keys if k in ec_opts}
+    # traction-loaded, weakly supported bodies (the bending beams of the reference examples): one dense coarse region
+    engine_kw.setdefault("coarse_region", 6144)
     options = {"newton": "dolfinx NewtonSolver semantics (residual criterion)", "rtol": ec_opts.get("newton_rtol", 1e-9),
                "atol": ec_opts.get("newton_atol", 1e-10), "max_it": ec_opts.get("newton_max_it", 50),
                "linear solver": "flexible GMRES on the bordered system, block-preconditioned by PCG solves, on GPU"}

@@ -33,7 +33,8 @@ class PfxParams(C.Structure):
                 ("fatigue_val", C.c_double), ("snes_rtol", C.c_double), ("snes_atol", C.c_double),
                 ("snes_stol", C.c_double), ("snes_max_it", C.c_int32), ("cg_rtol", C.c_double),
                 ("cg_max_it", C.c_int32), ("proj_rtol", C.c_double), ("quad_points_1d", C.c_int32),
-                ("block_nodes", C.c_int32), ("cg_chunk", C.c_int32), ("degradation_function", C.c_int32)]
+                ("block_nodes", C.c_int32), ("cg_chunk", C.c_int32), ("degradation_function", C.c_int32),
+                ("coarse_region", C.c_int32), ("coarse_agg_blocks", C.c_int32)]
 
 
 class PfxStepOpts(C.Structure):

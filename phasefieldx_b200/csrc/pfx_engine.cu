@@ -670,8 +670,11 @@ int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
     // (beam, 8 M tets: 1 499 iterations per step with 7 regions, 576 with one region of 5 730 dofs), so the
     // whole coarse space is one region of at most kCoarseMax dofs.
     const int total_cap = D == 3 ? kCoarseMax : kCoarseTotal;
-    const int reg_cap = std::min(kCoarseMax, std::max(m_u * 8, er ? atoi(er) : (D == 3 ? kCoarseMax : kCoarseRegion)));
+    const int reg_want = er ? atoi(er) : (c->prm.coarse_region > 0 ? c->prm.coarse_region : (D == 3 ? kCoarseMax : kCoarseRegion));
+    const int reg_cap = std::min(kCoarseMax, std::max(m_u * 8, reg_want));
     int g = (bm.nb * m_u + total_cap - 1) / total_cap;
+    if (reg_cap >= kCoarseMax) g = std::max(g, (bm.nb * m_u + kCoarseMax - 1) / kCoarseMax);      // one region holds them all
+    if (c->prm.coarse_agg_blocks > 0) g = c->prm.coarse_agg_blocks;
     if (eg && atoi(eg) > 0) g = atoi(eg);
     g = std::max(g, 1);
     const int reg_aggs = std::max(1, reg_cap / m_u);
@@ -1720,7 +1723,7 @@ void pfx_ec_default_opts(pfx_ec_opts* o) {
     memset(o, 0, sizeof(*o));
     o->c1 = 1.0; o->c2 = 1.0; o->variational = 1;
     o->newton_rtol = 1e-9; o->newton_atol = 1e-10; o->newton_max_it = 50;       // dolfinx NewtonSolver defaults
-    o->lin_rtol = 1e-10; o->gmres_restart = 40; o->lin_max_it = 2000; o->inner_rtol = 1e-2;
+    o->lin_rtol = 1e-10; o->gmres_restart = 40; o->lin_max_it = 2000; o->inner_rtol = 0.1;
 }
 
 int pfx_ec_solve(pfx_ctx* c, const pfx_ec_opts* o, double tau, double* lambda_inout, pfx_ec_report* rep) {
