@@ -70,6 +70,7 @@ def solve(Data, msh, final_time, V_u, bc_list_u=[], update_boundary_conditions=N
             append_results_to_file(os.path.join(folder, "total.energy"), '#step\tE', step, eng.energies()["E"])
             if run.vtk is not None:
                 run.vtk.write_function(msh, {"u": eng.get_field("u").reshape(-1, d)}, step, background=True)
+            run.write_xdmf({"u": eng.get_field("u").reshape(-1, d)} if run._xdmf_on else {}, step)
             t += dt
             step += 1
     finally:

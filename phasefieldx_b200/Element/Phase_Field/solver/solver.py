@@ -59,6 +59,7 @@ def solve(Data, msh, final_time, V_Φ, bc_list_phi=[], update_boundary_condition
                                    en["gamma"], en["gamma_phi"], en["gamma_gradphi"])
             if run.vtk is not None:
                 run.vtk.write_function(msh, {"phi": eng.get_field("phi")}, step, background=True)
+            run.write_xdmf({"phi": eng.get_field("phi")} if run._xdmf_on else {}, step)
             t += dt
             step += 1
     finally:

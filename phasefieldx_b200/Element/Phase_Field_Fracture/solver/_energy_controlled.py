@@ -24,8 +24,7 @@ def solve(variational, Data, msh, final_gamma, V_u, V_Φ, bc_list_u=[], bc_list_
     T0, ds0 = T_list_u[0][0], T_list_u[0][1]
     if not isinstance(ds0, fem.Measure):
         raise NotImplementedError("tractions need a measure from get_ds_bound_from_marker")
-    if Data.degradation_function not in _lib.DEGRADATION:
-        raise NotImplementedError("degradation_function must be 'quadratic' or 'borden' on the GPU path")
+    _lib.check_degradation_function(Data.degradation_function)
     if Data.degradation == "hybrid":
         raise NotImplementedError("the energy-controlled GPU solver needs sigma_a = d psi_a / d eps (no 'hybrid' degradation)")
     n_react = len(bc_list_u) - 1 if bc_list_phi != [] else len(bc_list_u)          # reference :141-146
@@ -141,6 +140,7 @@ def solve(variational, Data, msh, final_gamma, V_u, V_Φ, bc_list_u=[], bc_list_
                 if run.vtk is not None:
                     logger.info(f"Saving VTU Paraview files at step={step}, gamma={gamma:.6f}, tau={tau:.6f}")
                     run.vtk.write_function(msh, {"phi": eng.get_field("phi"), "u": u_now}, step, background=True)
+                run.write_xdmf({"phi": eng.get_field("phi"), "u": u_now} if run._xdmf_on else {}, step)
                 last_saved_gamma = gamma
     finally:
         run.finish()

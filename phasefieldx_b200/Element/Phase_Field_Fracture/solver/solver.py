@@ -17,6 +17,7 @@ import numpy as np
 from phasefieldx_b200 import _lib, fem
 from phasefieldx_b200.files import append_results_to_file, prepare_simulation
 from phasefieldx_b200.io_vtk import VTKFile
+from phasefieldx_b200.io_xdmf import XDMFFile
 from phasefieldx_b200.Logger.library_versions import (log_end_analysis, log_library_versions, log_model_information,
                                                       log_system_info, set_logger)
 
@@ -80,9 +81,7 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     logger.info(f"  stagger error tolerance: {stagger_error_tol}")
     if bcs_list_u_names is None:
         bcs_list_u_names = [f"bc_u_{i}" for i in range(len(bc_list_u))]
-    if Data.degradation_function not in _lib.DEGRADATION:
-        raise NotImplementedError("degradation_function must be 'quadratic' or 'borden' on the GPU path (SURVEY §8f N2; the "
-                                  "reference's sargado derivative overflows at form-build time, Appendix A Q10)")
+    _lib.check_degradation_function(Data.degradation_function)
     if Data.fatigue and Data.fatigue_degradation_function != "asymptotic":
         raise NotImplementedError("fatigue_degradation_function must be 'asymptotic' (reference returns an "
                                   "un-raised ValueError for 'logarithmic', fatigue_degradation_functions.py:64-65)")
@@ -135,8 +134,13 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     if Data.save_solution_vtu and (rank == 0 or pieces):
         vtk_sol = VTKFile(None, os.path.join(result_folder_name, "paraview-solutions_vtu", "phasefieldx.pvd"), "w", fmt=vtu_format,
                           rank=rank if pieces else 0, world=world if pieces else 1, keep_last=vtu_keep)
-    if getattr(Data, "save_solution_xdmf", False):
-        logger.info(" save_solution_xdmf: XDMF/HDF5 output needs dolfinx and is not written (VTU output is unaffected)")
+    xdmf_phi = xdmf_u = None
+    if getattr(Data, "save_solution_xdmf", False) and rank == 0:
+        # reference solver.py:259-278: phi.xdmf and u.xdmf in paraview-solutions_xdmf/ (heavy data in raw side files)
+        xdir = os.path.join(result_folder_name, "paraview-solutions_xdmf")
+        xdmf_phi, xdmf_u = XDMFFile(None, os.path.join(xdir, "phi.xdmf"), "w"), XDMFFile(None, os.path.join(xdir, "u.xdmf"), "w")
+        xdmf_phi.write_mesh(msh)
+        xdmf_u.write_mesh(msh)
     logger.info(" S t a r t i n g    A n a l y s i s ")
     logger.info(" ---------------------------------- ")
     logger.info(" ---------------------------------- ")
@@ -203,6 +207,15 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
             if rank == 0:
                 append_results_to_file(os.path.join(result_folder_name, "total.energy"), header, step,
                                        *[en[c] for c in _lib.ENERGY_COLUMNS])
+            if getattr(Data, "save_solution_xdmf", False):
+                if rmesh is None:
+                    phi_x, u_x = eng.get_field("phi"), eng.get_field("u").reshape(-1, d)
+                else:
+                    dev = f"cuda:{device}"
+                    phi_x, u_x = gather_field(eng, rmesh, "phi", dist, dev), gather_field(eng, rmesh, "u", dist, dev)
+                if xdmf_phi is not None:
+                    xdmf_phi.write_function("phi", phi_x, step)
+                    xdmf_u.write_function("u", u_x, step)
             if Data.save_solution_vtu and (step % max(1, int(vtu_every)) == 0):
                 if rmesh is None or pieces:
                     phi_out, u_out = eng.get_field("phi"), eng.get_field("u").reshape(-1, d)
@@ -218,6 +231,9 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     finally:
         if vtk_sol is not None:
             vtk_sol.close()
+        for xf in (xdmf_phi, xdmf_u):
+            if xf is not None:
+                xf.close()
         if dist is not None:
             dist.barrier()          # peers keep each other's buffers mapped: close together
         eng.close()

@@ -84,6 +84,7 @@ def solve(Data, msh, final_time, V_u, bc_list_u=[], update_boundary_conditions=N
             if run.vtk is not None:
                 run.vtk.write_function(msh, {"u": u.reshape(-1, d), "PSI_a": eng.project_psi("a"), "PSI_b": eng.project_psi("b")},
                                        step, background=True)
+            run.write_xdmf({"u": u.reshape(-1, d)} if run._xdmf_on else {}, step)
             t += dt
             step += 1
     finally:

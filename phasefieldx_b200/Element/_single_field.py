@@ -4,6 +4,7 @@ import time
 
 from phasefieldx_b200.files import prepare_simulation
 from phasefieldx_b200.io_vtk import VTKFile
+from phasefieldx_b200.io_xdmf import XDMFFile
 from phasefieldx_b200.Logger.library_versions import (log_end_analysis, log_library_versions, log_model_information,
                                                       log_system_info, set_logger)
 
@@ -29,8 +30,9 @@ class Run:
         self.vtk = None
         if Data.save_solution_vtu:
             self.vtk = VTKFile(None, os.path.join(self.folder, "paraview-solutions_vtu", "phasefieldx.pvd"), "w", fmt=vtu_format)
-        if getattr(Data, "save_solution_xdmf", False):
-            self.logger.info(" save_solution_xdmf: XDMF/HDF5 output needs dolfinx and is not written (VTU output is unaffected)")
+        self.xdmf = {}
+        self._xdmf_on = bool(getattr(Data, "save_solution_xdmf", False))
+        self._msh = msh
         self.logger.info(" S t a r t i n g    A n a l y s i s ")
         self.logger.info(" ---------------------------------- ")
         self.logger.info(" ---------------------------------- ")
@@ -39,7 +41,19 @@ class Run:
         self.logger.info(f"\n\nSolution at (pseudo) time = {t}, dt = {dt}, Step = {step} ")
         self.logger.info("===========================================================================")
 
+    def write_xdmf(self, fields, step):
+        """`<name>.xdmf` per field in paraview-solutions_xdmf/ (reference xdmf_phi / xdmf_u), when Data.save_solution_xdmf."""
+        if not self._xdmf_on:
+            return
+        for name, values in fields.items():
+            if name not in self.xdmf:
+                self.xdmf[name] = XDMFFile(None, os.path.join(self.folder, "paraview-solutions_xdmf", name + ".xdmf"), "w")
+                self.xdmf[name].write_mesh(self._msh)
+            self.xdmf[name].write_function(name, values, step)
+
     def finish(self):
         if self.vtk is not None:
             self.vtk.close()
+        for xf in self.xdmf.values():
+            xf.close()
         log_end_analysis(self.logger, time.perf_counter() - self.start)

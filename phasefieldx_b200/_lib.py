@@ -177,6 +177,22 @@ MODEL = {("isotropic", None): 0, ("anisotropic", "spectral"): 1, ("anisotropic",
 DEGRADATION = {"quadratic": 0, "borden": 1}
 
 
+def check_degradation_function(name):
+    """What the reference does with each `Input.degradation_function` (g_degradation_functions.py:127-174):
+    quadratic, borden -> on the GPU path; sargado -> its derivative evaluates exp(100 * 100) while the forms are
+    built, so the reference raises OverflowError before the first step (:97-124) and so does
+    this; alessi -> as coded its derivative has the wrong sign and a pole at phi = 0.01 (:67-94) — not restated;
+    anything else -> the reference's ValueError."""
+    if name in DEGRADATION:
+        return
+    if name == "sargado":
+        raise OverflowError("math range error")
+    if name == "alessi":
+        raise NotImplementedError("degradation_function 'alessi' is not on the GPU path: as coded in the reference its derivative "
+                                  "has the wrong sign and a pole at phi = 0.01 (g_degradation_functions.py:67-94)")
+    raise ValueError("Invalid degradation_type. Please choose from 'quadratic', 'borden', 'alessi', or 'sargado'.")
+
+
 def model_code(degradation, split_energy):
     """Dispatch of reference split_energy_stress_tangent_functions.py:234-354."""
     if degradation == "isotropic":

@@ -104,3 +104,19 @@ def test_unknown_degradation_function_is_rejected_before_any_device_work():
     for name in ("alessi", "sargado", "cubic"):
         with pytest.raises(NotImplementedError):
             _lib.Engine(msh.geometry.x, msh.cells, "triangle", 1.0, 1.0, 1.0, 0.1, degradation_function=name)
+
+
+def test_degradation_function_check_replicates_the_reference_behaviour():
+    """`check_degradation_function` (called first thing by the drop-in solve() modules): quadratic / borden pass;
+    'sargado' raises the OverflowError the reference raises while building its forms (exp(100 * 100) in
+    g_degradation_functions.py:120-124); 'alessi' is refused explicitly; unknown names give the reference's
+    ValueError (:149-150)."""
+    from phasefieldx_b200 import _lib
+    _lib.check_degradation_function("quadratic")
+    _lib.check_degradation_function("borden")
+    with pytest.raises(OverflowError):
+        _lib.check_degradation_function("sargado")
+    with pytest.raises(NotImplementedError, match="alessi"):
+        _lib.check_degradation_function("alessi")
+    with pytest.raises(ValueError, match="Invalid degradation_type"):
+        _lib.check_degradation_function("cubic")

@@ -99,7 +99,7 @@ def test_config1_through_solve_matches_stored_reference_files(tmp_path, c1_mesh)
     msh, _, _ = c1_mesh
     Data = Input(E=210.0, nu=0.3, Gc=0.0027, l=0.015, degradation="isotropic", split_energy="no",
                  degradation_function="quadratic", irreversibility="miehe", fatigue=False, k=0.0,
-                 save_solution_xdmf=False, save_solution_vtu=True, results_folder_name=str(tmp_path / "1711"))
+                 save_solution_xdmf=True, save_solution_vtu=True, results_folder_name=str(tmp_path / "1711"))
     fdim = msh.topology.dim - 1
     bottom = dolfinx.mesh.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[1], -0.5))
     top = dolfinx.mesh.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[1], 0.5))
@@ -128,3 +128,10 @@ def test_config1_through_solve_matches_stored_reference_files(tmp_path, c1_mesh)
     assert conv["iterU"].tolist() == [0] * 5 and conv["iterPhi"].tolist() == [0] * 5
     assert S.dof_files["top.dof"]["Uy"].tolist()[:3] == [0.0, 0.0001, 0.0002]
     assert sorted(f for f in S.paraview_filenames if f.endswith(".vtu")) == ["phasefieldx_p0_000000.vtu", "phasefieldx_p0_000004.vtu"]
+    # save_solution_xdmf=True (reference solver.py:259-278, 460-462): phi.xdmf / u.xdmf, one temporal grid per load step
+    from phasefieldx_b200 import io_vtk, io_xdmf
+    xd = os.path.join(Data.results_folder_name, "paraview-solutions_xdmf")
+    xphi, xu = io_xdmf.read_xdmf(os.path.join(xd, "phi.xdmf")), io_xdmf.read_xdmf(os.path.join(xd, "u.xdmf"))
+    assert [t for t, _, _ in xphi["steps"]] == [0.0, 1.0, 2.0, 3.0, 4.0] and len(xu["steps"]) == 5
+    last = io_vtk.read_vtu_points_cells(os.path.join(Data.results_folder_name, "paraview-solutions_vtu", "phasefieldx_p0_000004.vtu"))
+    assert np.array_equal(xphi["steps"][4][2].ravel(), last["phi"]) and np.array_equal(xu["steps"][4][2], last["u"])

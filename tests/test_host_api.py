@@ -325,3 +325,37 @@ def test_reference_stored_vtu_parses_and_writer_reproduces_its_layout(tmp_path):
     # the reference stores VTK_LAGRANGE_TRIANGLE (69) cells, offsets 3, 6, ...
     types = re.search(r'Name="types"[^>]*>([^<]*)<', mine_txt).group(1).split()
     assert set(types) == {"69"} == set(re.search(r'Name="types"[^>]*>([^<]*)<', ref_txt).group(1).split())
+
+
+@pytest.mark.parametrize("ctype", ["triangle", "quadrilateral", "tetrahedron"])
+def test_xdmf_time_series_round_trip(tmp_path, ctype):
+    """the XDMF output of `save_solution_xdmf=True` (reference solver.py:259-278, 460-462): mesh once,
+    one temporal grid per step and field; light data is XDMF 3 XML, heavy data raw binary."""
+    import xml.dom.minidom
+    from phasefieldx_b200 import io_xdmf, mesh as M
+    if ctype == "tetrahedron":
+        msh = M.create_box(None, [[0, 0, 0], [1, 1, 1]], [3, 2, 2])
+    else:
+        msh = M.create_rectangle(None, [[0, 0], [2, 1]], [4, 3], M.CellType.triangle if ctype == "triangle" else M.CellType.quadrilateral)
+    d = msh.geometry.dim
+    rng = np.random.default_rng(3)
+    xf = io_xdmf.XDMFFile(None, str(tmp_path / "paraview-solutions_xdmf" / "phi.xdmf"), "w")
+    xf.write_mesh(msh)
+    fields = []
+    for step in range(3):
+        phi, u = rng.uniform(size=msh.num_nodes), rng.normal(size=(msh.num_nodes, d))
+        xf.write_function("phi", phi, step)
+        xf.write_function("u", u, step)
+        fields.append((phi, u))
+    xf.close()
+    xml.dom.minidom.parse(str(tmp_path / "paraview-solutions_xdmf" / "phi.xdmf"))          # well-formed
+    back = io_xdmf.read_xdmf(str(tmp_path / "paraview-solutions_xdmf" / "phi.xdmf"))
+    assert np.array_equal(back["points"], msh.geometry.x[:, :d])
+    perm = [0, 1, 3, 2] if ctype == "quadrilateral" else list(range(msh.cells.shape[1]))
+    assert np.array_equal(back["cells"], msh.cells[:, perm])
+    phis = [a for t, n, a in back["steps"] if n == "phi"]
+    us = [a for t, n, a in back["steps"] if n == "u"]
+    assert len(phis) == 3 and len(us) == 3 and sorted({t for t, _, _ in back["steps"]}) == [0.0, 1.0, 2.0]
+    for k, (phi, u) in enumerate(fields):
+        assert np.array_equal(phis[k].ravel(), phi)
+        assert np.array_equal(us[k][:, :d], u) and (d == 3 or np.all(us[k][:, 2] == 0.0))
