@@ -258,6 +258,11 @@ int pfx_partition_create(int32_t cell_type, int64_t n_nodes, int64_t n_cells, co
                          const int32_t* cells, int n_ranks, const int32_t* cell_rank_in,
                          pfx_partition** out);
 int pfx_partition_destroy(pfx_partition* p);
+/* Graph partition: cell_rank[n_cells] by METIS k-way (the toolkit's libmetis_static.a, default options, deterministic)
+ * on the cell dual graph (cells adjacent when they share a facet) — what dolfinx's graph partitioner does at mesh
+ * creation.  Pass the result to pfx_partition_create as cell_rank_in.  edge_cut (may be NULL): facets cut. */
+int pfx_partition_graph_cell_rank(int32_t cell_type, int64_t n_nodes, int64_t n_cells, const int32_t* cells, int n_ranks,
+                                  int32_t* cell_rank /* [n_cells] */, int64_t* edge_cut);
 int pfx_partition_cell_rank(const pfx_partition* p, int32_t* cell_rank /* [n_cells] */);
 int pfx_partition_node_owner(const pfx_partition* p, int32_t* node_owner /* [n_nodes] */);
 /* sizes for rank r: out = {n_local_nodes, n_owned, n_local_cells, n_send_total, n_neighbors} */

@@ -76,7 +76,7 @@ SYMBOLS = [
     "pfx_ec_checkpoint", "pfx_reaction", "pfx_energies", "pfx_get_field",
     "pfx_set_field", "pfx_apply_u", "pfx_apply_phi", "pfx_apply_mass", "pfx_residual_u", "pfx_diag_u", "pfx_rhs_psi", "pfx_project_psi",
     "pfx_l2_error", "pfx_time_operator", "pfx_algorithmic_bytes", "pfx_launch_count", "pfx_block_stats", "pfx_coarse_stats",
-    "pfx_partition_create", "pfx_partition_destroy", "pfx_partition_cell_rank", "pfx_partition_node_owner",
+    "pfx_partition_create", "pfx_partition_destroy", "pfx_partition_graph_cell_rank", "pfx_partition_cell_rank", "pfx_partition_node_owner",
     "pfx_partition_rank_sizes", "pfx_partition_rank_maps", "pfx_partition_rank_plan", "pfx_comm_unique_id",
     "pfx_comm_attach", "pfx_comm_p2p_export", "pfx_comm_p2p_import", "pfx_format_f64", "pfx_format_i64",
 ]
@@ -136,6 +136,7 @@ def load():
     lib.pfx_device_count.argtypes = [C.POINTER(C.c_int)]
     lib.pfx_partition_create.argtypes = [C.c_int32, C.c_int64, C.c_int64, pd, pi, C.c_int, pi, C.POINTER(C.c_void_p)]
     lib.pfx_partition_destroy.argtypes = [C.c_void_p]
+    lib.pfx_partition_graph_cell_rank.argtypes = [C.c_int32, C.c_int64, C.c_int64, pi, C.c_int, pi, pl]
     lib.pfx_partition_cell_rank.argtypes = [C.c_void_p, pi]
     lib.pfx_partition_node_owner.argtypes = [C.c_void_p, pi]
     lib.pfx_partition_rank_sizes.argtypes = [C.c_void_p, C.c_int, pl]
@@ -207,6 +208,18 @@ class PfxError(RuntimeError):
     def __init__(self, status, message):
         super().__init__(message)
         self.status = status
+
+
+def graph_cell_rank(cell_type, n_nodes, cells, n_ranks):
+    """(cell_rank, edge_cut) of the METIS k-way partition of the cell dual graph (pfx_partition_graph_cell_rank)."""
+    lib = load()
+    cells = np.ascontiguousarray(cells, dtype=np.int32)
+    out = np.zeros(len(cells), dtype=np.int32)
+    cut = np.zeros(1, dtype=np.int64)
+    st = lib.pfx_partition_graph_cell_rank(CELL[cell_type], int(n_nodes), len(cells), _pi(cells), int(n_ranks), _pi(out), _pl(cut))
+    if st:
+        raise PfxError(st, "graph partition failed")
+    return out, int(cut[0])
 
 
 class Partition:

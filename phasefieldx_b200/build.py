@@ -27,6 +27,16 @@ def _nvcc():
     return nv
 
 
+def _metis():
+    """METIS 5 static library shipped with the CUDA toolkit (graph partitioner of pfx_partition_graph_cell_rank)."""
+    for d in (os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "lib64"), "/usr/local/cuda/lib64",
+              "/usr/local/cuda/targets/x86_64-linux/lib"):
+        p = os.path.join(d, "libmetis_static.a")
+        if os.path.exists(p):
+            return p
+    raise RuntimeError("libmetis_static.a (CUDA toolkit) not found")
+
+
 def _newer(target, sources):
     if not os.path.exists(target):
         return True
@@ -62,7 +72,7 @@ def build(force=False, verbose=False, ptxas_log=None):
     if ptxas_log:
         with open(ptxas_log, "w") as fh:
             fh.write(log)
-    cmd = [nv, "-shared", "-o", LIB] + objs + ["-ldl", "-lcusolver", "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nv, "-shared", "-o", LIB] + objs + [_metis(), "-ldl", "-lcusolver", "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
@@ -75,7 +85,7 @@ def build_hostcheck(force=False):
     deps = srcs + sources()
     if not force and not _newer(HOSTCHECK, deps):
         return HOSTCHECK
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", HOSTCHECK] + srcs
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", HOSTCHECK] + srcs + [_metis()]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"g++ failed:\n{r.stdout}")

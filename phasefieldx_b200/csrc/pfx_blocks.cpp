@@ -215,6 +215,64 @@ std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int6
     return "";
 }
 
+// =============================================================================== graph partition
+// METIS k-way partition of the cell dual graph (cells adjacent when they share a facet) — the role of dolfinx's graph
+// partitioner at mesh creation (dolfinx.mesh.create_mesh -> ParMETIS / SCOTCH; third-party, not in the reference tree).
+// METIS 5 from the CUDA toolkit's libmetis_static.a (idx_t = int64, real_t = float), default options: deterministic.
+extern "C" int METIS_PartGraphKway(int64_t* nvtxs, int64_t* ncon, int64_t* xadj, int64_t* adjncy, int64_t* vwgt, int64_t* vsize,
+                                   int64_t* adjwgt, int64_t* nparts, float* tpwgts, float* ubvec, int64_t* options, int64_t* objval,
+                                   int64_t* part);
+extern "C" int METIS_SetDefaultOptions(int64_t* options);
+
+std::string metis_cell_rank(int nv, int dim, int64_t n_nodes, int64_t n_cells, const int32_t* cells, int n_ranks, int32_t* cell_rank,
+                            int64_t* edge_cut) {
+    if (n_ranks < 1) return "n_ranks < 1";
+    if (edge_cut) *edge_cut = 0;
+    if (n_ranks == 1) { std::fill(cell_rank, cell_rank + n_cells, 0); return ""; }
+    // facets: simplices — every vertex subset of size nv-1; quadrilaterals (tensor vertex order) — the four edges
+    const int nf = nv, fv = (nv == 4 && dim == 2) ? 2 : nv - 1;
+    static const int quad_edges[4][2] = {{0, 1}, {1, 3}, {3, 2}, {2, 0}};
+    struct Facet { int32_t v[3]; int32_t cell; };
+    std::vector<Facet> F((size_t)n_cells * nf);
+    for (int64_t c = 0; c < n_cells; ++c)
+        for (int f = 0; f < nf; ++f) {
+            Facet& q = F[(size_t)c * nf + f];
+            q.v[0] = q.v[1] = q.v[2] = -1;
+            if (fv == 2 && nv == 4) { q.v[0] = cells[c * nv + quad_edges[f][0]]; q.v[1] = cells[c * nv + quad_edges[f][1]]; }
+            else { int k = 0; for (int a = 0; a < nv; ++a) if (a != f) q.v[k++] = cells[c * nv + a]; }
+            std::sort(q.v, q.v + fv);
+            q.cell = (int32_t)c;
+        }
+    std::sort(F.begin(), F.end(), [](const Facet& a, const Facet& b) {
+        if (a.v[0] != b.v[0]) return a.v[0] < b.v[0];
+        if (a.v[1] != b.v[1]) return a.v[1] < b.v[1];
+        if (a.v[2] != b.v[2]) return a.v[2] < b.v[2];
+        return a.cell < b.cell;
+    });
+    std::vector<int64_t> xadj(n_cells + 1, 0);
+    std::vector<std::pair<int32_t, int32_t>> pairs;
+    for (size_t i = 0; i + 1 < F.size(); ++i)
+        if (F[i].v[0] == F[i + 1].v[0] && F[i].v[1] == F[i + 1].v[1] && F[i].v[2] == F[i + 1].v[2]) {
+            pairs.emplace_back(F[i].cell, F[i + 1].cell);
+            ++xadj[F[i].cell + 1]; ++xadj[F[i + 1].cell + 1];
+        }
+    std::vector<Facet>().swap(F);
+    for (int64_t c = 0; c < n_cells; ++c) xadj[c + 1] += xadj[c];
+    std::vector<int64_t> adj(xadj[n_cells]), fill(xadj.begin(), xadj.end() - 1);
+    for (auto& p : pairs) { adj[fill[p.first]++] = p.second; adj[fill[p.second]++] = p.first; }
+    for (int64_t c = 0; c < n_cells; ++c) std::sort(adj.begin() + xadj[c], adj.begin() + xadj[c + 1]);
+    int64_t nvtx = n_cells, ncon = 1, nparts = n_ranks, objval = 0, options[64];
+    METIS_SetDefaultOptions(options);
+    std::vector<int64_t> part(n_cells, 0);
+    int rc = METIS_PartGraphKway(&nvtx, &ncon, xadj.data(), adj.data(), nullptr, nullptr, nullptr, &nparts, nullptr, nullptr, options,
+                                 &objval, part.data());
+    if (rc != 1) return "METIS_PartGraphKway failed (status " + std::to_string(rc) + ")";
+    for (int64_t c = 0; c < n_cells; ++c) cell_rank[c] = (int32_t)part[c];
+    if (edge_cut) *edge_cut = objval;
+    (void)n_nodes;
+    return "";
+}
+
 // =============================================================================== partition
 std::string build_partition(int nv, int64_t n_nodes, int64_t n_cells, const double* coords, const int32_t* cells,
                             int n_ranks, const int32_t* cell_rank_in, Partition& P) {

@@ -110,6 +110,9 @@ struct Partition {
 
 // cell_rank_in may be null -> recursive coordinate bisection of the cell centroids.
 // node owner = lowest rank among the adjacent cells' ranks (deterministic rule).
+// cell_rank[n_cells] by METIS k-way on the cell dual graph; edge_cut (optional) = facets shared by cells of two ranks
+std::string metis_cell_rank(int nv, int dim, int64_t n_nodes, int64_t n_cells, const int32_t* cells, int n_ranks, int32_t* cell_rank,
+                            int64_t* edge_cut);
 std::string build_partition(int nv, int64_t n_nodes, int64_t n_cells, const double* coords, const int32_t* cells,
                             int n_ranks, const int32_t* cell_rank_in, Partition& out);
 

@@ -2073,6 +2073,13 @@ int pfx_partition_create(int32_t cell_type, int64_t n_nodes, int64_t n_cells, co
     return PFX_OK;
 }
 int pfx_partition_destroy(pfx_partition* p) { delete p; return PFX_OK; }
+int pfx_partition_graph_cell_rank(int32_t cell_type, int64_t n_nodes, int64_t n_cells, const int32_t* cells, int n_ranks,
+                                  int32_t* cell_rank, int64_t* edge_cut) {
+    if (!cells || !cell_rank || n_cells <= 0 || n_ranks < 1) return PFX_ERR_BAD_ARG;
+    int nv = cell_type == PFX_CELL_TRIANGLE ? 3 : 4, dim = cell_type == PFX_CELL_TETRAHEDRON ? 3 : 2;
+    if (cell_type < PFX_CELL_TRIANGLE || cell_type > PFX_CELL_TETRAHEDRON) return PFX_ERR_BAD_ARG;
+    return metis_cell_rank(nv, dim, n_nodes, n_cells, cells, n_ranks, cell_rank, edge_cut).empty() ? PFX_OK : PFX_ERR_BAD_ARG;
+}
 int pfx_partition_cell_rank(const pfx_partition* p, int32_t* cr) {
     if (!p || !cr) return PFX_ERR_BAD_ARG;
     std::copy(p->P.cell_rank.begin(), p->P.cell_rank.end(), cr);

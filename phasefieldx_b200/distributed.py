@@ -18,8 +18,15 @@ from . import _lib
 class RankMesh:
     """Local view of the global mesh on one rank."""
 
-    def __init__(self, coords, cells, cell_type, world, rank, cell_rank=None):
+    def __init__(self, coords, cells, cell_type, world, rank, cell_rank=None, partitioner=None):
+        """partitioner: "rcb" (default: recursive coordinate bisection of the cell centroids) or "metis" (k-way graph
+        partition of the cell dual graph, deterministic: every rank computes the same one); env PFX_PARTITIONER."""
         self.world, self.rank = world, rank
+        partitioner = partitioner or os.environ.get("PFX_PARTITIONER", "rcb")
+        if partitioner not in ("rcb", "metis"):
+            raise ValueError("partitioner must be 'rcb' or 'metis'")
+        if cell_rank is None and partitioner == "metis" and world > 1:
+            cell_rank, self.edge_cut = _lib.graph_cell_rank(cell_type, len(coords), cells, world)
         self.partition = _lib.Partition(cell_type, coords, cells, world, cell_rank=cell_rank)
         R = self.partition.rank(rank)
         self.plan = R
