@@ -669,7 +669,8 @@ int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
     // ~6 cells across, and cutting the coarse matrix into regions costs far more than coarser aggregates do
     // (beam, 8 M tets: 1 499 iterations per step with 7 regions, 576 with one region of 5 730 dofs), so the
     // whole coarse space is one region of at most kCoarseMax dofs.
-    const int total_cap = D == 3 ? kCoarseMax : kCoarseTotal;
+    const char* et = getenv("PFX_COARSE_TOTAL");            // cap of the whole (per-rank) coarse space, coarse u-dofs
+    const int total_cap = (et && atoi(et) >= m_u * 8) ? atoi(et) : (D == 3 ? kCoarseMax : kCoarseTotal);
     const int reg_want = er ? atoi(er) : (c->prm.coarse_region > 0 ? c->prm.coarse_region : (D == 3 ? kCoarseMax : kCoarseRegion));
     const int reg_cap = std::min(kCoarseMax, std::max(m_u * 8, reg_want));
     int g = (bm.nb * m_u + total_cap - 1) / total_cap;
