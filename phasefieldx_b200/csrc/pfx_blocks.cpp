@@ -483,6 +483,8 @@ std::string build_aggregates(const BlockMesh& bm, int64_t n_cells, const double*
     const int64_t n_owned = bm.n_owned;
     std::vector<int32_t> node_agg(n_owned);
     out.rel.resize((size_t)n_owned * D);
+    out.cen.assign((size_t)n_agg * 3, 0.0);
+    out.half.assign(n_agg, 1.0);
     for (int a = 0; a < n_agg; ++a) {
         double cen[3] = {0, 0, 0}, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         const int n0 = out.agg_node0[a], n1 = out.agg_node0[a + 1];
@@ -494,6 +496,8 @@ std::string build_aggregates(const BlockMesh& bm, int64_t n_cells, const double*
         double size = 0;
         for (int k = 0; k < D; ++k) { cen[k] /= std::max(1, n1 - n0); size = std::max(size, 0.5 * (hi[k] - lo[k])); }
         const double sc = size > 0 ? 1.0 / size : 1.0;
+        for (int k = 0; k < D; ++k) out.cen[(size_t)a * 3 + k] = cen[k];
+        out.half[a] = size > 0 ? size : 1.0;
         for (int i = n0; i < n1; ++i) {
             node_agg[i] = a;
             for (int k = 0; k < D; ++k) out.rel[(size_t)i * D + k] = (float)((coords[3 * (int64_t)bm.perm[i] + k] - cen[k]) * sc);

@@ -64,6 +64,8 @@ struct AggregateSet {
     std::vector<int32_t> colour;         // [n_agg]
     std::vector<int32_t> nbrcol;         // [n_agg*n_col] the aggregate of that colour within distance one (or -1)
     std::vector<float> rel;              // [n_owned*dim] (x - centroid(aggregate)) / half extent(aggregate)
+    std::vector<double> cen;             // [n_agg*3] centroid of every aggregate
+    std::vector<double> half;            // [n_agg] the half extent used to scale rel (1 if degenerate)
 };
 
 // cells / coords in caller ids as given to build_blocks.  g blocks per aggregate, regions of at most

@@ -47,6 +47,19 @@ struct CoarseView {
 
 template <int NC, int GD> struct Modes { static constexpr int M = NC == 1 ? 1 : (GD == 2 ? 3 : 6); };
 
+// Third, rank-level coarse space of multi-GPU runs: the rank-local coarse matrices are block-diagonal over the ranks,
+// so the modes that span several ranks (the bending of a beam cut into slabs) are lost and the iteration count grows
+// with the number of GPUs (25 M-dof beam: 1.8 x at 8 GPUs).  One more additive term restores them:
+//   M^-1 = B^-1 + Z A_loc^-1 Z^T + Z T E^-1 T^T Z^T,   E = T^T (Z^T A Z) T  (with the couplings ACROSS ranks),
+// T = the rigid-body modes of a whole rank expressed in the modes of its aggregates ([n_agg*M][M] per rank), E of
+// dimension n_ranks * M (<= 48), inverted on the host and replicated.  Per iteration every rank pushes its M numbers
+// T^T w through the mailboxes (coarse3_reduce_kernel) and adds T y_g to its coarse solution (coarse_solve_kernel).
+struct Coarse3View {
+    const PeerView* pv = nullptr;     // null: third level off
+    const double* T = nullptr;        // [n_agg*M][M] row-major
+    const double* Einv = nullptr;     // [n_ranks*M][n_ranks*M]
+};
+
 // w += Z_node^T v   (modes: translations, then rotations about x, y, z / about z in 2D)
 template <int NC, int GD>
 __device__ __forceinline__ void restrict_add(const float* rl, const double* v, double* w) {
@@ -256,13 +269,28 @@ __device__ __forceinline__ float4 ld_keep(const float4* p, unsigned long long po
 // multi-GPU path) push (r.z, r.r) of this rank to every rank's mailbox.
 template <int M>
 __global__ void __launch_bounds__(kThreads, 3) coarse_solve_kernel(CoarseView cv, double* S, int par, int mode, double* partial,
-                                                                   unsigned int* counter, const PeerView* pv = nullptr) {
+                                                                   unsigned int* counter, const PeerView* pv = nullptr,
+                                                                   Coarse3View c3 = Coarse3View()) {
     constexpr int R = kCoarseRowsPerWarp;
     extern __shared__ __align__(16) double s_w[];          // [ld]
     __shared__ double s_red[kMaxRed * 32];
     __shared__ bool is_last;
+    __shared__ double s_yg[8];
     if (!(mode & 1) && S[S_DONE] != 0.0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (c3.pv && threadIdx.x < 32) {
+        // third level (pfx_coarse.cuh, "rank level"): every rank's restricted residual g_r = T_r^T w_r from the
+        // mailboxes, y_g = (E^-1 g)[rows of this rank]; added to y of every aggregate below as T_a y_g
+        double gall[kMaxRanks * 8];
+        mbox_gather(c3.pv, gall, M);
+        const int ng = c3.pv->n_ranks * M;
+        if (lane < M) {
+            const double* row = c3.Einv + (size_t)(c3.pv->rank * M + lane) * ng;
+            double t = 0.0;
+            for (int j = 0; j < ng; ++j) t += row[j] * gall[j];
+            s_yg[lane] = t;
+        }
+    }
     const int2 ct = cv.cta_tab[blockIdx.x];
     const int4 rt = cv.reg_tab[ct.x];             // {first aggregate, aggregates, inverse offset, ld}
     const int nc = rt.y * M, ld4 = rt.w >> 2;
@@ -321,8 +349,15 @@ __global__ void __launch_bounds__(kThreads, 3) coarse_solve_kernel(CoarseView cv
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            const double v = warp_sum(acc[r]);
-            if (lane == 0 && row0 + r < nc) { cv.y[(size_t)rt.x * M + row0 + r] = v; wy[0] += v * s_w[row0 + r]; }
+            double v = warp_sum(acc[r]);
+            if (lane == 0 && row0 + r < nc) {
+                if (c3.pv) {
+                    const double* Ta = c3.T + ((size_t)rt.x * M + row0 + r) * M;       // row (aggregate, component) of T
+#pragma unroll
+                    for (int j = 0; j < M; ++j) v += Ta[j] * s_yg[j];
+                }
+                cv.y[(size_t)rt.x * M + row0 + r] = v; wy[0] += v * s_w[row0 + r];
+            }
         }
     }
     block_sum<1>(wy, s_red);
@@ -503,6 +538,65 @@ __global__ void coarse_convert_kernel(int nc, const double* Ac, int ldc, float* 
     float v = 0.f;
     if (col < nc) v = (float)(row >= col ? Ac[(size_t)col * ldc + row] : Ac[(size_t)row * ldc + col]);
     Ainv[(size_t)row * ld + col] = v;
+}
+
+// ---- third level ------------------------------------------------------------------------------------------
+// v = Z T e_mode on the active rank (zero elsewhere, zero on Dirichlet dofs): probing vector of one column of E
+template <int NC, int GD>
+__global__ void __launch_bounds__(kThreads) coarse3_probe_kernel(CoarseView cv, const double* T, int active, int mode,
+                                                                 const uint8_t* mask, double* v) {
+    constexpr int M = Modes<NC, GD>::M;
+    const int ch = blockIdx.x, ag = ch / cv.S;
+    const int n0 = cv.chunk_node0[ch], n1 = cv.chunk_node0[ch + 1];
+    double y[M];
+#pragma unroll
+    for (int k = 0; k < M; ++k) y[k] = active ? T[((size_t)ag * M + k) * M + mode] : 0.0;
+    for (int nd = n0 + (int)threadIdx.x; nd < n1; nd += kThreads) {
+        double z[NC];
+        float rl[GD];
+        load_rel<NC, GD>(cv, nd, rl);
+        prolong<NC, GD>(rl, y, z);
+#pragma unroll
+        for (int k = 0; k < NC; ++k)
+            if (mask && mask[(size_t)nd * NC + k]) z[k] = 0.0;
+        store_vec<NC>(v, nd, z);
+    }
+}
+
+// g = T^T w (w = Z^T r summed from the per-chunk pieces), pushed to every rank's mailbox.  One CTA.
+// check_done != 0: skipped once the running PCG has converged (the launch sits inside the captured iteration).
+template <int M>
+__global__ void __launch_bounds__(kThreads) coarse3_reduce_kernel(CoarseView cv, const double* T, const double* S, int check_done,
+                                                                  const PeerView* pv) {
+    __shared__ double s_red[kMaxRed * 32];
+    if (check_done && S[S_DONE] != 0.0) return;
+    double g[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) g[j] = 0.0;
+    for (int i = threadIdx.x; i < cv.n_agg * M; i += blockDim.x) {
+        const int a = i / M, k = i - a * M;
+        double w = 0.0;
+        for (int s = 0; s < cv.S; ++s) w += __ldcg(&cv.wpart[((size_t)a * cv.S + s) * M + k]);
+        const double* Ta = T + (size_t)i * M;
+#pragma unroll
+        for (int j = 0; j < M; ++j) g[j] += Ta[j] * w;
+    }
+    block_sum<M>(g, s_red);
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int j = 0; j < M; ++j) g[j] = __shfl_sync(0xffffffffu, g[j], 0);
+        mbox_push(pv, g, M);
+    }
+}
+
+// column `col` of E from the gathered g of all ranks (set-up; one warp)
+template <int M>
+__global__ void coarse3_collect_kernel(const PeerView* pv, int col, double* E) {
+    double gall[kMaxRanks * 8];
+    mbox_gather(pv, gall, M);
+    const int ng = pv->n_ranks * M;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < ng; ++i) E[(size_t)i * ng + col] = gall[i];
 }
 
 }  // namespace pfx

@@ -97,6 +97,11 @@ struct Coarse {
     bool refresh_every_step = false;
     bool block_jacobi = true;        // PFX_BLOCK_JACOBI=0: plain diagonal smoother for J_u
     int64_t setups = 0;
+    // third, rank-level coarse space of J_u on the fused multi-GPU path (pfx_coarse.cuh: Coarse3View)
+    std::vector<double> h_cen, h_half;   // aggregate centroids [n_agg*3] and half extents [n_agg]
+    double *T3 = nullptr, *E3 = nullptr, *Einv3 = nullptr;
+    bool lvl3_ready = false, lvl3_on = false;
+    bool lvl3_wanted = true;             // PFX_NO_LEVEL3=1 switches it off
 };
 
 }  // namespace
@@ -687,6 +692,8 @@ int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
     const std::vector<int32_t>&chunk0 = as.chunk_node0, &colour = as.colour, &nbrcol = as.nbrcol, &agg_reg = as.agg_reg,
                               &reg_agg0 = as.reg_agg0;
     const std::vector<float>& rel = as.rel;
+    cs.h_cen = as.cen; cs.h_half = as.half;
+    { const char* n3 = getenv("PFX_NO_LEVEL3"); cs.lvl3_wanted = !(n3 && n3[0] == '1'); }
     int st;
     if ((st = dev_upload(c, &cs.chunk_node0, chunk0))) return st;
     if ((st = dev_upload(c, &cs.colour, colour))) return st;
@@ -828,9 +835,121 @@ int coarse_setup_t(pfx_ctx* c, int kind, const uint8_t* mask) {
     return PFX_OK;
 }
 
+// Third, rank-level coarse space of J_u (pfx_coarse.cuh: Coarse3View): T of this rank's aggregates, E by probing with
+// halo exchange (n_ranks * M applies), inverse on the host.  Collective: every rank runs the same sequence.
+template <int NC, int GD>
+int coarse3_setup_t(pfx_ctx* c, const uint8_t* mask) {
+    constexpr int M = Modes<NC, GD>::M;
+    Coarse& cs = c->coarse;
+    const int nR = c->n_ranks, ng = nR * M, n_agg = cs.n_agg;
+    int st;
+    if (!cs.lvl3_ready) {
+        // rank centroid / half extent from the aggregates; T_a = [[I, C(q_a)], [0, (s_a / s_R) I]], q_a = (c_a - c_R) / s_R
+        double cR[3] = {0, 0, 0}, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int a = 0; a < n_agg; ++a)
+            for (int k = 0; k < GD; ++k) {
+                const double x = cs.h_cen[(size_t)a * 3 + k];
+                cR[k] += x / n_agg; lo[k] = std::min(lo[k], x - cs.h_half[a]); hi[k] = std::max(hi[k], x + cs.h_half[a]);
+            }
+        double sR = 0.0;
+        for (int k = 0; k < GD; ++k) sR = std::max(sR, 0.5 * (hi[k] - lo[k]));
+        if (!(sR > 0.0)) sR = 1.0;
+        std::vector<double> T((size_t)n_agg * M * M, 0.0);
+        for (int a = 0; a < n_agg; ++a) {
+            double q[3] = {0, 0, 0};
+            for (int k = 0; k < GD; ++k) q[k] = (cs.h_cen[(size_t)a * 3 + k] - cR[k]) / sR;
+            const double sc = cs.h_half[a] / sR;
+            double* Ta = T.data() + (size_t)a * M * M;
+            auto at = [&](int i, int j) -> double& { return Ta[i * M + j]; };
+            if (GD == 2) {
+                at(0, 0) = 1.0; at(1, 1) = 1.0; at(0, 2) = -q[1]; at(1, 2) = q[0]; at(2, 2) = sc;
+            } else {
+                for (int k = 0; k < 3; ++k) { at(k, k) = 1.0; at(3 + k, 3 + k) = sc; }
+                // translation part of omega x q: (w_y q_z - w_z q_y, w_z q_x - w_x q_z, w_x q_y - w_y q_x)
+                at(0, 4) = q[2];  at(0, 5) = -q[1];
+                at(1, 3) = -q[2]; at(1, 5) = q[0];
+                at(2, 3) = q[1];  at(2, 4) = -q[0];
+            }
+        }
+        if ((st = dev_upload(c, &cs.T3, T))) return st;
+        if ((st = dev_alloc(c, &cs.E3, (size_t)ng * ng))) return st;
+        if ((st = dev_alloc(c, &cs.Einv3, (size_t)ng * ng))) return st;
+        cs.lvl3_ready = true;
+    }
+    CoarseView cv = coarse_view(c, LIN_U);
+    CK(cudaMemsetAsync(cs.E3, 0, (size_t)ng * ng * sizeof(double), c->stream));
+    for (int r = 0; r < nR; ++r)
+        for (int m = 0; m < M; ++m) {
+            CK(cudaMemsetAsync(c->w_p, 0, (size_t)c->n_nodes * NC * sizeof(double), c->stream));
+            coarse3_probe_kernel<NC, GD><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, cs.T3, r == c->rank ? 1 : 0, m, mask, c->w_p);
+            c->launches++;
+            if ((st = exchange(c, c->w_p, NC))) return st;
+            if ((st = apply_lin(c, LIN_U, c->w_p, c->w_Ap, mask, c->red, nullptr, 1))) return st;
+            coarse_restrict_kernel<NC, GD><<<cs.n_chunks, kThreads, 0, c->stream>>>(cv, c->w_Ap);
+            coarse3_reduce_kernel<M><<<1, kThreads, 0, c->stream>>>(cv, cs.T3, c->S, 0, c->d_pv);
+            coarse3_collect_kernel<M><<<1, 32, 0, c->stream>>>(c->d_pv, r * M + m, cs.E3);
+            c->launches += 3;
+        }
+    CK(cudaGetLastError());
+    std::vector<double> E((size_t)ng * ng), Ei((size_t)ng * ng, 0.0);
+    CK(cudaMemcpyAsync(E.data(), cs.E3, E.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    // symmetrise, decouple empty rows, Cholesky (E must be positive definite), inverse by two triangular solves per column
+    bool ok = true;
+    for (int i = 0; i < ng; ++i)
+        for (int j = 0; j < i; ++j) { const double v = 0.5 * (E[(size_t)i * ng + j] + E[(size_t)j * ng + i]); E[(size_t)i * ng + j] = E[(size_t)j * ng + i] = v; }
+    for (int i = 0; i < ng; ++i)
+        if (!(E[(size_t)i * ng + i] > 0.0)) {
+            for (int j = 0; j < ng; ++j) E[(size_t)i * ng + j] = E[(size_t)j * ng + i] = 0.0;
+            E[(size_t)i * ng + i] = 1.0;
+        }
+    std::vector<double> Lc(E);
+    for (int j = 0; j < ng && ok; ++j) {
+        double d = Lc[(size_t)j * ng + j];
+        for (int k = 0; k < j; ++k) d -= Lc[(size_t)j * ng + k] * Lc[(size_t)j * ng + k];
+        if (!(d > 0.0) || !std::isfinite(d)) { ok = false; break; }
+        d = std::sqrt(d);
+        Lc[(size_t)j * ng + j] = d;
+        for (int i = j + 1; i < ng; ++i) {
+            double v = Lc[(size_t)i * ng + j];
+            for (int k = 0; k < j; ++k) v -= Lc[(size_t)i * ng + k] * Lc[(size_t)j * ng + k];
+            Lc[(size_t)i * ng + j] = v / d;
+        }
+    }
+    if (ok) {
+        std::vector<double> y(ng);
+        for (int col = 0; col < ng; ++col) {
+            for (int i = 0; i < ng; ++i) {                       // L y = e_col
+                double v = (i == col) ? 1.0 : 0.0;
+                for (int k = 0; k < i; ++k) v -= Lc[(size_t)i * ng + k] * y[k];
+                y[i] = v / Lc[(size_t)i * ng + i];
+            }
+            for (int i = ng - 1; i >= 0; --i) {                  // L^T x = y
+                double v = y[i];
+                for (int k = i + 1; k < ng; ++k) v -= Lc[(size_t)k * ng + i] * Ei[(size_t)k * ng + col];
+                Ei[(size_t)i * ng + col] = v / Lc[(size_t)i * ng + i];
+            }
+        }
+        CK(cudaMemcpyAsync(cs.Einv3, Ei.data(), Ei.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    }
+    if (c->verbose) fprintf(stderr, "[pfx] rank-level coarse space: %d dofs, %s\n", ng, ok ? "on" : "matrix not positive definite: off");
+    if (ok != cs.lvl3_on && cs.op[LIN_U].graph) {        // the captured iteration changes with the third level
+        cudaGraphExecDestroy(cs.op[LIN_U].graph);
+        cs.op[LIN_U].graph = nullptr;
+    }
+    cs.lvl3_on = ok;
+    return PFX_OK;
+}
+
 int coarse_setup(pfx_ctx* c, int kind, const uint8_t* mask) {
     if (kind == LIN_PHI) return c->dim == 2 ? coarse_setup_t<1, 2>(c, kind, mask) : coarse_setup_t<1, 3>(c, kind, mask);
-    return c->dim == 2 ? coarse_setup_t<2, 2>(c, kind, mask) : coarse_setup_t<3, 3>(c, kind, mask);
+    int st = c->dim == 2 ? coarse_setup_t<2, 2>(c, kind, mask) : coarse_setup_t<3, 3>(c, kind, mask);
+    if (st) return st;
+    Coarse& cs = c->coarse;
+    if (c->n_ranks > 1 && c->p2p && c->p2p_fused && cs.lvl3_wanted && cs.op[LIN_U].valid)
+        return c->dim == 2 ? coarse3_setup_t<2, 2>(c, mask) : coarse3_setup_t<3, 3>(c, mask);
+    return PFX_OK;
 }
 
 // tail of one PCG iteration / start of a solve (init) with the coarse space: update, coarse solve, direction
@@ -850,8 +969,14 @@ int coarse_tail_t(pfx_ctx* c, int kind, int par, int init, const uint8_t* mask, 
                                                                                   cs.partial, c->counter, pv);
     const int solve_ctas = cs.op[kind].n_ctas;
     const int mode = init ? 3 : ((multi && !pv) ? 2 : 0);
+    Coarse3View c3;
+    if (kind == LIN_U && cs.lvl3_on && fused) {      // rank-level coarse space: one more mailbox hop of M numbers
+        c3.pv = c->d_pv; c3.T = cs.T3; c3.Einv = cs.Einv3;
+        coarse3_reduce_kernel<M><<<1, kThreads, 0, c->stream>>>(cv, cs.T3, c->S, init ? 0 : 1, c->d_pv);
+        c->launches++;
+    }
     coarse_solve_kernel<M><<<solve_ctas, kThreads, (size_t)cv.ld * sizeof(double), c->stream>>>(cv, c->S, par, mode, cs.partial,
-                                                                                              c->counter, pv);
+                                                                                              c->counter, pv, c3);
     c->launches += 2;
     if (init) {
         if ((st = allreduce(c, c->S + S_STAGE, 2))) return st;
@@ -1033,7 +1158,7 @@ int pcg_solve(pfx_ctx* c, int kind, double rtol, int64_t* iters, bool* converged
     c->launches++;
     if (coarse_on) {
         // z0 = (D^-1 + Z Ainv Z^T) r0: the init pass of the coarse kernels redoes the sums and the direction
-        if ((st = coarse_tail(c, kind, 0, 1, mask, dinv, rtol * rtol, bref_slot))) return st;
+        if ((st = coarse_tail(c, kind, 0, 1, mask, dinv, rtol * rtol, bref_slot, (c->n_ranks > 1 && c->p2p && c->p2p_fused) ? 1 : 0))) return st;
     } else {
         if ((st = allreduce(c, c->S + S_STAGE, 2))) return st;
         pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, rtol * rtol, bref_slot);
@@ -2007,7 +2132,7 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
             timed_coarse = c->coarse.op[LIN_U].valid;
         }
         if (timed_coarse) {
-            if ((st = coarse_tail(c, LIN_U, 0, 1, c->mask_u, c->w_dinv, 0.0, -1))) return st;
+            if ((st = coarse_tail(c, LIN_U, 0, 1, c->mask_u, c->w_dinv, 0.0, -1, (c->n_ranks > 1 && c->p2p && c->p2p_fused) ? 1 : 0))) return st;
         } else {
             if ((st = allreduce(c, c->S + S_STAGE, 2))) return st;
             pcg_setup_kernel<<<1, 1, 0, c->stream>>>(c->S, 0.0, -1);

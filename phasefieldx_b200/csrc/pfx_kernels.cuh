@@ -138,6 +138,26 @@ __device__ __forceinline__ void mbox_sum(const PeerView* pv, double* sums, int n
     }
 }
 
+// warp 0, all 32 lanes: wait for the current all-reduce sequence and return every rank's n values unsummed
+// (out[r * n + k], identical on every rank and in every CTA); valid in every lane of the warp
+__device__ __forceinline__ void mbox_gather(const PeerView* pv, double* out, int n) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long sq = pv->seq[0];
+    double v[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (lane < pv->n_ranks) {
+        const double* src = pv->mbox_local + ((size_t)(sq & 3ull) * pv->n_ranks + lane) * kMboxStride;
+        long long spins = 0;
+        while (ld_acquire_sys(reinterpret_cast<const unsigned long long*>(src + 8)) != sq) {
+            if (++spins > kSpinLimit) { *pv->err = 2.0; break; }
+        }
+        for (int k = 0; k < n; ++k) v[k] = __ldcv(src + k);
+    }
+    for (int r = 0; r < pv->n_ranks; ++r)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k < n) out[r * n + k] = __shfl_sync(0xffffffffu, v[k], r);
+}
+
 // every thread of the CTA: wait until all neighbours pushed the current halo sequence
 __device__ __forceinline__ void halo_wait_cta(const PeerView* pv) {
     if ((int)threadIdx.x < pv->n_nbrs) {
