@@ -38,7 +38,8 @@ enum {
 };
 
 /* ---- enumerations ---------------------------------------------------------------- */
-enum { PFX_CELL_TRIANGLE = 0, PFX_CELL_QUADRILATERAL = 1, PFX_CELL_TETRAHEDRON = 2 };
+enum { PFX_CELL_TRIANGLE = 0, PFX_CELL_QUADRILATERAL = 1, PFX_CELL_TETRAHEDRON = 2,
+       PFX_CELL_HEXAHEDRON = 3 /* Q1, tensor vertex order x + 2y + 4z (dolfinx) */ };
 /* pfx/Element/Phase_Field_Fracture/split_energy_stress_tangent_functions.py:234-354 */
 enum { PFX_MODEL_ISOTROPIC = 0, PFX_MODEL_SPECTRAL = 1, PFX_MODEL_DEVIATORIC = 2,
        PFX_MODEL_HYBRID_SPECTRAL = 3, PFX_MODEL_HYBRID_DEVIATORIC = 4 };

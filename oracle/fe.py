@@ -3,7 +3,7 @@ ORACLE (test infrastructure, not product code) — finite-element tables.
 
 CPU restatement of the FE facts the reference obtains from dolfinx/basix/FFCx (not vendored
 under /root/reference; pinned `fenics-dolfinx==0.10.0`, reference `environment.yml:5`):
-P1 Lagrange on affine triangles/tetrahedra, Q1 on bilinear quadrilaterals (tensor vertex
+P1 Lagrange on affine triangles/tetrahedra, Q1 on bilinear quadrilaterals and trilinear hexahedra (tensor vertex
 order), Gauss quadrature exact for the polynomial integrands of the staggered solver
 (SURVEY §7 H5).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 `--impl reference` leg may import this package.
@@ -11,8 +11,8 @@ order), Gauss quadrature exact for the polynomial integrands of the staggered so
 import numpy as np
 from scipy.special import roots_jacobi
 
-NV = {"triangle": 3, "quadrilateral": 4, "tetrahedron": 4}
-TDIM = {"triangle": 2, "quadrilateral": 2, "tetrahedron": 3}
+NV = {"triangle": 3, "quadrilateral": 4, "tetrahedron": 4, "hexahedron": 8}
+TDIM = {"triangle": 2, "quadrilateral": 2, "tetrahedron": 3, "hexahedron": 3}
 
 
 def _gauss01(n):
@@ -29,6 +29,11 @@ def quadrature(cell_type, degree):
         X, Y = np.meshgrid(x, x, indexing="ij")
         W = np.outer(w, w)
         return np.stack([X.ravel(), Y.ravel()], 1), W.ravel()
+    if cell_type == "hexahedron":
+        x, w = _gauss01(n)
+        X, Y, Z = np.meshgrid(x, x, x, indexing="ij")
+        W = w[:, None, None] * w[None, :, None] * w[None, None, :]
+        return np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1), W.ravel()
     if cell_type == "triangle":
         x0, w0 = _gauss01(n)
         x1, w1 = roots_jacobi(n, 1, 0)
@@ -71,6 +76,13 @@ def tabulate(cell_type, pts):
         N = np.stack([(1 - x) * (1 - y), x * (1 - y), (1 - x) * y, x * y], 1)
         dN = np.stack([np.stack([-(1 - y), -(1 - x)], 1), np.stack([(1 - y), -x], 1),
                        np.stack([-y, (1 - x)], 1), np.stack([y, x], 1)], 1)
+    elif cell_type == "hexahedron":
+        x, y, z = pts[:, 0], pts[:, 1], pts[:, 2]
+        lx, ly, lz = [1 - x, x], [1 - y, y], [1 - z, z]
+        dl = [-np.ones(q), np.ones(q)]
+        N = np.stack([lx[a & 1] * ly[(a >> 1) & 1] * lz[(a >> 2) & 1] for a in range(8)], 1)
+        dN = np.stack([np.stack([dl[a & 1] * ly[(a >> 1) & 1] * lz[(a >> 2) & 1], lx[a & 1] * dl[(a >> 1) & 1] * lz[(a >> 2) & 1],
+                                 lx[a & 1] * ly[(a >> 1) & 1] * dl[(a >> 2) & 1]], 1) for a in range(8)], 1)
     else:
         raise ValueError(cell_type)
     return N, dN
@@ -79,7 +91,7 @@ def tabulate(cell_type, pts):
 def default_degree(cell_type, fatigue=False):
     """Lowest rule that integrates every form of the staggered solver exactly on affine cells
     (SURVEY H5): simplices degree 3 (4 with the fatigue RHS g(φ)·V_c·w); Q1 3 points/direction."""
-    if cell_type == "quadrilateral":
+    if cell_type in ("quadrilateral", "hexahedron"):
         return 5
     return 4
 

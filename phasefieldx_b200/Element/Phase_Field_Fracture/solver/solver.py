@@ -89,7 +89,7 @@ def solve(Data, msh, final_time, V_u, V_Φ, bc_list_u=[], bc_list_phi=[], update
     # ---- device context (replaces the form / NonlinearProblem construction, solver.py:148-245)
     points, cells, ctype = fem.extract_mesh(msh)
     split = None if Data.split_energy == "no" else Data.split_energy
-    gdim = 3 if ctype == "tetrahedron" else 2
+    gdim = 3 if ctype in ("tetrahedron", "hexahedron") else 2
     rmesh, keep_u, keep_phi = None, [], []
     engine_kw = dict(k=float(Data.k), model=_lib.model_code(Data.degradation, split),
                      irreversibility=(Data.irreversibility == "miehe"), fatigue=bool(Data.fatigue),

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpfx_b200.so")
 
-CELL = {"triangle": 0, "quadrilateral": 1, "tetrahedron": 2}
+CELL = {"triangle": 0, "quadrilateral": 1, "tetrahedron": 2, "hexahedron": 3}
 FIELD = {"u": 0, "phi": 1, "H": 2, "V_c": 3, "V_n": 4, "fatigue": 5, "alpha_cum_bar_c": 6, "alpha_c": 7,
          "u_old": 8, "phi_old": 9, "alpha_n": 10, "alpha_cum_bar_n": 11}
 ENERGY_COLUMNS = ("EplusW", "E", "W", "W_phi", "W_gradphi", "gamma", "gamma_phi", "gamma_gradphi", "PSI_a", "PSI_b",
@@ -284,7 +284,7 @@ class Engine:
             raise ValueError("coords must be [N,3]")
         self.cells = np.ascontiguousarray(cells, dtype=np.int32)
         self.cell_type = cell_type
-        self.dim = 3 if cell_type == "tetrahedron" else 2
+        self.dim = 3 if cell_type in ("tetrahedron", "hexahedron") else 2
         self.n_nodes = len(self.coords)
         p = PfxParams()
         self.lib.pfx_default_params(C.byref(p))

@@ -91,7 +91,7 @@ std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int6
     std::vector<int32_t> cnt_p(nb, 0), cnt_l(nb, 0), cnt_s(nb, 0);
     auto visit = [&](auto&& fn) {
         for (int64_t c = 0; c < n_cells; ++c) {
-            int blk[4]; int nblk = 0; int32_t low = INT32_MAX; int lowb = -1;
+            int blk[8]; int nblk = 0; int32_t low = INT32_MAX; int lowb = -1;
             for (int a = 0; a < nv; ++a) {
                 int32_t nw = bm.iperm[cells[c * nv + a]];
                 int b = block_of_new(nw);
@@ -128,7 +128,10 @@ std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int6
     }
 
     // ---- 4. halo lists + local connectivity ------------------------------------------------
-    bm.lconn.assign(4 * bm.total_elems, 0);
+    // 4 (8 for hexahedra) 16-bit block-local vertex ids per listed cell; incidence codes (cell << vb | vertex)
+    const int ls = nv > 4 ? 8 : 4, vb = nv > 4 ? 3 : 2;
+    bm.lstride = ls; bm.vbits = vb;
+    bm.lconn.assign((size_t)ls * bm.total_elems, 0);
     bm.halo_off.assign(nb + 1, 0);
     std::vector<int32_t> stamp(n_nodes, -1), loc(n_nodes, 0), tmp;
     for (int b = 0; b < nb; ++b) {
@@ -148,14 +151,14 @@ std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int6
         int n_loc = n_own + (int)tmp.size();
         if (n_loc > 65535) return "block has more than 65535 local nodes";
         int ne = bm.elem_off[b + 1] - bm.elem_off[b];
-        if (ne > 16383) return "block has more than 16383 elements; lower block_nodes";
+        if (ne > (0xFFFF >> vb) - 1) return "block has too many elements for its 16-bit incidence codes; lower block_nodes";
         bm.max_own = std::max(bm.max_own, n_own);
         bm.max_loc = std::max(bm.max_loc, n_loc);
         bm.max_elems = std::max(bm.max_elems, ne);
         for (int32_t e = bm.elem_off[b]; e < bm.elem_off[b + 1]; ++e)
             for (int a = 0; a < nv; ++a) {
                 int32_t nw = bm.iperm[cells[(int64_t)bm.elem_gid[e] * nv + a]];
-                bm.lconn[4 * (int64_t)e + a] = (uint16_t)((nw >= n0 && nw < n1) ? nw - n0 : loc[nw]);
+                bm.lconn[ls * (int64_t)e + a] = (uint16_t)((nw >= n0 && nw < n1) ? nw - n0 : loc[nw]);
             }
     }
 
@@ -165,7 +168,7 @@ std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int6
         int n_own = bm.node0[b + 1] - bm.node0[b];
         for (int32_t e = bm.elem_off[b]; e < bm.elem_off[b + 1]; ++e)
             for (int a = 0; a < nv; ++a) {
-                int l = bm.lconn[4 * (int64_t)e + a];
+                int l = bm.lconn[ls * (int64_t)e + a];
                 if (l < n_own) bm.inc_ptr[bm.node0[b] + l + 1]++;
             }
     }
@@ -188,8 +191,8 @@ std::string build_blocks(int nv, int dim, int64_t n_nodes, int64_t n_owned, int6
             int n_own = bm.node0[b + 1] - bm.node0[b];
             for (int32_t e = bm.elem_off[b]; e < bm.elem_off[b + 1]; ++e)
                 for (int a = 0; a < nv; ++a) {
-                    int l = bm.lconn[4 * (int64_t)e + a];
-                    if (l < n_own) bm.inc[cur[bm.node0[b] + l]++] = (uint16_t)(((e - bm.elem_off[b]) << 2) | a);
+                    int l = bm.lconn[ls * (int64_t)e + a];
+                    if (l < n_own) bm.inc[cur[bm.node0[b] + l]++] = (uint16_t)(((e - bm.elem_off[b]) << vb) | a);
                 }
         }
     }
@@ -506,7 +509,7 @@ std::string build_aggregates(const BlockMesh& bm, int64_t n_cells, const double*
     // aggregate graph
     std::vector<std::vector<int32_t>> adj(n_agg);
     for (int64_t e = 0; e < n_cells; ++e) {
-        int32_t ag[4]; int na = 0;
+        int32_t ag[8]; int na = 0;
         for (int k = 0; k < nv; ++k) {
             int32_t nid = bm.iperm[cells[e * nv + k]];
             if (nid >= n_owned) continue;

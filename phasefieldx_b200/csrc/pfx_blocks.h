@@ -28,7 +28,8 @@ struct BlockMesh {
     std::vector<int32_t> halo;       // new ids of non-owned nodes referenced by the block, sorted
     std::vector<int32_t> elem_off;   // [nb+1]
     std::vector<int32_t> nprim;      // [nb] leading elements of the block integrated in scalar reductions
-    std::vector<uint16_t> lconn;     // [4*sum elems] block-local vertex ids (triangles: 4th = 0)
+    std::vector<uint16_t> lconn;     // [lstride*sum elems] block-local vertex ids (triangles: 4th = 0)
+    int lstride = 4, vbits = 2;      // hexahedra: 8 ids per cell, 3-bit vertex codes in the incidence lists
     std::vector<int32_t> elem_gid;   // [sum elems] caller cell id (diagnostics/tests)
     std::vector<int32_t> inc_ptr;    // [n_owned+1] into inc
     std::vector<uint16_t> inc;       // per owned node: (local elem << 2 | vertex), ascending

@@ -17,6 +17,7 @@ namespace pfx {
 struct Tri  { static constexpr int NV = 3, D = 2; static constexpr bool simplex = true; };
 struct Quad { static constexpr int NV = 4, D = 2; static constexpr bool simplex = false; };
 struct Tet  { static constexpr int NV = 4, D = 3; static constexpr bool simplex = true; };
+struct Hex  { static constexpr int NV = 8, D = 3; static constexpr bool simplex = false; };   // Q1, tensor vertex order x + 2y + 4z
 
 #if defined(__CUDACC__)
 static __constant__ double d_triq[9][3] = PFX_TRIQ_DATA;
@@ -114,6 +115,46 @@ template <> struct Geo<Quad> {
             Gq[a][0] = (dr[a][0] * J11 - dr[a][1] * J10) * inv;
             Gq[a][1] = (-dr[a][0] * J01 + dr[a][1] * J00) * inv;
         }
+        return ::fabs(det) * w;
+    }
+};
+
+template <> struct Geo<Hex> {
+    double X[24];
+    int n1d, nq;
+    PFX_HD void init(const double* X_, int n1d_) {
+        for (int i = 0; i < 24; ++i) X[i] = X_[i];
+        n1d = n1d_; nq = n1d_ * n1d_ * n1d_;
+    }
+    PFX_HD double eval(int q, double* N, double (*Gq)[3]) const {
+        const int qk = q / (n1d * n1d), qj = (q / n1d) % n1d, qi = q % n1d;
+        const double xi[3] = {PFX_TAB(gauss)[n1d - 1][qi], PFX_TAB(gauss)[n1d - 1][qj], PFX_TAB(gauss)[n1d - 1][qk]};
+        const double w = PFX_TAB(gauss)[n1d - 1][4 + qi] * PFX_TAB(gauss)[n1d - 1][4 + qj] * PFX_TAB(gauss)[n1d - 1][4 + qk];
+        double l[3][2], dl[3][2] = {{-1.0, 1.0}, {-1.0, 1.0}, {-1.0, 1.0}}, dr[8][3];
+        for (int d = 0; d < 3; ++d) { l[d][0] = 1.0 - xi[d]; l[d][1] = xi[d]; }
+        double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};             // J_ij = dx_i/dxi_j
+        for (int a = 0; a < 8; ++a) {
+            const int bx = a & 1, by = (a >> 1) & 1, bz = (a >> 2) & 1;
+            N[a] = l[0][bx] * l[1][by] * l[2][bz];
+            dr[a][0] = dl[0][bx] * l[1][by] * l[2][bz];
+            dr[a][1] = l[0][bx] * dl[1][by] * l[2][bz];
+            dr[a][2] = l[0][bx] * l[1][by] * dl[2][bz];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) J[i][j] += X[3 * a + i] * dr[a][j];
+        }
+        const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1], c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2],
+                     c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+        const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02, inv = 1.0 / det;
+        double Ji[3][3];                                                // Ji[j][i] = dxi_j/dx_i
+        Ji[0][0] = c00 * inv; Ji[1][0] = c01 * inv; Ji[2][0] = c02 * inv;
+        Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * inv;
+        Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * inv;
+        Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * inv;
+        Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * inv;
+        Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * inv;
+        Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * inv;
+        for (int a = 0; a < 8; ++a)
+            for (int i = 0; i < 3; ++i) Gq[a][i] = dr[a][0] * Ji[0][i] + dr[a][1] * Ji[1][i] + dr[a][2] * Ji[2][i];
         return ::fabs(det) * w;
     }
 };

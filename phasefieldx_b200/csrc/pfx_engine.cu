@@ -425,6 +425,7 @@ int launch_scatter_cell(pfx_ctx* c, int op, const KArgs& a) {
 int launch_scatter(pfx_ctx* c, int op, const KArgs& a) {
     if (c->cell_type == PFX_CELL_TRIANGLE) return launch_scatter_cell<Tri>(c, op, a);
     if (c->cell_type == PFX_CELL_QUADRILATERAL) return launch_scatter_cell<Quad>(c, op, a);
+    if (c->cell_type == PFX_CELL_HEXAHEDRON) return launch_scatter_cell<Hex>(c, op, a);
     return launch_scatter_cell<Tet>(c, op, a);
 }
 
@@ -449,6 +450,7 @@ template <int KIND>
 int launch_reduce(pfx_ctx* c, const KArgs& a) {
     if (c->cell_type == PFX_CELL_TRIANGLE) return launch_reduce_k<Tri, KIND>(c, a);
     if (c->cell_type == PFX_CELL_QUADRILATERAL) return launch_reduce_k<Quad, KIND>(c, a);
+    if (c->cell_type == PFX_CELL_HEXAHEDRON) return launch_reduce_k<Hex, KIND>(c, a);
     return launch_reduce_k<Tet, KIND>(c, a);
 }
 
@@ -1463,6 +1465,7 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
         case PFX_CELL_TRIANGLE: c->nv = 3; c->dim = 2; break;
         case PFX_CELL_QUADRILATERAL: c->nv = 4; c->dim = 2; break;
         case PFX_CELL_TETRAHEDRON: c->nv = 4; c->dim = 3; break;
+        case PFX_CELL_HEXAHEDRON: c->nv = 8; c->dim = 3; break;
         default: c->err = "unknown cell type"; return PFX_ERR_BAD_ARG;
     }
     if (prm->quad_points_1d < 1 || prm->quad_points_1d > 4) { c->err = "quad_points_1d must be 1..4"; return PFX_ERR_BAD_ARG; }
@@ -2191,7 +2194,7 @@ struct pfx_partition {
 int pfx_partition_create(int32_t cell_type, int64_t n_nodes, int64_t n_cells, const double* coords, const int32_t* cells,
                          int n_ranks, const int32_t* cell_rank_in, pfx_partition** out) {
     if (!coords || !cells || !out || n_nodes <= 0 || n_cells <= 0) return PFX_ERR_BAD_ARG;
-    int nv = (cell_type == PFX_CELL_TRIANGLE) ? 3 : 4;
+    int nv = (cell_type == PFX_CELL_TRIANGLE) ? 3 : (cell_type == PFX_CELL_HEXAHEDRON ? 8 : 4);
     pfx_partition* p = new pfx_partition();
     std::string er = build_partition(nv, n_nodes, n_cells, coords, cells, n_ranks, cell_rank_in, p->P);
     if (!er.empty()) { delete p; return PFX_ERR_BAD_ARG; }
@@ -2203,7 +2206,7 @@ int pfx_partition_graph_cell_rank(int32_t cell_type, int64_t n_nodes, int64_t n_
                                   int32_t* cell_rank, int64_t* edge_cut) {
     if (!cells || !cell_rank || n_cells <= 0 || n_ranks < 1) return PFX_ERR_BAD_ARG;
     int nv = cell_type == PFX_CELL_TRIANGLE ? 3 : 4, dim = cell_type == PFX_CELL_TETRAHEDRON ? 3 : 2;
-    if (cell_type < PFX_CELL_TRIANGLE || cell_type > PFX_CELL_TETRAHEDRON) return PFX_ERR_BAD_ARG;
+    if (cell_type < PFX_CELL_TRIANGLE || cell_type > PFX_CELL_TETRAHEDRON) return PFX_ERR_BAD_ARG;      // hexahedra: RCB only
     return metis_cell_rank(nv, dim, n_nodes, n_cells, cells, n_ranks, cell_rank, edge_cut).empty() ? PFX_OK : PFX_ERR_BAD_ARG;
 }
 int pfx_partition_cell_rank(const pfx_partition* p, int32_t* cr) {

@@ -571,10 +571,14 @@ __global__ void __launch_bounds__(kThreads, min_blocks<Op>::value) scatter_kerne
     double* s_nodes = smem;
     double* s_ebuf = smem + (size_t)bv.max_loc * NF;
     uint16_t* s_inc = reinterpret_cast<uint16_t*>(smem + ((((size_t)bv.max_loc * NF + (size_t)NV * NOUT * chunk) + 1) & ~(size_t)1));   // 16-byte aligned
+    constexpr int LW = NV > 4 ? 2 : 1;          // 64-bit connectivity words per cell (hexahedra: 8 x u16)
+    constexpr int VB = NV > 4 ? 3 : 2;          // bits of the vertex number in an incidence code
     // prefetch this thread's first two element connectivities (independent of phase A)
     ushort4 lc0 = make_ushort4(0, 0, 0, 0), lc1 = lc0;
-    if (tid < ne) lc0 = bv.lconn[e0 + tid];
-    if (tid + kThreads < ne) lc1 = bv.lconn[e0 + tid + kThreads];
+    if (LW == 1) {
+        if (tid < ne) lc0 = bv.lconn[e0 + tid];
+        if (tid + kThreads < ne) lc1 = bv.lconn[e0 + tid + kThreads];
+    }
     // ---- phase A: stage nodal fields and the block's incidence list
     const int i0 = bv.inc_ptr[n0], ninc = bv.inc_ptr[n0 + n_own] - i0;
     for (int i = tid; i < n_loc; i += kThreads) {
@@ -593,9 +597,18 @@ __global__ void __launch_bounds__(kThreads, min_blocks<Op>::value) scatter_kerne
         const int nc = min(chunk, ne - c0);
         // ---- phase B: element vectors
         for (int j = tid; j < nc; j += kThreads) {
-            ushort4 lc = (c0 + j == tid) ? lc0 : ((c0 + j == tid + kThreads) ? lc1 : bv.lconn[e0 + c0 + j]);
-            const double* nd[4] = {s_nodes + (size_t)lc.x * NF, s_nodes + (size_t)lc.y * NF,
-                                   s_nodes + (size_t)lc.z * NF, s_nodes + (size_t)lc.w * NF};
+            const double* nd[NV > 4 ? 8 : 4];
+            if (LW == 1) {
+                ushort4 lc = (c0 + j == tid) ? lc0 : ((c0 + j == tid + kThreads) ? lc1 : bv.lconn[e0 + c0 + j]);
+                nd[0] = s_nodes + (size_t)lc.x * NF; nd[1] = s_nodes + (size_t)lc.y * NF;
+                nd[2] = s_nodes + (size_t)lc.z * NF; nd[3] = s_nodes + (size_t)lc.w * NF;
+            } else {
+                const ushort4 la = bv.lconn[2 * (size_t)(e0 + c0 + j)], lb = bv.lconn[2 * (size_t)(e0 + c0 + j) + 1];
+                nd[0] = s_nodes + (size_t)la.x * NF; nd[1] = s_nodes + (size_t)la.y * NF;
+                nd[2] = s_nodes + (size_t)la.z * NF; nd[3] = s_nodes + (size_t)la.w * NF;
+                nd[4 % (NV > 4 ? 8 : 4)] = s_nodes + (size_t)lb.x * NF; nd[5 % (NV > 4 ? 8 : 4)] = s_nodes + (size_t)lb.y * NF;
+                nd[6 % (NV > 4 ? 8 : 4)] = s_nodes + (size_t)lb.z * NF; nd[7 % (NV > 4 ? 8 : 4)] = s_nodes + (size_t)lb.w * NF;
+            }
             double out[NV * NOUT];
             Op::elem(a, nd, out, gid0 + c0 + j);
 #pragma unroll
@@ -606,9 +619,9 @@ __global__ void __launch_bounds__(kThreads, min_blocks<Op>::value) scatter_kerne
         if (tid < n_own) {
             while (cur < end) {
                 int code = s_inc[cur];
-                int j = (code >> 2) - c0;
+                int j = (code >> VB) - c0;
                 if (j >= nc) break;
-                int v = code & 3;
+                int v = code & ((1 << VB) - 1);
 #pragma unroll
                 for (int c = 0; c < NOUT; ++c) acc[c] += s_ebuf[(v * NOUT + c) * chunk + j];
                 ++cur;
@@ -1531,9 +1544,18 @@ __global__ void __launch_bounds__(kThreads) reduce_kernel(BlockView bv, KArgs a)
     for (int k = 0; k < NR; ++k) vals[k] = 0.0;
     const int e0 = bv.elem_off[b], ne = bv.nprim[b];
     for (int j = tid; j < ne; j += kThreads) {
-        ushort4 lc = bv.lconn[e0 + j];
-        const double* nd[4] = {s_nodes + (size_t)lc.x * NF, s_nodes + (size_t)lc.y * NF,
-                               s_nodes + (size_t)lc.z * NF, s_nodes + (size_t)lc.w * NF};
+        const double* nd[NV > 4 ? 8 : 4];
+        if (NV <= 4) {
+            ushort4 lc = bv.lconn[e0 + j];
+            nd[0] = s_nodes + (size_t)lc.x * NF; nd[1] = s_nodes + (size_t)lc.y * NF;
+            nd[2] = s_nodes + (size_t)lc.z * NF; nd[3] = s_nodes + (size_t)lc.w * NF;
+        } else {
+            const ushort4 la = bv.lconn[2 * (size_t)(e0 + j)], lb = bv.lconn[2 * (size_t)(e0 + j) + 1];
+            nd[0] = s_nodes + (size_t)la.x * NF; nd[1] = s_nodes + (size_t)la.y * NF;
+            nd[2] = s_nodes + (size_t)la.z * NF; nd[3] = s_nodes + (size_t)la.w * NF;
+            nd[4 % (NV > 4 ? 8 : 4)] = s_nodes + (size_t)lb.x * NF; nd[5 % (NV > 4 ? 8 : 4)] = s_nodes + (size_t)lb.y * NF;
+            nd[6 % (NV > 4 ? 8 : 4)] = s_nodes + (size_t)lb.z * NF; nd[7 % (NV > 4 ? 8 : 4)] = s_nodes + (size_t)lb.w * NF;
+        }
         double X[NV * D];
         for (int k = 0; k < NV; ++k) for (int i = 0; i < D; ++i) X[k * D + i] = nd[k][i];
         if (KIND == RED_ENERGY) {

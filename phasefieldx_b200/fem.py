@@ -113,6 +113,22 @@ class Measure:
         for f in self.facets:
             v = fv[f]
             p = x[v]
+            if len(v) == 4:
+                # bilinear quadrilateral face (hexahedra); the sorted facet vertices are re-ordered into the tensor order
+                # of the owning cell face: w_a = int N_a ds by 2 x 2 Gauss
+                cell = self.mesh.cells[self.mesh.facets()[2][f]]
+                v = np.array([n for n in cell if n in set(v.tolist())])
+                p = x[v]
+                gp = [0.5 - 0.5 / np.sqrt(3.0), 0.5 + 0.5 / np.sqrt(3.0)]
+                for s_ in gp:
+                    for t_ in gp:
+                        N = np.array([(1 - s_) * (1 - t_), s_ * (1 - t_), (1 - s_) * t_, s_ * t_])
+                        ds_ = (p[1] - p[0]) * (1 - t_) + (p[3] - p[2]) * t_
+                        dt_ = (p[2] - p[0]) * (1 - s_) + (p[3] - p[1]) * s_
+                        jac = np.linalg.norm(np.cross(ds_, dt_)) * 0.25
+                        for a, n in enumerate(v):
+                            acc[int(n)] = acc.get(int(n), 0.0) + N[a] * jac
+                continue
             if len(v) == 2:
                 meas = np.linalg.norm(p[1] - p[0])
             else:

@@ -15,8 +15,9 @@ import os
 
 import numpy as np
 
-_VTK_TYPE = {"triangle": 69, "quadrilateral": 70, "tetrahedron": 71}
-_VTK_PERM = {"triangle": [0, 1, 2], "quadrilateral": [0, 1, 3, 2], "tetrahedron": [0, 1, 2, 3]}
+_VTK_TYPE = {"triangle": 69, "quadrilateral": 70, "tetrahedron": 71, "hexahedron": 72}
+_VTK_PERM = {"triangle": [0, 1, 2], "quadrilateral": [0, 1, 3, 2], "tetrahedron": [0, 1, 2, 3],
+             "hexahedron": [0, 1, 3, 2, 4, 5, 7, 6]}
 
 
 def _f64(a, ncomp_out=None):

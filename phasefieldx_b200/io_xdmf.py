@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _TOPOLOGY = {"triangle": ("Triangle", 3, [0, 1, 2]), "quadrilateral": ("Quadrilateral", 4, [0, 1, 3, 2]),
-             "tetrahedron": ("Tetrahedron", 4, [0, 1, 2, 3])}
+             "tetrahedron": ("Tetrahedron", 4, [0, 1, 2, 3]), "hexahedron": ("Hexahedron", 8, [0, 1, 3, 2, 4, 5, 7, 6])}
 
 
 class XDMFFile:
@@ -39,7 +39,7 @@ class XDMFFile:
     def write_mesh(self, msh):
         name, nv, perm = _TOPOLOGY[msh.cell_type]
         x = np.asarray(msh.geometry.x, dtype="<f8")
-        gdim = 3 if msh.cell_type == "tetrahedron" else 2
+        gdim = 3 if msh.cell_type in ("tetrahedron", "hexahedron") else 2
         cells = np.asarray(msh.cells, dtype="<i8")[:, perm]
         self.mesh = dict(topology=name, nv=nv, ne=len(cells), nn=len(x), gdim=gdim,
                          geo_seek=self._append(x[:, :gdim]), topo_seek=self._append(cells))

@@ -11,7 +11,7 @@ arrays it holds (`geometry.x` [N_n,3] f64, `cells` [N_e,n_v] i32) are exactly wh
 
 Vertex ordering conventions (restated from dolfinx/basix): triangles and tetrahedra in any
 order (orientation is handled with |det J|); quadrilaterals in tensor order
-(x0y0, x1y0, x0y1, x1y1) as written by dolfinx.
+(x0y0, x1y0, x0y1, x1y1) as written by dolfinx, hexahedra likewise (index x + 2y + 4z).
 """
 from __future__ import annotations
 
@@ -32,8 +32,8 @@ class DiagonalType(enum.Enum):
     left = 2
 
 
-_NV = {"triangle": 3, "quadrilateral": 4, "tetrahedron": 4}
-_TDIM = {"triangle": 2, "quadrilateral": 2, "tetrahedron": 3}
+_NV = {"triangle": 3, "quadrilateral": 4, "tetrahedron": 4, "hexahedron": 8}
+_TDIM = {"triangle": 2, "quadrilateral": 2, "tetrahedron": 3, "hexahedron": 3}
 
 
 class _Comm:
@@ -117,6 +117,8 @@ class Mesh:
             return np.array([[1, 2], [0, 2], [0, 1]])
         if self.cell_type == "quadrilateral":
             return np.array([[0, 1], [0, 2], [1, 3], [2, 3]])
+        if self.cell_type == "hexahedron":          # tensor vertex order x + 2y + 4z: the six quadrilateral faces
+            return np.array([[0, 1, 2, 3], [4, 5, 6, 7], [0, 1, 4, 5], [2, 3, 6, 7], [0, 2, 4, 6], [1, 3, 5, 7]])
         return np.array([[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]])
 
     def facets(self):
@@ -170,7 +172,8 @@ _KUHN = np.array([[0, 1, 3, 7], [0, 1, 5, 7], [0, 2, 3, 7], [0, 2, 6, 7], [0, 4,
 
 
 def create_box(comm, points, n, cell_type=CellType.tetrahedron):
-    """Structured box of tetrahedra (Kuhn 6-split), signature of `dolfinx.mesh.create_box`."""
+    """Structured box of tetrahedra (Kuhn 6-split) or Q1 hexahedra (tensor vertex order x + 2y + 4z, as dolfinx writes
+    them), signature of `dolfinx.mesh.create_box`."""
     p0, p1 = np.asarray(points[0], float), np.asarray(points[1], float)
     nx, ny, nz = (int(v) for v in n)
     xs = np.linspace(p0[0], p1[0], nx + 1)
@@ -184,8 +187,10 @@ def create_box(comm, points, n, cell_type=CellType.tetrahedron):
     corner = np.stack([base + (c & 1) * sx + ((c >> 1) & 1) * sy + ((c >> 2) & 1) * sz
                        for c in range(8)], axis=1)      # [n_cells, 8]
     name = cell_type.name if isinstance(cell_type, CellType) else cell_type
+    if name == "hexahedron":
+        return Mesh(pts, corner, "hexahedron", gdim=3, comm=comm)
     if name != "tetrahedron":
-        raise ValueError("only tetrahedra are supported in 3D")
+        raise ValueError("3D cells: tetrahedron or hexahedron")
     cells = corner[:, _KUHN].reshape(-1, 4)
     return Mesh(pts, cells, "tetrahedron", gdim=3, comm=comm)
 

@@ -45,6 +45,9 @@ def perturbed_meshes(rng):
     m = M.create_box(None, [[0, 0, 0], [1.0, 0.7, 0.5]], [5, 4, 3])
     m.geometry.x[:, :3] += rng.normal(size=(m.num_nodes, 3)) * 0.01
     out.append(("tetrahedron", m))
+    m = M.create_box(None, [[0, 0, 0], [1.0, 0.7, 0.5]], [4, 3, 2], M.CellType.hexahedron)
+    m.geometry.x[:, :3] += rng.normal(size=(m.num_nodes, 3)) * 0.01
+    out.append(("hexahedron", m))
     return out
 
 

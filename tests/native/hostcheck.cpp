@@ -85,6 +85,7 @@ void hc_assemble(int op, int cell_type, const double* mat, int smodel, int emode
     Material m{mat[0], mat[1], mat[2], mat[3], mat[4], smodel, emodel, fatigue & 1, 0.0, fatigue >> 8};   // bits 8..: degradation function
     if (cell_type == 0) assemble<Tri>(op, m, n1d, ne, coords, cells, f0, f1, f2, f3, out);
     else if (cell_type == 1) assemble<Quad>(op, m, n1d, ne, coords, cells, f0, f1, f2, f3, out);
+    else if (cell_type == 3) assemble<Hex>(op, m, n1d, ne, coords, cells, f0, f1, f2, f3, out);
     else assemble<Tet>(op, m, n1d, ne, coords, cells, f0, f1, f2, f3, out);
 }
 }
@@ -117,7 +118,7 @@ static void emulate_apply_u(const BlockMesh& bm, const Material& m, int n1d, con
         for (int c0 = 0; c0 < ne; c0 += chunk) {
             int nc = std::min(chunk, ne - c0);
             for (int j = 0; j < nc; ++j) {
-                const uint16_t* lc = &bm.lconn[4 * (size_t)(e0 + c0 + j)];
+                const uint16_t* lc = &bm.lconn[(size_t)bm.lstride * (size_t)(e0 + c0 + j)];
                 double X[NV * D], ph[NV], V[NV * D], U[NV * D], out[NV * D];
                 for (int k = 0; k < NV; ++k) {
                     const double* nd = &s_nodes[(size_t)lc[k] * NF];
@@ -129,9 +130,9 @@ static void emulate_apply_u(const BlockMesh& bm, const Material& m, int n1d, con
             }
             for (int t = 0; t < n_own; ++t)
                 while (cur[t] < end[t]) {
-                    int code = bm.inc[cur[t]], j = (code >> 2) - c0;
+                    int code = bm.inc[cur[t]], j = (code >> bm.vbits) - c0;
                     if (j >= nc) break;
-                    int vtx = code & 3;
+                    int vtx = code & ((1 << bm.vbits) - 1);
                     for (int c = 0; c < D; ++c) acc[(size_t)t * D + c] += s_ebuf[(size_t)(vtx * D + c) * chunk + j];
                     ++cur[t];
                 }
@@ -150,7 +151,7 @@ int hc_blocks_apply_u(int cell_type, const double* mat, int smodel, int n1d, int
                       int max_own, int chunk, const double* phi, const double* u, const double* v, double* y,
                       double* dot, int64_t* stats) {
     Material m{mat[0], mat[1], mat[2], mat[3], mat[4], smodel, smodel, 0, 0.0};
-    int nv = cell_type == 0 ? 3 : 4, dim = cell_type == 2 ? 3 : 2;
+    int nv = cell_type == 0 ? 3 : (cell_type == 3 ? 8 : 4), dim = cell_type >= 2 ? 3 : 2;
     BlockMesh bm;
     std::string er = build_blocks(nv, dim, n_nodes, n_owned, n_cells, coords, cells, cell_primary, max_own, bm);
     if (!er.empty()) return 1;
@@ -159,6 +160,7 @@ int hc_blocks_apply_u(int cell_type, const double* mat, int smodel, int n1d, int
     stats[0] = bm.nb; stats[1] = bm.max_own; stats[2] = bm.max_loc; stats[3] = bm.max_elems; stats[4] = bm.total_elems; stats[5] = np;
     if (cell_type == 0) emulate_apply_u<Tri>(bm, m, n1d, coords, phi, u, v, chunk, y, dot);
     else if (cell_type == 1) emulate_apply_u<Quad>(bm, m, n1d, coords, phi, u, v, chunk, y, dot);
+    else if (cell_type == 3) emulate_apply_u<Hex>(bm, m, n1d, coords, phi, u, v, chunk, y, dot);
     else emulate_apply_u<Tet>(bm, m, n1d, coords, phi, u, v, chunk, y, dot);
     return 0;
 }
@@ -168,7 +170,7 @@ int hc_blocks_apply_u(int cell_type, const double* mat, int smodel, int n1d, int
 int hc_aggregates(int cell_type, int64_t n_nodes, int64_t n_owned, int64_t n_cells, const double* coords,
                   const int32_t* cells, int max_own, int g, int reg_aggs, int chunk_nodes, int64_t* stats, int32_t* node_agg,
                   int32_t* chunk_node0, int32_t* colour, int32_t* agg_reg, int32_t* nbrcol, int64_t nbrcol_cap, float* rel) {
-    int nv = cell_type == 0 ? 3 : 4, dim = cell_type == 2 ? 3 : 2;
+    int nv = cell_type == 0 ? 3 : (cell_type == 3 ? 8 : 4), dim = cell_type >= 2 ? 3 : 2;
     BlockMesh bm;
     std::string er = build_blocks(nv, dim, n_nodes, n_owned, n_cells, coords, cells, nullptr, max_own, bm);
     if (!er.empty()) return 1;

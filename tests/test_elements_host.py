@@ -15,7 +15,7 @@ PD = ctypes.POINTER(ctypes.c_double)
 PI = ctypes.POINTER(ctypes.c_int32)
 CODES = {("isotropic", "no"): (0, 0), ("anisotropic", "spectral"): (1, 1), ("anisotropic", "deviatoric"): (2, 2),
          ("hybrid", "spectral"): (0, 1)}
-CT = {"triangle": 0, "quadrilateral": 1, "tetrahedron": 2}
+CT = {"triangle": 0, "quadrilateral": 1, "tetrahedron": 2, "hexahedron": 3}
 
 
 def dp(a):
@@ -127,7 +127,8 @@ def test_block_builder_drives_scatter_logic(hostcheck):
     rng = np.random.default_rng(2)
     cases = [("triangle", M.create_rectangle(None, [[0, 0], [1, 1]], [31, 27])),
              ("quadrilateral", M.create_rectangle(None, [[0, 0], [1, 1]], [23, 19], M.CellType.quadrilateral)),
-             ("tetrahedron", M.create_box(None, [[0, 0, 0], [1, 1, 1]], [9, 8, 7]))]
+             ("tetrahedron", M.create_box(None, [[0, 0, 0], [1, 1, 1]], [9, 8, 7])),
+             ("hexahedron", M.create_box(None, [[0, 0, 0], [1, 1, 1]], [8, 7, 6], M.CellType.hexahedron))]
     m0 = cases[0][1]
     cases.append(("triangle", M.cut_slit(m0, lambda x: np.isclose(x[1], 13 / 27) & (x[0] < 0.5), lambda c: c[1] > 13 / 27)))
     for ctype, m in cases:
@@ -158,7 +159,7 @@ def test_cached_tangent_apply_matches_direct(hostcheck, sp):
     rng = np.random.default_rng(4)
     sm = CODES[("anisotropic", sp)][0]
     for ctype, m in perturbed_meshes(rng):
-        if ctype == "quadrilateral":
+        if ctype in ("quadrilateral", "hexahedron"):
             continue
         Pm = Params(degradation="anisotropic", split_energy=sp, k=1e-3)
         o = Oracle(m.geometry.x, m.cells, m.cell_type, Pm)

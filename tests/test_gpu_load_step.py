@@ -386,3 +386,28 @@ def test_shear_through_peak_load_vs_oracle(path, monkeypatch):
     assert phimax[-1] > 0.95 and max(rx) >= 30            # crack formed; the peak took many stagger iterations
     if path == "two_level":
         assert coarse["active"] == 1 and coarse["setups"] >= 1
+
+
+def test_hexahedra_staggered_load_steps_vs_oracle():
+    """Q1 hexahedra (the cell type of the reference's 3D reaction test, test/Reactions/test_reaction_forces.py:96-100)
+    through the whole staggered step: notched block, spectral split, against the oracle."""
+    from phasefieldx_b200 import mesh as M
+    from oracle.solver import BC
+    msh = M.create_box(None, [[0, 0, 0], [2.0, 1.0, 0.5]], [8, 4, 2], M.CellType.hexahedron)
+    o, e, P = _pair(msh, "hexahedron", "anisotropic", "spectral", E=0.6, nu=0.2, Gc=0.00013, l=0.4)
+    x = msh.geometry.x
+    left = np.nonzero(np.isclose(x[:, 0], 0.0))[0]
+    right = np.nonzero(np.isclose(x[:, 0], 2.0))[0]
+    bcs = [BC((left[:, None] * 3 + np.arange(3)).ravel()), BC(right * 3 + 0)]
+    for i, bc in enumerate(bcs):
+        e.set_bc_u(i, bc.dofs)
+        e.set_bc_values_u(i, bc.values)
+    for step in range(1, 3):
+        bcs[1].values[:] = 1.0e-2 * step
+        e.set_bc_values_u(1, bcs[1].values)
+        ro = o.load_step(bcs, [], max_stagger_iter=40)
+        rg = e.load_step(max_stagger_iter=40)
+        assert rg["stagger"] == ro["stagger"], (step, rg["stagger"], ro["stagger"])
+        _compare_step(o, e, bcs, step)
+    assert o.phi.max() > 1e-3
+    e.close()

@@ -161,3 +161,57 @@ def test_anisotropic_decomposition_reference_test(tmp_path, split_energy_i):
     assert out["u"].shape == ((divx + 1) * (divy + 1), 3)
     txt = (tmp_path / "check" / "paraview-solutions_vtu" / "phasefieldx_p0_000005.vtu").read_text()
     assert 'Name="PSI_a"' in txt and 'Name="PSI_b"' in txt
+
+
+def test_reaction_forces_2d_quadrilateral_equals_3d_hexahedron_reference_test(tmp_path):
+    """reference test/Reactions/test_reaction_forces.py:16-178: the same uniaxial stretch on one Q1 quadrilateral and
+    on one Q1 hexahedron (Elasticity solver, bc_xy / bc_xyz on bottom and top) gives the same bottom reaction R_y
+    (rtol 1e-5 there)."""
+    import phasefieldx_b200.compat as compat
+    compat.install()
+    import dolfinx
+    import mpi4py
+    import petsc4py
+    from phasefieldx.Element.Elasticity.Input import Input
+    from phasefieldx.Element.Elasticity.solver.solver import solve
+    from phasefieldx.Boundary.boundary_conditions import bc_xy, bc_xyz, get_ds_bound_from_marker
+    from phasefieldx.PostProcessing.ReferenceResult import AllResults
+
+    def run(dim):
+        Data = Input(E=210.0, nu=0.3, save_solution_xdmf=False, save_solution_vtu=True, results_folder_name=str(tmp_path / f"{dim}_dimension"))
+        if dim == 2:
+            msh = dolfinx.mesh.create_rectangle(mpi4py.MPI.COMM_WORLD, [np.array([0, 0]), np.array([1.0, 1.0])], [1, 1],
+                                                cell_type=dolfinx.mesh.CellType.quadrilateral)
+        else:
+            msh = dolfinx.mesh.create_box(mpi4py.MPI.COMM_WORLD, [np.array([0, 0, 0]), np.array([1.0, 1.0, 1.0])], [1, 1, 1],
+                                          cell_type=dolfinx.mesh.CellType.hexahedron)
+        fdim = msh.topology.dim - 1
+        bottom = dolfinx.mesh.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[1], 0))
+        top = dolfinx.mesh.locate_entities_boundary(msh, fdim, lambda x: np.isclose(x[1], 1.0))
+        ds_list = np.array([[get_ds_bound_from_marker(top, msh, fdim), "top"], [get_ds_bound_from_marker(bottom, msh, fdim), "bottom"]])
+        V_u = dolfinx.fem.functionspace(msh, ("Lagrange", 1, (msh.geometry.dim,)))
+        if dim == 2:
+            bcs = [bc_xy(top, V_u, fdim, value_x=0.0, value_y=0.0), bc_xy(bottom, V_u, fdim, value_x=0.0, value_y=0.0)]
+        else:
+            bcs = [bc_xyz(top, V_u, fdim, value_x=0.0, value_y=0.0, value_z=0.0), bc_xyz(bottom, V_u, fdim, value_x=0.0, value_y=0.0, value_z=0.0)]
+
+        def update_boundary_conditions(bcs_, time):
+            val = 0.0003 * time
+            bcs_[0].g.value[1] = petsc4py.PETSc.ScalarType(val)
+            return 0, val, 0
+        solve(Data, msh, 10.0, V_u, bcs, update_boundary_conditions, None, None, None, ds_list, 1.0, path=str(tmp_path),
+              quadrature_degree=2, bcs_list_u_names=["top", "bottom"])
+        return AllResults(Data.results_folder_name)
+    S2, S3 = run(2), run(3)
+    r2, r3 = np.asarray(S2.reaction_files["bottom.reaction"]["Ry"]), np.asarray(S3.reaction_files["bottom.reaction"]["Ry"])
+    assert len(r2) == 10 and abs(r2[-1]) > 0
+    np.testing.assert_allclose(r2, r3, rtol=1e-5, atol=1e-8)
+    # plane strain == fully clamped lateral faces: R_y = (lambda + 2 mu) * strain on the unit face
+    lam, mu = 210.0 * 0.3 / (1.3 * 0.4), 210.0 / 2.6
+    np.testing.assert_allclose(np.abs(r3), (lam + 2 * mu) * 0.0003 * np.arange(10), rtol=1e-9, atol=1e-12)
+    import re
+    txt = open(str(tmp_path / "3_dimension" / "paraview-solutions_vtu" / "phasefieldx_p0_000009.vtu")).read()
+    assert 'NumberOfCells="1"' in txt
+    assert re.search(r'Name="types"[^>]*>([^<]*)<', txt).group(1).split() == ["72"]          # VTK_LAGRANGE_HEXAHEDRON
+    back = read_vtu_points_cells(str(tmp_path / "3_dimension" / "paraview-solutions_vtu" / "phasefieldx_p0_000009.vtu"))
+    assert back["cells"].shape == (1, 8) and sorted(back["cells"][0].tolist()) == list(range(8))
