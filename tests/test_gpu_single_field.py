@@ -210,6 +210,7 @@ def test_reaction_forces_2d_quadrilateral_equals_3d_hexahedron_reference_test(tm
     lam, mu = 210.0 * 0.3 / (1.3 * 0.4), 210.0 / 2.6
     np.testing.assert_allclose(np.abs(r3), (lam + 2 * mu) * 0.0003 * np.arange(10), rtol=1e-9, atol=1e-12)
     import re
+    from phasefieldx_b200.io_vtk import read_vtu_points_cells
     txt = open(str(tmp_path / "3_dimension" / "paraview-solutions_vtu" / "phasefieldx_p0_000009.vtu")).read()
     assert 'NumberOfCells="1"' in txt
     assert re.search(r'Name="types"[^>]*>([^<]*)<', txt).group(1).split() == ["72"]          # VTK_LAGRANGE_HEXAHEDRON
