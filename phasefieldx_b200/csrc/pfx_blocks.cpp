@@ -372,7 +372,7 @@ std::string build_partition(int nv, int64_t n_nodes, int64_t n_cells, const doub
 // =============================================================================== node graph (sliced ELL)
 std::string build_node_graph(const BlockMesh& bm, int64_t n_cells, const int32_t* cells, NodeGraph& g) {
     const int nv = bm.nv;
-    if (nv != 4 || bm.dim != 3) return "node graph: tetrahedra only";
+    if (nv != 4) return "node graph: cells of four nodes only (tetrahedra, quadrilaterals)";
     g = NodeGraph();
     const int64_t n_rows = bm.n_owned;
     g.n_rows = n_rows;

@@ -605,7 +605,8 @@ int apply_lin(pfx_ctx* c, int kind, const double* v, double* y, const uint8_t* m
         else if (kind == LIN_PHI && sp.phi_fresh) K = sp.Kphi;
         else if (kind == LIN_MASS) K = sp.Km;
         if (K) {
-            if (kind == LIN_U) spmv_u_tet_kernel<<<grid, kThreads, 0, c->stream>>>(sp.sv, K, v, y, mask, c->partial, result, c->counter, stop, pv);
+            if (kind == LIN_U && c->dim == 3) spmv_u_tet_kernel<<<grid, kThreads, 0, c->stream>>>(sp.sv, K, v, y, mask, c->partial, result, c->counter, stop, pv);
+            else if (kind == LIN_U) spmv_u_quad_kernel<<<grid, kThreads, 0, c->stream>>>(sp.sv, K, v, y, mask, c->partial, result, c->counter, stop, pv);
             else spmv_s_tet_kernel<<<grid, kThreads, 0, c->stream>>>(sp.sv, K, v, y, mask, c->partial, result, c->counter, stop, pv);
             c->launches++;
             CK(cudaGetLastError());
@@ -623,11 +624,19 @@ int apply_lin(pfx_ctx* c, int kind, const double* v, double* y, const uint8_t* m
 // Jacobi / block-Jacobi data of the PCG (the diagonal blocks fall out of the assembly)
 int refresh_tangent(pfx_ctx* c) {
     if (!c->sp.enabled) return PFX_OK;
+    const bool blk = c->coarse.enabled && c->coarse.block_jacobi;
+    const int grid = (int)((c->sp.sv.n_rows + 127) / 128);
+    if (c->cell_type == PFX_CELL_QUADRILATERAL) {
+        assemble_u_quad_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->mat, c->prm.quad_points_1d, c->X, c->u, c->phi, c->mask_u, c->sp.Ku,
+                                                            c->w_dinv, blk ? c->coarse.dblk : nullptr);
+        c->launches++;
+        CK(cudaGetLastError());
+        c->tan_fresh = true;
+        return PFX_OK;
+    }
     KArgs t = base_args(c);
     int st = launch_scatter(c, OP_TANGENT_U, t);
     if (st) return st;
-    const bool blk = c->coarse.enabled && c->coarse.block_jacobi;
-    const int grid = (int)((c->sp.sv.n_rows + 127) / 128);
     assemble_u_tet_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->X, c->tan, c->mask_u, c->sp.Ku, c->w_dinv, blk ? c->coarse.dblk : nullptr);
     c->launches++;
     CK(cudaGetLastError());
@@ -646,7 +655,10 @@ int refresh_phi_operator(pfx_ctx* c) {
     c->phi_coeff_fresh = true;
     if (c->sp.enabled) {
         const int grid = (int)((c->sp.sv.n_rows + 127) / 128);
-        assemble_s_tet_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->X, c->cm, c->cg, c->mask_phi, c->sp.Kphi, c->w_dinv);
+        if (c->cell_type == PFX_CELL_QUADRILATERAL)
+            assemble_s_quad_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->prm.quad_points_1d, c->X, c->cm, c->cg, c->mask_phi, c->sp.Kphi, c->w_dinv);
+        else
+            assemble_s_tet_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->X, c->cm, c->cg, c->mask_phi, c->sp.Kphi, c->w_dinv);
         c->launches++;
         c->sp.phi_fresh = true;
     }
@@ -1587,7 +1599,7 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     // matrix-free scatter kernels (slow in 3D; an independent cross-check of the assembly)
     {
         const char* ns = getenv("PFX_NO_SPARSE");
-        if (c->cell_type == PFX_CELL_TETRAHEDRON && !(ns && ns[0] == '1')) {
+        if ((c->cell_type == PFX_CELL_TETRAHEDRON || c->cell_type == PFX_CELL_QUADRILATERAL) && !(ns && ns[0] == '1')) {
             NodeGraph ng;
             std::string eg = build_node_graph(bm, mesh->n_cells, mesh->cells, ng);
             if (!eg.empty()) { c->err = eg; return PFX_ERR_BAD_ARG; }
@@ -1603,10 +1615,10 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
             sp.sv.n_rows = ng.n_rows; sp.sv.n_slices = ng.n_slices; sp.sv.slice_k0 = d_k0; sp.sv.col = d_col;
             sp.sv.cell_nodes = (const int4*)d_cn; sp.sv.nc_ptr = d_ncp; sp.sv.nc_code = d_ncc; sp.sv.nc_kpos = d_nck;
             sp.total_k = ng.total_k;
-            if ((st = dev_alloc(c, &sp.Ku, (size_t)ng.total_k * 9 * 32))) return st;
+            if ((st = dev_alloc(c, &sp.Ku, (size_t)ng.total_k * (c->dim * c->dim) * 32))) return st;
             if ((st = dev_alloc(c, &sp.Kphi, (size_t)ng.total_k * 32))) return st;
             if ((st = dev_alloc(c, &sp.Km, (size_t)ng.total_k * 32))) return st;
-            if ((st = dev_alloc(c, &c->tan, (size_t)21 * (size_t)std::max<int64_t>(bm.n_own_cells, 1)))) return st;
+            if (c->dim == 3 && (st = dev_alloc(c, &c->tan, (size_t)21 * (size_t)std::max<int64_t>(bm.n_own_cells, 1)))) return st;
             sp.enabled = true;
         }
     }
@@ -1636,7 +1648,10 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     // ---- constant data: 1/diag(M) (tetrahedra: the assembled mass matrix as well)
     if (c->sp.enabled) {
         const int grid = (int)((c->sp.sv.n_rows + 127) / 128);
-        assemble_s_tet_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->X, c->ones, c->zeros, nullptr, c->sp.Km, c->dinv_mass);
+        if (c->cell_type == PFX_CELL_QUADRILATERAL)
+            assemble_s_quad_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->prm.quad_points_1d, c->X, c->ones, c->zeros, nullptr, c->sp.Km, c->dinv_mass);
+        else
+            assemble_s_tet_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->X, c->ones, c->zeros, nullptr, c->sp.Km, c->dinv_mass);
         c->launches++;
         CK(cudaGetLastError());
     } else {
@@ -2070,7 +2085,7 @@ int pfx_algorithmic_bytes(pfx_ctx* c, int kind, double* bytes) {
             break;
         case 5:      // bytes the u-apply implementation streams: with cached element tangents X, v, y per node + 21 doubles per cell
             *bytes = conn + Nn * (8 * d + 8 + 8 * d + 8 * d + (nl ? 8 * d : 0));
-            if (c->sp.enabled) *bytes = (double)c->sp.total_k * 32.0 * (72.0 + 4.0) + Nn * (8 * d + 8 * d);
+            if (c->sp.enabled) *bytes = (double)c->sp.total_k * 32.0 * (8.0 * d * d + 4.0) + Nn * (8 * d + 8 * d);
             break;
         case 1: *bytes = conn + Nn * (8 * d + 24 + (c->mat.fatigue ? 8 : 0)); break;             // phi-apply
         case 2: *bytes = conn + Nn * (8 * d + 16); break;                                        // mass-apply

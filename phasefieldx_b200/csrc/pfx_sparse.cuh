@@ -206,4 +206,165 @@ __global__ void __launch_bounds__(kThreads) spmv_s_tet_kernel(SparseView sv, con
     grid_reduce<1>(red, partial, result, counter, s_red, pv);
 }
 
+// ============================================================================= Q1 quadrilaterals
+// The matrix-free Q1 forms integrate 3 x 3 Gauss points per cell in EVERY PCG iteration; assembled once per Newton
+// linearisation the same operator is a 2 x 2-block SpMV over ~9 entries per row.  Same graph / layout as above
+// (four nodes per cell); the element rows come from quadrature instead of a cached constant tangent.
+
+// row a of the element matrix of J_u at (u, phi): K[(b*2 + i)*2 + j] = int eps(N_a e_i) : dsigma(eps(N_b e_j))
+PFX_HD void elem_matrix_row_u_quad(const Material& m, int n1d, const double* X, const double* phi, const double* U, int a, double* K) {
+    for (int t = 0; t < 16; ++t) K[t] = 0.0;
+    Geo<Quad> geo; geo.init(X, n1d);
+    double N[4], G[4][2], e[3] = {0.0, 0.0, 0.0}, de[3], dsa[3], dsb[3];
+    for (int q = 0; q < geo.nq; ++q) {
+        const double w = geo.eval(q, N, G);
+        const double gq = g_fun(m.dfun, interp<4>(N, phi)) + m.k;
+        if (m.smodel != M_ISO) sym_grad<Quad>(G, U, e);
+        for (int b = 0; b < 4; ++b)
+            for (int j = 0; j < 2; ++j) {
+                unit_strain<2>(G[b], j, de);
+                dstress_split<2>(m, m.smodel, e, de, dsa, dsb);
+                const double S0 = gq * dsa[0] + dsb[0], S1 = gq * dsa[1] + dsb[1], S2 = gq * dsa[2] + dsb[2];
+                K[(b * 2 + 0) * 2 + j] += w * (S0 * G[a][0] + S2 * G[a][1]);
+                K[(b * 2 + 1) * 2 + j] += w * (S2 * G[a][0] + S1 * G[a][1]);
+            }
+    }
+}
+
+__global__ void __launch_bounds__(128) assemble_u_quad_kernel(SparseView sv, Material m, int n1d, const double* __restrict__ X,
+                                                              const double* __restrict__ u, const double* __restrict__ phi,
+                                                              const uint8_t* __restrict__ mask, double* __restrict__ K,
+                                                              double* __restrict__ dinv, double* __restrict__ dblk) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sv.n_rows) return;
+    const int lane = (int)(i & 31);
+    const int64_t k0 = sv.slice_k0[i >> 5];
+    const int len = sv.slice_k0[(i >> 5) + 1] - (int)k0;
+    for (int k = 0; k < len; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) K[((k0 + k) * 4 + e) * 32 + lane] = 0.0;
+    double Kd[4] = {0.0, 0.0, 0.0, 0.0};
+    int kdiag = 0;
+    for (int32_t q = sv.nc_ptr[i]; q < sv.nc_ptr[i + 1]; ++q) {
+        const int32_t code = sv.nc_code[q];
+        const uint32_t kp = sv.nc_kpos[q];
+        const int64_t c = code >> 2;
+        const int a = code & 3;
+        const int4 nd = sv.cell_nodes[c];
+        const int n4[4] = {nd.x, nd.y, nd.z, nd.w};
+        double Xc[8], Uc[8], ph[4], Kr[16];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            Xc[2 * v] = X[(size_t)n4[v] * 2]; Xc[2 * v + 1] = X[(size_t)n4[v] * 2 + 1];
+            Uc[2 * v] = u[(size_t)n4[v] * 2]; Uc[2 * v + 1] = u[(size_t)n4[v] * 2 + 1];
+            ph[v] = phi[n4[v]];
+        }
+        elem_matrix_row_u_quad(m, n1d, Xc, ph, Uc, a, Kr);
+        kdiag = (int)((kp >> (8 * a)) & 255u);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (b == a) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) Kd[e] += Kr[b * 4 + e];
+            } else {
+                const int64_t k = k0 + (int)((kp >> (8 * b)) & 255u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) K[(k * 4 + e) * 32 + lane] += Kr[b * 4 + e];
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) K[((k0 + kdiag) * 4 + e) * 32 + lane] = Kd[e];
+    bool fixed[2];
+    fixed[0] = mask && mask[(size_t)i * 2]; fixed[1] = mask && mask[(size_t)i * 2 + 1];
+    dinv[(size_t)i * 2] = fixed[0] ? 1.0 : 1.0 / Kd[0];
+    dinv[(size_t)i * 2 + 1] = fixed[1] ? 1.0 : 1.0 / Kd[3];
+    if (dblk) {
+        const double blk[3] = {Kd[0], Kd[3], 0.5 * (Kd[1] + Kd[2])};
+        double inv[3];
+        inv_sym_block<2>(blk, fixed, inv);
+        dblk[(size_t)i * 3] = inv[0]; dblk[(size_t)i * 3 + 1] = inv[1]; dblk[(size_t)i * 3 + 2] = inv[2];
+    }
+}
+
+// scalar operator with P1/Q1 nodal coefficients on quadrilaterals: K = int (cm N_a N_b + cg grad N_a . grad N_b)
+__global__ void __launch_bounds__(128) assemble_s_quad_kernel(SparseView sv, int n1d, const double* __restrict__ X, const double* __restrict__ cm,
+                                                              const double* __restrict__ cg, const uint8_t* __restrict__ mask,
+                                                              double* __restrict__ K, double* __restrict__ dinv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sv.n_rows) return;
+    const int lane = (int)(i & 31);
+    const int64_t k0 = sv.slice_k0[i >> 5];
+    const int len = sv.slice_k0[(i >> 5) + 1] - (int)k0;
+    for (int k = 0; k < len; ++k) K[(k0 + k) * 32 + lane] = 0.0;
+    double Kd = 0.0;
+    int kdiag = 0;
+    for (int32_t q = sv.nc_ptr[i]; q < sv.nc_ptr[i + 1]; ++q) {
+        const int32_t code = sv.nc_code[q];
+        const uint32_t kp = sv.nc_kpos[q];
+        const int64_t c = code >> 2;
+        const int a = code & 3;
+        const int4 nd = sv.cell_nodes[c];
+        const int n4[4] = {nd.x, nd.y, nd.z, nd.w};
+        double Xc[8], m4[4], g4[4], Kr[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            Xc[2 * v] = X[(size_t)n4[v] * 2]; Xc[2 * v + 1] = X[(size_t)n4[v] * 2 + 1];
+            m4[v] = cm[n4[v]]; g4[v] = cg[n4[v]];
+        }
+        Geo<Quad> geo; geo.init(Xc, n1d);
+        double N[4], G[4][2];
+        for (int qp = 0; qp < geo.nq; ++qp) {
+            const double w = geo.eval(qp, N, G);
+            const double cmq = interp<4>(N, m4), cgq = interp<4>(N, g4);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) Kr[b] += w * (cmq * N[a] * N[b] + cgq * (G[a][0] * G[b][0] + G[a][1] * G[b][1]));
+        }
+        kdiag = (int)((kp >> (8 * a)) & 255u);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            if (b == a) Kd += Kr[b];
+            else K[(k0 + (int)((kp >> (8 * b)) & 255u)) * 32 + lane] += Kr[b];
+        }
+    }
+    K[(k0 + kdiag) * 32 + lane] = Kd;
+    if (dinv) dinv[i] = (mask && mask[i]) ? 1.0 : 1.0 / Kd;
+}
+
+// y = K v (2 x 2 blocks)
+__global__ void __launch_bounds__(kThreads) spmv_u_quad_kernel(SparseView sv, const double* __restrict__ K, const double* __restrict__ v,
+                                                               double* __restrict__ y, const uint8_t* __restrict__ mask,
+                                                               double* partial, double* result, unsigned int* counter,
+                                                               const double* stop, const PeerView* pv) {
+    __shared__ double s_red[kMaxRed * 32];
+    if (stop && stop[0] != 0.0) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    double red[1] = {0.0};
+    if ((i >> 5) < sv.n_slices) {
+        const int64_t k0 = sv.slice_k0[i >> 5];
+        const int len = sv.slice_k0[(i >> 5) + 1] - (int)k0;
+        const int32_t* cp = sv.col + k0 * 32 + lane;
+        const double* kp = K + k0 * 4 * 32 + lane;
+        const double2* v2 = reinterpret_cast<const double2*>(v);
+        double a0 = 0.0, a1 = 0.0;
+        for (int k = 0; k < len; ++k) {
+            const double2 vj = v2[cp[k * 32]];
+            const double* e = kp + (size_t)k * 4 * 32;
+            a0 += e[0] * vj.x + e[32] * vj.y;
+            a1 += e[64] * vj.x + e[96] * vj.y;
+        }
+        if (i < sv.n_rows) {
+            if (mask) {
+                if (mask[(size_t)i * 2]) a0 = 0.0;
+                if (mask[(size_t)i * 2 + 1]) a1 = 0.0;
+            }
+            reinterpret_cast<double2*>(y)[i] = make_double2(a0, a1);
+            const double2 vi = v2[i];
+            red[0] = vi.x * a0 + vi.y * a1;
+        }
+    }
+    grid_reduce<1>(red, partial, result, counter, s_red, pv);
+}
+
 }  // namespace pfx
