@@ -117,6 +117,35 @@ class TwoLevel:
         return z
 
 
+class ThirdLevel:
+    """Additive third level over regions (restating pfx_coarse.cuh `Coarse3View`: the rank-level coarse space of
+    multi-GPU runs, where every rank is one region): rigid-body modes of whole regions, E = Z_g^T A Z_g WITH the
+    couplings across regions, M^-1 = two_level + Z_g E^-1 Z_g^T.  The region modes lie in the span of the aggregate
+    modes (up to the fp32 rounding of the mode geometry), which is how the kernels apply them (Z T)."""
+
+    def __init__(self, two_level, A, x, agg, d_field, mask, n_regions):
+        self.base = two_level
+        n_agg = int(agg.max()) + 1
+        reg = ((np.arange(n_agg) * n_regions) // n_agg)[agg]
+        free = ~mask
+        Af = sp.diags(free.astype(float)) @ A @ sp.diags(free.astype(float)) + sp.diags(mask.astype(float))
+        self.Zg = modes(x, reg, d_field, mask)
+        E = (self.Zg.T @ Af @ self.Zg).toarray()
+        E = 0.5 * (E + E.T)
+        zero = np.diag(E) <= 0
+        E[zero, :] = 0.0
+        E[:, zero] = 0.0
+        E[zero, zero] = 1.0
+        np.linalg.cholesky(E)                       # must be positive definite (raises otherwise)
+        self.Einv = np.linalg.inv(E)
+        self.mask = mask
+
+    def __call__(self, r):
+        z = self.base(r) + self.Zg @ (self.Einv @ (self.Zg.T @ r))
+        z[self.mask] = 0.0
+        return z
+
+
 def pcg(A, b, minv, mask, rtol=1e-11, max_it=20000):
     """Preconditioned CG on the free dofs (b, iterates zero on Dirichlet dofs); returns x, iterations."""
     free = ~mask
