@@ -233,6 +233,10 @@ int pfx_time_operator(pfx_ctx* ctx, int kind, int reps, int flush_l2, float* ms_
 /* algorithmic bytes of one launch of `kind` for this mesh (SURVEY §8d formulas); kind 5: the bytes the u-apply
  * implementation actually streams (with cached element tangents: 168 B per tetrahedron + X, v, y per node) */
 int pfx_algorithmic_bytes(pfx_ctx* ctx, int kind, double* bytes);
+/* test hook: inverse of a dense symmetric positive definite matrix (n x n, column-major host arrays; the lower
+ * triangle of the result is valid) by the in-tree blocked Cholesky that inverts the coarse matrices of the
+ * two-level PCG — the MUMPS stand-in has no library kernel on its path.  info_out: 1 if a pivot was not positive. */
+int pfx_dense_spd_inverse(int device, int n, const double* A_host, double* Ainv_host, int* info_out);
 /* kernels launched by this context since creation (bench `gpu_launches`) */
 int pfx_launch_count(pfx_ctx* ctx, int64_t* n);
 int pfx_block_stats(pfx_ctx* ctx, int64_t out[8]);

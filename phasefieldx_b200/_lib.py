@@ -75,7 +75,7 @@ SYMBOLS = [
     "pfx_set_traction", "pfx_set_traction_value", "pfx_load_step", "pfx_solve_u", "pfx_solve_phi", "pfx_ec_default_opts", "pfx_ec_solve",
     "pfx_ec_checkpoint", "pfx_reaction", "pfx_energies", "pfx_get_field",
     "pfx_set_field", "pfx_apply_u", "pfx_apply_phi", "pfx_apply_mass", "pfx_residual_u", "pfx_diag_u", "pfx_rhs_psi", "pfx_project_psi",
-    "pfx_l2_error", "pfx_time_operator", "pfx_algorithmic_bytes", "pfx_launch_count", "pfx_block_stats", "pfx_coarse_stats",
+    "pfx_l2_error", "pfx_dense_spd_inverse", "pfx_time_operator", "pfx_algorithmic_bytes", "pfx_launch_count", "pfx_block_stats", "pfx_coarse_stats",
     "pfx_partition_create", "pfx_partition_destroy", "pfx_partition_graph_cell_rank", "pfx_partition_cell_rank", "pfx_partition_node_owner",
     "pfx_partition_rank_sizes", "pfx_partition_rank_maps", "pfx_partition_rank_plan", "pfx_comm_unique_id",
     "pfx_comm_attach", "pfx_comm_p2p_export", "pfx_comm_p2p_import", "pfx_format_f64", "pfx_format_i64",
@@ -131,6 +131,7 @@ def load():
     lib.pfx_l2_error.argtypes = [C.c_void_p, C.c_int, C.c_int, pd]
     lib.pfx_time_operator.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]
     lib.pfx_algorithmic_bytes.argtypes = [C.c_void_p, C.c_int, pd]
+    lib.pfx_dense_spd_inverse.argtypes = [C.c_int, C.c_int, pd, pd, C.POINTER(C.c_int)]
     lib.pfx_launch_count.argtypes = [C.c_void_p, pl]
     lib.pfx_block_stats.argtypes = [C.c_void_p, pl]
     lib.pfx_device_count.argtypes = [C.POINTER(C.c_int)]
@@ -578,6 +579,20 @@ def format_i64(values):
     if m < 0:
         raise PfxError(2, "pfx_format_i64: bad arguments")
     return buf[:max(0, m - 1)].tobytes()
+
+
+def dense_spd_inverse(A, device=0):
+    """(A^-1 as a full symmetric matrix, info) by the library's own blocked Cholesky (pfx_dense_spd_inverse)."""
+    lib = load()
+    A = np.asfortranarray(A, dtype=np.float64)
+    n = A.shape[0]
+    out = np.zeros((n, n), order="F")
+    info = C.c_int(0)
+    st = lib.pfx_dense_spd_inverse(device, n, A.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(info))
+    if st:
+        raise PfxError(st, "dense inverse failed")
+    low = np.tril(out)
+    return low + np.tril(out, -1).T, info.value
 
 
 def device_count():

@@ -72,7 +72,7 @@ def build(force=False, verbose=False, ptxas_log=None):
     if ptxas_log:
         with open(ptxas_log, "w") as fh:
             fh.write(log)
-    cmd = [nv, "-shared", "-o", LIB] + objs + [_metis(), "-ldl", "-lcusolver", "-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [nv, "-shared", "-o", LIB] + objs + [_metis(), "-ldl", "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")

@@ -5,7 +5,6 @@
 // place of the MUMPS factorisation.  All arithmetic on fields runs in the kernels of
 // pfx_kernels.cuh; there is no CPU compute path.
 #include <cuda_runtime.h>
-#include <cusolverDn.h>
 
 #include <algorithm>
 #include <chrono>
@@ -22,6 +21,7 @@
 #include "pfx_comm.h"
 #include "pfx_kernels.cuh"
 #include "pfx_coarse.cuh"
+#include "pfx_dense.cuh"
 #include "pfx_sparse.cuh"
 #include "pfx_monolithic.cuh"
 
@@ -90,9 +90,8 @@ struct Coarse {
     float* rel = nullptr;
     double *wpart = nullptr, *y = nullptr, *Ac = nullptr, *partial = nullptr, *work = nullptr;
     double* dblk = nullptr;          // inverse nodal diagonal blocks of J_u (block-Jacobi smoother)
-    int lwork = 0;
+    double *workT = nullptr, *workL = nullptr;   // dense inverse (pfx_dense.cuh): panel and diagonal-block inverses; `work` = Y
     int* info = nullptr;
-    cusolverDnHandle_t solver = nullptr;
     CoarseOp op[2];
     bool refresh_every_step = false;
     bool block_jacobi = true;        // PFX_BLOCK_JACOBI=0: plain diagonal smoother for J_u
@@ -746,16 +745,10 @@ int build_coarse(pfx_ctx* c, const pfx_mesh* mesh) {
     if ((st = dev_alloc(c, &cs.partial, (size_t)std::max(2 * cs.n_chunks, cs.op[0].n_ctas)))) return st;
     if ((st = dev_alloc(c, &cs.info, (size_t)1))) return st;
     if ((st = dev_alloc(c, &cs.dblk, (size_t)c->n_nodes * (D * (D + 1) / 2)))) return st;
-    if (cusolverDnCreate(&cs.solver) != CUSOLVER_STATUS_SUCCESS) { c->err = "cusolverDnCreate failed"; return PFX_ERR_CUDA; }
-    cusolverDnSetStream(cs.solver, c->stream);
-    int l1 = 0, l2 = 0;
-    if (cusolverDnDpotrf_bufferSize(cs.solver, CUBLAS_FILL_MODE_LOWER, nc_max, cs.Ac, nc_max, &l1) != CUSOLVER_STATUS_SUCCESS ||
-        cusolverDnDpotri_bufferSize(cs.solver, CUBLAS_FILL_MODE_LOWER, nc_max, cs.Ac, nc_max, &l2) != CUSOLVER_STATUS_SUCCESS) {
-        c->err = "cusolver workspace query failed";
-        return PFX_ERR_CUDA;
-    }
-    cs.lwork = std::max(l1, l2);
-    if ((st = dev_alloc(c, &cs.work, (size_t)std::max(1, cs.lwork)))) return st;
+    // work space of the dense inverses (pfx_dense.cuh): Y (largest region squared), a 64-wide panel, the diagonal blocks
+    if ((st = dev_alloc(c, &cs.work, (size_t)nc_max * nc_max))) return st;
+    if ((st = dev_alloc(c, &cs.workT, (size_t)nc_max * kDenseNB))) return st;
+    if ((st = dev_alloc(c, &cs.workL, (size_t)((nc_max + kDenseNB - 1) / kDenseNB) * kDenseNB * kDenseNB))) return st;
     {   // the coarse solve stages w of one region (up to kCoarseMax doubles) in dynamic shared memory
         const int smem = kCoarseMax * (int)sizeof(double);
         CK(cudaFuncSetAttribute(coarse_solve_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -811,14 +804,9 @@ int coarse_setup_t(pfx_ctx* c, int kind, const uint8_t* mask) {
         const int ncr = op.h_reg[r].y * M;
         double* A = cs.Ac + op.h_ac_off[r];
         coarse_fixdiag_kernel<<<(ncr + 127) / 128, 128, 0, c->stream>>>(ncr, A, ncr);
-        if (cusolverDnDpotrf(cs.solver, CUBLAS_FILL_MODE_LOWER, ncr, A, ncr, cs.work, cs.lwork, cs.info) != CUSOLVER_STATUS_SUCCESS) {
-            c->err = "cusolverDnDpotrf failed"; return PFX_ERR_CUDA;
-        }
+        CK(cudaMemsetAsync(cs.info, 0, sizeof(int), c->stream));
+        c->launches += dense_spd_inverse(c->stream, ncr, A, cs.work, cs.workT, cs.workL, cs.info);
         CK(cudaMemcpyAsync(&h_info[2 * r], cs.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        if (cusolverDnDpotri(cs.solver, CUBLAS_FILL_MODE_LOWER, ncr, A, ncr, cs.work, cs.lwork, cs.info) != CUSOLVER_STATUS_SUCCESS) {
-            c->err = "cusolverDnDpotri failed"; return PFX_ERR_CUDA;
-        }
-        CK(cudaMemcpyAsync(&h_info[2 * r + 1], cs.info, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         dim3 grid((op.h_reg[r].w + 127) / 128, ncr);
         coarse_convert_kernel<<<grid, 128, 0, c->stream>>>(ncr, A, ncr, op.Ainv + op.h_reg[r].z, op.h_reg[r].w);
         c->launches += 2;
@@ -1672,7 +1660,6 @@ int pfx_destroy(pfx_ctx* c) {
         if (c->graph[k]) cudaGraphExecDestroy(c->graph[k]);
     for (int k = 0; k < 2; ++k)
         if (c->coarse.op[k].graph) cudaGraphExecDestroy(c->coarse.op[k].graph);
-    if (c->coarse.solver) cusolverDnDestroy(c->coarse.solver);
     for (void* p : c->ipc_opened) cudaIpcCloseMemHandle(p);
     if (c->comm) nccl().CommDestroy(c->comm);
     for (void* p : c->allocs) cudaFree(p);
@@ -2180,6 +2167,30 @@ int pfx_time_operator(pfx_ctx* c, int kind, int reps, int flush_l2, float* ms_ou
     cudaEventDestroy(e1);
     if (kind == 1) c->phi_coeff_fresh = c->sp.phi_fresh = false;
     return PFX_OK;
+}
+
+// test hook: the in-tree dense SPD inverse used for the coarse matrices (pfx_dense.cuh)
+int pfx_dense_spd_inverse(int device, int n, const double* A_host, double* Ainv_host, int* info_out) {
+    if (n <= 0 || !A_host || !Ainv_host) return PFX_ERR_BAD_ARG;
+    if (cudaSetDevice(device) != cudaSuccess) return PFX_ERR_NO_DEVICE;
+    double *A = nullptr, *Y = nullptr, *T = nullptr, *L = nullptr;
+    int* info = nullptr;
+    const size_t nn = (size_t)n * n, nblk = (n + kDenseNB - 1) / kDenseNB;
+    bool ok = cudaMalloc(&A, nn * 8) == cudaSuccess && cudaMalloc(&Y, nn * 8) == cudaSuccess &&
+              cudaMalloc(&T, (size_t)n * kDenseNB * 8) == cudaSuccess && cudaMalloc(&L, nblk * kDenseNB * kDenseNB * 8) == cudaSuccess &&
+              cudaMalloc(&info, sizeof(int)) == cudaSuccess;
+    int h_info = 0;
+    if (ok) {
+        cudaMemcpy(A, A_host, nn * 8, cudaMemcpyHostToDevice);
+        cudaMemset(info, 0, sizeof(int));
+        dense_spd_inverse(nullptr, n, A, Y, T, L, info);
+        ok = cudaDeviceSynchronize() == cudaSuccess;
+        cudaMemcpy(Ainv_host, A, nn * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&h_info, info, sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(A); cudaFree(Y); cudaFree(T); cudaFree(L); cudaFree(info);
+    if (info_out) *info_out = h_info;
+    return ok ? PFX_OK : PFX_ERR_CUDA;
 }
 
 int pfx_launch_count(pfx_ctx* c, int64_t* n) {

@@ -139,3 +139,24 @@ def test_coarse_space_with_tractions_phi_dirichlet_and_fatigue(no_coop):
         assert np.allclose(e.get_field("phi")[seed], 1.0)
     assert np.allclose(e.reaction(0)[:2], -T, rtol=1e-6, atol=1e-10)
     e.close()
+
+
+@pytest.mark.parametrize("n", [37, 64, 333, 1500])
+def test_in_tree_dense_spd_inverse_matches_lapack(n):
+    """pfx_dense.cuh (blocked Cholesky + L^-1 + Y^T Y: the inverse of the coarse matrices, in place of the cuSOLVER
+    potrf / potri of round 1) against numpy on random SPD matrices with a 1e6 condition number; a matrix that is not
+    positive definite raises the info flag."""
+    from phasefieldx_b200 import _lib
+    rng = np.random.default_rng(n)
+    Q, _ = np.linalg.qr(rng.normal(size=(n, n)))
+    A = (Q * np.logspace(0, 6, n)) @ Q.T
+    A = 0.5 * (A + A.T)
+    Ainv, info = _lib.dense_spd_inverse(A)
+    assert info == 0
+    ref = np.linalg.inv(A)
+    assert np.abs(Ainv - ref).max() <= 1e-9 * np.abs(ref).max()
+    assert np.abs(Ainv @ A - np.eye(n)).max() < 1e-7
+    B = A.copy()
+    B[n // 2, n // 2] = -1.0
+    _, info = _lib.dense_spd_inverse(B)
+    assert info == 1
