@@ -372,7 +372,7 @@ std::string build_partition(int nv, int64_t n_nodes, int64_t n_cells, const doub
 // =============================================================================== node graph (sliced ELL)
 std::string build_node_graph(const BlockMesh& bm, int64_t n_cells, const int32_t* cells, NodeGraph& g) {
     const int nv = bm.nv;
-    if (nv != 4) return "node graph: cells of four nodes only (tetrahedra, quadrilaterals)";
+    if (nv != 4 && nv != 3) return "node graph: cells of three or four nodes only (triangles, quadrilaterals, tetrahedra)";
     g = NodeGraph();
     const int64_t n_rows = bm.n_owned;
     g.n_rows = n_rows;
@@ -381,13 +381,13 @@ std::string build_node_graph(const BlockMesh& bm, int64_t n_cells, const int32_t
     for (int b = 0; b < bm.nb; ++b)
         for (int j = 0; j < bm.nlow[b]; ++j) {
             const int64_t c = bm.elem_gid[bm.elem_off[b] + j];
-            for (int a = 0; a < 4; ++a) g.cell_nodes[4 * ((size_t)bm.own_c0[b] + j) + a] = bm.iperm[cells[c * 4 + a]];
+            for (int a = 0; a < nv; ++a) g.cell_nodes[4 * ((size_t)bm.own_c0[b] + j) + a] = bm.iperm[cells[c * nv + a]];
         }
     (void)n_cells;
     // node -> incident cells
     g.nc_ptr.assign(n_rows + 1, 0);
     for (int64_t c = 0; c < bm.n_own_cells; ++c)
-        for (int a = 0; a < 4; ++a) {
+        for (int a = 0; a < nv; ++a) {
             const int32_t n = g.cell_nodes[4 * c + a];
             if (n < n_rows) g.nc_ptr[n + 1]++;
         }
@@ -398,7 +398,7 @@ std::string build_node_graph(const BlockMesh& bm, int64_t n_cells, const int32_t
     {
         std::vector<int32_t> cur(g.nc_ptr.begin(), g.nc_ptr.end() - 1);
         for (int64_t c = 0; c < bm.n_own_cells; ++c)
-            for (int a = 0; a < 4; ++a) {
+            for (int a = 0; a < nv; ++a) {
                 const int32_t n = g.cell_nodes[4 * c + a];
                 if (n < n_rows) g.nc_code[cur[n]++] = (int32_t)((c << 2) | a);
             }
@@ -413,7 +413,7 @@ std::string build_node_graph(const BlockMesh& bm, int64_t n_cells, const int32_t
         tmp.push_back((int32_t)i);
         for (int32_t q = g.nc_ptr[i]; q < g.nc_ptr[i + 1]; ++q) {
             const int64_t c = g.nc_code[q] >> 2;
-            for (int a = 0; a < 4; ++a) tmp.push_back(g.cell_nodes[4 * c + a]);
+            for (int a = 0; a < nv; ++a) tmp.push_back(g.cell_nodes[4 * c + a]);
         }
         std::sort(tmp.begin(), tmp.end());
         tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
@@ -447,7 +447,7 @@ std::string build_node_graph(const BlockMesh& bm, int64_t n_cells, const int32_t
         for (int32_t q = g.nc_ptr[i]; q < g.nc_ptr[i + 1]; ++q) {
             const int64_t c = g.nc_code[q] >> 2;
             uint32_t kp = 0;
-            for (int a = 0; a < 4; ++a) {
+            for (int a = 0; a < nv; ++a) {
                 const int32_t* f = std::lower_bound(rc, rc + len, g.cell_nodes[4 * c + a]);
                 kp |= (uint32_t)(f - rc) << (8 * a);
             }

@@ -589,6 +589,7 @@ __global__ void pcg_setup_kernel(double* S, double rtol2, int bref_slot) {
 
 // does the apply of this operator run on a kernel that waits for the halo in its own prologue?
 bool apply_waits_for_halo(const pfx_ctx* c, int kind) {
+    if (c->sp.enabled) return false;            // assembled operators: the SpMV does not wait itself
     if (c->cell_type != PFX_CELL_TRIANGLE || c->apply_variant < 3 || c->bm.max_elems > 2 * kThreads || c->mat.dfun != 0) return false;
     return kind == LIN_U || (kind == LIN_PHI && c->cm && c->phi_coeff_fresh);
 }
@@ -625,9 +626,13 @@ int refresh_tangent(pfx_ctx* c) {
     if (!c->sp.enabled) return PFX_OK;
     const bool blk = c->coarse.enabled && c->coarse.block_jacobi;
     const int grid = (int)((c->sp.sv.n_rows + 127) / 128);
-    if (c->cell_type == PFX_CELL_QUADRILATERAL) {
-        assemble_u_quad_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->mat, c->prm.quad_points_1d, c->X, c->u, c->phi, c->mask_u, c->sp.Ku,
-                                                            c->w_dinv, blk ? c->coarse.dblk : nullptr);
+    if (c->cell_type == PFX_CELL_QUADRILATERAL || c->cell_type == PFX_CELL_TRIANGLE) {
+        if (c->cell_type == PFX_CELL_TRIANGLE)
+            assemble_u_tri_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->mat, c->X, c->u, c->phi, c->mask_u, c->sp.Ku, c->w_dinv,
+                                                               blk ? c->coarse.dblk : nullptr);
+        else
+            assemble_u_quad_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->mat, c->prm.quad_points_1d, c->X, c->u, c->phi, c->mask_u, c->sp.Ku,
+                                                                c->w_dinv, blk ? c->coarse.dblk : nullptr);
         c->launches++;
         CK(cudaGetLastError());
         c->tan_fresh = true;
@@ -656,6 +661,8 @@ int refresh_phi_operator(pfx_ctx* c) {
         const int grid = (int)((c->sp.sv.n_rows + 127) / 128);
         if (c->cell_type == PFX_CELL_QUADRILATERAL)
             assemble_s_quad_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->prm.quad_points_1d, c->X, c->cm, c->cg, c->mask_phi, c->sp.Kphi, c->w_dinv);
+        else if (c->cell_type == PFX_CELL_TRIANGLE)
+            assemble_s_tri_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->X, c->cm, c->cg, c->mask_phi, c->sp.Kphi, c->w_dinv);
         else
             assemble_s_tet_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->X, c->cm, c->cg, c->mask_phi, c->sp.Kphi, c->w_dinv);
         c->launches++;
@@ -1587,7 +1594,12 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     // matrix-free scatter kernels (slow in 3D; an independent cross-check of the assembly)
     {
         const char* ns = getenv("PFX_NO_SPARSE");
-        if ((c->cell_type == PFX_CELL_TETRAHEDRON || c->cell_type == PFX_CELL_QUADRILATERAL) && !(ns && ns[0] == '1')) {
+        // triangles stay matrix-free by default: measured on the 2 M-triangle bench mesh the 2 x 2-block SpMV takes 88 us
+        // (3.2 TB/s on 285 MB: rows of 7 entries give a thread too few loads in flight) against 57 us for the persistent
+        // matrix-free kernel, and the scalar SpMV 64 us against 43 us.  PFX_TRI_SPARSE=1 selects the assembled path.
+        const char* tsp = getenv("PFX_TRI_SPARSE");
+        const bool tri_sparse = c->cell_type == PFX_CELL_TRIANGLE && tsp && tsp[0] == '1';
+        if ((c->cell_type == PFX_CELL_TETRAHEDRON || c->cell_type == PFX_CELL_QUADRILATERAL || tri_sparse) && !(ns && ns[0] == '1')) {
             NodeGraph ng;
             std::string eg = build_node_graph(bm, mesh->n_cells, mesh->cells, ng);
             if (!eg.empty()) { c->err = eg; return PFX_ERR_BAD_ARG; }
@@ -1638,6 +1650,8 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
         const int grid = (int)((c->sp.sv.n_rows + 127) / 128);
         if (c->cell_type == PFX_CELL_QUADRILATERAL)
             assemble_s_quad_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->prm.quad_points_1d, c->X, c->ones, c->zeros, nullptr, c->sp.Km, c->dinv_mass);
+        else if (c->cell_type == PFX_CELL_TRIANGLE)
+            assemble_s_tri_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->X, c->ones, c->zeros, nullptr, c->sp.Km, c->dinv_mass);
         else
             assemble_s_tet_kernel<<<grid, 128, 0, c->stream>>>(c->sp.sv, c->X, c->ones, c->zeros, nullptr, c->sp.Km, c->dinv_mass);
         c->launches++;

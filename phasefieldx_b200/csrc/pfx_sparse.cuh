@@ -367,4 +367,106 @@ __global__ void __launch_bounds__(kThreads) spmv_u_quad_kernel(SparseView sv, co
     grid_reduce<1>(red, partial, result, counter, s_red, pv);
 }
 
+// ============================================================================= P1 triangles
+// Opt-in (PFX_TRI_SPARSE=1) and kept as a second implementation for the parity tests: measured on the 2 M-triangle bench
+// mesh the 2 x 2-block SpMV (285 MB per apply) takes 88 us = 3.2 TB/s — rows of only 7 entries leave a thread too few
+// loads in flight — against 57 us for the matrix-free pipeline kernel of pfx_kernels.cuh, which therefore stays the
+// default on triangles (scalar J_phi / mass: 64 us against 43 us).
+__global__ void __launch_bounds__(128) assemble_u_tri_kernel(SparseView sv, Material m, const double* __restrict__ X,
+                                                             const double* __restrict__ u, const double* __restrict__ phi,
+                                                             const uint8_t* __restrict__ mask, double* __restrict__ K,
+                                                             double* __restrict__ dinv, double* __restrict__ dblk) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sv.n_rows) return;
+    const int lane = (int)(i & 31);
+    const int64_t k0 = sv.slice_k0[i >> 5];
+    const int len = sv.slice_k0[(i >> 5) + 1] - (int)k0;
+    for (int k = 0; k < len; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) K[((k0 + k) * 4 + e) * 32 + lane] = 0.0;
+    double Kd[4] = {0.0, 0.0, 0.0, 0.0};
+    int kdiag = 0;
+    for (int32_t q = sv.nc_ptr[i]; q < sv.nc_ptr[i + 1]; ++q) {
+        const int32_t code = sv.nc_code[q];
+        const uint32_t kp = sv.nc_kpos[q];
+        const int64_t c = code >> 2;
+        const int a = code & 3;
+        const int4 nd = sv.cell_nodes[c];
+        const int n3[3] = {nd.x, nd.y, nd.z};
+        double Xc[6], Uc[6], ph[3], T[6], Kr[12];
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            Xc[2 * v] = X[(size_t)n3[v] * 2]; Xc[2 * v + 1] = X[(size_t)n3[v] * 2 + 1];
+            Uc[2 * v] = u[(size_t)n3[v] * 2]; Uc[2 * v + 1] = u[(size_t)n3[v] * 2 + 1];
+            ph[v] = phi[n3[v]];
+        }
+        elem_tangent_u<Tri>(m, Xc, ph, Uc, T);
+        Geo<Tri> geo; geo.init(Xc, 1);
+        elem_matrix_row_tan<Tri>(geo.G, T, a, Kr);
+        kdiag = (int)((kp >> (8 * a)) & 255u);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            if (b == a) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) Kd[e] += Kr[b * 4 + e];
+            } else {
+                const int64_t k = k0 + (int)((kp >> (8 * b)) & 255u);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) K[(k * 4 + e) * 32 + lane] += Kr[b * 4 + e];
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) K[((k0 + kdiag) * 4 + e) * 32 + lane] = Kd[e];
+    bool fixed[2];
+    fixed[0] = mask && mask[(size_t)i * 2]; fixed[1] = mask && mask[(size_t)i * 2 + 1];
+    dinv[(size_t)i * 2] = fixed[0] ? 1.0 : 1.0 / Kd[0];
+    dinv[(size_t)i * 2 + 1] = fixed[1] ? 1.0 : 1.0 / Kd[3];
+    if (dblk) {
+        const double blk[3] = {Kd[0], Kd[3], 0.5 * (Kd[1] + Kd[2])};
+        double inv[3];
+        inv_sym_block<2>(blk, fixed, inv);
+        dblk[(size_t)i * 3] = inv[0]; dblk[(size_t)i * 3 + 1] = inv[1]; dblk[(size_t)i * 3 + 2] = inv[2];
+    }
+}
+
+// scalar operator with P1 nodal coefficients on triangles (closed form: int N_a N_b N_c = area/60 (1 + d_ab + d_ac + d_bc + 2 d_abc))
+__global__ void __launch_bounds__(128) assemble_s_tri_kernel(SparseView sv, const double* __restrict__ X, const double* __restrict__ cm,
+                                                             const double* __restrict__ cg, const uint8_t* __restrict__ mask,
+                                                             double* __restrict__ K, double* __restrict__ dinv) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sv.n_rows) return;
+    const int lane = (int)(i & 31);
+    const int64_t k0 = sv.slice_k0[i >> 5];
+    const int len = sv.slice_k0[(i >> 5) + 1] - (int)k0;
+    for (int k = 0; k < len; ++k) K[(k0 + k) * 32 + lane] = 0.0;
+    double Kd = 0.0;
+    int kdiag = 0;
+    for (int32_t q = sv.nc_ptr[i]; q < sv.nc_ptr[i + 1]; ++q) {
+        const int32_t code = sv.nc_code[q];
+        const uint32_t kp = sv.nc_kpos[q];
+        const int64_t c = code >> 2;
+        const int a = code & 3;
+        const int4 nd = sv.cell_nodes[c];
+        const int n3[3] = {nd.x, nd.y, nd.z};
+        double Xc[6], m3v[3], C = 0.0, G = 0.0;
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            Xc[2 * v] = X[(size_t)n3[v] * 2]; Xc[2 * v + 1] = X[(size_t)n3[v] * 2 + 1];
+            m3v[v] = cm[n3[v]]; C += m3v[v]; G += cg[n3[v]];
+        }
+        Geo<Tri> geo; geo.init(Xc, 1);
+        const double vb = geo.vol * (1.0 / 60.0), cgm = geo.vol * (1.0 / 3.0) * G;
+        kdiag = (int)((kp >> (8 * a)) & 255u);
+#pragma unroll
+        for (int b = 0; b < 3; ++b) {
+            const double gg = geo.G[a][0] * geo.G[b][0] + geo.G[a][1] * geo.G[b][1];
+            if (b == a) Kd += vb * (2.0 * C + 4.0 * m3v[a]) + cgm * gg;
+            else K[(k0 + (int)((kp >> (8 * b)) & 255u)) * 32 + lane] += vb * (C + m3v[a] + m3v[b]) + cgm * gg;
+        }
+    }
+    K[(k0 + kdiag) * 32 + lane] = Kd;
+    if (dinv) dinv[i] = (mask && mask[i]) ? 1.0 : 1.0 / Kd;
+}
+
 }  // namespace pfx

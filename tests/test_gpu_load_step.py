@@ -353,13 +353,16 @@ def _run_workload_pair(w, steps, times, monkeypatch=None, max_stagger=500, **opt
     return out, stats
 
 
-def test_shear_n160_two_level_graph_path_vs_oracle(monkeypatch):
+@pytest.mark.parametrize("path", ["assembled", "matrix_free"])
+def test_shear_n160_two_level_graph_path_vs_oracle(path, monkeypatch):
     """The bench workload (config 2, reference plot_1712.py) at the size the CPU baseline of bench.py samples:
     160 x 160 x 2 triangles, 25.9 k nodes — large enough for the production solver path (persistent TMA-staged
     apply kernels, two-level PCG with the aggregate coarse space, CUDA-graph iterations, adaptive absolute PCG
     floor) instead of the single-launch cooperative kernels of the small parity meshes."""
     from phasefieldx_b200 import workloads as W
     monkeypatch.setenv("PFX_NO_COOP", "1")
+    if path == "assembled":                    # the opt-in 2 x 2-block SpMV instead of the persistent matrix-free kernels
+        monkeypatch.setenv("PFX_TRI_SPARSE", "1")
     w = W.sen_shear(160)
     out, (blocks, coarse) = _run_workload_pair(w, range(4), [0.0, 1.0, 2.0, 3.0])
     assert coarse["active"] == 1 and coarse["setups"] >= 1 and blocks["n_blocks"] >= 32

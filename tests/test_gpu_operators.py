@@ -34,7 +34,15 @@ def _setup(ctype, m, deg, sp, fat, rng, block_nodes=0, k=1e-3):
 
 @pytest.mark.parametrize("deg,sp", MODELS)
 @pytest.mark.parametrize("fat", [False, True])
-def test_operators_match_oracle(deg, sp, fat):
+@pytest.mark.parametrize("path", ["assembled", "matrix_free"])
+def test_operators_match_oracle(deg, sp, fat, path, monkeypatch):
+    """Every operator of the load step against the assembled oracle matrices, on every cell type — once with the
+    operators assembled per linearisation where the engine does that (triangles, quadrilaterals, tetrahedra: sliced-ELL
+    SpMV) and once matrix-free everywhere (PFX_NO_SPARSE=1: the pipeline / block-scatter kernels)."""
+    if path == "matrix_free":
+        monkeypatch.setenv("PFX_NO_SPARSE", "1")
+    else:
+        monkeypatch.setenv("PFX_TRI_SPARSE", "1")          # triangles are matrix-free by default
     rng = np.random.default_rng(7)
     for ctype, m in perturbed_meshes(rng):
         o, e, P = _setup(ctype, m, deg, sp, fat, rng, block_nodes=64)
