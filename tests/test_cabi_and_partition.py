@@ -70,8 +70,10 @@ def test_partition_and_ghost_maps_bit_exact(n_ranks):
         assert np.array_equal(P2.cell_rank(), cr[::-1])
 
 
-def test_rank_mesh_local_views_cover_the_mesh():
-    """distributed.RankMesh: local meshes, Dirichlet dof maps and peer ghost offsets (host logic)."""
+@pytest.mark.parametrize("partitioner", ["rcb", "metis"])
+def test_rank_mesh_local_views_cover_the_mesh(partitioner):
+    """distributed.RankMesh: local meshes, Dirichlet dof maps and peer ghost offsets (host logic), for the coordinate
+    bisection and for the METIS graph partition."""
     from phasefieldx_b200 import _lib, mesh as M
     from phasefieldx_b200.distributed import RankMesh
     m = M.create_rectangle(None, [[0, 0], [1, 1]], [12, 9])
@@ -80,7 +82,7 @@ def test_rank_mesh_local_views_cover_the_mesh():
     dofs = (top[:, None] * 2 + np.arange(2)).ravel()
     owned_seen = np.zeros(m.num_nodes, dtype=int)
     for r in range(world):
-        rm = RankMesh(m.geometry.x, m.cells, m.cell_type, world, r)
+        rm = RankMesh(m.geometry.x, m.cells, m.cell_type, world, r, partitioner=partitioner)
         owned_seen[rm.l2g[: rm.n_owned]] += 1
         assert np.array_equal(rm.coords, m.geometry.x[rm.l2g])
         assert rm.cells.min() >= 0 and rm.cells.max() < len(rm.l2g)
