@@ -1595,8 +1595,8 @@ int pfx_create(const pfx_mesh* mesh, const pfx_params* prm, int device, pfx_ctx*
     {
         const char* ns = getenv("PFX_NO_SPARSE");
         // triangles stay matrix-free by default: measured on the 2 M-triangle bench mesh the 2 x 2-block SpMV takes 88 us
-        // (3.2 TB/s on 285 MB: rows of 7 entries give a thread too few loads in flight) against 57 us for the persistent
-        // matrix-free kernel, and the scalar SpMV 64 us against 43 us.  PFX_TRI_SPARSE=1 selects the assembled path.
+        // (3.2 TB/s on 285 MB; the gathers of the input vector cost as much L2 traffic as the matrix stream) against 57 us
+        // for the persistent matrix-free kernel, and the scalar SpMV 64 us against 43 us.  PFX_TRI_SPARSE=1 selects it.
         const char* tsp = getenv("PFX_TRI_SPARSE");
         const bool tri_sparse = c->cell_type == PFX_CELL_TRIANGLE && tsp && tsp[0] == '1';
         if ((c->cell_type == PFX_CELL_TETRAHEDRON || c->cell_type == PFX_CELL_QUADRILATERAL || tri_sparse) && !(ns && ns[0] == '1')) {

@@ -369,9 +369,11 @@ __global__ void __launch_bounds__(kThreads) spmv_u_quad_kernel(SparseView sv, co
 
 // ============================================================================= P1 triangles
 // Opt-in (PFX_TRI_SPARSE=1) and kept as a second implementation for the parity tests: measured on the 2 M-triangle bench
-// mesh the 2 x 2-block SpMV (285 MB per apply) takes 88 us = 3.2 TB/s — rows of only 7 entries leave a thread too few
-// loads in flight — against 57 us for the matrix-free pipeline kernel of pfx_kernels.cuh, which therefore stays the
-// default on triangles (scalar J_phi / mass: 64 us against 43 us).
+// mesh the 2 x 2-block SpMV (285 MB per apply) takes 88 us = 3.2 TB/s against 57 us for the matrix-free pipeline kernel
+// of pfx_kernels.cuh, which therefore stays the default on triangles (scalar J_phi / mass: 64 us against 43 us).  With
+// 7 entries of 32 B per row the sector-granular gathers of the input vector (7 x 32 sectors per warp and row slice)
+// move as many bytes through L2 as the matrix stream itself — batching four entries per pass changed nothing (87.9 us)
+// — whereas the matrix-free kernel stages the vector once, coalesced, in shared memory.
 __global__ void __launch_bounds__(128) assemble_u_tri_kernel(SparseView sv, Material m, const double* __restrict__ X,
                                                              const double* __restrict__ u, const double* __restrict__ phi,
                                                              const uint8_t* __restrict__ mask, double* __restrict__ K,
