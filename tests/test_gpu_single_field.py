@@ -216,3 +216,43 @@ def test_reaction_forces_2d_quadrilateral_equals_3d_hexahedron_reference_test(tm
     assert re.search(r'Name="types"[^>]*>([^<]*)<', txt).group(1).split() == ["72"]          # VTK_LAGRANGE_HEXAHEDRON
     back = read_vtu_points_cells(str(tmp_path / "3_dimension" / "paraview-solutions_vtu" / "phasefieldx_p0_000009.vtu"))
     assert back["cells"].shape == (1, 8) and sorted(back["cells"][0].tolist()) == list(range(8))
+
+
+def test_phase_field_AT1_profile(tmp_path):
+    """`case='AT1'` of the Phase_Field solver (reference Element/Phase_Field/solver/solver.py:116-117 with
+    geometric_crack.py:22-23, 47-48, 72-73: w = phi, c0 = 8/3): the linear boundary value problem
+    (2 l / c0) phi'' = 1 / (c0 l) on a strip with phi(0) = 1 and a natural boundary at x = L has the parabola
+    phi = 1 - L x / (2 l^2) + x^2 / (4 l^2) as its solution (nodally exact for linear elements on a uniform strip);
+    gamma = (1/(c0 l)) int phi + (l/c0) int phi'^2 by the same case.  WU / DOUBLE are refused."""
+    import phasefieldx_b200.compat as compat
+    compat.install()
+    import dolfinx
+    import mpi4py
+    from phasefieldx.Element.Phase_Field.Input import Input
+    from phasefieldx.Element.Phase_Field.solver.solver import solve
+    from phasefieldx.Boundary.boundary_conditions import bc_phi, get_ds_bound_from_marker
+    from phasefieldx.PostProcessing.ReferenceResult import AllResults
+    from phasefieldx_b200.io_vtk import read_vtu_points_cells
+    lx, ly, divx, divy, l = 2.0, 0.5, 160, 2, 1.5
+    msh = dolfinx.mesh.create_rectangle(mpi4py.MPI.COMM_WORLD, [np.array([0.0, 0.0]), np.array([lx, ly])], [divx, divy],
+                                        cell_type=dolfinx.mesh.CellType.quadrilateral)
+    Data = Input(l=l, save_solution_xdmf=False, save_solution_vtu=True, results_folder_name=str(tmp_path / "at1"))
+    fdim = msh.topology.dim - 1
+    left = dolfinx.mesh.locate_entities_boundary(msh, fdim, lambda x: np.equal(x[0], 0))
+    ds_list = np.array([[get_ds_bound_from_marker(left, msh, fdim), "left"]])
+    V_phi = dolfinx.fem.functionspace(msh, ("Lagrange", 1))
+    bcs = [bc_phi(left, V_phi, fdim, value=1.0)]
+    solve(Data, msh, 1.0, V_phi, bcs, None, None, ds_list, 1.0, path=str(tmp_path), quadrature_degree=2, case="AT1")
+    out = read_vtu_points_cells(str(tmp_path / "at1" / "paraview-solutions_vtu" / "phasefieldx_p0_000000.vtu"))
+    x = out["points"][:, 0]
+    phi = 1.0 - lx * x / (2 * l * l) + x * x / (4 * l * l)
+    assert np.abs(out["phi"] - phi).max() < 1e-8
+    en = AllResults(Data.results_folder_name).energy_files["total.energy"]
+    c0 = 8.0 / 3.0
+    g_phi = ly / (c0 * l) * (lx - lx**3 / (4 * l * l) + lx**3 / (12 * l * l))
+    g_grad = ly * l / c0 * (lx**3 / (12 * l**4))                  # int (x - L)^2 / (4 l^4)
+    np.testing.assert_allclose(en["gamma_phi"][0], g_phi, rtol=1e-4)
+    np.testing.assert_allclose(en["gamma_gradphi"][0], g_grad, rtol=1e-3)
+    np.testing.assert_allclose(en["gamma"][0], g_phi + g_grad, rtol=1e-4)
+    with pytest.raises(NotImplementedError, match="WU"):
+        solve(Data, msh, 1.0, V_phi, bcs, None, None, ds_list, 1.0, path=str(tmp_path), quadrature_degree=2, case="WU")
