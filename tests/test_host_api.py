@@ -359,3 +359,31 @@ def test_xdmf_time_series_round_trip(tmp_path, ctype):
     for k, (phi, u) in enumerate(fields):
         assert np.array_equal(phis[k].ravel(), phi)
         assert np.array_equal(us[k][:, :d], u) and (d == 3 or np.all(us[k][:, 2] == 0.0))
+
+
+def test_energy_controlled_dropins_validate_their_arguments_before_touching_the_gpu():
+    """`solver_ener_variational.solve` / `solver_ener_non_variational.solve` keep the reference signature
+    (solver_ener_variational.py:41-58) and refuse what the GPU path does not cover before any device work."""
+    import inspect
+    from phasefieldx_b200 import fem, mesh as M
+    from phasefieldx_b200.Element.Phase_Field_Fracture.Input import Input
+    from phasefieldx_b200.Element.Phase_Field_Fracture.solver import solver_ener_non_variational, solver_ener_variational
+    ref_names = ["Data", "msh", "final_gamma", "V_u", "V_Φ", "bc_list_u", "bc_list_phi", "f_list_u", "T_list_u", "ds_bound", "dtau",
+                 "dtau_min", "dtau_max", "path", "bcs_list_u_names", "c1", "c2", "threshold_gamma_save"]
+    for mod in (solver_ener_variational, solver_ener_non_variational):
+        sig = inspect.signature(mod.solve)
+        assert list(sig.parameters)[: len(ref_names)] == ref_names
+        assert sig.parameters["dtau"].default == 0.0005 and sig.parameters["dtau_min"].default == 1e-12
+        assert sig.parameters["dtau_max"].default == 0.1 and sig.parameters["c1"].default == 1.0
+    msh = M.create_rectangle(None, [[0, 0], [1, 1]], [2, 2], M.CellType.quadrilateral)
+    V_u, V_phi = fem.functionspace(msh, ("Lagrange", 1, (2,))), fem.functionspace(msh, ("Lagrange", 1))
+    base = dict(E=1.0, nu=0.3, Gc=1.0, l=0.1, degradation="isotropic", split_energy="no", degradation_function="quadratic",
+                irreversibility="no", fatigue=False, k=0.0, save_solution_vtu=False, results_folder_name="unused")
+    with pytest.raises(ValueError, match="T_list_u"):
+        solver_ener_variational.solve(Input(**base), msh, 1.0, V_u, V_phi, [], [], None, None)
+    top = M.locate_entities_boundary(msh, 1, lambda x: np.isclose(x[1], 1.0))
+    T = [[fem.Constant(msh, np.array([0.0, 1.0])), fem.Measure(msh, top)]]
+    with pytest.raises(NotImplementedError, match="hybrid"):
+        solver_ener_non_variational.solve(Input(**dict(base, degradation="hybrid", split_energy="spectral")), msh, 1.0, V_u, V_phi, [], [], None, T)
+    with pytest.raises(OverflowError):
+        solver_ener_variational.solve(Input(**dict(base, degradation_function="sargado")), msh, 1.0, V_u, V_phi, [], [], None, T)
