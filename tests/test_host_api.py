@@ -387,3 +387,22 @@ def test_energy_controlled_dropins_validate_their_arguments_before_touching_the_
         solver_ener_non_variational.solve(Input(**dict(base, degradation="hybrid", split_energy="spectral")), msh, 1.0, V_u, V_phi, [], [], None, T)
     with pytest.raises(OverflowError):
         solver_ener_variational.solve(Input(**dict(base, degradation_function="sargado")), msh, 1.0, V_u, V_phi, [], [], None, T)
+
+
+def test_vtu_keep_last_bounds_the_files_on_disk(tmp_path):
+    """`VTKFile(keep_last=k)` / `solve(..., vtu_keep=k)`: only the k most recent step files stay on disk (what bench.py
+    uses for the 1.5 GB-per-step files of the 25 M-dof beam); the .pvd index lists exactly those; default keeps all."""
+    from phasefieldx_b200 import io_vtk, mesh as M
+    msh = M.create_rectangle(None, [[0, 0], [1, 1]], [3, 3])
+    for keep, expect in ((2, [4, 5]), (None, [0, 1, 2, 3, 4, 5])):
+        d = tmp_path / f"k{keep}"
+        vt = io_vtk.VTKFile(None, str(d / "phasefieldx.pvd"), "w", fmt="binary", keep_last=keep)
+        for step in range(6):
+            vt.write_function(msh, {"phi": np.full(msh.num_nodes, float(step))}, step, background=True)
+        vt.close()
+        files = sorted(f for f in os.listdir(d) if f.endswith(".vtu"))
+        assert files == [f"phasefieldx_p0_{s:06d}.vtu" for s in expect]
+        pvd = (d / "phasefieldx.pvd").read_text()
+        assert [f in pvd for f in files] == [True] * len(files) and pvd.count("<DataSet") == len(expect)
+        last = io_vtk.read_vtu_points_cells(str(d / files[-1]))
+        assert np.all(last["phi"] == 5.0)
