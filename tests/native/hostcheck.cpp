@@ -5,6 +5,7 @@
 #include <cstring>
 #include <vector>
 #include "../../phasefieldx_b200/csrc/pfx_elements.cuh"
+#include "../../phasefieldx_b200/csrc/pfx_elements_coupled.cuh"
 
 using namespace pfx;
 
@@ -65,7 +66,47 @@ static void assemble(int op, const Material& m, int n1d, int64_t ne, const doubl
     }
 }
 
+// coupled (u, phi) forms of the energy-controlled solvers (pfx_elements_coupled.cuh):
+// which = 0: out_p = F_phi(u, phi; coef);  1: out_p = K_gamma phi;  2: (out_u, out_p) = J (vu, vp) at (u, phi)
+template <class Cell>
+static void assemble_coupled(int which, const Material& m, int n1d, int64_t ne, const double* coords, const int32_t* cells,
+                             const double* u, const double* phi, const double* vu, const double* vp, double coef, double* out_u,
+                             double* out_p) {
+    constexpr int NV = Cell::NV, D = Cell::D;
+    for (int64_t e = 0; e < ne; ++e) {
+        const int32_t* c = cells + e * NV;
+        double X[NV * D], U[NV * D], P[NV], VU[NV * D], VP[NV], o[NV * (D + 1)];
+        for (int a = 0; a < NV; ++a) {
+            for (int i = 0; i < D; ++i) {
+                X[a * D + i] = coords[c[a] * 3 + i]; U[a * D + i] = u[c[a] * D + i];
+                VU[a * D + i] = vu ? vu[c[a] * D + i] : 0.0;
+            }
+            P[a] = phi[c[a]]; VP[a] = vp ? vp[c[a]] : 0.0;
+        }
+        if (which < 2) {
+            elem_residual_phi_e<Cell>(which, m, n1d, X, U, P, coef, o);
+            for (int a = 0; a < NV; ++a) out_p[c[a]] += o[a];
+        } else {
+            elem_apply_up<Cell>(m, n1d, X, P, U, VU, VP, coef, o);
+            for (int a = 0; a < NV; ++a) {
+                for (int i = 0; i < D; ++i) out_u[c[a] * D + i] += o[a * (D + 1) + i];
+                out_p[c[a]] += o[a * (D + 1) + D];
+            }
+        }
+    }
+}
+
 extern "C" {
+void hc_coupled(int which, int cell_type, const double* mat, int smodel, int emodel, int dfun, int n1d, int64_t ne,
+                const double* coords, const int32_t* cells, const double* u, const double* phi, const double* vu, const double* vp,
+                double coef, double* out_u, double* out_p) {
+    Material m{mat[0], mat[1], mat[2], mat[3], mat[4], smodel, emodel, 0, 0.0, dfun};
+    if (cell_type == 0) assemble_coupled<Tri>(which, m, n1d, ne, coords, cells, u, phi, vu, vp, coef, out_u, out_p);
+    else if (cell_type == 1) assemble_coupled<Quad>(which, m, n1d, ne, coords, cells, u, phi, vu, vp, coef, out_u, out_p);
+    else if (cell_type == 3) assemble_coupled<Hex>(which, m, n1d, ne, coords, cells, u, phi, vu, vp, coef, out_u, out_p);
+    else assemble_coupled<Tet>(which, m, n1d, ne, coords, cells, u, phi, vu, vp, coef, out_u, out_p);
+}
+
 void hc_split(int d, const double* mat /*lam,mu,Gc,l,k*/, int smodel, int emodel, int64_t n, const double* e,
               const double* de, double* sa, double* sb, double* pa, double* pb, double* dsa, double* dsb) {
     Material m{mat[0], mat[1], mat[2], mat[3], mat[4], smodel, emodel, 0, 0.0};

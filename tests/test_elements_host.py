@@ -283,3 +283,38 @@ def test_general_degradation_element_integrals_match_oracle(hostcheck, deg, sp, 
         phi_old, Vc = rng.uniform(0, 1, nn), rng.uniform(0, 1, nn)
         fe = np.einsum("eq,eq,qa->ea", o.t.W, o.g(o.at_qp(phi_old)) * o.at_qp(Vc), o.t.N)
         assert rel(asm(9, phi_old, Vc), o._vec(fe, o.edof_s, nn)) < tol
+
+
+@pytest.mark.parametrize("deg,sp", [("isotropic", "no"), ("anisotropic", "spectral"), ("anisotropic", "deviatoric")])
+@pytest.mark.parametrize("variational", [True, False])
+def test_coupled_forms_of_the_energy_controlled_solvers_match_the_oracle(hostcheck, deg, sp, variational):
+    """pfx_elements_coupled.cuh compiled on the host (the code the `OpResidualPhiE` / `OpApplyUP` kernels run) against
+    the blocked residual and Jacobian of oracle/energy_controlled.py (reference solver_ener_variational.py:167-203),
+    on every cell type: F_phi, K_gamma phi and the action of [[J_uu, J_uphi], [J_phiu, J_phiphi]]."""
+    from oracle.energy_controlled import EnergyControlled
+    rng = np.random.default_rng(11)
+    sm, em = CODES[(deg, sp)]
+    for ctype, m in perturbed_meshes(rng):
+        Pm = Params(E=210.0, nu=0.3, Gc=0.0027, l=0.1, degradation=deg, split_energy=sp, k=1e-3)
+        o = EnergyControlled(m.geometry.x, m.cells, m.cell_type, Pm, variational=variational, c1=3.0, c2=1.0)
+        nn, d = o.nn, o.d
+        u, phi, lam = rng.normal(size=nn * d) * 1e-3, rng.uniform(0, 0.9, nn), 0.37
+        vu, vp = rng.normal(size=nn * d), rng.normal(size=nn)
+        coef = Pm.Gc + (lam * o.c1 if variational else 0.0)
+        mat = np.array([Pm.lambda_, Pm.mu, Pm.Gc, Pm.l, Pm.k])
+        cells = np.ascontiguousarray(m.cells, dtype=np.int32)
+        X = np.ascontiguousarray(m.geometry.x)
+
+        def run(which, with_v):
+            ou, op = np.zeros(nn * d), np.zeros(nn)
+            hostcheck.hc_coupled(which, CT[ctype], dp(mat), sm, em, 0, 3, ctypes.c_int64(len(cells)), dp(X), cells.ctypes.data_as(PI),
+                                 dp(u), dp(phi), dp(vu) if with_v else None, dp(vp) if with_v else None, ctypes.c_double(coef), dp(ou), dp(op))
+            return ou, op
+        Fu, Fp, _ = o.residual(u, phi, lam, 0.0)
+        assert rel(run(0, False)[1], Fp) < 1e-11
+        assert rel(run(1, False)[1], o.Kg @ phi) < 1e-11
+        J = o.jacobian(u, phi, lam).tocsr()
+        nu = nn * d
+        y = J[: nu + nn, : nu + nn] @ np.concatenate([vu, vp])
+        ou, op = run(2, True)
+        assert rel(ou, y[:nu]) < 1e-10 and rel(op, y[nu:]) < 1e-10
