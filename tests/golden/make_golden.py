@@ -12,7 +12,7 @@ container only; the GPU box has no /root/reference).
                      phi, u), gzip-compressed as is: pins the VTU writer / reader to the reference's own file layout
   ref_energy_controlled.npz  first 12 rows of the stored outputs of the energy-controlled examples
                      (examples/PhaseFieldFractureEnergyControlled/results_three_point_[non_]var: total.energy,
-                     bottom_left.reaction, lambda.dof)
+                     bottom_left.reaction, lambda.dof; results_central_cracked_non_var: total.energy, bottom.reaction)
   ref_degradation.npz   g and dg of the reference's own g_degradation_functions.py (quadratic, borden) on a grid of
                      phi, executed unmodified (plain Python arithmetic; loaded by file path)
   ref_constitutive.npz  outputs of the reference's own constitutive layer
@@ -62,7 +62,9 @@ def main():
                         var_reaction=table(os.path.join(ec, "results_three_point_var", "bottom_left.reaction"), 12),
                         var_lambda=table(os.path.join(ec, "results_three_point_var", "lambda.dof"), 12),
                         nonvar_energy=table(os.path.join(ec, "results_three_point_non_var", "total.energy"), 12),
-                        nonvar_reaction=table(os.path.join(ec, "results_three_point_non_var", "bottom_left.reaction"), 12))
+                        nonvar_reaction=table(os.path.join(ec, "results_three_point_non_var", "bottom_left.reaction"), 12),
+                        cc_energy=table(os.path.join(ec, "results_central_cracked_non_var", "total.energy"), 12),
+                        cc_reaction=table(os.path.join(ec, "results_central_cracked_non_var", "bottom.reaction"), 12))
     import gzip
     vtu = os.path.join(EX, "1711_Single_Edge_Notched_Tension_Test", "paraview-solutions_vtu", "phasefieldx_p0_000149.vtu")
     with open(vtu, "rb") as src, gzip.GzipFile(os.path.join(HERE, "ref_1711_final.vtu.gz"), "wb", mtime=0) as dst:

@@ -79,3 +79,31 @@ def test_three_point_bending_reproduces_the_stored_reference_rows(scheme, steps)
         seen.append(k)
     o.run(kw["final_gamma"], bcs, dtau=kw["dtau"], dtau_min=kw["dtau_min"], dtau_max=kw["dtau_max"], max_steps=steps, callback=cb)
     assert seen == list(range(steps))
+
+
+def test_central_cracked_plate_reproduces_the_stored_reference_row():
+    """Third stored example (plot_central_cracked_non_var.py:82-131, 208-245: 100 x 300 Q1 cells, the crack is the free
+    part x < a0 of the bottom edge, non-variational scheme, c1 = c2 = 1, dtau = 1e-4): external work, E, gamma and the
+    bottom reaction of the first row to 1e-10 relative (measured: 1e-14) — gamma is already 5e-9 there, so the
+    phase-field side of the blocked system is pinned too."""
+    from oracle.energy_controlled import EnergyControlled
+    from oracle.solver import BC, Params
+    from phasefieldx_b200 import fem, mesh as M
+    divx, divy, lx, ly, a0 = 100, 300, 1.0, 3.0, 0.3
+    msh = M.create_rectangle(None, [np.array([0.0, 0.0]), np.array([lx, ly])], [divx, divy], M.CellType.quadrilateral)
+    o = EnergyControlled(msh.geometry.x, msh.cells, "quadrilateral", Params(E=210.0, nu=0.3, Gc=0.0027, l=0.025), variational=False)
+    fb = M.locate_entities_boundary(msh, 1, lambda x: np.logical_and(np.isclose(x[1], 0), np.greater_equal(x[0], a0)))
+    fl = M.locate_entities_boundary(msh, 1, lambda x: np.isclose(x[0], 0.0))
+    ft = M.locate_entities_boundary(msh, 1, lambda x: np.isclose(x[1], ly))
+    bcs = [BC(M.facet_nodes(msh, fb) * 2 + 1), BC(M.facet_nodes(msh, fl) * 2 + 0)]
+    nodes, w = fem.Measure(msh, ft).nodal_weights()
+    o.set_traction(nodes, w, np.array([0.0, 1.0]))
+    ref = np.load(os.path.join(GOLDEN, "ref_energy_controlled.npz"))
+    en, re = ref["cc_energy"], ref["cc_reaction"]
+    rec = o.run(0.5, bcs, dtau=0.0001, dtau_min=1e-12, dtau_max=1.0, max_steps=1)[0]
+    e = rec["energies"]
+    assert abs(rec["external"] - en[0, 11]) <= 1e-10 * abs(en[0, 11])
+    assert abs(e["E"] - en[0, 2]) <= 1e-10 * abs(en[0, 2])
+    assert abs(e["gamma"] - en[0, 6]) <= 1e-10 * abs(en[0, 6])
+    assert abs(e["gamma_gradphi"] - en[0, 8]) <= 1e-10 * abs(en[0, 8])
+    assert abs(o.reaction(bcs[0])[1] - re[0, 2]) <= 1e-10 * abs(re[0, 2])
